@@ -58,7 +58,7 @@ def synth_day_frame(
     day_index: int = 0,
     seed: int = 0,
     cancel_frac: float = 0.0,
-    zipf_s: float = 0.85,
+    zipf_s: float = 0.6,
     date: Optional[str] = None,
 ) -> pd.DataFrame:
     """One synthetic network day as a dataframe (rows sorted by scheduled

@@ -1,0 +1,68 @@
+"""Shared helpers for the tests: golden-fixture loading and noise tables."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+from bayesair_b200.compiler import DaySpec
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LATENT_KEYS = ("mean_turnaround", "mean_service", "travel",
+               "log_initial_aircraft", "base_cancel_logprob")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+class Golden:
+    """One fixture written by tests/golden/make_golden.py."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+        self.name = name
+        self.z = z
+        self.n_days = int(z["n_days"])
+        self.global_codes = [str(c) for c in z["global_codes"]]
+        self.delta_t = float(z["delta_t"])
+        self.max_t = float(z["max_t"])
+        self.include_cancellations = bool(int(z["include_cancellations"]))
+        self.scales = tuple(float(s) for s in z["scales"])
+        self.noise = z["noise"]                       # [D, Fmax, 4]
+        self.latents = {k: z["lat_" + k] for k in LATENT_KEYS if "lat_" + k in z}
+        self.specs = []
+        for d in range(self.n_days):
+            self.specs.append(DaySpec(
+                codes=[str(c) for c in z[f"day{d}_codes"]],
+                airport_global=z[f"day{d}_airport_global"],
+                sched_dep=z[f"day{d}_sched_dep"], act_dep=z[f"day{d}_act_dep"],
+                act_arr=z[f"day{d}_act_arr"], cancel_obs=z[f"day{d}_cancel_obs"],
+                origin=z[f"day{d}_origin"], dest=z[f"day{d}_dest"],
+                flight_names=[str(c) for c in z[f"day{d}_names"]]))
+        self.ref_per_flight = float(z["ref_per_flight"])
+        self.ref_total = float(z["ref_total"])
+        self.ref_values = z["ref_values"]             # [D, Fmax, 4]
+        self.ref_class = {k[len("ref_class_"):]: float(z[k]) for k in z.files
+                          if k.startswith("ref_class_")}
+        self.ref_grads = {k[len("ref_grad_"):]: z[k] for k in z.files
+                          if k.startswith("ref_grad_") and k != "ref_grad_scales"}
+        self.ref_grad_scales = z["ref_grad_scales"]
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def std_noise(P, D, Fmax, seed):
+    """[P, D, Fmax, 4] standard draws: Exp(1), N(0,1), Exp(1), N(0,1)."""
+    rng = np.random.default_rng([seed, 424242])
+    z = np.empty((P, D, Fmax, 4), np.float32)
+    z[..., 0] = rng.exponential(size=(P, D, Fmax))
+    z[..., 1] = rng.standard_normal((P, D, Fmax))
+    z[..., 2] = rng.exponential(size=(P, D, Fmax))
+    z[..., 3] = rng.standard_normal((P, D, Fmax))
+    return z
