@@ -1,0 +1,353 @@
+// C ABI of libbayesair_b200.so (declared in include/bayesair_b200.h).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/bayesair_b200.h"
+#include "ba_kernels.cuh"
+#include "ba_plan_build.h"
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static BaStatus set_err(BaStatus s, const std::string &m)
+{
+    g_err = m;
+    return s;
+}
+
+#define BA_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess)                                                          \
+            return set_err(BA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct BaPlan {
+    BaHostPlan host;
+    int device = 0;
+    std::vector<void *> allocs;          // device allocations owned by the plan
+    BaDayView *d_days = nullptr;
+    BaPlanView dev_view;                 // .days = d_days
+    int block = 0;
+    size_t smem_fast = 0, smem_exact = 0;
+    bool fast_ok = false;
+    int grid_fast = 0, grid_exact = 0;
+    uint32_t *d_scratch = nullptr;
+    uint64_t stride_fast = 0, stride_exact = 0;
+    unsigned int *d_counters = nullptr;  // [0] fast work, [1] exact work, [2] rerun count
+    int32_t *d_worklist = nullptr;
+    size_t worklist_cap = 0;
+    // staging of ba_logjoint_host (grown on demand)
+    void *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaStream_t host_stream = nullptr;
+};
+
+template <typename T>
+static cudaError_t upload(BaPlan *pl, const std::vector<T> &v, const T **out)
+{
+    void *d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return e;
+    pl->allocs.push_back(d);
+    if (!v.empty()) e = cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *out = (const T *)d;
+    return e;
+}
+
+extern "C" int ba_version(void) { return BA_VERSION; }
+extern "C" const char *ba_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t ba_launch_count(void) { return g_launches.load(); }
+
+extern "C" void ba_plan_destroy(BaPlan *pl)
+{
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    for (void *p : pl->allocs) cudaFree(p);
+    if (pl->d_worklist) cudaFree(pl->d_worklist);
+    if (pl->d_stage) cudaFree(pl->d_stage);
+    if (pl->host_stream) cudaStreamDestroy(pl->host_stream);
+    delete pl;
+}
+
+extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32_t n_airports,
+                                   float delta_t, float max_t, int32_t include_cancellations,
+                                   int32_t max_ticks, int32_t device, BaPlan **out)
+{
+    if (!out) return set_err(BA_ERR_BAD_ARG, "ba_plan_create: out is null");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(BA_ERR_NO_DEVICE,
+                       "ba_plan_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return set_err(BA_ERR_BAD_ARG, "ba_plan_create: bad device");
+    BaPlan *pl = new (std::nothrow) BaPlan();
+    if (!pl) return set_err(BA_ERR_BAD_ARG, "ba_plan_create: out of host memory");
+    std::string err;
+    int rc = ba_build_host_plan(days, n_days, n_airports, delta_t, max_t, include_cancellations,
+                                max_ticks, &pl->host, &err);
+    if (rc != BA_OK) { delete pl; return set_err((BaStatus)rc, err); }
+    pl->device = device;
+#define BA_PCUDA(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            std::string m = std::string(#expr) + ": " + cudaGetErrorString(_e);         \
+            ba_plan_destroy(pl);                                                        \
+            return set_err(BA_ERR_CUDA, m);                                             \
+        }                                                                               \
+    } while (0)
+    BA_PCUDA(cudaSetDevice(device));
+    // upload day tables
+    std::vector<BaDayView> dviews(n_days);
+    for (int d = 0; d < n_days; ++d) {
+        BaHostDay &H = pl->host.days[d];
+        BaDayView v = H.view;
+        BA_PCUDA(upload(pl, H.flights, &v.flights));
+        BA_PCUDA(upload(pl, H.route, &v.route));
+        BA_PCUDA(upload(pl, H.dep_fid, &v.dep_fid));
+        BA_PCUDA(upload(pl, H.airports, &v.airports));
+        BA_PCUDA(upload(pl, H.lane_airport, &v.lane_airport));
+        dviews[d] = v;
+    }
+    const BaDayView *dd = nullptr;
+    BA_PCUDA(upload(pl, dviews, &dd));
+    pl->d_days = const_cast<BaDayView *>(dd);
+    pl->dev_view = pl->host.view;
+    pl->dev_view.days = pl->d_days;
+
+    // launch geometry
+    const int N = n_airports;
+    pl->block = ba_forward_block_threads(N);
+    pl->smem_fast = ba_forward_smem_bytes(N, pl->host.smem_list_words, false);
+    pl->smem_exact = ba_forward_smem_bytes(N, 0, true);
+    int max_optin = 0;
+    BA_PCUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (pl->smem_exact > (size_t)max_optin) {
+        ba_plan_destroy(pl);
+        return set_err(BA_ERR_LIMIT, "ba_plan_create: too many airports for one CTA's shared memory");
+    }
+    pl->fast_ok = pl->smem_fast <= (size_t)max_optin;
+    BA_PCUDA(ba_forward_configure(pl->block, pl->fast_ok ? pl->smem_fast : 0, pl->smem_exact));
+    pl->grid_exact = ba_forward_max_resident(pl->block, pl->smem_exact, true, device);
+    pl->grid_fast = pl->fast_ok ? ba_forward_max_resident(pl->block, pl->smem_fast, false, device) : 0;
+    if (pl->grid_exact <= 0 || (pl->fast_ok && pl->grid_fast <= 0)) {
+        ba_plan_destroy(pl);
+        return set_err(BA_ERR_CUDA, "ba_plan_create: occupancy query failed");
+    }
+    pl->stride_fast = (pl->host.scratch_words_fast + 31) & ~31ull;
+    pl->stride_exact = (pl->host.scratch_words_exact + 31) & ~31ull;
+    uint64_t words = std::max<uint64_t>((uint64_t)pl->grid_fast * pl->stride_fast,
+                                        (uint64_t)pl->grid_exact * pl->stride_exact);
+    words = std::max<uint64_t>(words, 32);
+    void *scr = nullptr;
+    BA_PCUDA(cudaMalloc(&scr, words * 4));
+    pl->allocs.push_back(scr);
+    pl->d_scratch = (uint32_t *)scr;
+    void *cnt = nullptr;
+    BA_PCUDA(cudaMalloc(&cnt, 4 * sizeof(unsigned int)));
+    pl->allocs.push_back(cnt);
+    pl->d_counters = (unsigned int *)cnt;
+    BA_PCUDA(cudaStreamCreateWithFlags(&pl->host_stream, cudaStreamNonBlocking));
+#undef BA_PCUDA
+    *out = pl;
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_plan_info(const BaPlan *pl, BaPlanInfo *o)
+{
+    if (!pl || !o) return set_err(BA_ERR_BAD_ARG, "ba_plan_info: null argument");
+    const BaPlanView &v = pl->host.view;
+    o->n_days = v.D; o->n_airports = v.N; o->max_flights = v.Fmax; o->n_routes = v.R;
+    o->n_airport_latents = v.C; o->grad_stride = v.grad_stride;
+    o->include_cancellations = v.include_cancellations; o->device = pl->device;
+    o->delta_t = v.delta_t; o->max_t = v.max_t; o->max_ticks = v.max_ticks;
+    o->block_threads = pl->block;
+    o->smem_bytes = (int32_t)(pl->fast_ok ? pl->smem_fast : pl->smem_exact);
+    o->resident_ctas = pl->fast_ok ? pl->grid_fast : pl->grid_exact;
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_plan_routes(const BaPlan *pl, int32_t *h_origin, int32_t *h_dest)
+{
+    if (!pl || !h_origin || !h_dest) return set_err(BA_ERR_BAD_ARG, "ba_plan_routes: null argument");
+    const size_t R = pl->host.route_origin.size();
+    std::memcpy(h_origin, pl->host.route_origin.data(), R * sizeof(int32_t));
+    std::memcpy(h_dest, pl->host.route_dest.data(), R * sizeof(int32_t));
+    return BA_OK;
+}
+
+extern "C" size_t ba_tape_bytes(const BaPlan *pl, int32_t P)
+{
+    if (!pl || P <= 0) return 0;
+    return (size_t)P * pl->host.view.D * pl->host.view.grad_stride * sizeof(float);
+}
+
+extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport,
+                               const float *d_lat_route, const float *d_scales,
+                               const float *d_noise, const BaForwardOpts *opts, float *d_logp,
+                               uint32_t *d_status, int32_t *d_ticks, void *d_tape, void *stream)
+{
+    if (!pl || P <= 0 || !d_lat_airport || !d_lat_route || !d_scales || !d_logp || !d_status)
+        return set_err(BA_ERR_BAD_ARG, "ba_forward: null / empty argument");
+    BaForwardOpts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    if (o.want_grad && !d_tape) return set_err(BA_ERR_BAD_ARG, "ba_forward: want_grad needs d_tape");
+    if (o.noise_is_value && !d_noise)
+        return set_err(BA_ERR_BAD_ARG, "ba_forward: noise_is_value needs d_noise");
+    cudaStream_t s = (cudaStream_t)stream;
+    BA_CUDA(cudaSetDevice(pl->device));
+    const int D = pl->host.view.D;
+    const long long n_work = (long long)P * D;
+    if (n_work > 0x7fffffffLL) return set_err(BA_ERR_LIMIT, "ba_forward: P*D too large");
+    if (pl->worklist_cap < (size_t)n_work) {
+        if (pl->d_worklist) BA_CUDA(cudaFree(pl->d_worklist));
+        pl->d_worklist = nullptr;
+        BA_CUDA(cudaMalloc((void **)&pl->d_worklist, (size_t)n_work * sizeof(int32_t)));
+        pl->worklist_cap = (size_t)n_work;
+    }
+    BA_CUDA(cudaMemsetAsync(pl->d_counters, 0, 4 * sizeof(unsigned int), s));
+
+    BaFwdParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.plan = pl->dev_view;
+    prm.P = P;
+    prm.lat_airport = d_lat_airport; prm.lat_route = d_lat_route; prm.scales = d_scales;
+    prm.noise = d_noise; prm.seed = o.seed;
+    prm.value_mode = o.noise_is_value; prm.want_grad = o.want_grad;
+    prm.logp = d_logp; prm.status = d_status; prm.ticks = d_ticks;
+    prm.tape = (float *)d_tape; prm.pop_tick = o.d_pop_tick;
+    prm.scratch = pl->d_scratch;
+    prm.n_work = (int)n_work;
+
+    const bool use_fast = pl->fast_ok && !o.force_exact_lists;
+    if (use_fast) {
+        prm.scratch_stride = pl->stride_fast;
+        prm.work_counter = pl->d_counters + 0;
+        int grid = (int)std::min<long long>(n_work, pl->grid_fast);
+        BA_CUDA(ba_launch_forward(prm, false, grid, pl->block, pl->smem_fast, s));
+        g_launches++;
+        if (!o.no_overflow_rerun) {
+            // particle-days whose shared-memory lists overflowed are re-run with
+            // exact-capacity lists; the count stays on the device (no host sync)
+            BA_CUDA(ba_launch_collect(d_status, (int)n_work, BA_PD_OVERFLOW, pl->d_worklist,
+                                      pl->d_counters + 2, s));
+            g_launches++;
+            BaFwdParams rr = prm;
+            rr.scratch_stride = pl->stride_exact;
+            rr.work_counter = pl->d_counters + 1;
+            rr.work_list = pl->d_worklist;
+            rr.n_work_dev = pl->d_counters + 2;
+            int rgrid = (int)std::min<long long>(n_work, pl->grid_exact);
+            BA_CUDA(ba_launch_forward(rr, true, rgrid, pl->block, pl->smem_exact, s));
+            g_launches++;
+        }
+    } else {
+        prm.scratch_stride = pl->stride_exact;
+        prm.work_counter = pl->d_counters + 1;
+        int grid = (int)std::min<long long>(n_work, pl->grid_exact);
+        BA_CUDA(ba_launch_forward(prm, true, grid, pl->block, pl->smem_exact, s));
+        g_launches++;
+    }
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_backward(BaPlan *pl, int32_t P, const float *d_dlogp, const void *d_tape,
+                                float *d_g_airport, float *d_g_route, float *d_g_scales,
+                                void *stream)
+{
+    if (!pl || P <= 0 || !d_dlogp || !d_tape || !d_g_airport || !d_g_route || !d_g_scales)
+        return set_err(BA_ERR_BAD_ARG, "ba_backward: null / empty argument");
+    BA_CUDA(cudaSetDevice(pl->device));
+    const BaPlanView &v = pl->host.view;
+    BaBwdParams b;
+    b.P = P; b.D = v.D; b.C = v.C; b.N = v.N; b.R = v.R; b.stride = v.grad_stride;
+    b.dlogp = d_dlogp; b.tape = (const float *)d_tape;
+    b.g_airport = d_g_airport; b.g_route = d_g_route; b.g_scales = d_g_scales;
+    BA_CUDA(ba_launch_backward(b, (cudaStream_t)stream));
+    g_launches++;
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_generate_noise(BaPlan *pl, int32_t P, uint64_t seed, float *d_noise,
+                                      void *stream)
+{
+    if (!pl || P <= 0 || !d_noise) return set_err(BA_ERR_BAD_ARG, "ba_generate_noise: null argument");
+    BA_CUDA(cudaSetDevice(pl->device));
+    BA_CUDA(ba_launch_noise(pl->host.view, P, seed, d_noise, (cudaStream_t)stream));
+    g_launches++;
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_logjoint_host(BaPlan *pl, int32_t P, const float *h_lat_airport,
+                                     const float *h_lat_route, const float *h_scales,
+                                     const float *h_noise, const BaForwardOpts *opts,
+                                     float *h_logp, uint32_t *h_status, float *h_g_airport,
+                                     float *h_g_route, float *h_g_scales)
+{
+    if (!pl || P <= 0 || !h_lat_airport || !h_lat_route || !h_scales || !h_logp || !h_status)
+        return set_err(BA_ERR_BAD_ARG, "ba_logjoint_host: null / empty argument");
+    BA_CUDA(cudaSetDevice(pl->device));
+    const BaPlanView &v = pl->host.view;
+    const bool grad = h_g_airport && h_g_route && h_g_scales;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_la = al((size_t)P * v.C * v.N * 4), b_lr = al((size_t)P * v.R * 4),
+                 b_sc = al(3 * 4), b_nz = h_noise ? al((size_t)P * v.D * v.Fmax * 16) : 0,
+                 b_lp = al((size_t)P * v.D * 4), b_st = al((size_t)P * v.D * 4),
+                 b_tape = grad ? al(ba_tape_bytes(pl, P)) : 0, b_dl = grad ? b_lp : 0,
+                 b_ga = grad ? b_la : 0, b_gr = grad ? b_lr : 0, b_gs = grad ? al((size_t)P * 12) : 0;
+    const size_t total = b_la + b_lr + b_sc + b_nz + b_lp + b_st + b_tape + b_dl + b_ga + b_gr + b_gs;
+    if (pl->stage_bytes < total) {
+        if (pl->d_stage) BA_CUDA(cudaFree(pl->d_stage));
+        pl->d_stage = nullptr; pl->stage_bytes = 0;
+        BA_CUDA(cudaMalloc(&pl->d_stage, total));
+        pl->stage_bytes = total;
+    }
+    char *q = (char *)pl->d_stage;
+    float *d_la = (float *)q; q += b_la;
+    float *d_lr = (float *)q; q += b_lr;
+    float *d_sc = (float *)q; q += b_sc;
+    float *d_nz = h_noise ? (float *)q : nullptr; q += b_nz;
+    float *d_lp = (float *)q; q += b_lp;
+    uint32_t *d_st = (uint32_t *)q; q += b_st;
+    void *d_tape = grad ? (void *)q : nullptr; q += b_tape;
+    float *d_dl = (float *)q; q += b_dl;
+    float *d_ga = (float *)q; q += b_ga;
+    float *d_gr = (float *)q; q += b_gr;
+    float *d_gs = (float *)q;
+    cudaStream_t s = pl->host_stream;
+    BA_CUDA(cudaMemcpyAsync(d_la, h_lat_airport, (size_t)P * v.C * v.N * 4, cudaMemcpyHostToDevice, s));
+    BA_CUDA(cudaMemcpyAsync(d_lr, h_lat_route, (size_t)P * v.R * 4, cudaMemcpyHostToDevice, s));
+    BA_CUDA(cudaMemcpyAsync(d_sc, h_scales, 12, cudaMemcpyHostToDevice, s));
+    if (h_noise)
+        BA_CUDA(cudaMemcpyAsync(d_nz, h_noise, (size_t)P * v.D * v.Fmax * 16, cudaMemcpyHostToDevice, s));
+    BaForwardOpts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    o.want_grad = grad ? 1 : 0;
+    o.d_pop_tick = nullptr;
+    BaStatus rc = ba_forward(pl, P, d_la, d_lr, d_sc, d_nz, &o, d_lp, d_st, nullptr, d_tape, s);
+    if (rc != BA_OK) return rc;
+    if (grad) {
+        // unit cotangent on every logp[p, d]: fill with 1.0f via the bit pattern
+        std::vector<float> ones((size_t)P * v.D, 1.0f);
+        BA_CUDA(cudaMemcpyAsync(d_dl, ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, s));
+        rc = ba_backward(pl, P, d_dl, d_tape, d_ga, d_gr, d_gs, s);
+        if (rc != BA_OK) return rc;
+        BA_CUDA(cudaMemcpyAsync(h_g_airport, d_ga, (size_t)P * v.C * v.N * 4, cudaMemcpyDeviceToHost, s));
+        BA_CUDA(cudaMemcpyAsync(h_g_route, d_gr, (size_t)P * v.R * 4, cudaMemcpyDeviceToHost, s));
+        BA_CUDA(cudaMemcpyAsync(h_g_scales, d_gs, (size_t)P * 12, cudaMemcpyDeviceToHost, s));
+    }
+    BA_CUDA(cudaMemcpyAsync(h_logp, d_lp, (size_t)P * v.D * 4, cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaMemcpyAsync(h_status, d_st, (size_t)P * v.D * 4, cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+    return BA_OK;
+}

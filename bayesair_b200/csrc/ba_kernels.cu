@@ -1,0 +1,297 @@
+// sm_100a kernels of the BayesAir hot path.
+//
+//   ba_forward_kernel<EXACT>   persistent CTAs; each pulls (particle, day) work items
+//                              from an atomic counter and runs the tick loop of
+//                              ba_sim.cuh with one lane per airport.  EXACT=false keeps
+//                              the runway-queue rings and inbound bags in shared memory
+//                              (plan-time capacities); EXACT=true keeps them in per-CTA
+//                              global scratch with capacities no schedule can overflow.
+//   ba_backward_kernel         contracts the per-(particle, day) gradient rows written by
+//                              the forward kernel with the cotangent d logp.
+//   ba_noise_kernel            materialises the Philox per-flight noise (tests / callers
+//                              that want to keep their draws).
+//   ba_collect_kernel          compacts the particle-days that must be re-run.
+//
+// Nothing here is a dense contraction: no tensor cores, by design.
+#include "ba_kernels.cuh"
+#include "ba_sim.cuh"
+
+#define BA_RED_WORDS (32 * 5 + 4)
+
+int ba_forward_block_threads(int n_airports)
+{
+    int t = ((n_airports + 31) / 32) * 32;
+    if (t < 32) t = 32;
+    if (t > 1024) t = 1024;
+    return t;
+}
+
+size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact)
+{
+    size_t w = (size_t)BA_NWORDS_STATE * n_airports + BA_RED_WORDS;
+    if (!exact) w += list_words;
+    return w * 4;
+}
+
+template <bool EXACT, int MAXT>
+__global__ void __launch_bounds__(MAXT) ba_forward_kernel(const BaFwdParams prm)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
+    const BaPlanView &plan = prm.plan;
+    const int N = plan.N, D = plan.D, C = plan.C, R = plan.R;
+
+    uint32_t *state_w = smem;
+    uint32_t *red = smem + (size_t)BA_NWORDS_STATE * N;     // [BA_RED_WORDS]
+    uint32_t *pool = red + BA_RED_WORDS;                     // shared list pools (fast)
+    uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
+
+    BaCtx c;
+    ba_carve_state(c, state_w, N);
+    c.sigma = prm.scales[0]; c.v_t = prm.scales[1]; c.v_u = prm.scales[2];
+    c.inv_sigma = 1.0f / c.sigma;
+    c.inv_sigma2 = c.inv_sigma * c.inv_sigma;
+    c.inv_sigma3 = c.inv_sigma2 * c.inv_sigma;
+    c.log_sigma = logf(c.sigma);
+    c.inv_vt = 1.0f / c.v_t; c.inv_vu = 1.0f / c.v_u;
+    c.c0_lp = ba_relaxed_bernoulli_lp(0.0f, 0.0f, nullptr);
+    c.c1_lp = ba_relaxed_bernoulli_lp(0.0f, 1.0f, nullptr);
+    c.value_mode = prm.value_mode; c.want_grad = prm.want_grad && prm.tape != nullptr;
+    c.cancel_mode = plan.include_cancellations;
+    c.max_t = plan.max_t;
+    c.seed = prm.seed;
+    c.route_base = C * N;
+    const float dt = plan.delta_t;
+
+    for (;;) {
+        // ---- next work item ------------------------------------------------
+        if (tid == 0) red[BA_RED_WORDS - 1] = atomicAdd(prm.work_counter, 1u);
+        __syncthreads();
+        const int wi = (int)red[BA_RED_WORDS - 1];
+        const int n_work = prm.n_work_dev ? (int)*prm.n_work_dev : prm.n_work;
+        if (wi >= n_work) break;
+        int p, d;
+        if (prm.work_list) { const int pd = prm.work_list[wi]; p = pd / D; d = pd - p * D; }
+        else { d = wi / prm.P; p = wi - d * prm.P; }     // same-day items adjacent in time
+        const size_t pd = (size_t)p * D + d;
+        const BaDayView day = plan.days[d];
+
+        c.N = N; c.F = day.F;
+        c.flights = day.flights; c.route = day.route; c.dep_fid = day.dep_fid; c.ap = day.airports;
+        c.lat_route = prm.lat_route + (size_t)p * R;
+        c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
+        c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
+        c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
+        c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
+        {
+            uint32_t *g = gscr;
+            if (EXACT) {
+                c.qf = g; g += day.q_total_x;
+                c.qs = (float *)g; g += day.q_total_x;
+                c.qw = (float *)g; g += day.q_total_x;
+                c.qx = (float *)g; g += day.q_total_x;
+                c.bf = g; g += day.bag_total_x;
+                c.ba = (float *)g; g += day.bag_total_x;
+            } else {
+                uint32_t *s = pool;
+                c.qf = s; s += day.q_total_s;
+                c.qs = (float *)s; s += day.q_total_s;
+                c.qw = (float *)s; s += day.q_total_s;
+                c.qx = (float *)s; s += day.q_total_s;
+                c.bf = s; s += day.bag_total_s;
+                c.ba = (float *)s;
+            }
+            c.tt = (float *)g; g += day.turn_total;
+            c.te = (float *)g; g += day.turn_total;
+            c.at = (float *)g; g += day.av_total;
+            c.ae = (float *)g; g += day.av_total;
+            c.dl = g;
+        }
+
+        // ---- setup -----------------------------------------------------------
+        const float *lat_airport = prm.lat_airport + (size_t)p * C * N;
+        for (int a = tid; a < N; a += nthr) ba_init_airport<EXACT>(c, a, lat_airport, N);
+        if (c.grow)
+            for (int i = tid; i < plan.grad_stride; i += nthr) c.grow[i] = 0.0f;
+        if (c.pop_tick)
+            for (int i = tid; i < 2 * plan.Fmax; i += nthr) c.pop_tick[i] = -1;
+        BaAcc acc = {0.0f, 0.0f, 0.0f, 0.0f, 0u};
+        __syncthreads();
+
+        // ---- tick loop (model.py:158-200) --------------------------------------
+        float t = day.t_before_first;
+        int tick = day.first_tick - 1;
+        bool busy = day.F > 0;
+        while (busy) {
+            if (tick >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
+            t = BA_ADD(t, dt);                                  // model.py:161
+            ++tick;
+            for (int s = tid; s < N; s += nthr) {
+                const int a = day.lane_airport[s];
+                ba_phase_a<EXACT>(c, acc, a, t, tick);
+            }
+            __syncthreads();
+            int more = 0;
+            for (int s = tid; s < N; s += nthr) {
+                const int a = day.lane_airport[s];
+                more |= ba_phase_b(c, acc, a, t) ? 1 : 0;
+            }
+            busy = __syncthreads_or(more) != 0;
+        }
+
+        // ---- epilogue ----------------------------------------------------------
+        if (c.grow)
+            for (int a = tid; a < N; a += nthr) ba_airport_epilogue(c, a, N);
+        // deterministic block reduction: lanes -> warp (shuffle tree) -> warps in order
+        float v0 = acc.lp, v1 = acc.g_sigma, v2 = acc.g_vt, v3 = acc.g_vu;
+        uint32_t st = acc.status;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_down_sync(0xffffffffu, v0, o);
+            v1 += __shfl_down_sync(0xffffffffu, v1, o);
+            v2 += __shfl_down_sync(0xffffffffu, v2, o);
+            v3 += __shfl_down_sync(0xffffffffu, v3, o);
+            st |= __shfl_down_sync(0xffffffffu, st, o);
+        }
+        float *redf = (float *)red;
+        if (lane == 0) {
+            redf[warp * 5 + 0] = v0; redf[warp * 5 + 1] = v1; redf[warp * 5 + 2] = v2;
+            redf[warp * 5 + 3] = v3; red[warp * 5 + 4] = st;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            uint32_t ss = 0;
+            for (int w = 0; w < nwarp; ++w) {
+                s0 += redf[w * 5 + 0]; s1 += redf[w * 5 + 1]; s2 += redf[w * 5 + 2];
+                s3 += redf[w * 5 + 3]; ss |= red[w * 5 + 4];
+            }
+            prm.logp[pd] = (float)s0;
+            prm.status[pd] = ss;
+            if (prm.ticks) prm.ticks[pd] = tick;
+            if (c.grow) {
+                c.grow[c.route_base + R + 0] = (float)s1;
+                c.grow[c.route_base + R + 1] = (float)s2;
+                c.grow[c.route_base + R + 2] = (float)s3;
+            }
+        }
+        __syncthreads();     // red[] and the state arrays are reused by the next item
+    }
+}
+
+// g[p, j] = sum_d dlogp[p, d] * tape[p, d, j]
+__global__ void __launch_bounds__(256) ba_backward_kernel(const BaBwdParams prm)
+{
+    const int CN = prm.C * prm.N;
+    const int stride = prm.stride;
+    const int p = blockIdx.y;
+    const float *tp = prm.tape + (size_t)p * prm.D * stride;
+    const float *dl = prm.dlogp + (size_t)p * prm.D;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < stride; j += gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        for (int d = 0; d < prm.D; ++d) s = fmaf(__ldg(dl + d), __ldg(tp + (size_t)d * stride + j), s);
+        if (j < CN) prm.g_airport[(size_t)p * CN + j] = s;
+        else if (j < CN + prm.R) prm.g_route[(size_t)p * prm.R + (j - CN)] = s;
+        else prm.g_scales[(size_t)p * 3 + (j - CN - prm.R)] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) ba_noise_kernel(int P, int D, int Fmax, uint64_t seed,
+                                                      float4 *noise)
+{
+    const size_t total = (size_t)P * D * Fmax;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t f = (uint32_t)(i % Fmax);
+        const size_t pd = i / Fmax;
+        const uint32_t d = (uint32_t)(pd % D), p = (uint32_t)(pd / D);
+        const BaNoise4 z = ba_philox_noise(seed, p, d, f);
+        noise[i] = make_float4(z.e_dep, z.eps_travel, z.e_arr, z.eps_turn);
+    }
+}
+
+__global__ void __launch_bounds__(256) ba_collect_kernel(const uint32_t *status, int n,
+                                                        uint32_t bit, int32_t *list,
+                                                        unsigned int *count)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (status[i] & bit) list[atomicAdd(count, 1u)] = i;
+}
+
+// ---------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------
+// block-size classes: the register budget follows the CTA size actually used
+#define BA_DISPATCH(EX, BLOCK, STMT)                                                   \
+    do {                                                                               \
+        if ((BLOCK) <= 128) { auto kfn = ba_forward_kernel<EX, 128>; STMT; }           \
+        else if ((BLOCK) <= 256) { auto kfn = ba_forward_kernel<EX, 256>; STMT; }      \
+        else if ((BLOCK) <= 512) { auto kfn = ba_forward_kernel<EX, 512>; STMT; }      \
+        else { auto kfn = ba_forward_kernel<EX, 1024>; STMT; }                         \
+    } while (0)
+
+cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact)
+{
+    cudaError_t e = cudaSuccess;
+    if (smem_fast)
+        BA_DISPATCH(false, block, e = cudaFuncSetAttribute(
+            kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
+    if (e != cudaSuccess) return e;
+    BA_DISPATCH(true, block, e = cudaFuncSetAttribute(
+        kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact));
+    return e;
+}
+
+int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, int device)
+{
+    int per_sm = 0, sms = 0;
+    cudaError_t e;
+    if (exact)
+        BA_DISPATCH(true, block_threads, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, kfn, block_threads, smem_bytes));
+    else
+        BA_DISPATCH(false, block_threads, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, kfn, block_threads, smem_bytes));
+    if (e != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+        return -1;
+    return per_sm * sms;
+}
+
+cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, int grid, int block,
+                              size_t smem, cudaStream_t s)
+{
+    if (exact) BA_DISPATCH(true, block, (kfn<<<grid, block, smem, s>>>(p)));
+    else BA_DISPATCH(false, block, (kfn<<<grid, block, smem, s>>>(p)));
+    return cudaGetLastError();
+}
+
+cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s)
+{
+    dim3 grid((unsigned)((p.stride + 255) / 256), (unsigned)p.P);
+    if (grid.x > 64) grid.x = 64;
+    ba_backward_kernel<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t ba_launch_noise(const BaPlanView &plan, int P, uint64_t seed, float *noise,
+                            cudaStream_t s)
+{
+    const size_t total = (size_t)P * plan.D * plan.Fmax;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    ba_noise_kernel<<<grid, 256, 0, s>>>(P, plan.D, plan.Fmax, seed, (float4 *)noise);
+    return cudaGetLastError();
+}
+
+cudaError_t ba_launch_collect(const uint32_t *status, int n, uint32_t bit, int32_t *list,
+                              unsigned int *count, cudaStream_t s)
+{
+    int grid = (n + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid < 1) grid = 1;
+    ba_collect_kernel<<<grid, 256, 0, s>>>(status, n, bit, list, count);
+    return cudaGetLastError();
+}

@@ -1,0 +1,52 @@
+// Internal: kernel parameter blocks + launch wrappers (implemented in ba_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ba_plan.h"
+
+struct BaFwdParams {
+    BaPlanView plan;              // .days = DEVICE array of BaDayView with device pointers
+    int32_t P;
+    const float *lat_airport;     // [P, C, N]
+    const float *lat_route;       // [P, R]
+    const float *scales;          // [3]
+    const float *noise;           // [P, D, Fmax, 4] or nullptr
+    uint64_t seed;
+    int32_t value_mode, want_grad;
+    float *logp;                  // [P, D]
+    uint32_t *status;             // [P, D]
+    int32_t *ticks;               // [P, D] or nullptr
+    float *tape;                  // [P, D, grad_stride] or nullptr
+    int32_t *pop_tick;            // [P, D, Fmax, 2] or nullptr
+    uint32_t *scratch;            // per-CTA global scratch
+    uint64_t scratch_stride;      // words per CTA
+    unsigned int *work_counter;   // dynamic work distribution
+    const int32_t *work_list;     // optional explicit list of pd = p*D + d
+    int32_t n_work;
+    const unsigned int *n_work_dev; // if set, overrides n_work (device-side count)
+    uint32_t smem_state_words;    // 35 * N
+};
+
+struct BaBwdParams {
+    int32_t P, D, C, N, R, stride;
+    const float *dlogp;           // [P, D]
+    const float *tape;            // [P, D, stride]
+    float *g_airport;             // [P, C*N]
+    float *g_route;               // [P, R]
+    float *g_scales;              // [P, 3]
+};
+
+int ba_forward_block_threads(int n_airports);
+size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact);
+cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact);
+int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, int device);
+
+cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, int grid, int block,
+                              size_t smem, cudaStream_t s);
+cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s);
+cudaError_t ba_launch_noise(const BaPlanView &plan, int P, uint64_t seed, float *noise,
+                            cudaStream_t s);
+// gathers the particle-days whose status has `bit` set into list (device), count in *n
+cudaError_t ba_launch_collect(const uint32_t *status, int n, uint32_t bit, int32_t *list,
+                              unsigned int *count, cudaStream_t s);

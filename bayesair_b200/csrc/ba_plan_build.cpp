@@ -1,0 +1,213 @@
+// Host-side schedule compiler: BaDayTable (flights in stable scheduled-departure
+// order, airports in day order) -> static tables of the kernel.
+//
+// What it fixes at plan time (none of it depends on a particle's latents):
+//   * per-airport departure lists in pending order (the reference scans ALL pending
+//     flights every tick and buckets them by origin, bayes_air/network.py:57-68;
+//     restricted to one origin the scan order is this list);
+//   * the compact route table (dense [N,N] travel times -> [R]);
+//   * which airports need aircraft bookkeeping at all (ba_plan.h:
+//     BA_SIMPLE_MAX_DEPARTURES);
+//   * list capacities: a small shared-memory ring per airport sized from the
+//     airport's daily traffic (fast variant) and exact-capacity rings in global
+//     scratch (the variant a particle-day is re-run with if a ring overflows);
+//   * the lane -> airport assignment, sorted by daily traffic so that the airports
+//     of one warp have similar trip counts.
+#include "ba_plan_build.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <map>
+#include <numeric>
+
+static uint32_t pow2ceil(uint32_t v)
+{
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static double env_double(const char *name, double dflt)
+{
+    const char *s = std::getenv(name);
+    return s ? std::atof(s) : dflt;
+}
+
+int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float delta_t,
+                       float max_t, int include_cancellations, int max_ticks,
+                       BaHostPlan *out, std::string *err)
+{
+    auto fail = [&](int code, const std::string &m) { if (err) *err = m; return code; };
+    if (!days || n_days <= 0 || n_airports <= 0 || !out)
+        return fail(BA_ERR_BAD_ARG, "ba_plan_create: null / empty argument");
+    if (!(delta_t > 0.0f) || max_ticks <= 0)
+        return fail(BA_ERR_BAD_ARG, "ba_plan_create: delta_t and max_ticks must be positive");
+    if (n_airports > BA_MAX_AIRPORTS)
+        return fail(BA_ERR_LIMIT, "ba_plan_create: more than 4096 airports");
+
+    // tunables of the shared-memory variant (documented in DESIGN.md)
+    const double q_div = env_double("BA_Q_DIV", 16.0);        // ring = traffic / q_div
+    const double q_min = env_double("BA_Q_MIN", 8.0);
+    const double bag_frac = env_double("BA_BAG_FRAC", 0.40);  // of daily arrivals
+    const double bag_min = env_double("BA_BAG_MIN", 8.0);
+
+    const int N = n_airports;
+    out->days.clear();
+    out->days.resize(n_days);
+
+    // ---- route table over all days ----------------------------------------
+    std::map<int64_t, int32_t> route_id;
+    for (int d = 0; d < n_days; ++d) {
+        const BaDayTable &T = days[d];
+        if (T.n_airports != N)
+            return fail(BA_ERR_BAD_ARG, "ba_plan_create: every day must have the same airports");
+        if (T.n_flights < 0 || T.n_flights >= BA_MAX_FLIGHTS)
+            return fail(BA_ERR_LIMIT, "ba_plan_create: flights per day out of range");
+        for (int a = 0; a < N; ++a)
+            if (T.h_airport_global[a] < 0 || T.h_airport_global[a] >= N)
+                return fail(BA_ERR_BAD_ARG, "ba_plan_create: airport_global out of range");
+        for (int f = 0; f < T.n_flights; ++f) {
+            int o = T.h_origin[f], e = T.h_dest[f];
+            if (o < 0 || o >= N || e < 0 || e >= N || o == e)
+                return fail(BA_ERR_BAD_ARG, "ba_plan_create: bad origin/destination index");
+            if (f > 0 && T.h_sched_dep[f] < T.h_sched_dep[f - 1])
+                return fail(BA_ERR_BAD_ARG,
+                            "ba_plan_create: flights must be sorted by scheduled departure");
+            int64_t key = (int64_t)T.h_airport_global[o] * N + T.h_airport_global[e];
+            route_id.emplace(key, 0);
+        }
+    }
+    out->route_origin.clear();
+    out->route_dest.clear();
+    {
+        int32_t r = 0;
+        for (auto &kv : route_id) {
+            kv.second = r++;
+            out->route_origin.push_back((int32_t)(kv.first / N));
+            out->route_dest.push_back((int32_t)(kv.first % N));
+        }
+    }
+    const int R = (int)route_id.size();
+
+    int Fmax = 0;
+    uint64_t scratch_fast = 0, scratch_exact = 0;
+    uint32_t smem_words = 0;
+    for (int d = 0; d < n_days; ++d) {
+        const BaDayTable &T = days[d];
+        BaHostDay &H = out->days[d];
+        const int F = T.n_flights;
+        Fmax = std::max(Fmax, F);
+        H.flights.resize(F);
+        H.route.resize(F);
+        H.airports.assign(N, BaAirport{});
+        std::vector<int> dep_cnt(N, 0), arr_cnt(N, 0);
+        for (int f = 0; f < F; ++f) {
+            int o = T.h_origin[f], e = T.h_dest[f];
+            int c = T.h_cancel_obs[f];
+            uint32_t cc = c < 0 ? 3u : (c ? 1u : 0u);
+            H.flights[f].sched_dep = T.h_sched_dep[f];
+            H.flights[f].act_dep = T.h_act_dep[f];
+            H.flights[f].act_arr = T.h_act_arr[f];
+            H.flights[f].od = (uint32_t)o | ((uint32_t)e << 12) | (cc << 24);
+            H.route[f] = route_id[(int64_t)T.h_airport_global[o] * N + T.h_airport_global[e]];
+            dep_cnt[o]++;
+            // a flight observed as cancelled never reaches a queue (network.py:127-129)
+            if (cc != 1u) arr_cnt[e]++;
+        }
+        // departures grouped by origin, ascending flight index (= pending order)
+        H.dep_fid.resize(F);
+        {
+            std::vector<int> off(N + 1, 0);
+            for (int a = 0; a < N; ++a) off[a + 1] = off[a] + dep_cnt[a];
+            std::vector<int> cur(off.begin(), off.end() - 1);
+            for (int f = 0; f < F; ++f) H.dep_fid[cur[T.h_origin[f]]++] = f;
+            for (int a = 0; a < N; ++a) { H.airports[a].dep_off = off[a]; }
+        }
+        uint32_t q_s = 0, bag_s = 0, q_x = 0, bag_x = 0, turn = 0, av = 0, dl = 0;
+        for (int a = 0; a < N; ++a) {
+            BaAirport &A = H.airports[a];
+            A.dep_cnt = dep_cnt[a];
+            A.arr_cnt = arr_cnt[a];
+            A.global = T.h_airport_global[a];
+            uint32_t flags = 0;
+            if (include_cancellations) flags = BA_AP_TRACK_T | BA_AP_TRACK_A;
+            else {
+                if (dep_cnt[a] > BA_SIMPLE_MAX_DEPARTURES) flags |= BA_AP_TRACK_T;
+                if (dep_cnt[a] >= 1000) flags |= BA_AP_TRACK_T | BA_AP_TRACK_A;
+            }
+            A.flags = flags;
+            const uint32_t traffic = (uint32_t)(dep_cnt[a] + arr_cnt[a]);
+            // exact variant
+            uint32_t qx = pow2ceil(std::max(1u, traffic));
+            A.q_off_x = q_x; A.q_mask_x = qx - 1; q_x += qx;
+            uint32_t bx = std::max(1u, (uint32_t)arr_cnt[a]);
+            A.bag_off_x = bag_x; A.bag_cap_x = bx; bag_x += bx;
+            // shared variant
+            uint32_t want_q = (uint32_t)std::ceil(std::max(q_min, traffic / q_div));
+            uint32_t qs = std::min(qx, pow2ceil(std::max(1u, want_q)));
+            A.q_off_s = q_s; A.q_mask_s = qs - 1; q_s += qs;
+            uint32_t want_b = (uint32_t)std::ceil(bag_min + bag_frac * arr_cnt[a]);
+            uint32_t bs = std::min(bx, std::max(1u, want_b));
+            A.bag_off_s = bag_s; A.bag_cap_s = bs; bag_s += bs;
+            // always-global lists (only for airports that track aircraft)
+            A.turn_off = turn; A.av_off = av; A.dl_off = dl;
+            A.av_mask = 0; A.dl_mask = 0;
+            if (flags & BA_AP_TRACK_T) {
+                turn += std::max(1, arr_cnt[a]);
+                uint32_t dc = pow2ceil(std::max(1, dep_cnt[a]));
+                A.dl_mask = dc - 1; dl += dc;
+            }
+            if (flags & BA_AP_TRACK_A) {
+                // releases + run-length-encoded reserve markers (ba_sim.cuh)
+                uint32_t ac = pow2ceil(2u * (uint32_t)arr_cnt[a] + 4u);
+                A.av_mask = ac - 1; av += ac;
+            }
+        }
+        // lane -> airport, heaviest first
+        H.lane_airport.resize(N);
+        std::iota(H.lane_airport.begin(), H.lane_airport.end(), 0);
+        std::stable_sort(H.lane_airport.begin(), H.lane_airport.end(), [&](int x, int y) {
+            return dep_cnt[x] + arr_cnt[x] > dep_cnt[y] + arr_cnt[y];
+        });
+        // idle prefix of the day: ticks before the first scheduled departure do nothing
+        // (no pending flight is ready, nothing is queued or in transit) as long as the
+        // reserve injection (t >= max_t, model.py:170-174) has not started.
+        int first_tick = 1;
+        float t_before = 0.0f;
+        if (F > 0) {
+            float t = 0.0f;
+            const float first_sched = T.h_sched_dep[0];
+            for (int k = 1; k <= max_ticks; ++k) {
+                float tn = t + delta_t;             // fp32, model.py:161
+                if (first_sched <= tn || tn >= max_t) { first_tick = k; t_before = t; break; }
+                t = tn;
+                first_tick = k + 1; t_before = t;
+            }
+        }
+        BaDayView &V = H.view;
+        V.N = N; V.F = F;
+        V.flights = H.flights.data(); V.route = H.route.data(); V.dep_fid = H.dep_fid.data();
+        V.airports = H.airports.data(); V.lane_airport = H.lane_airport.data();
+        V.q_total_s = q_s; V.bag_total_s = bag_s; V.q_total_x = q_x; V.bag_total_x = bag_x;
+        V.turn_total = turn; V.av_total = av; V.dl_total = dl;
+        V.first_tick = first_tick; V.t_before_first = t_before;
+        scratch_fast = std::max(scratch_fast, ba_scratch_words(V, false));
+        scratch_exact = std::max(scratch_exact, ba_scratch_words(V, true));
+        smem_words = std::max(smem_words, 4u * q_s + 2u * bag_s);
+    }
+
+    out->day_views.resize(n_days);
+    for (int d = 0; d < n_days; ++d) out->day_views[d] = out->days[d].view;
+    BaPlanView &P = out->view;
+    P.D = n_days; P.N = N; P.Fmax = Fmax; P.R = R;
+    P.C = include_cancellations ? 4 : 2;
+    P.include_cancellations = include_cancellations ? 1 : 0;
+    P.max_ticks = max_ticks; P.delta_t = delta_t; P.max_t = max_t;
+    P.grad_stride = P.C * N + R + 3;
+    P.days = out->day_views.data();
+    out->scratch_words_fast = scratch_fast;
+    out->scratch_words_exact = scratch_exact;
+    out->smem_list_words = smem_words;
+    return BA_OK;
+}

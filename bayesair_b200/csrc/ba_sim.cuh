@@ -1,0 +1,679 @@
+// Core of the hot path: one (particle, day) of the air-traffic-network simulation
+// with the log-joint and its pathwise gradient fused into the scan.
+//
+// Decomposition: one CTA per (particle, day); one lane per airport.
+// Every tick has two phases separated by CTA barriers:
+//
+//   phase A (per airport, no cross-airport reads):
+//       turnaround release -> reserve injection -> pop-ready / cancellation ->
+//       enqueue departures -> runway service loop.          model.py:163-196
+//       A served departure is appended (atomic slot) to the DESTINATION airport's
+//       inbound "bag" = that airport's slice of the reference's in-transit list.
+//   phase B (per airport): order the entries appended this tick by origin airport
+//       (restores the reference's global in-transit order restricted to this
+//       destination, model.py:186-196), then move every entry whose arrival time
+//       has passed into the runway queue.                   network.py:178-198
+//
+// All arithmetic that feeds a decision (a `<=` against the clock) is IEEE fp32 in
+// the reference's operation order, with contraction disabled (BA_ADD / BA_MUL /
+// BA_DIV), see SURVEY.md H1.
+//
+// The same source is compiled (a) by nvcc into the sm_100a kernel and (b) by g++
+// into tests/hostemu (a debugging harness that runs the phases lane by lane on the
+// CPU; it is not part of the product and not reachable from the Python package).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "ba_plan.h"
+
+#if defined(__CUDACC__)
+#define BA_DEV __device__ __forceinline__
+#else
+#define BA_DEV static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define BA_ADD(a, b) __fadd_rn((a), (b))
+#define BA_MUL(a, b) __fmul_rn((a), (b))
+#define BA_DIV(a, b) __fdiv_rn((a), (b))
+#define BA_ATOMIC_INC(p) atomicAdd((p), 1u)
+#define BA_RED_ADD(p, v) atomicAdd((p), (v))
+#define BA_LOG(x) logf(x)
+#define BA_EXP(x) expf(x)
+#define BA_LOG1P(x) log1pf(x)
+#else
+// host emulation: build with -ffp-contract=off
+#define BA_ADD(a, b) ((float)(a) + (float)(b))
+#define BA_MUL(a, b) ((float)(a) * (float)(b))
+#define BA_DIV(a, b) ((float)(a) / (float)(b))
+static inline uint32_t ba_host_inc(uint32_t *p) { return (*p)++; }
+#define BA_ATOMIC_INC(p) ba_host_inc(p)
+#define BA_RED_ADD(p, v) (*(p) += (v))
+#define BA_LOG(x) logf(x)
+#define BA_EXP(x) expf(x)
+#define BA_LOG1P(x) log1pf(x)
+#endif
+
+// status bits (mirror include/bayesair_b200.h)
+#define BA_S_TICK_CAP 1u
+#define BA_S_OVERFLOW 2u
+#define BA_S_UNOBSERVED 4u
+#define BA_S_INTERNAL 8u
+
+#define BA_LOG_SQRT_2PI 0.918938533204672741780329736406f
+#define BA_F32_EPS 1.1920928955078125e-07f
+#define BA_F32_TINY 1.17549435082228750797e-38f
+
+struct BaNoise4 { float e_dep, eps_travel, e_arr, eps_turn; };
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011): counter = (flight, day, particle lo, hi),
+// key = seed.  One call yields the four per-flight draws.
+// ---------------------------------------------------------------------------
+BA_DEV void ba_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                      uint32_t k1, uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+BA_DEV float ba_u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+BA_DEV BaNoise4 ba_philox_noise(uint64_t seed, uint32_t particle, uint32_t day, uint32_t flight)
+{
+    uint32_t r[4];
+    ba_philox(flight, day, particle, 0x42413230u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    BaNoise4 z;
+    float u1 = ba_u01(r[0]), u2 = ba_u01(r[1]), u3 = ba_u01(r[2]), u4 = ba_u01(r[3]);
+    z.e_dep = -BA_LOG(u1);
+    z.e_arr = -BA_LOG(u4);
+    float rad = sqrtf(-2.0f * BA_LOG(u2));
+    float ang = 6.283185307179586f * u3;
+    z.eps_travel = rad * cosf(ang);
+    z.eps_turn = rad * sinf(ang);
+    return z;
+}
+
+// ---------------------------------------------------------------------------
+// torch.distributions arithmetic (fp32)
+// ---------------------------------------------------------------------------
+BA_DEV float ba_softplus(float x) { return x > 20.0f ? x : BA_LOG1P(BA_EXP(x)); }
+
+// RelaxedBernoulli(temperature 0.5, probs=p).log_prob(v), and d/dp
+// (bayes_air/network.py:102-109; torch relaxed_bernoulli.py + SigmoidTransform)
+BA_DEV float ba_relaxed_bernoulli_lp(float p, float v, float *dlp_dp)
+{
+    float q = fminf(fmaxf(p, BA_F32_EPS), 1.0f - BA_F32_EPS);
+    float logits = BA_LOG(q) - BA_LOG1P(-q);
+    float y = fminf(fmaxf(v, BA_F32_TINY), 1.0f - BA_F32_EPS);
+    float x = BA_LOG(y) - BA_LOG1P(-y);
+    float diff = logits - 0.5f * x;
+    float ed = BA_EXP(diff);
+    float lp = -0.69314718055994530942f + diff - 2.0f * BA_LOG1P(ed);
+    lp += ba_softplus(-x) + ba_softplus(x);
+    if (dlp_dp) {
+        float pass = (p >= BA_F32_EPS && p <= 1.0f - BA_F32_EPS) ? 1.0f : 0.0f;
+        float sig = isinf(ed) ? 1.0f : ed / (1.0f + ed);
+        *dlp_dp = pass * (1.0f / q + 1.0f / (1.0f - q)) * (1.0f - 2.0f * sig);
+    }
+    return lp;
+}
+
+// ---------------------------------------------------------------------------
+// per-CTA context
+// ---------------------------------------------------------------------------
+struct BaCtx {
+    // static day tables
+    int N, F;
+    const BaFlight *flights;
+    const int32_t *route;
+    const int32_t *dep_fid;
+    const BaAirport *ap;
+    // particle inputs
+    const float *lat_route;       // [R]
+    const float *noise;           // [Fmax*4] of this (particle, day) or nullptr
+    uint64_t seed;
+    uint32_t particle, dayidx;
+    float sigma, v_t, v_u;        // the three scales
+    float inv_sigma2, inv_sigma3, inv_sigma, log_sigma;
+    float inv_vt, inv_vu;
+    float c0_lp, c1_lp;           // cancellation log-prob at p == 0 for v = 0 / 1
+    int value_mode, want_grad, cancel_mode;
+    float max_t;
+    // per-airport dynamic state (shared memory), indexed by day-local airport
+    float *m, *rate, *mt, *tstd, *base, *n_avail, *q_asg;
+    float *acc_rw, *acc_turn, *acc_ln0, *acc_bc;
+    float *n0, *lograte, *logtstd, *next_sched;
+    uint32_t *next_dep, *q_head, *q_tail, *bag_n, *bag_sorted, *turn_n;
+    uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail, *cnt_entries, *cnt_land;
+    // per-airport static copies (shared memory)
+    uint32_t *s_flags, *s_qoff, *s_qmask, *s_bagoff, *s_bagcap, *s_depoff, *s_depcnt;
+    // list pools
+    uint32_t *qf; float *qs, *qw, *qx;     // runway queues  (shared or global)
+    uint32_t *bf; float *ba;               // inbound bags   (shared or global)
+    float *tt, *te;                        // turnaround lists (global scratch)
+    float *at, *ae;                        // aircraft FIFOs   (global scratch)
+    uint32_t *dl;                          // delayed deques   (global scratch)
+    // outputs
+    float *grow;                  // gradient row [C*N + R + 3] or nullptr
+    int32_t *pop_tick;            // [Fmax*2] of this (particle, day) or nullptr
+    int route_base;               // C*N
+};
+
+struct BaAcc {
+    float lp;
+    float g_sigma, g_vt, g_vu;
+    uint32_t status;
+};
+
+#define BA_NWORDS_STATE 35        // per-airport words of shared state (see ba_carve_state)
+
+// Assigns the per-airport arrays out of one contiguous word buffer.
+BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N)
+{
+    float *f = (float *)w;
+    c.m = f + 0 * N; c.rate = f + 1 * N; c.mt = f + 2 * N; c.tstd = f + 3 * N;
+    c.base = f + 4 * N; c.n_avail = f + 5 * N; c.q_asg = f + 6 * N;
+    c.acc_rw = f + 7 * N; c.acc_turn = f + 8 * N; c.acc_ln0 = f + 9 * N; c.acc_bc = f + 10 * N;
+    c.next_dep = w + 11 * N; c.q_head = w + 12 * N; c.q_tail = w + 13 * N;
+    c.bag_n = w + 14 * N; c.bag_sorted = w + 15 * N; c.turn_n = w + 16 * N;
+    c.av_head = w + 17 * N; c.av_tail = w + 18 * N; c.zeros_left = w + 19 * N;
+    c.dl_head = w + 20 * N; c.dl_tail = w + 21 * N; c.cnt_entries = w + 22 * N;
+    c.cnt_land = w + 23 * N;
+    c.s_flags = w + 24 * N; c.s_qoff = w + 25 * N; c.s_qmask = w + 26 * N;
+    c.s_bagoff = w + 27 * N; c.s_bagcap = w + 28 * N; c.s_depoff = w + 29 * N;
+    c.s_depcnt = w + 30 * N;
+    c.n0 = f + 31 * N; c.lograte = f + 32 * N; c.logtstd = f + 33 * N; c.next_sched = f + 34 * N;
+}
+
+BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
+{
+    if (c.noise) {
+#if defined(__CUDA_ARCH__)
+        float4 v = __ldg(reinterpret_cast<const float4 *>(c.noise) + f);
+        BaNoise4 z = {v.x, v.y, v.z, v.w};
+        return z;
+#else
+        BaNoise4 z = {c.noise[4 * f], c.noise[4 * f + 1], c.noise[4 * f + 2], c.noise[4 * f + 3]};
+        return z;
+#endif
+    }
+    return ba_philox_noise(c.seed, c.particle, c.dayidx, (uint32_t)f);
+}
+
+BA_DEV BaFlight ba_flight(const BaCtx &c, int f)
+{
+#if defined(__CUDA_ARCH__)
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(c.flights) + f);
+    BaFlight fl;
+    fl.sched_dep = __uint_as_float(v.x); fl.act_dep = __uint_as_float(v.y);
+    fl.act_arr = __uint_as_float(v.z); fl.od = v.w;
+    return fl;
+#else
+    return c.flights[f];
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// per-airport initialisation (model.py:139-155)
+// ---------------------------------------------------------------------------
+template <bool EXACT>
+BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] */, int Ng)
+{
+    const BaAirport A = c.ap[a];
+    const int g = A.global;
+    const float mt = lat_airport[0 * Ng + g];
+    const float m = lat_airport[1 * Ng + g];
+    c.mt[a] = mt;
+    c.m[a] = m;
+    c.rate[a] = BA_DIV(1.0f, m);                 // airport.py:146
+    c.tstd[a] = BA_MUL(c.v_u, mt);               // model.py:143-145
+    float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
+    if (c.cancel_mode) {
+        n0 = BA_EXP(lat_airport[2 * Ng + g]);    // model.py:91-99
+        base = BA_EXP(lat_airport[3 * Ng + g]);  // model.py:103-111
+    }
+    c.base[a] = base;
+    c.n_avail[a] = n0;
+    c.n0[a] = n0;
+    c.lograte[a] = BA_LOG(c.rate[a]);
+    c.logtstd[a] = BA_LOG(c.tstd[a]);
+    c.next_sched[a] = A.dep_cnt > 0 ? c.flights[c.dep_fid[A.dep_off]].sched_dep : INFINITY;
+    // while i < n0: append(0.0)  -> ceil(n0) zero-time aircraft (model.py:152-155)
+    uint32_t nz = 0;
+    if (n0 > 0.0f) {
+        float cz = ceilf(n0);
+        nz = cz > 4.0e9f ? 4000000000u : (uint32_t)cz;
+    }
+    c.zeros_left[a] = nz;
+    c.q_asg[a] = NAN;
+    c.acc_rw[a] = 0.0f; c.acc_turn[a] = 0.0f; c.acc_ln0[a] = 0.0f; c.acc_bc[a] = 0.0f;
+    c.next_dep[a] = 0; c.q_head[a] = 0; c.q_tail[a] = 0; c.bag_n[a] = 0; c.bag_sorted[a] = 0;
+    c.turn_n[a] = 0; c.av_head[a] = 0; c.av_tail[a] = 0; c.dl_head[a] = 0; c.dl_tail[a] = 0;
+    c.cnt_entries[a] = 0; c.cnt_land[a] = 0;
+    c.s_flags[a] = A.flags;
+    c.s_qoff[a] = EXACT ? A.q_off_x : A.q_off_s;
+    c.s_qmask[a] = EXACT ? A.q_mask_x : A.q_mask_s;
+    c.s_bagoff[a] = EXACT ? A.bag_off_x : A.bag_off_s;
+    c.s_bagcap[a] = EXACT ? A.bag_cap_x : A.bag_cap_s;
+    c.s_depoff[a] = (uint32_t)A.dep_off;
+    c.s_depcnt[a] = (uint32_t)A.dep_cnt;
+}
+
+// ---------------------------------------------------------------------------
+// runway-queue append (model.py:181-183 / network.py:186-191)
+// ---------------------------------------------------------------------------
+BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float aux)
+{
+    const uint32_t head = c.q_head[a], tail = c.q_tail[a], mask = c.s_qmask[a];
+    if (tail - head > mask) { acc.status |= BA_S_OVERFLOW; return; }
+    const uint32_t i = c.s_qoff[a] + (tail & mask);
+    c.qf[i] = word; c.qs[i] = qstart; c.qw[i] = 0.0f; c.qx[i] = aux;
+    c.q_tail[a] = tail + 1;
+}
+
+// available_aircraft.pop(0) for one departing flight (network.py:118-126).
+// Returns the ready time max(aircraft, sched); *wcode / *src_eps describe the
+// aircraft branch for the adjoint (0 none, 1 tie, 2 aircraft time strictly later).
+BA_DEV float ba_take_aircraft(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, float sched,
+                              float t, uint32_t *wcode, float *src_eps)
+{
+    *wcode = 0; *src_eps = 0.0f;
+    c.n_avail[a] = c.n_avail[a] - 1.0f;
+    float ac_time = 0.0f;
+    bool has_src = false;
+    if (c.s_flags[a] & BA_AP_TRACK_A) {
+        if (c.zeros_left[a] > 0) {
+            c.zeros_left[a] -= 1;
+        } else {
+            uint32_t h = c.av_head[a];
+            if (h == c.av_tail[a]) { acc.status |= BA_S_INTERNAL; return sched; }
+            uint32_t i = A->av_off + (h & A->av_mask);
+            float tm = c.at[i];
+            if (isnan(tm)) {
+                // run of reserve aircraft: the reference appended the clock tensor
+                // itself (model.py:174), so its value is the clock at pop time
+                ac_time = t;
+                float left = c.ae[i] - 1.0f;
+                if (left <= 0.0f) c.av_head[a] = h + 1; else c.ae[i] = left;
+            } else {
+                ac_time = tm; *src_eps = c.ae[i]; has_src = !c.value_mode;
+                c.av_head[a] = h + 1;
+            }
+        }
+    }
+    float ready = fmaxf(ac_time, sched);          // torch.maximum
+    if (has_src) *wcode = ac_time > sched ? 2u : (ac_time == sched ? 1u : 0u);
+    return ready;
+}
+
+// ---------------------------------------------------------------------------
+// phase A
+// ---------------------------------------------------------------------------
+template <bool EXACT>
+BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
+{
+    const uint32_t flags = c.s_flags[a];
+    const BaAirport *A = &c.ap[a];      // only dereferenced on the tracked paths
+
+    // 1. update_available_aircraft (airport.py:66-84)
+    if (flags & BA_AP_TRACK_T) {
+        uint32_t n = c.turn_n[a];
+        if (n) {
+            const uint32_t off = A->turn_off;
+            uint32_t w = 0;
+            float navail = c.n_avail[a];
+            for (uint32_t i = 0; i < n; ++i) {
+                float tm = c.tt[off + i], ep = c.te[off + i];
+                if (tm <= t) {
+                    navail = navail + 1.0f;
+                    if (flags & BA_AP_TRACK_A) {
+                        uint32_t tl = c.av_tail[a];
+                        if (tl - c.av_head[a] > A->av_mask) acc.status |= BA_S_INTERNAL;
+                        else {
+                            uint32_t j = A->av_off + (tl & A->av_mask);
+                            c.at[j] = tm; c.ae[j] = ep; c.av_tail[a] = tl + 1;
+                        }
+                    }
+                } else {
+                    if (w != i) { c.tt[off + w] = tm; c.te[off + w] = ep; }
+                    ++w;
+                }
+            }
+            c.turn_n[a] = w;
+            c.n_avail[a] = navail;
+        }
+        // 2. reserve injection (model.py:170-174)
+        if (t >= c.max_t) {
+            c.n_avail[a] = c.n_avail[a] + 1.0f;
+            if (flags & BA_AP_TRACK_A) {
+                uint32_t tl = c.av_tail[a], hd = c.av_head[a];
+                bool merged = false;
+                if (tl != hd) {
+                    uint32_t j = A->av_off + ((tl - 1) & A->av_mask);
+                    if (isnan(c.at[j])) { c.ae[j] = c.ae[j] + 1.0f; merged = true; }
+                }
+                if (!merged) {
+                    if (tl - hd > A->av_mask) acc.status |= BA_S_INTERNAL;
+                    else {
+                        uint32_t j = A->av_off + (tl & A->av_mask);
+                        c.at[j] = NAN; c.ae[j] = 1.0f; c.av_tail[a] = tl + 1;
+                    }
+                }
+            }
+        }
+    }
+
+    // 3. pop_ready_to_depart_flights restricted to this origin (network.py:57-134)
+    {
+        const uint32_t dep_cnt = c.s_depcnt[a], dep_off = c.s_depoff[a];
+        uint32_t nd = c.next_dep[a];
+        uint32_t n_new = 0;
+        if (c.next_sched[a] <= t) {
+            // the cached head of this origin's pending list is due: count the due prefix
+            n_new = 1;
+            float nxt = INFINITY;
+            while (nd + n_new < dep_cnt) {
+                nxt = ba_flight(c, c.dep_fid[dep_off + nd + n_new]).sched_dep;
+                if (!(nxt <= t)) break;
+                ++n_new;
+                nxt = INFINITY;
+            }
+            c.next_sched[a] = nxt;
+        }
+        if (!(flags & BA_AP_TRACK_T)) {
+            // cancellation probability is exactly 0 and aircraft are never scarce
+            for (uint32_t i = 0; i < n_new; ++i) {
+                const int f = c.dep_fid[dep_off + nd + i];
+                const BaFlight fl = ba_flight(c, f);
+                const uint32_t cobs = (fl.od >> 24) & 3u;
+                if (cobs == 3u) { acc.status |= BA_S_UNOBSERVED; continue; }
+                acc.lp += cobs ? c.c1_lp : c.c0_lp;
+                if (!cobs)
+                    ba_q_push(c, acc, a, BA_Q_DEP | (uint32_t)f, fmaxf(0.0f, fl.sched_dep), 0.0f);
+            }
+            c.next_dep[a] = nd + n_new;
+        } else {
+            const uint32_t n_old = c.dl_tail[a] - c.dl_head[a];
+            const uint32_t n_ready = n_new + n_old;
+            if (n_ready) {
+                const float n_start = c.n_avail[a];
+                const float base = c.base[a];
+                // network.py:80-84, fp32 in the reference's operation order
+                const float ratio = BA_DIV(n_start, (float)n_ready);
+                const float z = BA_MUL(10.0f, BA_ADD(ratio, -0.25f));
+                const float sg = 1.0f / (1.0f + BA_EXP(-z));
+                const float p = 1.0f - (1.0f - base) * sg;
+                float dl0 = 0.0f, dl1 = 0.0f;
+                const float lp0 = ba_relaxed_bernoulli_lp(p, 0.0f, &dl0);
+                const float lp1 = ba_relaxed_bernoulli_lp(p, 1.0f, &dl1);
+                // d p / d base = sg ; d p / d n = -(1-base) sg (1-sg) * 10 / n_ready
+                const float dp_dn = -(1.0f - base) * sg * (1.0f - sg) * 10.0f / (float)n_ready;
+                float g_p = 0.0f;          // sum over newly scored flights of d lp / d p
+                uint32_t first_delayed = n_new;
+                for (uint32_t i = 0; i < n_new; ++i) {
+                    const int f = c.dep_fid[dep_off + nd + i];
+                    const BaFlight fl = ba_flight(c, f);
+                    const uint32_t cobs = (fl.od >> 24) & 3u;
+                    if (cobs == 3u) { acc.status |= BA_S_UNOBSERVED; continue; }
+                    acc.lp += cobs ? lp1 : lp0;
+                    g_p += cobs ? dl1 : dl0;
+                    if (cobs) continue;                       // cancelled -> completed
+                    if (c.n_avail[a] <= 0.0f) {               // delayed (network.py:112-114)
+                        if (first_delayed == n_new) first_delayed = i;
+                        continue;
+                    }
+                    uint32_t wcode; float src_eps;
+                    float ready = ba_take_aircraft(c, acc, a, A, fl.sched_dep, t, &wcode, &src_eps);
+                    ba_q_push(c, acc, a, BA_Q_DEP | (wcode << BA_Q_W_SHIFT) | (uint32_t)f, ready, src_eps);
+                }
+                if (c.cancel_mode && c.want_grad) {
+                    c.acc_bc[a] += g_p * sg * base;                       // b = exp(c)
+                    // n = exp(l) + integers: d n / d l = exp(l) = initial count
+                    c.acc_ln0[a] += g_p * dp_dn;                          // times n0 at the end
+                }
+                // newly delayed flights go IN FRONT of the previously delayed ones
+                // (they precede them in the re-built pending list, network.py:60-68,112-114)
+                if (first_delayed < n_new) {
+                    uint32_t hd = c.dl_head[a];
+                    for (uint32_t i = n_new; i-- > first_delayed;) {
+                        const int f = c.dep_fid[dep_off + nd + i];
+                        const uint32_t cobs = (ba_flight(c, f).od >> 24) & 3u;
+                        if (cobs != 0u) continue;
+                        hd -= 1;
+                        c.dl[A->dl_off + (hd & A->dl_mask)] = (uint32_t)f;
+                    }
+                    c.dl_head[a] = hd;
+                } else {
+                    // previously delayed flights, oldest first, while aircraft remain
+                    uint32_t hd = c.dl_head[a];
+                    const uint32_t tl = c.dl_tail[a];
+                    while (hd != tl && c.n_avail[a] > 0.0f) {
+                        const int f = (int)c.dl[A->dl_off + (hd & A->dl_mask)];
+                        const BaFlight fl = ba_flight(c, f);
+                        uint32_t wcode; float src_eps;
+                        float ready = ba_take_aircraft(c, acc, a, A, fl.sched_dep, t, &wcode, &src_eps);
+                        ba_q_push(c, acc, a, BA_Q_DEP | (wcode << BA_Q_W_SHIFT) | (uint32_t)f, ready, src_eps);
+                        ++hd;
+                    }
+                    c.dl_head[a] = hd;
+                }
+                c.next_dep[a] = nd + n_new;
+            }
+        }
+    }
+
+    // 5. update_runway_queue (airport.py:101-128)
+    {
+        uint32_t head = c.q_head[a];
+        const uint32_t tail = c.q_tail[a];
+        if (head == tail) return;
+        const uint32_t qoff = c.s_qoff[a], qmask = c.s_qmask[a];
+        const float rate = c.rate[a];
+        float asg = c.q_asg[a];
+        float s_rw = 0.0f, s_turn = 0.0f;
+        uint32_t n_served = 0, n_land = 0;
+        while (head != tail) {
+            const uint32_t hi = qoff + (head & qmask);
+            const uint32_t word = c.qf[hi];
+            const int f = (int)(word & BA_FID_MASK);
+            const bool dep = (word & BA_Q_DEP) != 0u;
+            BaNoise4 nz;
+            bool have_nz = false;
+            if (isnan(asg)) {
+                // _assign_service_time (airport.py:130-158)
+                nz = ba_noise(c, f); have_nz = true;
+                const float e = dep ? nz.e_dep : nz.e_arr;
+                const float x = c.value_mode ? e : BA_DIV(e, rate);   // Exponential.rsample
+                acc.lp += c.lograte[a] - rate * x;
+                for (uint32_t j = head; j != tail; ++j) {
+                    const uint32_t ji = qoff + (j & qmask);
+                    c.qw[ji] = BA_ADD(c.qw[ji], x);
+                }
+                asg = BA_ADD(c.qs[hi], c.qw[hi]);
+                if (c.want_grad && c.value_mode) c.acc_rw[a] += x;    // sum of x (value mode)
+            }
+            if (!(asg <= t)) break;
+            // served
+            if (!have_nz) nz = ba_noise(c, f);
+            const BaFlight fl = ba_flight(c, f);
+            const float wait = c.qw[hi];
+            const float mu = asg;                 // queue_start + total_wait
+            const int rid = c.route[f];
+            const float T = c.lat_route[rid];
+            ++n_served;
+            if (dep) {
+                // _assign_departure_time (airport.py:164-182), observed
+                const float y = fl.act_dep;
+                if (isnan(y)) acc.status |= BA_S_UNOBSERVED;
+                const float dy = y - mu;
+                acc.lp += -(dy * dy) * (0.5f * c.inv_sigma2) - c.log_sigma - BA_LOG_SQRT_2PI;
+                // add_in_transit_flights (network.py:136-168)
+                const float sc = BA_MUL(T, c.v_t);
+                const float tau = c.value_mode ? nz.eps_travel
+                                               : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
+                const float dz = (tau - T) / sc;
+                acc.lp += -0.5f * dz * dz - BA_LOG(sc) - BA_LOG_SQRT_2PI;
+                const float arrival = BA_ADD(y, tau);
+                const int dst = (int)((fl.od >> 12) & 0xFFFu);
+                const uint32_t slot = BA_ATOMIC_INC(&c.bag_n[dst]);
+                if (slot >= c.s_bagcap[dst]) acc.status |= BA_S_OVERFLOW;
+                else {
+                    const uint32_t bi = c.s_bagoff[dst] + slot;
+                    c.bf[bi] = ((uint32_t)a << BA_BAG_O_SHIFT) | (uint32_t)f;
+                    c.ba[bi] = arrival;
+                }
+                if (c.pop_tick) c.pop_tick[2 * f] = tick;
+                if (c.want_grad) {
+                    const float r = dy * c.inv_sigma2;
+                    acc.g_sigma += dy * dy * c.inv_sigma3 - c.inv_sigma;
+                    if (!c.value_mode) {
+                        s_rw += r * wait;
+                        const uint32_t wcode = (word >> BA_Q_W_SHIFT) & 3u;
+                        if (wcode) {
+                            const float w = wcode == 2u ? 1.0f : 0.5f;
+                            const float se = c.qx[hi];
+                            s_turn += w * r * (1.0f + c.v_u * se);
+                            acc.g_vu += w * r * se * c.mt[a];
+                        }
+                    }
+                }
+            } else {
+                // _assign_arrival_time (airport.py:188-204), observed
+                const float y = fl.act_arr;
+                if (isnan(y)) acc.status |= BA_S_UNOBSERVED;
+                const float dy = y - mu;
+                acc.lp += -(dy * dy) * (0.5f * c.inv_sigma2) - c.log_sigma - BA_LOG_SQRT_2PI;
+                // _assign_turnaround_time (airport.py:210-221)
+                const float mt = c.mt[a], tstd = c.tstd[a];
+                const float u = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, tstd));
+                const float du = (u - mt) / tstd;
+                acc.lp += -0.5f * du * du - c.logtstd[a] - BA_LOG_SQRT_2PI;
+                ++n_land;
+                if (c.s_flags[a] & BA_AP_TRACK_T) {
+                    const uint32_t n = c.turn_n[a];
+                    c.tt[A->turn_off + n] = BA_ADD(y, u);
+                    c.te[A->turn_off + n] = nz.eps_turn;
+                    c.turn_n[a] = n + 1;
+                }
+                if (c.pop_tick) c.pop_tick[2 * f + 1] = tick;
+                if (c.want_grad) {
+                    const float r = dy * c.inv_sigma2;
+                    acc.g_sigma += dy * dy * c.inv_sigma3 - c.inv_sigma;
+                    const float sc = T * c.v_t;
+                    if (!c.value_mode) {
+                        s_rw += r * wait;
+                        // arrival queue_start = act_dep + tau, tau = T (1 + v_t eps)
+                        BA_RED_ADD(&c.grow[c.route_base + rid],
+                                   r * (1.0f + c.v_t * nz.eps_travel) - 1.0f / T);
+                        acc.g_vt += r * nz.eps_travel * T - c.inv_vt;
+                        acc.g_vu += -c.inv_vu;
+                    } else {
+                        const float zt = (nz.eps_travel - T) / sc;   // value of tau in .eps_travel
+                        BA_RED_ADD(&c.grow[c.route_base + rid], zt / sc + (zt * zt - 1.0f) / T);
+                        acc.g_vt += (zt * zt - 1.0f) * c.inv_vt;
+                        s_turn += du / tstd + (du * du - 1.0f) / mt;
+                        acc.g_vu += (du * du - 1.0f) * c.inv_vu;
+                    }
+                }
+            }
+            ++head;
+            asg = NAN;
+        }
+        c.q_head[a] = head;
+        c.q_asg[a] = asg;
+        if (n_served) {
+            c.cnt_entries[a] += n_served;
+            c.cnt_land[a] += n_land;
+            if (c.want_grad) {
+                c.acc_rw[a] += s_rw;
+                c.acc_turn[a] += s_turn;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// phase B: in-transit -> destination runway queue (network.py:178-198)
+// Returns whether this airport still has work (for the completion vote,
+// network.py:34-41).
+// ---------------------------------------------------------------------------
+BA_DEV bool ba_phase_b(BaCtx &c, BaAcc &acc, int a, float t)
+{
+    uint32_t n = c.bag_n[a];
+    const uint32_t cap = c.s_bagcap[a];
+    if (n > cap) n = cap;                     // overflow already flagged by the producer
+    if (n) {
+        const uint32_t off = c.s_bagoff[a];
+        const uint32_t ns = c.bag_sorted[a];
+        // entries [ns, n) were appended this tick by several origin lanes in arbitrary
+        // interleaving; entries of one origin are in service order.  A stable insertion
+        // sort by origin airport (day order) restores the reference's list order.
+        for (uint32_t i = ns + 1; i < n; ++i) {
+            const uint32_t w = c.bf[off + i];
+            const float av = c.ba[off + i];
+            const uint32_t key = w >> BA_BAG_O_SHIFT;
+            uint32_t j = i;
+            while (j > ns && (c.bf[off + j - 1] >> BA_BAG_O_SHIFT) > key) {
+                c.bf[off + j] = c.bf[off + j - 1];
+                c.ba[off + j] = c.ba[off + j - 1];
+                --j;
+            }
+            if (j != i) { c.bf[off + j] = w; c.ba[off + j] = av; }
+        }
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const float av = c.ba[off + i];
+            const uint32_t word = c.bf[off + i];
+            if (av <= t) {
+                ba_q_push(c, acc, a, word & BA_FID_MASK, av, 0.0f);
+            } else {
+                if (w != i) { c.bf[off + w] = word; c.ba[off + w] = av; }
+                ++w;
+            }
+        }
+        c.bag_n[a] = w;
+        c.bag_sorted[a] = w;
+        n = w;
+    }
+    return n != 0u || c.q_head[a] != c.q_tail[a] || c.next_dep[a] < c.s_depcnt[a] ||
+           c.dl_head[a] != c.dl_tail[a];
+}
+
+// ---------------------------------------------------------------------------
+// per-airport gradient epilogue: writes the airport rows of the gradient row
+// ---------------------------------------------------------------------------
+BA_DEV void ba_airport_epilogue(BaCtx &c, int a, int Ng)
+{
+    const int g = c.ap[a].global;
+    const float m = c.m[a], mt = c.mt[a];
+    const float n_ent = (float)c.cnt_entries[a], n_land = (float)c.cnt_land[a];
+    float g_turn, g_serv;
+    if (!c.value_mode) {
+        // x = e m  =>  d/dm = sum r W / m  - (#entries)/m ;  u = m~ (1 + v_u eps)
+        g_serv = c.acc_rw[a] / m - n_ent / m;
+        g_turn = c.acc_turn[a] - n_land / mt;
+    } else {
+        // log Exponential(x; 1/m) = -log m - x/m
+        g_serv = -n_ent / m + c.acc_rw[a] / (m * m);
+        g_turn = c.acc_turn[a];
+    }
+    c.grow[0 * Ng + g] = g_turn;
+    c.grow[1 * Ng + g] = g_serv;
+    if (c.cancel_mode) {
+        // acc_ln0 holds sum d lp/d p * d p/d n ; n = exp(l) + k  =>  * exp(l)
+        c.grow[2 * Ng + g] = c.acc_ln0[a] * c.n0[a];
+        c.grow[3 * Ng + g] = c.acc_bc[a];
+    }
+}

@@ -1,0 +1,181 @@
+// TEST INFRASTRUCTURE ONLY -- host emulation of the CUDA forward kernel.
+//
+// Compiles bayesair_b200/csrc/ba_sim.cuh (the very code the sm_100a kernel runs) with
+// g++ and executes the two phases of every tick lane by lane on the CPU, in a
+// SHUFFLED lane order per tick so that the cross-lane protocol (atomic bag append +
+// per-destination re-ordering) is exercised under arbitrary interleavings.  It lets
+// the build container (which has no GPU) check the kernel logic against the oracle
+// before any GPU time is spent.  It is not part of the product: nothing in
+// bayesair_b200/ loads it, and the product has no CPU path.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../bayesair_b200/csrc/ba_plan_build.h"
+#include "../../bayesair_b200/csrc/ba_sim.cuh"
+
+struct EmuPlan { BaHostPlan host; };
+
+extern "C" int ba_emu_plan_create(const BaDayTable *days, int n_days, int n_airports, float dt,
+                                  float max_t, int canc, int max_ticks, EmuPlan **out)
+{
+    EmuPlan *p = new EmuPlan();
+    std::string err;
+    int rc = ba_build_host_plan(days, n_days, n_airports, dt, max_t, canc, max_ticks, &p->host, &err);
+    if (rc != 0) { fprintf(stderr, "emu plan: %s\n", err.c_str()); delete p; return rc; }
+    *out = p;
+    return 0;
+}
+extern "C" void ba_emu_plan_destroy(EmuPlan *p) { delete p; }
+extern "C" void ba_emu_plan_info(const EmuPlan *p, int *out /* D,N,Fmax,R,C,stride */)
+{
+    const BaPlanView &v = p->host.view;
+    out[0] = v.D; out[1] = v.N; out[2] = v.Fmax; out[3] = v.R; out[4] = v.C; out[5] = v.grad_stride;
+}
+extern "C" void ba_emu_plan_routes(const EmuPlan *p, int32_t *o, int32_t *d)
+{
+    memcpy(o, p->host.route_origin.data(), p->host.route_origin.size() * 4);
+    memcpy(d, p->host.route_dest.data(), p->host.route_dest.size() * 4);
+}
+
+template <bool EXACT>
+static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d, int P,
+                     const float *lat_airport, const float *lat_route, const float *scales,
+                     const float *noise, uint64_t seed, int value_mode, int want_grad,
+                     unsigned shuffle_seed, float *logp, uint32_t *status, int32_t *ticks,
+                     float *tape, int32_t *pop_tick)
+{
+    (void)P;
+    const int N = plan.N, C = plan.C, R = plan.R, D = plan.D;
+    std::vector<uint32_t> state((size_t)BA_NWORDS_STATE * N, 0);
+    const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
+    const uint32_t bt = EXACT ? day.bag_total_x : day.bag_total_s;
+    std::vector<uint32_t> pool(4ull * qt + 2ull * bt + 8, 0);
+    std::vector<uint32_t> gs(2ull * day.turn_total + 2ull * day.av_total + day.dl_total + 8, 0);
+    BaCtx c;
+    memset(&c, 0, sizeof(c));
+    ba_carve_state(c, state.data(), N);
+    c.sigma = scales[0]; c.v_t = scales[1]; c.v_u = scales[2];
+    c.inv_sigma = 1.0f / c.sigma; c.inv_sigma2 = c.inv_sigma * c.inv_sigma;
+    c.inv_sigma3 = c.inv_sigma2 * c.inv_sigma; c.log_sigma = logf(c.sigma);
+    c.inv_vt = 1.0f / c.v_t; c.inv_vu = 1.0f / c.v_u;
+    c.c0_lp = ba_relaxed_bernoulli_lp(0.0f, 0.0f, nullptr);
+    c.c1_lp = ba_relaxed_bernoulli_lp(0.0f, 1.0f, nullptr);
+    c.value_mode = value_mode; c.want_grad = want_grad && tape;
+    c.cancel_mode = plan.include_cancellations; c.max_t = plan.max_t; c.seed = seed;
+    c.route_base = C * N;
+    const size_t pd = (size_t)p * D + d;
+    c.N = N; c.F = day.F; c.flights = day.flights; c.route = day.route; c.dep_fid = day.dep_fid;
+    c.ap = day.airports;
+    c.lat_route = lat_route + (size_t)p * R;
+    c.noise = noise ? noise + pd * (size_t)plan.Fmax * 4 : nullptr;
+    c.particle = p; c.dayidx = d;
+    c.grow = c.want_grad ? tape + pd * (size_t)plan.grad_stride : nullptr;
+    c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
+    uint32_t *s = pool.data();
+    c.qf = s; s += qt; c.qs = (float *)s; s += qt; c.qw = (float *)s; s += qt;
+    c.qx = (float *)s; s += qt; c.bf = s; s += bt; c.ba = (float *)s;
+    uint32_t *g = gs.data();
+    c.tt = (float *)g; g += day.turn_total; c.te = (float *)g; g += day.turn_total;
+    c.at = (float *)g; g += day.av_total; c.ae = (float *)g; g += day.av_total; c.dl = g;
+
+    const float *la = lat_airport + (size_t)p * C * N;
+    for (int a = 0; a < N; ++a) ba_init_airport<EXACT>(c, a, la, N);
+    if (c.grow) for (int i = 0; i < plan.grad_stride; ++i) c.grow[i] = 0.0f;
+    if (c.pop_tick) for (int i = 0; i < 2 * plan.Fmax; ++i) c.pop_tick[i] = -1;
+
+    // one accumulator per lane, reduced in lane order (as the kernel does per warp)
+    std::vector<BaAcc> acc(N, BaAcc{0, 0, 0, 0, 0});
+    std::vector<int> order(N);
+    for (int i = 0; i < N; ++i) order[i] = i;
+    std::mt19937 rng(shuffle_seed + 977u * (unsigned)pd);
+    float t = day.t_before_first;
+    int tick = day.first_tick - 1;
+    bool busy = day.F > 0;
+    uint32_t st = 0;
+    while (busy) {
+        if (tick >= plan.max_ticks) { st |= BA_S_TICK_CAP; break; }
+        t = BA_ADD(t, plan.delta_t);
+        ++tick;
+        if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
+        for (int i = 0; i < N; ++i) {
+            int a = day.lane_airport[order[i]];
+            ba_phase_a<EXACT>(c, acc[order[i]], a, t, tick);
+        }
+        bool more = false;
+        if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
+        for (int i = 0; i < N; ++i) {
+            int a = day.lane_airport[order[i]];
+            more |= ba_phase_b(c, acc[order[i]], a, t);
+        }
+        busy = more;
+    }
+    if (c.grow) for (int a = 0; a < N; ++a) ba_airport_epilogue(c, a, N);
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int i = 0; i < N; ++i) {
+        s0 += acc[i].lp; s1 += acc[i].g_sigma; s2 += acc[i].g_vt; s3 += acc[i].g_vu;
+        st |= acc[i].status;
+    }
+    logp[pd] = (float)s0; status[pd] = st;
+    if (ticks) ticks[pd] = tick;
+    if (c.grow) {
+        c.grow[c.route_base + R + 0] = (float)s1;
+        c.grow[c.route_base + R + 1] = (float)s2;
+        c.grow[c.route_base + R + 2] = (float)s3;
+    }
+}
+
+extern "C" int ba_emu_forward(const EmuPlan *pl, int P, const float *lat_airport,
+                              const float *lat_route, const float *scales, const float *noise,
+                              uint64_t seed, int value_mode, int want_grad, int exact,
+                              int rerun_overflow, unsigned shuffle_seed, float *logp,
+                              uint32_t *status, int32_t *ticks, float *tape, int32_t *pop_tick)
+{
+    const BaPlanView &plan = pl->host.view;
+    for (int d = 0; d < plan.D; ++d)
+        for (int p = 0; p < P; ++p) {
+            const BaDayView &day = plan.days[d];
+            if (exact)
+                run_item<true>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
+                               value_mode, want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick);
+            else {
+                run_item<false>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
+                                value_mode, want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick);
+                if (rerun_overflow && (status[(size_t)p * plan.D + d] & BA_S_OVERFLOW))
+                    run_item<true>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
+                                   value_mode, want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick);
+            }
+        }
+    return 0;
+}
+
+extern "C" void ba_emu_backward(const EmuPlan *pl, int P, const float *dlogp, const float *tape,
+                                float *g_airport, float *g_route, float *g_scales)
+{
+    const BaPlanView &v = pl->host.view;
+    const int CN = v.C * v.N, S = v.grad_stride;
+    for (int p = 0; p < P; ++p)
+        for (int j = 0; j < S; ++j) {
+            float s = 0.0f;
+            for (int d = 0; d < v.D; ++d)
+                s = fmaf(dlogp[(size_t)p * v.D + d], tape[((size_t)p * v.D + d) * S + j], s);
+            if (j < CN) g_airport[(size_t)p * CN + j] = s;
+            else if (j < CN + v.R) g_route[(size_t)p * v.R + (j - CN)] = s;
+            else g_scales[(size_t)p * 3 + (j - CN - v.R)] = s;
+        }
+}
+
+extern "C" void ba_emu_noise(const EmuPlan *pl, int P, uint64_t seed, float *noise)
+{
+    const BaPlanView &v = pl->host.view;
+    for (int p = 0; p < P; ++p)
+        for (int d = 0; d < v.D; ++d)
+            for (int f = 0; f < v.Fmax; ++f) {
+                BaNoise4 z = ba_philox_noise(seed, p, d, f);
+                float *o = noise + (((size_t)p * v.D + d) * v.Fmax + f) * 4;
+                o[0] = z.e_dep; o[1] = z.eps_travel; o[2] = z.e_arr; o[3] = z.eps_turn;
+            }
+}
