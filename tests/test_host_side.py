@@ -1,0 +1,183 @@
+"""CPU tests of the host side: schedule compiler orderings, the C-ABI library
+(loads, exports every symbol of include/bayesair_b200.h, refuses to run without a
+GPU), the PPL surface, and the emulated kernel against golden vectors + oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import Golden, golden_names, rel_err, std_noise
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------- C ABI -----
+def test_library_exports_every_declared_symbol():
+    from bayesair_b200 import _capi
+    lib = _capi.load_library()
+    header = open(os.path.join(ROOT, "include", "bayesair_b200.h")).read()
+    declared = set(re.findall(r"\b(ba_[a-z_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ba_version() == 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    import bayesair_b200 as ba
+    from bayesair_b200._capi import BayesAirLibraryError
+    from bayesair_b200.synth import synth_day_frame
+    fl, ap = ba.parse_schedule(synth_day_frame(4, 60))
+    st = ba.NetworkState({a.code: a for a in ap}, fl)
+    with pytest.raises(BayesAirLibraryError):
+        ba.air_traffic_network_model([st], 0.2)
+    with pytest.raises(BayesAirLibraryError):
+        ba.air_traffic_network_model([st], 0.2, device=torch.device("cpu"))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "bayesair_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "ba_oracle" not in src, f
+                assert "hostemu" not in src or f == "ba_sim.cuh", f
+
+
+# ------------------------------------------------------- schedule compiler --
+def test_compiler_orderings():
+    import bayesair_b200 as ba
+    from bayesair_b200.compiler import compile_states, day_spec_from_frame, used_routes
+    from bayesair_b200.synth import synth_day_frame
+    frames = [synth_day_frame(6, 120, d, seed=3, cancel_frac=0.1) for d in range(2)]
+    states = []
+    for df in frames:
+        # shuffle rows: NetworkState must restore stable scheduled-departure order
+        fl, ap = ba.parse_schedule(df)
+        states.append(ba.NetworkState({a.code: a for a in ap}, fl))
+    codes, specs = compile_states(states)
+    assert codes == list(states[0].airports.keys())
+    for df, s in zip(frames, specs):
+        assert np.all(np.diff(s.sched_dep) >= 0)
+        v = day_spec_from_frame(df, codes)
+        for k in ("sched_dep", "act_dep", "act_arr", "cancel_obs", "origin", "dest", "airport_global"):
+            assert np.array_equal(getattr(s, k), getattr(v, k), equal_nan=True), k
+        assert s.flight_names == v.flight_names
+        assert np.isnan(s.act_dep[s.cancel_obs == 1]).all()
+    # day 1 lists airports in its own first-appearance order, mapped to day-0 indices
+    assert sorted(specs[1].airport_global.tolist()) == list(range(6))
+    assert [codes[g] for g in specs[1].airport_global] == specs[1].codes
+    r = used_routes(specs, 6)
+    assert len(r) == len(set(r.tolist())) and (r // 6 != r % 6).all()
+
+
+def test_stable_sort_keeps_tie_order():
+    import bayesair_b200 as ba
+    t = lambda x: torch.tensor(x)  # noqa: E731
+    fl = [ba.Flight(str(i), "A", "B", t(s), t(s + 1.0), t(0.0), actual_departure_time=t(s),
+                    actual_arrival_time=t(s + 1)) for i, s in enumerate([7.0, 6.0, 7.0, 6.0, 5.0])]
+    assert str(fl[0]) == "0_A_B"
+    st = ba.NetworkState({"A": ba.Airport("A"), "B": ba.Airport("B")}, fl)
+    assert [f.flight_number for f in st.pending_flights] == ["4", "1", "3", "0", "2"]
+    assert not st.complete
+
+
+# -------------------------------------------------------------- PPL surface --
+def test_mini_ppl_handlers():
+    from bayesair_b200.ppl import USING_REAL_PYRO, dist, poutine, pyro
+    pyro.clear_param_store()
+
+    def model():
+        s = pyro.param("s", torch.tensor(0.1), constraint=dist.constraints.positive)
+        a = pyro.sample("a", dist.Gamma(torch.tensor(1.5), torch.tensor(10.0)))
+        pyro.factor("f", -(a / s) ** 2)
+        return a
+
+    a0 = torch.tensor(0.3, requires_grad=True)
+    tr = poutine.trace(poutine.condition(model, data={"a": a0})).get_trace()
+    expect = torch.distributions.Gamma(1.5, 10.0).log_prob(a0) - (a0 / 0.1) ** 2
+    assert abs(float(tr.log_prob_sum()) - float(expect)) < 1e-4
+    tr2 = poutine.trace(poutine.scale(poutine.condition(model, data={"a": a0}), scale=0.5)).get_trace()
+    assert abs(float(tr2.log_prob_sum()) - 0.5 * float(expect)) < 1e-4
+    assert abs(float(pyro.param("s")) - 0.1) < 1e-7
+    if not USING_REAL_PYRO:
+        with pytest.raises(RuntimeError):
+            poutine.trace(lambda: (model(), model())).get_trace()
+
+
+# ---------------------------------------------- emulated kernel (CPU, g++) --
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "wn100"])
+def test_emulated_kernel_vs_golden(name, exact):
+    from tests.hostemu import EmuPlan
+    g = Golden(name)
+    plan = EmuPlan(g.specs, len(g.global_codes), g.delta_t, g.max_t, g.include_cancellations)
+    lat = {k: v[None] for k, v in g.latents.items()}
+    o = plan.forward(lat, g.scales, g.noise[None], exact=exact, shuffle_seed=3)
+    assert (o["status"] == 0).all()
+    ref = sum(g.ref_class.values())
+    assert abs(float(o["logp"].astype(np.float64).sum()) - ref) <= 5e-6 * abs(ref)
+    for k, v in g.ref_grads.items():
+        assert rel_err(o["grads"][k][0], v) <= 1e-4, k
+    assert rel_err(o["grads"]["scales"][0], g.ref_grad_scales) <= 1e-4
+
+
+@pytest.mark.parametrize("canc", [False, True])
+def test_emulated_kernel_decisions_vs_oracle(canc):
+    """Pop tick of every flight (the queue decisions) identical to the oracle for
+    several particles and lane interleavings, incl. a starved-aircraft regime."""
+    from bayesair_b200.compiler import day_spec_from_frame
+    from bayesair_b200.synth import synth_day_frame, synth_latents
+    from oracle import ba_oracle
+    from tests.hostemu import EmuPlan
+    N, F, P = 8, 320, 6
+    frames = [synth_day_frame(N, F, d, seed=77, cancel_frac=0.05 if canc else 0.0) for d in range(2)]
+    specs = [day_spec_from_frame(frames[0])]
+    specs.append(day_spec_from_frame(frames[1], specs[0].codes))
+    lat = synth_latents(N, P, seed=9, service_scale=0.06, spread=0.6,
+                        include_cancellations=canc, n_aircraft_mean=2.5)
+    noise = std_noise(P, 2, F, seed=5)
+    sc = (0.1, 0.1, 0.1)
+    plan = EmuPlan(specs, N, 0.2, 30.0, canc)
+    for shuffle in (1, 2):
+        o = plan.forward(lat, sc, noise, shuffle_seed=shuffle, want_pop=True)
+        assert (o["status"] == 0).all()
+        for p in range(P):
+            for d in range(2):
+                r = ba_oracle.run_day(specs[d], {k: v[p] for k, v in lat.items()}, sc,
+                                      noise[p, d], delta_t=0.2, include_cancellations=canc)
+                assert r["n_ticks"] == o["ticks"][p, d]
+                assert np.array_equal(o["pop_tick"][p, d], r["pop_tick"])
+                assert abs(r["logp"] - o["logp"][p, d]) <= 5e-6 * abs(r["logp"])
+
+
+def test_emulated_overflow_rerun(monkeypatch):
+    from tests.hostemu import EmuPlan
+    g = Golden("congested6")
+    monkeypatch.setenv("BA_Q_MIN", "1"); monkeypatch.setenv("BA_Q_DIV", "1e9")
+    monkeypatch.setenv("BA_BAG_MIN", "1"); monkeypatch.setenv("BA_BAG_FRAC", "0")
+    plan = EmuPlan(g.specs, len(g.global_codes), g.delta_t, g.max_t, False)
+    lat = {k: v[None] for k, v in g.latents.items()}
+    flagged = plan.forward(lat, g.scales, g.noise[None], rerun_overflow=False)
+    assert (flagged["status"] & 2).all()
+    fixed = plan.forward(lat, g.scales, g.noise[None])
+    exact = plan.forward(lat, g.scales, g.noise[None], exact=True)
+    assert (fixed["status"] == 0).all() and np.array_equal(fixed["logp"], exact["logp"])
+
+
+def test_clock_matches_torch_inplace_add():
+    """The kernel's clock (sequential fp32 adds, model.py:158-161) equals torch's
+    in-place `t += delta_t` on an fp32 tensor, tick for tick."""
+    t = torch.tensor(0.0)
+    c = np.float32(0.0)
+    for k in range(400):
+        t += 0.2
+        c = np.float32(c + np.float32(0.2))
+        assert float(t) == float(c)
+    assert abs(float(c) - 80.0) > 1e-5     # i.e. NOT k * dt
