@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: WN-network particle-days/s (log-joint + gradient).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+                    [--workload cfg3|cfg2|cfg1|cfg5s]
+
+One "step" = one pass of the hot path over one batch: forward simulation +
+fused log-joint (`ba_forward`) and the VJP contraction (`ba_backward`) for
+P particles x D days of a synthetic WN-like network (the WN data is absent from
+the reference mount).  Prints ONE JSON line (contract in the task
+statement): `value` = whole-job particle-days/s with inputs resident in HBM,
+`e2e` = the same through the host-buffer C-ABI call `ba_logjoint_host` (H2D of
+latents, both kernels, D2H of log-probs + gradients inside the timed region),
+`roofline` for the forward kernel, `cpu_baseline` = the C oracle on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_days_per_s"
+UNIT = "particle-days/s"
+
+# name -> (N airports, flights per day, particles per GPU, service scale)
+WORKLOADS = {
+    # BASELINE.json configs[2] (the north star's stated target size): full WN network,
+    # Dec 21-30 2022 meltdown flight counts, 4096 particles x 10 days
+    "cfg3": (100, [3876, 3876, 3876, 3200, 3552, 3876, 3876, 3876, 3876, 3876], 4096, 0.02),
+    # configs[1]: full WN network, one day, 1024 particles
+    "cfg2": (100, [3876], 1024, 0.02),
+    # configs[0]: top-10 airports, one day (the reference's own CPU-runnable case)
+    "cfg1": (10, [480], 1024, 0.03),
+    # configs[4] scaled to fit a quick run: 500 airports, 20k flights/day, 4 days
+    "cfg5s": (500, [20000] * 4, 512, 0.01),
+}
+
+
+def build_workload(name, seed=21):
+    from bayesair_b200.compiler import day_spec_from_frame
+    from bayesair_b200.synth import synth_day_frame
+    N, Fs, P, svc = WORKLOADS[name]
+    frames = [synth_day_frame(N, F, d, seed=seed) for d, F in enumerate(Fs)]
+    specs = [day_spec_from_frame(frames[0])]
+    specs += [day_spec_from_frame(f, specs[0].codes) for f in frames[1:]]
+    return N, Fs, P, svc, specs
+
+
+def algorithmic_bytes_per_particle_day(N, Fs, R, with_noise=True):
+    """16 F (noise in) + 4 (2N+R) (latents in) + 4 (2N+R) (grads out)
+    + 4 (logp) + 12 (scale grads), static flight tables amortised over particles."""
+    F = float(np.mean(Fs))
+    return (16.0 * F if with_noise else 0.0) + 8.0 * (2 * N + R) + 16.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def std_noise(P, D, F, seed):
+    rng = np.random.default_rng([seed, 99])
+    z = np.empty((P, D, F, 4), np.float32)
+    z[..., 0] = rng.standard_exponential((P, D, F), dtype=np.float32)
+    z[..., 1] = rng.standard_normal((P, D, F), dtype=np.float32)
+    z[..., 2] = rng.standard_exponential((P, D, F), dtype=np.float32)
+    z[..., 3] = rng.standard_normal((P, D, F), dtype=np.float32)
+    return z
+
+
+def cpu_baseline(specs, N, svc, n_particles, threads, seed=3):
+    """The C oracle (a port of the reference algorithm) on the host cores, on a
+    bounded sample of the same workload."""
+    from bayesair_b200.synth import synth_latents
+    from oracle import ba_oracle
+    lat = synth_latents(N, n_particles, seed=seed, service_scale=svc)
+    Fmax = max(s.n_flights for s in specs)
+    noise = std_noise(n_particles, len(specs), Fmax, seed)
+    t0 = time.perf_counter()
+    out = ba_oracle.run_batch(specs, lat, (0.1, 0.1, 0.1), noise, delta_t=0.2, want_grad=True,
+                              n_threads=threads)
+    dt = time.perf_counter() - t0
+    assert (out["status"] == 0).all()
+    return n_particles * len(specs) / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The
+    reference is pure Python + Pyro and cannot travel to the GPU box (Pyro is not
+    installable, /root/reference is not mounted there), so this arm times the C
+    port of its algorithm (oracle/ba_oracle.c, pinned to the reference by golden
+    vectors) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    N, Fs, P, svc, specs = build_workload(name)
+    cores = os.cpu_count() or 1
+    # bounded sample per step: about 2-4 s of CPU work
+    probe_rate, _ = cpu_baseline(specs, N, svc, cores, cores)
+    n_particles = max(1, int(probe_rate * 3.0 / len(specs)))
+    for _ in range(args.warmup):
+        cpu_baseline(specs, N, svc, max(1, n_particles // 4), cores)
+    t_tot = 0.0
+    for k in range(args.steps):
+        _, dt = cpu_baseline(specs, N, svc, n_particles, cores, seed=10 + k)
+        t_tot += dt
+    value = args.steps * n_particles * len(specs) / t_tot
+    sample = f"{n_particles} particles x {len(specs)} days per step ({name} network), {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}: N={N} airports, F/day={Fs}", "delta_t": 0.2},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C port of the reference algorithm (oracle/ba_oracle.c); the reference's own "
+                "Pyro path measured 13.7 s per particle-day (0.073 particle-days/s, 1 core) "
+                "at this network size in the build container (tests/golden/wn100.npz ref_times)",
+    }
+    print(json.dumps(line))
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from bayesair_b200 import _capi
+    from bayesair_b200.plan import SimulationPlan
+    from bayesair_b200.synth import synth_latents
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; bayesair_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    name = args.workload
+    N, Fs, P, svc, specs = build_workload(name)
+    if args.particles:
+        P = args.particles
+    D = len(Fs)
+    plan = SimulationPlan(specs, specs[0].codes, delta_t=0.2, device=dev)
+    R, C = plan.n_routes, plan.n_airport_latents
+    lat = synth_latents(N, P, seed=1000 + rank, service_scale=svc)
+    tl = {k: torch.tensor(v, device=dev) for k, v in lat.items()}
+    la, lr = plan.pack_latents(tl["mean_turnaround"], tl["mean_service"], tl["travel"])
+    la, lr = la.contiguous(), lr.contiguous()
+    scales = torch.tensor([0.1, 0.1, 0.1], device=dev)
+    noise = plan.generate_noise(P, seed=77 + rank)        # resident in HBM, like the latents
+    ones = torch.ones((P, D), device=dev)
+    # guide-parameter gradient buffer of a mean-field guide over 2N + N^2 log-latents
+    # (scripts/wn/train.py:228-232): the only thing that crosses GPUs per step
+    n_latent = 2 * N + N * N
+    guide_grad = torch.zeros(2 * n_latent + 4, device=dev)
+
+    def step():
+        out = plan.forward(la, lr, scales, noise, want_grad=True)
+        ga, gr, gs = plan.backward(ones, out["tape"])
+        if world > 1:
+            guide_grad[:N * 2] = ga.sum(0).reshape(-1)[:N * 2]
+            dist.all_reduce(guide_grad)
+        return out, ga, gr, gs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out, ga, gr, gs = step()
+    barrier()
+    SimulationPlan.check_status(out["status"])
+
+    launches0 = _capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _capi.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * P * D / (ms_per_step * 1e-3)
+
+    # ---- forward kernel alone (roofline): one launch per call, no re-run kernels --
+    fwd_ms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.forward(la, lr, scales, noise, want_grad=True, no_overflow_rerun=True)
+        e1.record()
+        torch.cuda.synchronize()
+        fwd_ms.append(e0.elapsed_time(e1))
+    fwd = float(np.mean(fwd_ms))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    B = algorithmic_bytes_per_particle_day(N, Fs, R)
+    achieved = B * P * D / (fwd * 1e-3) / 1e9
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "forward_kernel_summary.json")))
+        if prof.get("workload") == name:
+            traffic = prof.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- Philox variant (no noise tensor read): production configuration --------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(max(2, args.steps // 2)):
+        o = plan.forward(la, lr, scales, None, seed=5, want_grad=True)
+        plan.backward(ones, o["tape"])
+    e1.record()
+    torch.cuda.synchronize()
+    philox_value = P * D * max(2, args.steps // 2) / (e0.elapsed_time(e1) * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI --------------------------------
+    h_la = torch.empty(la.shape, dtype=torch.float32, pin_memory=True).copy_(la.cpu())
+    h_lr = torch.empty(lr.shape, dtype=torch.float32, pin_memory=True).copy_(lr.cpu())
+    h_sc = np.array([0.1, 0.1, 0.1], np.float32)
+    outbuf = {
+        "logp": torch.empty((P, D), dtype=torch.float32, pin_memory=True).numpy(),
+        "status": torch.empty((P, D), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32),
+        "g_airport": torch.empty((P, C, N), dtype=torch.float32, pin_memory=True).numpy(),
+        "g_route": torch.empty((P, R), dtype=torch.float32, pin_memory=True).numpy(),
+        "g_scales": torch.empty((P, 3), dtype=torch.float32, pin_memory=True).numpy(),
+    }
+    for _ in range(2):
+        plan.logjoint_host(h_la.numpy(), h_lr.numpy(), h_sc, None, seed=5, out=outbuf)
+    barrier()
+    n_e2e = max(2, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        plan.logjoint_host(h_la.numpy(), h_lr.numpy(), h_sc, None, seed=5, out=outbuf)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * P * D * n_e2e / e2e_s
+    h2d = int(h_la.numel() * 4 + h_lr.numel() * 4 + 12)
+    d2h = int(sum(v.nbytes for v in outbuf.values()))
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{name}: WN-like network N={N} airports, D={D} days, F/day={Fs}, "
+                            f"P={P} particles per GPU, delta_t=0.2, no cancellations",
+                "particles_per_gpu": P, "days": D, "routes": R,
+                "noise": "explicit [P,D,F,4] fp32 tensor resident in HBM "
+                         f"({noise.numel() * 4 / 1e9:.2f} GB per GPU > 126 MB L2: inputs larger than L2)",
+                "parallelism": f"particles sharded over {world} GPU(s); allreduce of guide-gradient "
+                               "buffer only" if world > 1 else "single GPU",
+                "block_threads": plan.block_threads, "smem_bytes": plan.smem_bytes,
+                "resident_ctas": plan.resident_ctas,
+            },
+            "clocks": clocks.summary(),
+            "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "note": "ba_logjoint_host: pinned host latents in, Philox noise in-kernel, "
+                            "log-probs + gradients out, synchronised"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "ba_forward_kernel", "kernel_ms": fwd,
+                         "algorithmic_bytes_per_particle_day": B,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
+                         if peaks else "fallback 6650 GB/s (of fallback)",
+                         "note": "serial tick loop per particle-day: latency/issue bound by "
+                                 "construction (SURVEY.md §8d); see profiles/ for issue-slot use"},
+            "philox_value": philox_value,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_cpu = max(cores, 16) if name != "cfg1" else 256
+            rate, dt = cpu_baseline(specs, N, svc, n_cpu, cores)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{n_cpu} particles x {D} days of the same network in {dt:.1f} s "
+                          f"(oracle/ba_oracle.c, {cores} threads)",
+                "reference_python_recorded": "13.7 s per particle-day = 0.073 particle-days/s on 1 "
+                                             "core for the unmodified Pyro reference at N=100/F=3876 "
+                                             "(build container, tests/golden/wn100.npz ref_times)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
+    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()
