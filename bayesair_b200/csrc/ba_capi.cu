@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -113,6 +114,13 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         BA_PCUDA(upload(pl, H.flights, &v.flights));
         BA_PCUDA(upload(pl, H.route, &v.route));
         BA_PCUDA(upload(pl, H.dep_fid, &v.dep_fid));
+        BA_PCUDA(upload(pl, H.dep_sched, &v.dep_sched));
+        BA_PCUDA(upload(pl, H.dep_word, &v.dep_word));
+        BA_PCUDA(upload(pl, H.pos_dep, &v.pos_dep));
+        BA_PCUDA(upload(pl, H.pos_arr, &v.pos_arr));
+        BA_PCUDA(upload(pl, H.rt_gid, &v.rt_gid));
+        BA_PCUDA(upload(pl, H.rt_off, &v.rt_off));
+        BA_PCUDA(upload(pl, H.rt_flt, &v.rt_flt));
         BA_PCUDA(upload(pl, H.airports, &v.airports));
         BA_PCUDA(upload(pl, H.lane_airport, &v.lane_airport));
         dviews[d] = v;
@@ -126,6 +134,10 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     // launch geometry
     const int N = n_airports;
     pl->block = ba_forward_block_threads(N);
+    if (const char *e = std::getenv("BA_BLOCK_THREADS")) {
+        int b = std::atoi(e);
+        if (b >= 32 && b <= 1024 && b % 32 == 0) pl->block = b;
+    }
     pl->smem_fast = ba_forward_smem_bytes(N, pl->host.smem_list_words, false);
     pl->smem_exact = ba_forward_smem_bytes(N, 0, true);
     int max_optin = 0;

@@ -16,7 +16,7 @@
 #include "ba_kernels.cuh"
 #include "ba_sim.cuh"
 
-#define BA_RED_WORDS (32 * 5 + 4)
+#define BA_RED_WORDS (32 * 6 + 4)
 
 int ba_forward_block_threads(int n_airports)
 {
@@ -28,13 +28,19 @@ int ba_forward_block_threads(int n_airports)
 
 size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact)
 {
-    size_t w = (size_t)BA_NWORDS_STATE * n_airports + BA_RED_WORDS;
-    if (!exact) w += list_words;
+    size_t w = (((size_t)BA_NWORDS_STATE * n_airports + 3) & ~(size_t)3) + BA_RED_WORDS;
+    if (!exact) w += list_words;   // 6 words per queue entry + 3 per bag entry
     return w * 4;
 }
 
+// resident CTAs per SM the register allocation aims for, per block-size class
+#ifndef BA_MIN_BLOCKS_128
+#define BA_MIN_BLOCKS_128 6
+#endif
+#define BA_MIN_BLOCKS(MAXT) ((MAXT) == 128 ? BA_MIN_BLOCKS_128 : ((MAXT) == 256 ? 3 : 1))
+
 template <bool EXACT, int MAXT>
-__global__ void __launch_bounds__(MAXT) ba_forward_kernel(const BaFwdParams prm)
+__global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(const BaFwdParams prm)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -43,7 +49,7 @@ __global__ void __launch_bounds__(MAXT) ba_forward_kernel(const BaFwdParams prm)
     const int N = plan.N, D = plan.D, C = plan.C, R = plan.R;
 
     uint32_t *state_w = smem;
-    uint32_t *red = smem + (size_t)BA_NWORDS_STATE * N;     // [BA_RED_WORDS]
+    uint32_t *red = smem + (((size_t)BA_NWORDS_STATE * N + 3) & ~(size_t)3);  // [BA_RED_WORDS], 16 B aligned
     uint32_t *pool = red + BA_RED_WORDS;                     // shared list pools (fast)
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
 
@@ -78,36 +84,16 @@ __global__ void __launch_bounds__(MAXT) ba_forward_kernel(const BaFwdParams prm)
         const BaDayView day = plan.days[d];
 
         c.N = N; c.F = day.F;
-        c.flights = day.flights; c.route = day.route; c.dep_fid = day.dep_fid; c.ap = day.airports;
+        c.flights = day.flights; c.route = day.route; c.ap = day.airports;
+        c.dep_sched = day.dep_sched; c.dep_word = day.dep_word; c.pos_dep = day.pos_dep;
+        c.pos_arr = day.pos_arr; c.rt_gid = day.rt_gid; c.rt_off = day.rt_off;
+        c.rt_flt = day.rt_flt; c.Rd = day.Rd;
         c.lat_route = prm.lat_route + (size_t)p * R;
         c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
         c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
-        {
-            uint32_t *g = gscr;
-            if (EXACT) {
-                c.qf = g; g += day.q_total_x;
-                c.qs = (float *)g; g += day.q_total_x;
-                c.qw = (float *)g; g += day.q_total_x;
-                c.qx = (float *)g; g += day.q_total_x;
-                c.bf = g; g += day.bag_total_x;
-                c.ba = (float *)g; g += day.bag_total_x;
-            } else {
-                uint32_t *s = pool;
-                c.qf = s; s += day.q_total_s;
-                c.qs = (float *)s; s += day.q_total_s;
-                c.qw = (float *)s; s += day.q_total_s;
-                c.qx = (float *)s; s += day.q_total_s;
-                c.bf = s; s += day.bag_total_s;
-                c.ba = (float *)s;
-            }
-            c.tt = (float *)g; g += day.turn_total;
-            c.te = (float *)g; g += day.turn_total;
-            c.at = (float *)g; g += day.av_total;
-            c.ae = (float *)g; g += day.av_total;
-            c.dl = g;
-        }
+        ba_carve_lists<EXACT>(c, day, pool, gscr);
 
         // ---- setup -----------------------------------------------------------
         const float *lat_airport = prm.lat_airport + (size_t)p * C * N;
@@ -116,7 +102,11 @@ __global__ void __launch_bounds__(MAXT) ba_forward_kernel(const BaFwdParams prm)
             for (int i = tid; i < plan.grad_stride; i += nthr) c.grow[i] = 0.0f;
         if (c.pop_tick)
             for (int i = tid; i < 2 * plan.Fmax; i += nthr) c.pop_tick[i] = -1;
-        BaAcc acc = {0.0f, 0.0f, 0.0f, 0.0f, 0u};
+        BaAcc acc = {0.0, 0.0f, 0.0f, 0.0f, 0u};
+        __syncthreads();
+
+        // ---- prologue: flight-parallel, coalesced ------------------------------
+        for (int f = tid; f < day.F; f += nthr) ba_prologue_flight(c, acc, f);
         __syncthreads();
 
         // ---- tick loop (model.py:158-200) --------------------------------------
@@ -141,10 +131,16 @@ __global__ void __launch_bounds__(MAXT) ba_forward_kernel(const BaFwdParams prm)
         }
 
         // ---- epilogue ----------------------------------------------------------
-        if (c.grow)
-            for (int a = tid; a < N; a += nthr) ba_airport_epilogue(c, a, N);
+        __syncthreads();          // every wait of the tape is written
+        for (int f = tid; f < day.F; f += nthr) ba_epilogue_flight(c, acc, f);
+        if (c.grow) {
+            __syncthreads();
+            for (int s = tid; s < N; s += nthr) ba_epilogue_airport(c, day.lane_airport[s], N);
+            for (int r = tid; r < day.Rd; r += nthr) ba_epilogue_route(c, r);
+        }
         // deterministic block reduction: lanes -> warp (shuffle tree) -> warps in order
-        float v0 = acc.lp, v1 = acc.g_sigma, v2 = acc.g_vt, v3 = acc.g_vu;
+        double v0 = acc.lp;
+        float v1 = acc.g_sigma, v2 = acc.g_vt, v3 = acc.g_vu;
         uint32_t st = acc.status;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -155,17 +151,19 @@ __global__ void __launch_bounds__(MAXT) ba_forward_kernel(const BaFwdParams prm)
             st |= __shfl_down_sync(0xffffffffu, st, o);
         }
         float *redf = (float *)red;
+        double *redd = (double *)red;          // red is 16-byte aligned; 6 words per warp
         if (lane == 0) {
-            redf[warp * 5 + 0] = v0; redf[warp * 5 + 1] = v1; redf[warp * 5 + 2] = v2;
-            redf[warp * 5 + 3] = v3; red[warp * 5 + 4] = st;
+            redd[warp * 3 + 0] = v0;
+            redf[warp * 6 + 2] = v1; redf[warp * 6 + 3] = v2;
+            redf[warp * 6 + 4] = v3; red[warp * 6 + 5] = st;
         }
         __syncthreads();
         if (tid == 0) {
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
             uint32_t ss = 0;
             for (int w = 0; w < nwarp; ++w) {
-                s0 += redf[w * 5 + 0]; s1 += redf[w * 5 + 1]; s2 += redf[w * 5 + 2];
-                s3 += redf[w * 5 + 3]; ss |= red[w * 5 + 4];
+                s0 += redd[w * 3 + 0]; s1 += redf[w * 6 + 2]; s2 += redf[w * 6 + 3];
+                s3 += redf[w * 6 + 4]; ss |= red[w * 6 + 5];
             }
             prm.logp[pd] = (float)s0;
             prm.status[pd] = ss;

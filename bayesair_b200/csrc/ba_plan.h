@@ -11,9 +11,12 @@
 #define BA_MAX_FLIGHTS (1 << 18)      // 18 bits of flight id in queue / bag words
 #define BA_FID_MASK 0x3FFFFu
 
-// queue entry word: [31] departure, [30:29] aircraft-branch weight code, [17:0] flight
+// queue entry word: [31] departure, [29:18] destination airport, [17:0] flight
 #define BA_Q_DEP 0x80000000u
-#define BA_Q_W_SHIFT 29
+#define BA_Q_DST_SHIFT 18
+// dep_word: [31:30] observed cancellation (0, 1, 3 = None), [29:18] destination, [17:0] flight
+#define BA_DW_CANCEL_SHIFT 30
+#define BA_DW_ENTRY_MASK 0x3FFFFFFFu
 // bag entry word: [31:18] origin airport (day order), [17:0] flight
 #define BA_BAG_O_SHIFT 18
 
@@ -46,19 +49,29 @@ struct BaAirport {                    // 80 B static row per (day, airport)
     uint32_t turn_off;                // turnaround list (cap = arr_cnt), global scratch
     uint32_t av_off, av_mask;         // aircraft FIFO ring, global scratch
     uint32_t dl_off, dl_mask;         // delayed-departure deque ring, global scratch
-    uint32_t pad0, pad1;
+    int32_t arr_off;                  // slice of arrival order (arr_cnt entries)
+    int32_t dep_live;                 // departures not observed as cancelled
 };
 
 struct BaDayView {
     int32_t N, F;
     const BaFlight *flights;          // [F]
     const int32_t *route;             // [F] compact global route id
-    const int32_t *dep_fid;           // [F] flights grouped by origin, ascending
+    const int32_t *dep_fid;           // [F] flights grouped by origin, ascending ("dep order")
+    const float *dep_sched;           // [F] scheduled departure, dep order
+    const uint32_t *dep_word;         // [F] flight | dest << 18 | cancel obs << 30, dep order
+    const int32_t *pos_dep;           // [F] flight -> position in dep order
+    const int32_t *pos_arr;           // [F] flight -> position in arrival order (-1: cancelled)
+    const int32_t *rt_gid;            // [Rd] global route id of the day's r-th used route
+    const int32_t *rt_off;            // [Rd+1] CSR offsets into rt_flt
+    const int32_t *rt_flt;            // [sum arr_cnt] flights of each used route, ascending
+    int32_t Rd;                       // routes used on this day
     const BaAirport *airports;        // [N] day order
     const int32_t *lane_airport;      // [N] airport handled by lane slot i (load-sorted)
     uint32_t q_total_s, bag_total_s;  // pool sizes (entries) of the shared variant
     uint32_t q_total_x, bag_total_x;  // pool sizes of the exact variant
     uint32_t turn_total, av_total, dl_total;
+    uint32_t any_track_t, any_track_a; // does any airport of the day track aircraft
     int32_t first_tick;               // ticks [1, first_tick) are provably idle
     float t_before_first;             // clock after first_tick-1 sequential fp32 adds
 };
@@ -72,11 +85,24 @@ struct BaPlanView {
     const BaDayView *days;            // [D]
 };
 
-// scratch words (4 B) one CTA needs for the exact variant / the always-global lists
+// Per-CTA global scratch layout (4-byte words), in this order:
+//   xdk, xak, atk   [F] each, dep order : service draws x_dep, x_arr and the arrival
+//                                         time y_dep + tau, derived by the prologue;
+//                                         dead after the scan and reused by the epilogue
+//                                         for per-flight gradient contributions
+//   ct              [F]                 : epilogue contributions to d/d mean_turnaround
+//   wd, wa          [F] each            : waits recorded by the scan ("tape")
+//   trl, tre        [F] each if any_track_t : turnaround release time / its noise
+//   qd, se, sw      [F] each if any_track_a : departure queue start, aircraft-source
+//                                         noise and branch weight (adjoint of max())
+//   exact variant only: runway queues 6 x q_total_x, bags 3 x bag_total_x
+//   turnaround lists 2 x turn_total, aircraft FIFOs 2 x av_total, delayed deques dl_total
 static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact)
 {
-    uint64_t w = 0;
-    if (exact) w += 4ull * d.q_total_x + 2ull * d.bag_total_x;
+    uint64_t w = 6ull * (uint64_t)d.F;
+    if (d.any_track_t) w += 2ull * (uint64_t)d.F;
+    if (d.any_track_a) w += 3ull * (uint64_t)d.F;
+    if (exact) w += 6ull * d.q_total_x + 3ull * d.bag_total_x;
     w += 2ull * d.turn_total + 2ull * d.av_total + 1ull * d.dl_total;
-    return w;
+    return w + 16;
 }

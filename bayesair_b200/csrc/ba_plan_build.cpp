@@ -124,11 +124,44 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             for (int f = 0; f < F; ++f) H.dep_fid[cur[T.h_origin[f]]++] = f;
             for (int a = 0; a < N; ++a) { H.airports[a].dep_off = off[a]; }
         }
+        H.dep_sched.resize(F); H.dep_word.resize(F); H.pos_dep.resize(F);
+        for (int k = 0; k < F; ++k) {
+            const int f = H.dep_fid[k];
+            H.pos_dep[f] = k;
+            H.dep_sched[k] = T.h_sched_dep[f];
+            H.dep_word[k] = (uint32_t)f | (((H.flights[f].od >> 12) & 0xFFFu) << BA_Q_DST_SHIFT) |
+                            (((H.flights[f].od >> 24) & 3u) << BA_DW_CANCEL_SHIFT);
+        }
+        // arrival order: flights grouped by destination, ascending flight index
+        // (cancelled-as-observed flights never arrive); and the day's route CSR
+        {
+            std::vector<int> off(N + 1, 0);
+            for (int a = 0; a < N; ++a) off[a + 1] = off[a] + arr_cnt[a];
+            H.pos_arr.assign(F, -1);
+            std::vector<int> cur(off.begin(), off.end() - 1);
+            for (int f = 0; f < F; ++f)
+                if (((H.flights[f].od >> 24) & 3u) != 1u) H.pos_arr[f] = cur[T.h_dest[f]]++;
+            for (int a = 0; a < N; ++a) H.airports[a].arr_off = off[a];
+            std::map<int32_t, std::vector<int32_t>> by_route;
+            for (int f = 0; f < F; ++f)
+                if (((H.flights[f].od >> 24) & 3u) != 1u) by_route[H.route[f]].push_back(f);
+            H.rt_gid.clear(); H.rt_off.assign(1, 0); H.rt_flt.clear();
+            for (auto &kv : by_route) {
+                H.rt_gid.push_back(kv.first);
+                for (int32_t f : kv.second) H.rt_flt.push_back(f);
+                H.rt_off.push_back((int32_t)H.rt_flt.size());
+            }
+        }
+        std::vector<int> dep_live(N, 0);
+        for (int f = 0; f < F; ++f)
+            if (((H.flights[f].od >> 24) & 3u) != 1u) dep_live[T.h_origin[f]]++;
         uint32_t q_s = 0, bag_s = 0, q_x = 0, bag_x = 0, turn = 0, av = 0, dl = 0;
+        uint32_t any_t = 0, any_a = 0;
         for (int a = 0; a < N; ++a) {
             BaAirport &A = H.airports[a];
             A.dep_cnt = dep_cnt[a];
             A.arr_cnt = arr_cnt[a];
+            A.dep_live = dep_live[a];
             A.global = T.h_airport_global[a];
             uint32_t flags = 0;
             if (include_cancellations) flags = BA_AP_TRACK_T | BA_AP_TRACK_A;
@@ -137,6 +170,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
                 if (dep_cnt[a] >= 1000) flags |= BA_AP_TRACK_T | BA_AP_TRACK_A;
             }
             A.flags = flags;
+            if (flags & BA_AP_TRACK_T) any_t = 1;
+            if (flags & BA_AP_TRACK_A) any_a = 1;
             const uint32_t traffic = (uint32_t)(dep_cnt[a] + arr_cnt[a]);
             // exact variant
             uint32_t qx = pow2ceil(std::max(1u, traffic));
@@ -188,13 +223,18 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         BaDayView &V = H.view;
         V.N = N; V.F = F;
         V.flights = H.flights.data(); V.route = H.route.data(); V.dep_fid = H.dep_fid.data();
+        V.dep_sched = H.dep_sched.data(); V.dep_word = H.dep_word.data();
+        V.pos_dep = H.pos_dep.data(); V.pos_arr = H.pos_arr.data();
+        V.rt_gid = H.rt_gid.data(); V.rt_off = H.rt_off.data(); V.rt_flt = H.rt_flt.data();
+        V.Rd = (int32_t)H.rt_gid.size();
+        V.any_track_t = any_t; V.any_track_a = any_a;
         V.airports = H.airports.data(); V.lane_airport = H.lane_airport.data();
         V.q_total_s = q_s; V.bag_total_s = bag_s; V.q_total_x = q_x; V.bag_total_x = bag_x;
         V.turn_total = turn; V.av_total = av; V.dl_total = dl;
         V.first_tick = first_tick; V.t_before_first = t_before;
         scratch_fast = std::max(scratch_fast, ba_scratch_words(V, false));
         scratch_exact = std::max(scratch_exact, ba_scratch_words(V, true));
-        smem_words = std::max(smem_words, 4u * q_s + 2u * bag_s);
+        smem_words = std::max(smem_words, 6u * q_s + 3u * bag_s);
     }
 
     out->day_views.resize(n_days);

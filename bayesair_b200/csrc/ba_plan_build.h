@@ -8,7 +8,9 @@
 
 struct BaHostDay {
     std::vector<BaFlight> flights;
-    std::vector<int32_t> route, dep_fid, lane_airport;
+    std::vector<int32_t> route, dep_fid, lane_airport, pos_dep, pos_arr, rt_gid, rt_off, rt_flt;
+    std::vector<float> dep_sched;
+    std::vector<uint32_t> dep_word;
     std::vector<BaAirport> airports;
     BaDayView view;   // pointers into the vectors above (host view)
 };
@@ -20,7 +22,7 @@ struct BaHostPlan {
     BaPlanView view;                    // .days -> day_views.data()
     uint64_t scratch_words_fast = 0;    // per-CTA scratch, shared-memory variant
     uint64_t scratch_words_exact = 0;   // per-CTA scratch, exact variant
-    uint32_t smem_list_words = 0;       // max over days: 4*q_total_s + 2*bag_total_s
+    uint32_t smem_list_words = 0;       // max over days: 6*q_total_s + 3*bag_total_s
 };
 
 // Returns BA_OK or an error status with *err filled.

@@ -1,18 +1,31 @@
 // Core of the hot path: one (particle, day) of the air-traffic-network simulation
 // with the log-joint and its pathwise gradient fused into the scan.
 //
-// Decomposition: one CTA per (particle, day); one lane per airport.
-// Every tick has two phases separated by CTA barriers:
+// Decomposition: one CTA per (particle, day), three stages.
 //
-//   phase A (per airport, no cross-airport reads):
-//       turnaround release -> reserve injection -> pop-ready / cancellation ->
-//       enqueue departures -> runway service loop.          model.py:163-196
-//       A served departure is appended (atomic slot) to the DESTINATION airport's
-//       inbound "bag" = that airport's slice of the reference's in-transit list.
-//   phase B (per airport): order the entries appended this tick by origin airport
-//       (restores the reference's global in-transit order restricted to this
-//       destination, model.py:186-196), then move every entry whose arrival time
-//       has passed into the runway queue.                   network.py:178-198
+//   PROLOGUE (flight-parallel, coalesced 16-byte loads of the flight table and the
+//       noise tensor): everything about a flight that does not depend on queue
+//       dynamics -- its two service-time draws, its travel time and hence (the
+//       departure time being observed) the time it reaches its destination -- is
+//       derived once and written to L2-resident per-CTA scratch in per-airport
+//       departure order.
+//   SCAN (one lane per airport; the serial part): the tick loop of model.py:158-200.
+//       It touches shared memory only, apart from contiguous reads of the prologue's
+//       output when flights become ready and fire-and-forget stores of each entry's
+//       total wait W (the "tape").  Every tick has two phases separated by barriers:
+//       phase A (per airport, no cross-airport reads): turnaround release -> reserve
+//           injection -> pop-ready / cancellation -> enqueue departures -> runway
+//           service loop (model.py:163-196).  A served departure is appended (atomic
+//           slot) to the DESTINATION airport's inbound "bag" = that airport's slice
+//           of the reference's in-transit list.
+//       phase B (per airport): order the entries appended this tick by origin airport
+//           (restores the reference's global in-transit order restricted to this
+//           destination, model.py:186-196), then move every entry whose arrival time
+//           has passed into the runway queue (network.py:178-198).
+//   EPILOGUE (one lane per airport over its static departure / arrival lists; all
+//       loads independent): mu = queue_start + W for every entry, the seven per-flight
+//       log-densities and the pathwise gradient sums.  Deterministic: every sum has a
+//       single owner and a fixed order; no floating-point atomics anywhere.
 //
 // All arithmetic that feeds a decision (a `<=` against the clock) is IEEE fp32 in
 // the reference's operation order, with contraction disabled (BA_ADD / BA_MUL /
@@ -138,7 +151,11 @@ struct BaCtx {
     int N, F;
     const BaFlight *flights;
     const int32_t *route;
-    const int32_t *dep_fid;
+    const float *dep_sched;
+    const uint32_t *dep_word;
+    const int32_t *pos_dep;
+    const int32_t *pos_arr, *rt_gid, *rt_off, *rt_flt;
+    int Rd;
     const BaAirport *ap;
     // particle inputs
     const float *lat_route;       // [R]
@@ -151,20 +168,26 @@ struct BaCtx {
     float c0_lp, c1_lp;           // cancellation log-prob at p == 0 for v = 0 / 1
     int value_mode, want_grad, cancel_mode;
     float max_t;
-    // per-airport dynamic state (shared memory), indexed by day-local airport
-    float *m, *rate, *mt, *tstd, *base, *n_avail, *q_asg;
-    float *acc_rw, *acc_turn, *acc_ln0, *acc_bc;
-    float *n0, *lograte, *logtstd, *next_sched;
+    // per-airport state (shared memory), indexed by day-local airport
+    float *m, *rate, *lograte, *mt, *tstd, *logtstd, *base, *n_avail, *n0, *q_asg, *next_sched;
+    float *acc_ln0, *acc_bc;
     uint32_t *next_dep, *q_head, *q_tail, *bag_n, *bag_sorted, *turn_n;
-    uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail, *cnt_entries, *cnt_land;
-    // per-airport static copies (shared memory)
+    uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail;
     uint32_t *s_flags, *s_qoff, *s_qmask, *s_bagoff, *s_bagcap, *s_depoff, *s_depcnt;
-    // list pools
-    uint32_t *qf; float *qs, *qw, *qx;     // runway queues  (shared or global)
-    uint32_t *bf; float *ba;               // inbound bags   (shared or global)
-    float *tt, *te;                        // turnaround lists (global scratch)
-    float *at, *ae;                        // aircraft FIFOs   (global scratch)
-    uint32_t *dl;                          // delayed deques   (global scratch)
+    // list pools (shared memory in the fast variant, global scratch in the exact one)
+    uint32_t *qf; float *qs, *qw, *qx, *qy, *qz;   // runway queues: word, start, wait, x,
+                                                   //   arrival time, x at destination
+    uint32_t *bf; float *ba, *bx;                  // inbound bags: word, arrival time, x
+    // per-flight global scratch
+    float *xdk, *xak, *atk;       // prologue outputs, dep order (reused by the epilogue)
+    float *ct;                    // epilogue: per-flight d/d mean_turnaround contributions
+    float *wd, *wa;               // tape: total wait of the departure / arrival entry
+    float *trl, *tre;             // turnaround release time and its noise (tracked days)
+    float *qd, *se, *sw;          // departure queue start, aircraft-source noise, weight
+    // always-global lists
+    float *tt, *te;               // turnaround lists
+    float *at, *ae;               // aircraft FIFOs
+    uint32_t *dl;                 // delayed deques
     // outputs
     float *grow;                  // gradient row [C*N + R + 3] or nullptr
     int32_t *pop_tick;            // [Fmax*2] of this (particle, day) or nullptr
@@ -172,29 +195,57 @@ struct BaCtx {
 };
 
 struct BaAcc {
-    float lp;
+    double lp;                    // ~7F terms of mixed sign per particle-day: keep the sum exact-ish
     float g_sigma, g_vt, g_vu;
     uint32_t status;
 };
 
-#define BA_NWORDS_STATE 35        // per-airport words of shared state (see ba_carve_state)
+#define BA_NWORDS_STATE 31        // per-airport words of shared state (see ba_carve_state)
+#define BA_Q_WORDS 6              // words per runway-queue entry
+#define BA_BAG_WORDS 3            // words per bag entry
 
 // Assigns the per-airport arrays out of one contiguous word buffer.
 BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N)
 {
     float *f = (float *)w;
-    c.m = f + 0 * N; c.rate = f + 1 * N; c.mt = f + 2 * N; c.tstd = f + 3 * N;
-    c.base = f + 4 * N; c.n_avail = f + 5 * N; c.q_asg = f + 6 * N;
-    c.acc_rw = f + 7 * N; c.acc_turn = f + 8 * N; c.acc_ln0 = f + 9 * N; c.acc_bc = f + 10 * N;
-    c.next_dep = w + 11 * N; c.q_head = w + 12 * N; c.q_tail = w + 13 * N;
-    c.bag_n = w + 14 * N; c.bag_sorted = w + 15 * N; c.turn_n = w + 16 * N;
-    c.av_head = w + 17 * N; c.av_tail = w + 18 * N; c.zeros_left = w + 19 * N;
-    c.dl_head = w + 20 * N; c.dl_tail = w + 21 * N; c.cnt_entries = w + 22 * N;
-    c.cnt_land = w + 23 * N;
+    c.m = f + 0 * N; c.rate = f + 1 * N; c.lograte = f + 2 * N; c.mt = f + 3 * N;
+    c.tstd = f + 4 * N; c.logtstd = f + 5 * N; c.base = f + 6 * N; c.n_avail = f + 7 * N;
+    c.n0 = f + 8 * N; c.q_asg = f + 9 * N; c.next_sched = f + 10 * N;
+    c.acc_ln0 = f + 11 * N; c.acc_bc = f + 12 * N;
+    c.next_dep = w + 13 * N; c.q_head = w + 14 * N; c.q_tail = w + 15 * N;
+    c.bag_n = w + 16 * N; c.bag_sorted = w + 17 * N; c.turn_n = w + 18 * N;
+    c.av_head = w + 19 * N; c.av_tail = w + 20 * N; c.zeros_left = w + 21 * N;
+    c.dl_head = w + 22 * N; c.dl_tail = w + 23 * N;
     c.s_flags = w + 24 * N; c.s_qoff = w + 25 * N; c.s_qmask = w + 26 * N;
     c.s_bagoff = w + 27 * N; c.s_bagcap = w + 28 * N; c.s_depoff = w + 29 * N;
     c.s_depcnt = w + 30 * N;
-    c.n0 = f + 31 * N; c.lograte = f + 32 * N; c.logtstd = f + 33 * N; c.next_sched = f + 34 * N;
+}
+
+// Carves the list pools (shared or global) and the per-flight / list scratch.
+// `lists` = start of the queue+bag pools, `g` = start of this CTA's global scratch.
+template <bool EXACT>
+BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, uint32_t *shared_pool, uint32_t *g)
+{
+    const uint32_t F = (uint32_t)day.F;
+    c.xdk = (float *)g; g += F; c.xak = (float *)g; g += F; c.atk = (float *)g; g += F;
+    c.ct = (float *)g; g += F;
+    c.wd = (float *)g; g += F; c.wa = (float *)g; g += F;
+    c.trl = c.tre = nullptr;
+    if (day.any_track_t) { c.trl = (float *)g; g += F; c.tre = (float *)g; g += F; }
+    c.qd = c.se = c.sw = nullptr;
+    if (day.any_track_a) {
+        c.qd = (float *)g; g += F; c.se = (float *)g; g += F; c.sw = (float *)g; g += F;
+    }
+    uint32_t *s = EXACT ? g : shared_pool;
+    const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
+    const uint32_t bt = EXACT ? day.bag_total_x : day.bag_total_s;
+    c.qf = s; s += qt; c.qs = (float *)s; s += qt; c.qw = (float *)s; s += qt;
+    c.qx = (float *)s; s += qt; c.qy = (float *)s; s += qt; c.qz = (float *)s; s += qt;
+    c.bf = s; s += bt; c.ba = (float *)s; s += bt; c.bx = (float *)s; s += bt;
+    if (EXACT) g = s;
+    c.tt = (float *)g; g += day.turn_total; c.te = (float *)g; g += day.turn_total;
+    c.at = (float *)g; g += day.av_total; c.ae = (float *)g; g += day.av_total;
+    c.dl = g;
 }
 
 BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
@@ -237,8 +288,10 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     const float m = lat_airport[1 * Ng + g];
     c.mt[a] = mt;
     c.m[a] = m;
-    c.rate[a] = BA_DIV(1.0f, m);                 // airport.py:146
-    c.tstd[a] = BA_MUL(c.v_u, mt);               // model.py:143-145
+    const float rate = BA_DIV(1.0f, m);          // airport.py:146
+    const float tstd = BA_MUL(c.v_u, mt);        // model.py:143-145
+    c.rate[a] = rate; c.tstd[a] = tstd;
+    c.lograte[a] = BA_LOG(rate); c.logtstd[a] = BA_LOG(tstd);
     float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
     if (c.cancel_mode) {
         n0 = BA_EXP(lat_airport[2 * Ng + g]);    // model.py:91-99
@@ -247,9 +300,6 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     c.base[a] = base;
     c.n_avail[a] = n0;
     c.n0[a] = n0;
-    c.lograte[a] = BA_LOG(c.rate[a]);
-    c.logtstd[a] = BA_LOG(c.tstd[a]);
-    c.next_sched[a] = A.dep_cnt > 0 ? c.flights[c.dep_fid[A.dep_off]].sched_dep : INFINITY;
     // while i < n0: append(0.0)  -> ceil(n0) zero-time aircraft (model.py:152-155)
     uint32_t nz = 0;
     if (n0 > 0.0f) {
@@ -258,10 +308,10 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     }
     c.zeros_left[a] = nz;
     c.q_asg[a] = NAN;
-    c.acc_rw[a] = 0.0f; c.acc_turn[a] = 0.0f; c.acc_ln0[a] = 0.0f; c.acc_bc[a] = 0.0f;
+    c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
+    c.acc_ln0[a] = 0.0f; c.acc_bc[a] = 0.0f;
     c.next_dep[a] = 0; c.q_head[a] = 0; c.q_tail[a] = 0; c.bag_n[a] = 0; c.bag_sorted[a] = 0;
     c.turn_n[a] = 0; c.av_head[a] = 0; c.av_tail[a] = 0; c.dl_head[a] = 0; c.dl_tail[a] = 0;
-    c.cnt_entries[a] = 0; c.cnt_land[a] = 0;
     c.s_flags[a] = A.flags;
     c.s_qoff[a] = EXACT ? A.q_off_x : A.q_off_s;
     c.s_qmask[a] = EXACT ? A.q_mask_x : A.q_mask_s;
@@ -272,24 +322,58 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
 }
 
 // ---------------------------------------------------------------------------
+// PROLOGUE: one flight (call for f = tid, tid + nthreads, ...)
+// ---------------------------------------------------------------------------
+BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
+{
+    const BaFlight fl = ba_flight(c, f);
+    const uint32_t cobs = (fl.od >> 24) & 3u;
+    const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
+    const BaNoise4 nz = ba_noise(c, f);
+    const float T = c.lat_route[c.route[f]];
+    // Exponential(1/m).rsample = e / rate  (airport.py:144-147)
+    const float xd = c.value_mode ? nz.e_dep : BA_DIV(nz.e_dep, c.rate[o]);
+    const float xa = c.value_mode ? nz.e_arr : BA_DIV(nz.e_arr, c.rate[d]);
+    // Normal(T, T v_t).rsample = T + eps * (T v_t)  (network.py:158-163)
+    const float sc = BA_MUL(T, c.v_t);
+    const float tau = c.value_mode ? nz.eps_travel : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
+    float y_dep = fl.act_dep, y_arr = fl.act_arr;
+    if (cobs != 1u && (isnan(y_dep) || isnan(y_arr))) {
+        acc.status |= BA_S_UNOBSERVED;      // this entry point is the fully observed path
+        y_dep = fl.sched_dep; y_arr = fl.sched_dep;
+    }
+    const int k = c.pos_dep[f];
+    c.xdk[k] = xd; c.xak[k] = xa;
+    c.atk[k] = BA_ADD(y_dep, tau);          // network.py:166-168 with the observed departure
+    if (c.trl) {
+        // Normal(m~, v_u m~).rsample (airport.py:217-221)
+        const float mt = c.mt[d];
+        const float u = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, c.tstd[d]));
+        c.trl[f] = BA_ADD(y_arr, u);
+        c.tre[f] = nz.eps_turn;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // runway-queue append (model.py:181-183 / network.py:186-191)
 // ---------------------------------------------------------------------------
-BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float aux)
+BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float x,
+                      float y, float z)
 {
     const uint32_t head = c.q_head[a], tail = c.q_tail[a], mask = c.s_qmask[a];
     if (tail - head > mask) { acc.status |= BA_S_OVERFLOW; return; }
     const uint32_t i = c.s_qoff[a] + (tail & mask);
-    c.qf[i] = word; c.qs[i] = qstart; c.qw[i] = 0.0f; c.qx[i] = aux;
+    c.qf[i] = word; c.qs[i] = qstart; c.qw[i] = 0.0f; c.qx[i] = x; c.qy[i] = y; c.qz[i] = z;
     c.q_tail[a] = tail + 1;
 }
 
 // available_aircraft.pop(0) for one departing flight (network.py:118-126).
-// Returns the ready time max(aircraft, sched); *wcode / *src_eps describe the
-// aircraft branch for the adjoint (0 none, 1 tie, 2 aircraft time strictly later).
+// Returns the ready time max(aircraft, sched); *weight / *src_eps describe the
+// aircraft branch for the adjoint (0 none, 0.5 tie, 1 aircraft time strictly later).
 BA_DEV float ba_take_aircraft(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, float sched,
-                              float t, uint32_t *wcode, float *src_eps)
+                              float t, float *weight, float *src_eps)
 {
-    *wcode = 0; *src_eps = 0.0f;
+    *weight = 0.0f; *src_eps = 0.0f;
     c.n_avail[a] = c.n_avail[a] - 1.0f;
     float ac_time = 0.0f;
     bool has_src = false;
@@ -314,12 +398,25 @@ BA_DEV float ba_take_aircraft(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, f
         }
     }
     float ready = fmaxf(ac_time, sched);          // torch.maximum
-    if (has_src) *wcode = ac_time > sched ? 2u : (ac_time == sched ? 1u : 0u);
+    if (has_src) *weight = ac_time > sched ? 1.0f : (ac_time == sched ? 0.5f : 0.0f);
     return ready;
 }
 
+// one ready departure of a tracked airport: take an aircraft, enqueue, record the branch
+BA_DEV void ba_depart_tracked(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, uint32_t k,
+                              float t)
+{
+    const uint32_t w = c.dep_word[k];
+    const int f = (int)(w & BA_FID_MASK);
+    const float sched = c.dep_sched[k];
+    float weight, src_eps;
+    const float ready = ba_take_aircraft(c, acc, a, A, sched, t, &weight, &src_eps);
+    if (c.qd) { c.qd[f] = ready; c.se[f] = src_eps; c.sw[f] = weight; }
+    ba_q_push(c, acc, a, BA_Q_DEP | (w & BA_DW_ENTRY_MASK), ready, c.xdk[k], c.atk[k], c.xak[k]);
+}
+
 // ---------------------------------------------------------------------------
-// phase A
+// SCAN, phase A
 // ---------------------------------------------------------------------------
 template <bool EXACT>
 BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
@@ -376,32 +473,35 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
     }
 
     // 3. pop_ready_to_depart_flights restricted to this origin (network.py:57-134)
-    {
+    const bool due = c.next_sched[a] <= t;
+    if (due || (flags & BA_AP_TRACK_T)) {
         const uint32_t dep_cnt = c.s_depcnt[a], dep_off = c.s_depoff[a];
-        uint32_t nd = c.next_dep[a];
+        const uint32_t nd = c.next_dep[a];
         uint32_t n_new = 0;
-        if (c.next_sched[a] <= t) {
+        if (due) {
             // the cached head of this origin's pending list is due: count the due prefix
             n_new = 1;
             float nxt = INFINITY;
             while (nd + n_new < dep_cnt) {
-                nxt = ba_flight(c, c.dep_fid[dep_off + nd + n_new]).sched_dep;
+                nxt = c.dep_sched[dep_off + nd + n_new];
                 if (!(nxt <= t)) break;
                 ++n_new;
                 nxt = INFINITY;
             }
             c.next_sched[a] = nxt;
         }
+        const uint32_t k0 = dep_off + nd;
         if (!(flags & BA_AP_TRACK_T)) {
             // cancellation probability is exactly 0 and aircraft are never scarce
             for (uint32_t i = 0; i < n_new; ++i) {
-                const int f = c.dep_fid[dep_off + nd + i];
-                const BaFlight fl = ba_flight(c, f);
-                const uint32_t cobs = (fl.od >> 24) & 3u;
+                const uint32_t k = k0 + i;
+                const uint32_t w = c.dep_word[k];
+                const uint32_t cobs = (w >> BA_DW_CANCEL_SHIFT) & 3u;
                 if (cobs == 3u) { acc.status |= BA_S_UNOBSERVED; continue; }
                 acc.lp += cobs ? c.c1_lp : c.c0_lp;
                 if (!cobs)
-                    ba_q_push(c, acc, a, BA_Q_DEP | (uint32_t)f, fmaxf(0.0f, fl.sched_dep), 0.0f);
+                    ba_q_push(c, acc, a, BA_Q_DEP | (w & BA_DW_ENTRY_MASK),
+                              fmaxf(0.0f, c.dep_sched[k]), c.xdk[k], c.atk[k], c.xak[k]);
             }
             c.next_dep[a] = nd + n_new;
         } else {
@@ -410,22 +510,23 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
             if (n_ready) {
                 const float n_start = c.n_avail[a];
                 const float base = c.base[a];
-                // network.py:80-84, fp32 in the reference's operation order
-                const float ratio = BA_DIV(n_start, (float)n_ready);
-                const float z = BA_MUL(10.0f, BA_ADD(ratio, -0.25f));
-                const float sg = 1.0f / (1.0f + BA_EXP(-z));
-                const float p = 1.0f - (1.0f - base) * sg;
-                float dl0 = 0.0f, dl1 = 0.0f;
-                const float lp0 = ba_relaxed_bernoulli_lp(p, 0.0f, &dl0);
-                const float lp1 = ba_relaxed_bernoulli_lp(p, 1.0f, &dl1);
-                // d p / d base = sg ; d p / d n = -(1-base) sg (1-sg) * 10 / n_ready
-                const float dp_dn = -(1.0f - base) * sg * (1.0f - sg) * 10.0f / (float)n_ready;
+                float lp0 = 0.0f, lp1 = 0.0f, dl0 = 0.0f, dl1 = 0.0f, sg = 1.0f, dp_dn = 0.0f;
+                if (n_new) {
+                    // network.py:80-84, fp32 in the reference's operation order
+                    const float ratio = BA_DIV(n_start, (float)n_ready);
+                    const float z = BA_MUL(10.0f, BA_ADD(ratio, -0.25f));
+                    sg = 1.0f / (1.0f + BA_EXP(-z));
+                    const float p = 1.0f - (1.0f - base) * sg;
+                    lp0 = ba_relaxed_bernoulli_lp(p, 0.0f, &dl0);
+                    lp1 = ba_relaxed_bernoulli_lp(p, 1.0f, &dl1);
+                    // d p / d base = sg ; d p / d n = -(1-base) sg (1-sg) * 10 / n_ready
+                    dp_dn = -(1.0f - base) * sg * (1.0f - sg) * 10.0f / (float)n_ready;
+                }
                 float g_p = 0.0f;          // sum over newly scored flights of d lp / d p
                 uint32_t first_delayed = n_new;
                 for (uint32_t i = 0; i < n_new; ++i) {
-                    const int f = c.dep_fid[dep_off + nd + i];
-                    const BaFlight fl = ba_flight(c, f);
-                    const uint32_t cobs = (fl.od >> 24) & 3u;
+                    const uint32_t k = k0 + i;
+                    const uint32_t cobs = (c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u;
                     if (cobs == 3u) { acc.status |= BA_S_UNOBSERVED; continue; }
                     acc.lp += cobs ? lp1 : lp0;
                     g_p += cobs ? dl1 : dl0;
@@ -434,25 +535,22 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                         if (first_delayed == n_new) first_delayed = i;
                         continue;
                     }
-                    uint32_t wcode; float src_eps;
-                    float ready = ba_take_aircraft(c, acc, a, A, fl.sched_dep, t, &wcode, &src_eps);
-                    ba_q_push(c, acc, a, BA_Q_DEP | (wcode << BA_Q_W_SHIFT) | (uint32_t)f, ready, src_eps);
+                    ba_depart_tracked(c, acc, a, A, k, t);
                 }
-                if (c.cancel_mode && c.want_grad) {
-                    c.acc_bc[a] += g_p * sg * base;                       // b = exp(c)
-                    // n = exp(l) + integers: d n / d l = exp(l) = initial count
-                    c.acc_ln0[a] += g_p * dp_dn;                          // times n0 at the end
+                if (c.cancel_mode && c.want_grad && n_new) {
+                    c.acc_bc[a] += g_p * sg * base;           // b = exp(c)
+                    // n = exp(l) + integers: d n / d l = exp(l); multiplied in the epilogue
+                    c.acc_ln0[a] += g_p * dp_dn;
                 }
                 // newly delayed flights go IN FRONT of the previously delayed ones
                 // (they precede them in the re-built pending list, network.py:60-68,112-114)
                 if (first_delayed < n_new) {
                     uint32_t hd = c.dl_head[a];
                     for (uint32_t i = n_new; i-- > first_delayed;) {
-                        const int f = c.dep_fid[dep_off + nd + i];
-                        const uint32_t cobs = (ba_flight(c, f).od >> 24) & 3u;
-                        if (cobs != 0u) continue;
+                        const uint32_t k = k0 + i;
+                        if (((c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u) != 0u) continue;
                         hd -= 1;
-                        c.dl[A->dl_off + (hd & A->dl_mask)] = (uint32_t)f;
+                        c.dl[A->dl_off + (hd & A->dl_mask)] = k;      // dep-order position
                     }
                     c.dl_head[a] = hd;
                 } else {
@@ -460,11 +558,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                     uint32_t hd = c.dl_head[a];
                     const uint32_t tl = c.dl_tail[a];
                     while (hd != tl && c.n_avail[a] > 0.0f) {
-                        const int f = (int)c.dl[A->dl_off + (hd & A->dl_mask)];
-                        const BaFlight fl = ba_flight(c, f);
-                        uint32_t wcode; float src_eps;
-                        float ready = ba_take_aircraft(c, acc, a, A, fl.sched_dep, t, &wcode, &src_eps);
-                        ba_q_push(c, acc, a, BA_Q_DEP | (wcode << BA_Q_W_SHIFT) | (uint32_t)f, ready, src_eps);
+                        ba_depart_tracked(c, acc, a, A, c.dl[A->dl_off + (hd & A->dl_mask)], t);
                         ++hd;
                     }
                     c.dl_head[a] = hd;
@@ -474,138 +568,64 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
         }
     }
 
-    // 5. update_runway_queue (airport.py:101-128)
+    // 5. update_runway_queue (airport.py:101-128): shared memory only
     {
         uint32_t head = c.q_head[a];
         const uint32_t tail = c.q_tail[a];
         if (head == tail) return;
         const uint32_t qoff = c.s_qoff[a], qmask = c.s_qmask[a];
-        const float rate = c.rate[a];
         float asg = c.q_asg[a];
-        float s_rw = 0.0f, s_turn = 0.0f;
-        uint32_t n_served = 0, n_land = 0;
         while (head != tail) {
             const uint32_t hi = qoff + (head & qmask);
-            const uint32_t word = c.qf[hi];
-            const int f = (int)(word & BA_FID_MASK);
-            const bool dep = (word & BA_Q_DEP) != 0u;
-            BaNoise4 nz;
-            bool have_nz = false;
             if (isnan(asg)) {
-                // _assign_service_time (airport.py:130-158)
-                nz = ba_noise(c, f); have_nz = true;
-                const float e = dep ? nz.e_dep : nz.e_arr;
-                const float x = c.value_mode ? e : BA_DIV(e, rate);   // Exponential.rsample
-                acc.lp += c.lograte[a] - rate * x;
+                // _assign_service_time (airport.py:130-158): the draw x joins the wait
+                // of every entry currently queued, head included
+                const float x = c.qx[hi];
                 for (uint32_t j = head; j != tail; ++j) {
                     const uint32_t ji = qoff + (j & qmask);
                     c.qw[ji] = BA_ADD(c.qw[ji], x);
                 }
                 asg = BA_ADD(c.qs[hi], c.qw[hi]);
-                if (c.want_grad && c.value_mode) c.acc_rw[a] += x;    // sum of x (value mode)
             }
             if (!(asg <= t)) break;
-            // served
-            if (!have_nz) nz = ba_noise(c, f);
-            const BaFlight fl = ba_flight(c, f);
+            // served (airport.py:111-126)
+            const uint32_t word = c.qf[hi];
+            const int f = (int)(word & BA_FID_MASK);
             const float wait = c.qw[hi];
-            const float mu = asg;                 // queue_start + total_wait
-            const int rid = c.route[f];
-            const float T = c.lat_route[rid];
-            ++n_served;
-            if (dep) {
-                // _assign_departure_time (airport.py:164-182), observed
-                const float y = fl.act_dep;
-                if (isnan(y)) acc.status |= BA_S_UNOBSERVED;
-                const float dy = y - mu;
-                acc.lp += -(dy * dy) * (0.5f * c.inv_sigma2) - c.log_sigma - BA_LOG_SQRT_2PI;
-                // add_in_transit_flights (network.py:136-168)
-                const float sc = BA_MUL(T, c.v_t);
-                const float tau = c.value_mode ? nz.eps_travel
-                                               : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
-                const float dz = (tau - T) / sc;
-                acc.lp += -0.5f * dz * dz - BA_LOG(sc) - BA_LOG_SQRT_2PI;
-                const float arrival = BA_ADD(y, tau);
-                const int dst = (int)((fl.od >> 12) & 0xFFFu);
+            if (word & BA_Q_DEP) {
+                c.wd[f] = wait;
+                // add_in_transit_flights (network.py:136-168): into the destination's bag
+                const int dst = (int)((word >> BA_Q_DST_SHIFT) & 0xFFFu);
                 const uint32_t slot = BA_ATOMIC_INC(&c.bag_n[dst]);
                 if (slot >= c.s_bagcap[dst]) acc.status |= BA_S_OVERFLOW;
                 else {
                     const uint32_t bi = c.s_bagoff[dst] + slot;
                     c.bf[bi] = ((uint32_t)a << BA_BAG_O_SHIFT) | (uint32_t)f;
-                    c.ba[bi] = arrival;
+                    c.ba[bi] = c.qy[hi];
+                    c.bx[bi] = c.qz[hi];
                 }
                 if (c.pop_tick) c.pop_tick[2 * f] = tick;
-                if (c.want_grad) {
-                    const float r = dy * c.inv_sigma2;
-                    acc.g_sigma += dy * dy * c.inv_sigma3 - c.inv_sigma;
-                    if (!c.value_mode) {
-                        s_rw += r * wait;
-                        const uint32_t wcode = (word >> BA_Q_W_SHIFT) & 3u;
-                        if (wcode) {
-                            const float w = wcode == 2u ? 1.0f : 0.5f;
-                            const float se = c.qx[hi];
-                            s_turn += w * r * (1.0f + c.v_u * se);
-                            acc.g_vu += w * r * se * c.mt[a];
-                        }
-                    }
-                }
             } else {
-                // _assign_arrival_time (airport.py:188-204), observed
-                const float y = fl.act_arr;
-                if (isnan(y)) acc.status |= BA_S_UNOBSERVED;
-                const float dy = y - mu;
-                acc.lp += -(dy * dy) * (0.5f * c.inv_sigma2) - c.log_sigma - BA_LOG_SQRT_2PI;
+                c.wa[f] = wait;
                 // _assign_turnaround_time (airport.py:210-221)
-                const float mt = c.mt[a], tstd = c.tstd[a];
-                const float u = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, tstd));
-                const float du = (u - mt) / tstd;
-                acc.lp += -0.5f * du * du - c.logtstd[a] - BA_LOG_SQRT_2PI;
-                ++n_land;
-                if (c.s_flags[a] & BA_AP_TRACK_T) {
+                if (flags & BA_AP_TRACK_T) {
                     const uint32_t n = c.turn_n[a];
-                    c.tt[A->turn_off + n] = BA_ADD(y, u);
-                    c.te[A->turn_off + n] = nz.eps_turn;
+                    c.tt[A->turn_off + n] = c.trl[f];
+                    c.te[A->turn_off + n] = c.tre[f];
                     c.turn_n[a] = n + 1;
                 }
                 if (c.pop_tick) c.pop_tick[2 * f + 1] = tick;
-                if (c.want_grad) {
-                    const float r = dy * c.inv_sigma2;
-                    acc.g_sigma += dy * dy * c.inv_sigma3 - c.inv_sigma;
-                    const float sc = T * c.v_t;
-                    if (!c.value_mode) {
-                        s_rw += r * wait;
-                        // arrival queue_start = act_dep + tau, tau = T (1 + v_t eps)
-                        BA_RED_ADD(&c.grow[c.route_base + rid],
-                                   r * (1.0f + c.v_t * nz.eps_travel) - 1.0f / T);
-                        acc.g_vt += r * nz.eps_travel * T - c.inv_vt;
-                        acc.g_vu += -c.inv_vu;
-                    } else {
-                        const float zt = (nz.eps_travel - T) / sc;   // value of tau in .eps_travel
-                        BA_RED_ADD(&c.grow[c.route_base + rid], zt / sc + (zt * zt - 1.0f) / T);
-                        acc.g_vt += (zt * zt - 1.0f) * c.inv_vt;
-                        s_turn += du / tstd + (du * du - 1.0f) / mt;
-                        acc.g_vu += (du * du - 1.0f) * c.inv_vu;
-                    }
-                }
             }
             ++head;
             asg = NAN;
         }
         c.q_head[a] = head;
         c.q_asg[a] = asg;
-        if (n_served) {
-            c.cnt_entries[a] += n_served;
-            c.cnt_land[a] += n_land;
-            if (c.want_grad) {
-                c.acc_rw[a] += s_rw;
-                c.acc_turn[a] += s_turn;
-            }
-        }
     }
 }
 
 // ---------------------------------------------------------------------------
-// phase B: in-transit -> destination runway queue (network.py:178-198)
+// SCAN, phase B: in-transit -> destination runway queue (network.py:178-198)
 // Returns whether this airport still has work (for the completion vote,
 // network.py:34-41).
 // ---------------------------------------------------------------------------
@@ -622,24 +642,24 @@ BA_DEV bool ba_phase_b(BaCtx &c, BaAcc &acc, int a, float t)
         // sort by origin airport (day order) restores the reference's list order.
         for (uint32_t i = ns + 1; i < n; ++i) {
             const uint32_t w = c.bf[off + i];
-            const float av = c.ba[off + i];
+            const float av = c.ba[off + i], xv = c.bx[off + i];
             const uint32_t key = w >> BA_BAG_O_SHIFT;
             uint32_t j = i;
             while (j > ns && (c.bf[off + j - 1] >> BA_BAG_O_SHIFT) > key) {
                 c.bf[off + j] = c.bf[off + j - 1];
                 c.ba[off + j] = c.ba[off + j - 1];
+                c.bx[off + j] = c.bx[off + j - 1];
                 --j;
             }
-            if (j != i) { c.bf[off + j] = w; c.ba[off + j] = av; }
+            if (j != i) { c.bf[off + j] = w; c.ba[off + j] = av; c.bx[off + j] = xv; }
         }
         uint32_t w = 0;
         for (uint32_t i = 0; i < n; ++i) {
             const float av = c.ba[off + i];
-            const uint32_t word = c.bf[off + i];
             if (av <= t) {
-                ba_q_push(c, acc, a, word & BA_FID_MASK, av, 0.0f);
+                ba_q_push(c, acc, a, c.bf[off + i] & BA_FID_MASK, av, c.bx[off + i], 0.0f, 0.0f);
             } else {
-                if (w != i) { c.bf[off + w] = word; c.ba[off + w] = av; }
+                if (w != i) { c.bf[off + w] = c.bf[off + i]; c.ba[off + w] = av; c.bx[off + w] = c.bx[off + i]; }
                 ++w;
             }
         }
@@ -652,28 +672,133 @@ BA_DEV bool ba_phase_b(BaCtx &c, BaAcc &acc, int a, float t)
 }
 
 // ---------------------------------------------------------------------------
-// per-airport gradient epilogue: writes the airport rows of the gradient row
+// EPILOGUE, stage 1 (flight-parallel, coalesced): the seven per-flight log-densities
+// and every per-flight gradient contribution.  Global sums
+// (log-prob, d/d scales) stay in the thread's accumulator; contributions owned by an
+// airport or a route are written to scratch for stage 2:
+//   xdk[k]   (dep order)     origin's  sum r W        (value mode: x_dep)
+//   xak[j]   (arrival order) dest's    sum r W        (value mode: x_arr)
+//   atk[f]                   route's   d/dT term
+//   ct[k|j]                  d/d mean_turnaround term (noise mode: aircraft branch of the
+//                            departure, dep order; value mode: landing term, arrival order)
 // ---------------------------------------------------------------------------
-BA_DEV void ba_airport_epilogue(BaCtx &c, int a, int Ng)
+BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
 {
-    const int g = c.ap[a].global;
-    const float m = c.m[a], mt = c.mt[a];
-    const float n_ent = (float)c.cnt_entries[a], n_land = (float)c.cnt_land[a];
-    float g_turn, g_serv;
-    if (!c.value_mode) {
-        // x = e m  =>  d/dm = sum r W / m  - (#entries)/m ;  u = m~ (1 + v_u eps)
-        g_serv = c.acc_rw[a] / m - n_ent / m;
-        g_turn = c.acc_turn[a] - n_land / mt;
-    } else {
-        // log Exponential(x; 1/m) = -log m - x/m
-        g_serv = -n_ent / m + c.acc_rw[a] / (m * m);
-        g_turn = c.acc_turn[a];
+    const BaFlight fl = ba_flight(c, f);
+    const uint32_t cobs = (fl.od >> 24) & 3u;
+    const int k = c.pos_dep[f];
+    if (cobs == 1u) {                 // observed as cancelled: never queued anywhere
+        if (c.want_grad) { c.xdk[k] = 0.0f; c.ct[k] = 0.0f; c.atk[f] = 0.0f; }
+        return;
     }
+    const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
+    const int j = c.pos_arr[f];
+    const BaNoise4 nz = ba_noise(c, f);
+    const int rid = c.route[f];
+    const float T = c.lat_route[rid];
+    const bool grad = c.want_grad != 0;
+    const float half_inv_var = 0.5f * c.inv_sigma2;
+    const float lp_const = -c.log_sigma - BA_LOG_SQRT_2PI;
+
+    // ---- departure side: *_departure_service_time, *_simulated_departure_time
+    //      (airport.py:144-147,175-182)
+    const float rate_o = c.rate[o];
+    const float xd = c.value_mode ? nz.e_dep : BA_DIV(nz.e_dep, rate_o);
+    const float wdep = c.wd[f];
+    const bool track_a = (c.s_flags[o] & BA_AP_TRACK_A) != 0u;
+    const float qstart_d = track_a ? c.qd[f] : fmaxf(0.0f, fl.sched_dep);
+    const float mu_d = BA_ADD(qstart_d, wdep);              // queue_start + total_wait
+    const float dy_d = fl.act_dep - mu_d;
+    float lp = (c.lograte[o] - rate_o * xd) + (lp_const - dy_d * dy_d * half_inv_var);
+
+    // ---- arrival side: *_travel_time, *_arrival_service_time,
+    //      *_simulated_arrival_time, *_turnaround_time
+    //      (network.py:158-163; airport.py:144-147,197-204,217-220)
+    const float rate_d = c.rate[d], mt = c.mt[d], tstd = c.tstd[d];
+    const float sc = BA_MUL(T, c.v_t);
+    const float tau = c.value_mode ? nz.eps_travel : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
+    const float qstart_a = BA_ADD(fl.act_dep, tau);
+    const float warr = c.wa[f];
+    const float mu_a = BA_ADD(qstart_a, warr);
+    const float dy_a = fl.act_arr - mu_a;
+    const float xa = c.value_mode ? nz.e_arr : BA_DIV(nz.e_arr, rate_d);
+    const float u = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, tstd));
+    const float dz = (tau - T) / sc;
+    const float du = (u - mt) / tstd;
+    lp += (c.lograte[d] - rate_d * xa) + (lp_const - dy_a * dy_a * half_inv_var);
+    float lp2 = (-0.5f * dz * dz - BA_LOG(sc) - BA_LOG_SQRT_2PI)
+              + (-0.5f * du * du - c.logtstd[d] - BA_LOG_SQRT_2PI);
+    acc.lp += (double)lp + (double)lp2;
+
+    if (grad) {
+        const float r_d = dy_d * c.inv_sigma2, r_a = dy_a * c.inv_sigma2;
+        acc.g_sigma += (dy_d * dy_d + dy_a * dy_a) * c.inv_sigma3 - 2.0f * c.inv_sigma;
+        if (!c.value_mode) {
+            c.xdk[k] = r_d * wdep;
+            c.xak[j] = r_a * warr;
+            // arrival queue_start = act_dep + tau, tau = T (1 + v_t eps)
+            c.atk[f] = r_a * (1.0f + c.v_t * nz.eps_travel) - 1.0f / T;
+            acc.g_vt += r_a * nz.eps_travel * T - c.inv_vt;
+            float gvu = -c.inv_vu, turn = 0.0f;
+            if (track_a) {
+                const float wgt = c.sw[f];
+                if (wgt > 0.0f) {
+                    // ready = max(act_arr_g + u_g, sched), u_g = m~ (1 + v_u eps_g)
+                    const float se = c.se[f];
+                    turn = wgt * r_d * (1.0f + c.v_u * se);
+                    gvu += wgt * r_d * se * c.mt[o];
+                }
+            }
+            c.ct[k] = turn;
+            acc.g_vu += gvu;
+        } else {
+            c.xdk[k] = xd;
+            c.xak[j] = xa;
+            c.atk[f] = dz / sc + (dz * dz - 1.0f) / T;
+            acc.g_vt += (dz * dz - 1.0f) * c.inv_vt;
+            c.ct[j] = du / tstd + (du * du - 1.0f) / mt;
+            acc.g_vu += (du * du - 1.0f) * c.inv_vu;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// EPILOGUE, stage 2: owner sums over contiguous slices, fixed order, no atomics.
+// ---------------------------------------------------------------------------
+BA_DEV void ba_epilogue_airport(BaCtx &c, int a, int Ng)
+{
+    const BaAirport A = c.ap[a];
+    const float m = c.m[a], mt = c.mt[a];
+    float s_dep = 0.0f, s_arr = 0.0f, s_turn = 0.0f;
+    for (int i = 0; i < A.dep_cnt; ++i) s_dep += c.xdk[A.dep_off + i];
+    for (int i = 0; i < A.arr_cnt; ++i) s_arr += c.xak[A.arr_off + i];
+    const float n_ent = (float)(A.dep_live + A.arr_cnt), n_land = (float)A.arr_cnt;
+    float g_serv, g_turn;
+    if (!c.value_mode) {
+        if (A.flags & BA_AP_TRACK_A)
+            for (int i = 0; i < A.dep_cnt; ++i) s_turn += c.ct[A.dep_off + i];
+        // x = e m  =>  d/dm = sum r W / m - (#entries)/m ;  u = m~ (1 + v_u eps)
+        g_serv = (s_dep + s_arr) / m - n_ent / m;
+        g_turn = s_turn - n_land / mt;
+    } else {
+        for (int i = 0; i < A.arr_cnt; ++i) s_turn += c.ct[A.arr_off + i];
+        // log Exponential(x; 1/m) = -log m - x/m
+        g_serv = -n_ent / m + (s_dep + s_arr) / (m * m);
+        g_turn = s_turn;
+    }
+    const int g = A.global;
     c.grow[0 * Ng + g] = g_turn;
     c.grow[1 * Ng + g] = g_serv;
     if (c.cancel_mode) {
-        // acc_ln0 holds sum d lp/d p * d p/d n ; n = exp(l) + k  =>  * exp(l)
         c.grow[2 * Ng + g] = c.acc_ln0[a] * c.n0[a];
         c.grow[3 * Ng + g] = c.acc_bc[a];
     }
+}
+
+BA_DEV void ba_epilogue_route(BaCtx &c, int r)
+{
+    float s = 0.0f;
+    const int b = c.rt_off[r], e = c.rt_off[r + 1];
+    for (int i = b; i < e; ++i) s += c.atk[c.rt_flt[i]];
+    c.grow[c.route_base + c.rt_gid[r]] = s;
 }

@@ -52,6 +52,31 @@ def route_times(n_airports: int, seed: int = 0) -> np.ndarray:
     return np.round(base * 60.0) / 60.0
 
 
+def route_network(n_airports: int, seed: int = 0, zipf_s: float = 0.6,
+                  routes_per_airport: float = 15.0) -> np.ndarray:
+    """Boolean ``[N,N]`` adjacency of the served (directed, symmetric) routes.  The
+    real WN network flies ~1 500 of the 9 900 possible pairs of its top-100
+    airports; small networks are fully connected."""
+    N = n_airports
+    adj = ~np.eye(N, dtype=bool)
+    target = int(routes_per_airport * N) // 2           # undirected pairs
+    if N * (N - 1) // 2 <= target:
+        return adj
+    rng = np.random.default_rng([seed, 4242])
+    w = 1.0 / np.arange(1, N + 1) ** zipf_s
+    score = np.log(np.outer(w, w)) + rng.gumbel(size=(N, N)) * 4.0
+    score = np.triu(score, 1) + np.tril(np.full((N, N), -np.inf))
+    iu = np.dstack(np.unravel_index(np.argsort(-score, axis=None), (N, N)))[0][:target]
+    adj = np.zeros((N, N), bool)
+    adj[iu[:, 0], iu[:, 1]] = True
+    adj |= adj.T
+    for i in range(N):                                   # everyone reaches two hubs
+        for h in (0, 1, 2):
+            if h != i and adj[i].sum() < 2:
+                adj[i, h] = adj[h, i] = True
+    return adj
+
+
 def synth_day_frame(
     n_airports: int,
     n_flights: int,
@@ -70,6 +95,8 @@ def synth_day_frame(
     w = 1.0 / np.arange(1, n_airports + 1) ** zipf_s
     w /= w.sum()
     rt = route_times(n_airports, seed)
+    adj = route_network(n_airports, seed, zipf_s)
+    dest_p = [np.where(adj[i], w, 0.0) / np.where(adj[i], w, 0.0).sum() for i in range(n_airports)]
 
     orig = np.empty(n_flights, np.int64)
     dest = np.empty(n_flights, np.int64)
@@ -79,10 +106,7 @@ def synth_day_frame(
     aarr = np.empty(n_flights)
 
     def pick_other(cur):
-        while True:
-            d = int(rng.choice(n_airports, p=w))
-            if d != cur:
-                return d
+        return int(rng.choice(n_airports, p=dest_p[cur]))
 
     # every airport must appear (the model requires identical airport sets on
     # all days): aircraft i < n_airports starts at airport i.

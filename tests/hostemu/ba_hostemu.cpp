@@ -51,10 +51,8 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     (void)P;
     const int N = plan.N, C = plan.C, R = plan.R, D = plan.D;
     std::vector<uint32_t> state((size_t)BA_NWORDS_STATE * N, 0);
-    const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
-    const uint32_t bt = EXACT ? day.bag_total_x : day.bag_total_s;
-    std::vector<uint32_t> pool(4ull * qt + 2ull * bt + 8, 0);
-    std::vector<uint32_t> gs(2ull * day.turn_total + 2ull * day.av_total + day.dl_total + 8, 0);
+    std::vector<uint32_t> pool(6ull * day.q_total_s + 3ull * day.bag_total_s + 8, 0);
+    std::vector<uint32_t> gs(ba_scratch_words(day, true) + 8, 0);
     BaCtx c;
     memset(&c, 0, sizeof(c));
     ba_carve_state(c, state.data(), N);
@@ -68,19 +66,16 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     c.cancel_mode = plan.include_cancellations; c.max_t = plan.max_t; c.seed = seed;
     c.route_base = C * N;
     const size_t pd = (size_t)p * D + d;
-    c.N = N; c.F = day.F; c.flights = day.flights; c.route = day.route; c.dep_fid = day.dep_fid;
-    c.ap = day.airports;
+    c.N = N; c.F = day.F; c.flights = day.flights; c.route = day.route; c.ap = day.airports;
+    c.dep_sched = day.dep_sched; c.dep_word = day.dep_word; c.pos_dep = day.pos_dep;
+    c.pos_arr = day.pos_arr; c.rt_gid = day.rt_gid; c.rt_off = day.rt_off;
+    c.rt_flt = day.rt_flt; c.Rd = day.Rd;
     c.lat_route = lat_route + (size_t)p * R;
     c.noise = noise ? noise + pd * (size_t)plan.Fmax * 4 : nullptr;
     c.particle = p; c.dayidx = d;
     c.grow = c.want_grad ? tape + pd * (size_t)plan.grad_stride : nullptr;
     c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
-    uint32_t *s = pool.data();
-    c.qf = s; s += qt; c.qs = (float *)s; s += qt; c.qw = (float *)s; s += qt;
-    c.qx = (float *)s; s += qt; c.bf = s; s += bt; c.ba = (float *)s;
-    uint32_t *g = gs.data();
-    c.tt = (float *)g; g += day.turn_total; c.te = (float *)g; g += day.turn_total;
-    c.at = (float *)g; g += day.av_total; c.ae = (float *)g; g += day.av_total; c.dl = g;
+    ba_carve_lists<EXACT>(c, day, pool.data(), gs.data());
 
     const float *la = lat_airport + (size_t)p * C * N;
     for (int a = 0; a < N; ++a) ba_init_airport<EXACT>(c, a, la, N);
@@ -89,6 +84,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
 
     // one accumulator per lane, reduced in lane order (as the kernel does per warp)
     std::vector<BaAcc> acc(N, BaAcc{0, 0, 0, 0, 0});
+    for (int f = 0; f < day.F; ++f) ba_prologue_flight(c, acc[f % N], f);
     std::vector<int> order(N);
     for (int i = 0; i < N; ++i) order[i] = i;
     std::mt19937 rng(shuffle_seed + 977u * (unsigned)pd);
@@ -113,7 +109,11 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         }
         busy = more;
     }
-    if (c.grow) for (int a = 0; a < N; ++a) ba_airport_epilogue(c, a, N);
+    for (int f = 0; f < day.F; ++f) ba_epilogue_flight(c, acc[f % N], f);
+    if (c.grow) {
+        for (int i = 0; i < N; ++i) ba_epilogue_airport(c, day.lane_airport[i], N);
+        for (int r = 0; r < day.Rd; ++r) ba_epilogue_route(c, r);
+    }
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     for (int i = 0; i < N; ++i) {
         s0 += acc[i].lp; s1 += acc[i].g_sigma; s2 += acc[i].g_vt; s3 += acc[i].g_vu;
