@@ -130,6 +130,7 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     pl->d_days = const_cast<BaDayView *>(dd);
     pl->dev_view = pl->host.view;
     pl->dev_view.days = pl->d_days;
+    BA_PCUDA(upload(pl, pl->host.tick_time, &pl->dev_view.tick_time));
 
     // launch geometry
     const int N = n_airports;

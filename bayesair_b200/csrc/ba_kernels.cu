@@ -28,8 +28,9 @@ int ba_forward_block_threads(int n_airports)
 
 size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact)
 {
-    size_t w = (((size_t)BA_NWORDS_STATE * n_airports + 3) & ~(size_t)3) + BA_RED_WORDS;
-    if (!exact) w += list_words;   // 6 words per queue entry + 3 per bag entry
+    size_t w = (((size_t)BA_NWORDS_STATE * n_airports + 3) & ~(size_t)3) + BA_RED_WORDS + BA_CTA_WORDS;
+    // list_words = 6 words per queue entry; plus calendar counters and the due buffer
+    if (!exact) w += list_words + BA_KCAL + BA_DUE_WORDS * BA_DUE_CAP_S;
     return w * 4;
 }
 
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
 
     uint32_t *state_w = smem;
     uint32_t *red = smem + (((size_t)BA_NWORDS_STATE * N + 3) & ~(size_t)3);  // [BA_RED_WORDS], 16 B aligned
-    uint32_t *pool = red + BA_RED_WORDS;                     // shared list pools (fast)
+    uint32_t *ctaw = red + BA_RED_WORDS;                     // [BA_CTA_WORDS]
+    uint32_t *pool = ctaw + BA_CTA_WORDS;                    // shared list structures (fast)
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
 
     BaCtx c;
@@ -68,7 +70,8 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
     c.max_t = plan.max_t;
     c.seed = prm.seed;
     c.route_base = C * N;
-    const float dt = plan.delta_t;
+    c.tick_time = plan.tick_time;
+    c.cta = ctaw;
 
     for (;;) {
         // ---- next work item ------------------------------------------------
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
-        ba_carve_lists<EXACT>(c, day, pool, gscr);
+        ba_carve_lists<EXACT>(c, day, plan.max_ticks, pool, gscr);
 
         // ---- setup -----------------------------------------------------------
         const float *lat_airport = prm.lat_airport + (size_t)p * C * N;
@@ -103,29 +106,41 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         if (c.pop_tick)
             for (int i = tid; i < 2 * plan.Fmax; i += nthr) c.pop_tick[i] = -1;
         BaAcc acc = {0.0, 0.0f, 0.0f, 0.0f, 0u};
+        for (uint32_t k = tid; k < c.cal_cap; k += nthr) c.cal_cnt[k] = 0;
+        if (tid < BA_CTA_WORDS) c.cta[tid] = 0;
         __syncthreads();
 
         // ---- prologue: flight-parallel, coalesced ------------------------------
         for (int f = tid; f < day.F; f += nthr) ba_prologue_flight(c, acc, f);
         __syncthreads();
+        if (tid == 0) ba_calendar_scan(c);
+        __syncthreads();
+        for (int f = tid; f < day.F; f += nthr) ba_calendar_scatter(c, f);
+        __syncthreads();
 
         // ---- tick loop (model.py:158-200) --------------------------------------
-        float t = day.t_before_first;
         int tick = day.first_tick - 1;
         bool busy = day.F > 0;
         while (busy) {
             if (tick >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
-            t = BA_ADD(t, dt);                                  // model.py:161
             ++tick;
-            for (int s = tid; s < N; s += nthr) {
-                const int a = day.lane_airport[s];
-                ba_phase_a<EXACT>(c, acc, a, t, tick);
+            const float t = c.tick_time[tick];                  // model.py:161
+            for (int s = tid; s < N; s += nthr) ba_phase_a<EXACT>(c, acc, day.lane_airport[s], t, tick);
+            __syncthreads();
+            if ((uint32_t)tick < c.cal_cap) {
+                const uint32_t lo = c.cal_cnt[tick - 1], hi = c.cal_cnt[tick];
+                for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_record(c, acc, i);
             }
             __syncthreads();
-            int more = 0;
-            for (int s = tid; s < N; s += nthr) {
-                const int a = day.lane_airport[s];
-                more |= ba_phase_b(c, acc, a, t) ? 1 : 0;
+            uint32_t n_due = c.cta[0];
+            if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
+            int more = (n_due != 0u) || (c.cta[1] != 0u);
+            for (int s = tid; s < N; s += nthr) more |= ba_airport_busy(c, day.lane_airport[s]) ? 1 : 0;
+            if (n_due) {
+                for (uint32_t i = tid; i < n_due; i += nthr) ba_phase_c_rank(c, acc, i, n_due);
+                __syncthreads();
+                for (uint32_t i = tid; i < n_due; i += nthr) ba_phase_c_push(c, i);
+                if (tid == 0) c.cta[0] = 0;
             }
             busy = __syncthreads_or(more) != 0;
         }

@@ -17,8 +17,13 @@
 // dep_word: [31:30] observed cancellation (0, 1, 3 = None), [29:18] destination, [17:0] flight
 #define BA_DW_CANCEL_SHIFT 30
 #define BA_DW_ENTRY_MASK 0x3FFFFFFFu
-// bag entry word: [31:18] origin airport (day order), [17:0] flight
-#define BA_BAG_O_SHIFT 18
+// in-transit ordering key: [27:12] tick of the departure's service, [11:0] origin airport
+#define BA_KEY_TICK_SHIFT 12
+#define BA_KEY_INVALID 0xFFFFFFFFu
+// arrival calendar: buckets (ticks) kept in shared memory by the fast variant
+#define BA_KCAL 1024
+#define BA_DUE_CAP_S 128              // due-buffer entries in shared memory (fast variant)
+#define BA_DUE_WORDS 7
 
 // airport flags
 #define BA_AP_TRACK_T 1u              // turnaround list needed (n_avail can matter)
@@ -43,9 +48,8 @@ struct BaAirport {                    // 80 B static row per (day, airport)
     int32_t global;                   // latent index
     uint32_t flags;
     uint32_t q_off_s, q_mask_s;       // runway-queue ring, shared-memory variant
-    uint32_t bag_off_s, bag_cap_s;    // inbound bag,       shared-memory variant
-    uint32_t q_off_x, q_mask_x;       // exact-capacity variants (global scratch)
-    uint32_t bag_off_x, bag_cap_x;
+    uint32_t q_off_x, q_mask_x;       // exact-capacity variant (global scratch)
+    uint32_t pad2, pad3, pad4, pad5;
     uint32_t turn_off;                // turnaround list (cap = arr_cnt), global scratch
     uint32_t av_off, av_mask;         // aircraft FIFO ring, global scratch
     uint32_t dl_off, dl_mask;         // delayed-departure deque ring, global scratch
@@ -68,8 +72,8 @@ struct BaDayView {
     int32_t Rd;                       // routes used on this day
     const BaAirport *airports;        // [N] day order
     const int32_t *lane_airport;      // [N] airport handled by lane slot i (load-sorted)
-    uint32_t q_total_s, bag_total_s;  // pool sizes (entries) of the shared variant
-    uint32_t q_total_x, bag_total_x;  // pool sizes of the exact variant
+    uint32_t q_total_s;               // queue pool size (entries) of the shared variant
+    uint32_t q_total_x;               // queue pool size of the exact variant
     uint32_t turn_total, av_total, dl_total;
     uint32_t any_track_t, any_track_a; // does any airport of the day track aircraft
     int32_t first_tick;               // ticks [1, first_tick) are provably idle
@@ -82,6 +86,7 @@ struct BaPlanView {
     int32_t max_ticks;
     float delta_t, max_t;
     int32_t grad_stride;              // C*N + R + 3
+    const float *tick_time;           // [max_ticks + 2] clock after k sequential fp32 adds
     const BaDayView *days;            // [D]
 };
 
@@ -92,17 +97,22 @@ struct BaPlanView {
 //                                         for per-flight gradient contributions
 //   ct              [F]                 : epilogue contributions to d/d mean_turnaround
 //   wd, wa          [F] each            : waits recorded by the scan ("tape")
+//   karr            [F]                 : arrival tick of every flight
+//   cal             [3F]                : arrival calendar records {flight|dest, arrival
+//                                         time, x_arr}, counting-sorted by arrival tick
+//   popkey, popseq  [F] each            : in-transit ordering key of served departures
 //   trl, tre        [F] each if any_track_t : turnaround release time / its noise
 //   qd, se, sw      [F] each if any_track_a : departure queue start, aircraft-source
 //                                         noise and branch weight (adjoint of max())
-//   exact variant only: runway queues 6 x q_total_x, bags 3 x bag_total_x
+//   exact variant only: runway queues 6 x q_total_x, due buffer 7 x F,
+//                       calendar counters max_ticks + 2
 //   turnaround lists 2 x turn_total, aircraft FIFOs 2 x av_total, delayed deques dl_total
-static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact)
+static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_ticks)
 {
-    uint64_t w = 6ull * (uint64_t)d.F;
+    uint64_t w = 12ull * (uint64_t)d.F;
     if (d.any_track_t) w += 2ull * (uint64_t)d.F;
     if (d.any_track_a) w += 3ull * (uint64_t)d.F;
-    if (exact) w += 6ull * d.q_total_x + 3ull * d.bag_total_x;
+    if (exact) w += 6ull * d.q_total_x + (uint64_t)BA_DUE_WORDS * (uint64_t)d.F + (uint64_t)max_ticks + 2;
     w += 2ull * d.turn_total + 2ull * d.av_total + 1ull * d.dl_total;
     return w + 16;
 }

@@ -49,8 +49,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
     // tunables of the shared-memory variant (documented in DESIGN.md)
     const double q_div = env_double("BA_Q_DIV", 16.0);        // ring = traffic / q_div
     const double q_min = env_double("BA_Q_MIN", 8.0);
-    const double bag_frac = env_double("BA_BAG_FRAC", 0.40);  // of daily arrivals
-    const double bag_min = env_double("BA_BAG_MIN", 8.0);
+    if (max_ticks > 65000)
+        return fail(BA_ERR_LIMIT, "ba_plan_create: max_ticks must be <= 65000");
 
     const int N = n_airports;
     out->days.clear();
@@ -155,7 +155,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         std::vector<int> dep_live(N, 0);
         for (int f = 0; f < F; ++f)
             if (((H.flights[f].od >> 24) & 3u) != 1u) dep_live[T.h_origin[f]]++;
-        uint32_t q_s = 0, bag_s = 0, q_x = 0, bag_x = 0, turn = 0, av = 0, dl = 0;
+        uint32_t q_s = 0, q_x = 0, turn = 0, av = 0, dl = 0;
         uint32_t any_t = 0, any_a = 0;
         for (int a = 0; a < N; ++a) {
             BaAirport &A = H.airports[a];
@@ -176,15 +176,10 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             // exact variant
             uint32_t qx = pow2ceil(std::max(1u, traffic));
             A.q_off_x = q_x; A.q_mask_x = qx - 1; q_x += qx;
-            uint32_t bx = std::max(1u, (uint32_t)arr_cnt[a]);
-            A.bag_off_x = bag_x; A.bag_cap_x = bx; bag_x += bx;
             // shared variant
             uint32_t want_q = (uint32_t)std::ceil(std::max(q_min, traffic / q_div));
             uint32_t qs = std::min(qx, pow2ceil(std::max(1u, want_q)));
             A.q_off_s = q_s; A.q_mask_s = qs - 1; q_s += qs;
-            uint32_t want_b = (uint32_t)std::ceil(bag_min + bag_frac * arr_cnt[a]);
-            uint32_t bs = std::min(bx, std::max(1u, want_b));
-            A.bag_off_s = bag_s; A.bag_cap_s = bs; bag_s += bs;
             // always-global lists (only for airports that track aircraft)
             A.turn_off = turn; A.av_off = av; A.dl_off = dl;
             A.av_mask = 0; A.dl_mask = 0;
@@ -229,14 +224,17 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         V.Rd = (int32_t)H.rt_gid.size();
         V.any_track_t = any_t; V.any_track_a = any_a;
         V.airports = H.airports.data(); V.lane_airport = H.lane_airport.data();
-        V.q_total_s = q_s; V.bag_total_s = bag_s; V.q_total_x = q_x; V.bag_total_x = bag_x;
+        V.q_total_s = q_s; V.q_total_x = q_x;
         V.turn_total = turn; V.av_total = av; V.dl_total = dl;
         V.first_tick = first_tick; V.t_before_first = t_before;
-        scratch_fast = std::max(scratch_fast, ba_scratch_words(V, false));
-        scratch_exact = std::max(scratch_exact, ba_scratch_words(V, true));
-        smem_words = std::max(smem_words, 6u * q_s + 3u * bag_s);
+        scratch_fast = std::max(scratch_fast, ba_scratch_words(V, false, max_ticks));
+        scratch_exact = std::max(scratch_exact, ba_scratch_words(V, true, max_ticks));
+        smem_words = std::max(smem_words, 6u * q_s);
     }
 
+    // the clock: t_k = fl32(t_{k-1} + fl32(delta_t))  (model.py:158-161)
+    out->tick_time.assign((size_t)max_ticks + 2, 0.0f);
+    for (int k = 1; k <= max_ticks + 1; ++k) out->tick_time[k] = out->tick_time[k - 1] + delta_t;
     out->day_views.resize(n_days);
     for (int d = 0; d < n_days; ++d) out->day_views[d] = out->days[d].view;
     BaPlanView &P = out->view;
@@ -246,6 +244,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
     P.max_ticks = max_ticks; P.delta_t = delta_t; P.max_t = max_t;
     P.grad_stride = P.C * N + R + 3;
     P.days = out->day_views.data();
+    P.tick_time = out->tick_time.data();
     out->scratch_words_fast = scratch_fast;
     out->scratch_words_exact = scratch_exact;
     out->smem_list_words = smem_words;

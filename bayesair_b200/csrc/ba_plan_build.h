@@ -22,7 +22,8 @@ struct BaHostPlan {
     BaPlanView view;                    // .days -> day_views.data()
     uint64_t scratch_words_fast = 0;    // per-CTA scratch, shared-memory variant
     uint64_t scratch_words_exact = 0;   // per-CTA scratch, exact variant
-    uint32_t smem_list_words = 0;       // max over days: 6*q_total_s + 3*bag_total_s
+    uint32_t smem_list_words = 0;       // max over days: 6*q_total_s
+    std::vector<float> tick_time;       // [max_ticks + 2]
 };
 
 // Returns BA_OK or an error status with *err filled.

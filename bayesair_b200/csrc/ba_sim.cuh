@@ -15,13 +15,19 @@
 //       total wait W (the "tape").  Every tick has two phases separated by barriers:
 //       phase A (per airport, no cross-airport reads): turnaround release -> reserve
 //           injection -> pop-ready / cancellation -> enqueue departures -> runway
-//           service loop (model.py:163-196).  A served departure is appended (atomic
-//           slot) to the DESTINATION airport's inbound "bag" = that airport's slice
-//           of the reference's in-transit list.
-//       phase B (per airport): order the entries appended this tick by origin airport
-//           (restores the reference's global in-transit order restricted to this
-//           destination, model.py:186-196), then move every entry whose arrival time
-//           has passed into the runway queue (network.py:178-198).
+//           service loop (model.py:163-196).  A served departure records its
+//           in-transit ordering key (tick, origin, per-origin sequence).
+//       phase B (flight-parallel): the reference's in-transit list (network.py:178-198)
+//           is never materialised.  The prologue has counting-sorted all flights by the
+//           tick at which their arrival time passes (the ARRIVAL CALENDAR, exact: it
+//           uses the same fp32 clock table); at tick k the CTA reads that tick's slice
+//           and moves the flights whose departure has been served into a small "due"
+//           buffer.  A departure served at or after its own arrival tick goes to the
+//           due buffer directly from phase A.
+//       phase C (one thread per due entry): rank the due entries of each destination
+//           by their key -- this IS the reference's in-transit list order restricted to
+//           that destination (model.py:186-196) -- and append them to the destination
+//           runway queues.
 //   EPILOGUE (one lane per airport over its static departure / arrival lists; all
 //       loads independent): mu = queue_start + W for every entry, the seven per-flight
 //       log-densities and the pathwise gradient sums.  Deterministic: every sum has a
@@ -51,7 +57,9 @@
 #define BA_MUL(a, b) __fmul_rn((a), (b))
 #define BA_DIV(a, b) __fdiv_rn((a), (b))
 #define BA_ATOMIC_INC(p) atomicAdd((p), 1u)
-#define BA_RED_ADD(p, v) atomicAdd((p), (v))
+#define BA_ATOMIC_DEC(p) atomicSub((p), 1u)
+#define __float_as_uint_portable(x) __float_as_uint(x)
+#define __uint_as_float_portable(x) __uint_as_float(x)
 #define BA_LOG(x) logf(x)
 #define BA_EXP(x) expf(x)
 #define BA_LOG1P(x) log1pf(x)
@@ -60,9 +68,13 @@
 #define BA_ADD(a, b) ((float)(a) + (float)(b))
 #define BA_MUL(a, b) ((float)(a) * (float)(b))
 #define BA_DIV(a, b) ((float)(a) / (float)(b))
+#include <string.h>
 static inline uint32_t ba_host_inc(uint32_t *p) { return (*p)++; }
+static inline uint32_t ba_host_dec(uint32_t *p) { return (*p)--; }
+static inline uint32_t __float_as_uint_portable(float x) { uint32_t u; memcpy(&u, &x, 4); return u; }
+static inline float __uint_as_float_portable(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
 #define BA_ATOMIC_INC(p) ba_host_inc(p)
-#define BA_RED_ADD(p, v) (*(p) += (v))
+#define BA_ATOMIC_DEC(p) ba_host_dec(p)
 #define BA_LOG(x) logf(x)
 #define BA_EXP(x) expf(x)
 #define BA_LOG1P(x) log1pf(x)
@@ -171,13 +183,26 @@ struct BaCtx {
     // per-airport state (shared memory), indexed by day-local airport
     float *m, *rate, *lograte, *mt, *tstd, *logtstd, *base, *n_avail, *n0, *q_asg, *next_sched;
     float *acc_ln0, *acc_bc;
-    uint32_t *next_dep, *q_head, *q_tail, *bag_n, *bag_sorted, *turn_n;
+    uint32_t *next_dep, *q_head, *q_tail, *dep_pops, *turn_n;
     uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail;
-    uint32_t *s_flags, *s_qoff, *s_qmask, *s_bagoff, *s_bagcap, *s_depoff, *s_depcnt;
+    uint32_t *s_flags, *s_qoff, *s_qmask, *s_depoff, *s_depcnt;
+    // CTA-wide scalars (shared memory): [0] entries in the due buffer, [1] flights in
+    // transit, [2] first calendar bucket not yet consumed
+    uint32_t *cta;
+    // arrival calendar
+    const float *tick_time;       // [max_ticks + 2]
+    uint32_t *cal_cnt;            // [cal_cap] bucket end offsets (shared or global)
+    uint32_t cal_cap;             // ticks covered by the calendar
+    uint32_t *karr;               // [F] arrival tick of every flight (global scratch)
+    uint32_t *cal;                // [3F] records {word, arrival time, x_arr} sorted by tick
+    uint32_t *popkey, *popseq;    // [F] ordering key of served departures (global scratch)
+    // due buffer {word, key, seq, arrival time, x, target slot, count}: shared / global
+    uint32_t *due_w, *due_key, *due_seq, *due_tgt, *due_cnt; float *due_av, *due_x;
+    uint32_t due_cap;
+    int first_tick;
     // list pools (shared memory in the fast variant, global scratch in the exact one)
     uint32_t *qf; float *qs, *qw, *qx, *qy, *qz;   // runway queues: word, start, wait, x,
                                                    //   arrival time, x at destination
-    uint32_t *bf; float *ba, *bx;                  // inbound bags: word, arrival time, x
     // per-flight global scratch
     float *xdk, *xak, *atk;       // prologue outputs, dep order (reused by the epilogue)
     float *ct;                    // epilogue: per-flight d/d mean_turnaround contributions
@@ -200,9 +225,9 @@ struct BaAcc {
     uint32_t status;
 };
 
-#define BA_NWORDS_STATE 31        // per-airport words of shared state (see ba_carve_state)
+#define BA_NWORDS_STATE 28        // per-airport words of shared state (see ba_carve_state)
 #define BA_Q_WORDS 6              // words per runway-queue entry
-#define BA_BAG_WORDS 3            // words per bag entry
+#define BA_CTA_WORDS 4            // CTA-wide scalars
 
 // Assigns the per-airport arrays out of one contiguous word buffer.
 BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N)
@@ -213,23 +238,33 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N)
     c.n0 = f + 8 * N; c.q_asg = f + 9 * N; c.next_sched = f + 10 * N;
     c.acc_ln0 = f + 11 * N; c.acc_bc = f + 12 * N;
     c.next_dep = w + 13 * N; c.q_head = w + 14 * N; c.q_tail = w + 15 * N;
-    c.bag_n = w + 16 * N; c.bag_sorted = w + 17 * N; c.turn_n = w + 18 * N;
-    c.av_head = w + 19 * N; c.av_tail = w + 20 * N; c.zeros_left = w + 21 * N;
-    c.dl_head = w + 22 * N; c.dl_tail = w + 23 * N;
-    c.s_flags = w + 24 * N; c.s_qoff = w + 25 * N; c.s_qmask = w + 26 * N;
-    c.s_bagoff = w + 27 * N; c.s_bagcap = w + 28 * N; c.s_depoff = w + 29 * N;
-    c.s_depcnt = w + 30 * N;
+    c.dep_pops = w + 16 * N; c.turn_n = w + 17 * N;
+    c.av_head = w + 18 * N; c.av_tail = w + 19 * N; c.zeros_left = w + 20 * N;
+    c.dl_head = w + 21 * N; c.dl_tail = w + 22 * N;
+    c.s_flags = w + 23 * N; c.s_qoff = w + 24 * N; c.s_qmask = w + 25 * N;
+    c.s_depoff = w + 26 * N; c.s_depcnt = w + 27 * N;
 }
 
-// Carves the list pools (shared or global) and the per-flight / list scratch.
-// `lists` = start of the queue+bag pools, `g` = start of this CTA's global scratch.
+// Words of shared memory the list structures of the fast variant need.
+BA_DEV uint32_t ba_shared_list_words(uint32_t q_total_s)
+{
+    return BA_Q_WORDS * q_total_s + BA_KCAL + BA_DUE_WORDS * BA_DUE_CAP_S;
+}
+
+// Carves the queue pool / calendar counters / due buffer (shared or global) and the
+// per-flight scratch.  `shared_pool` = shared memory after the state arrays,
+// `g` = start of this CTA's global scratch.
 template <bool EXACT>
-BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, uint32_t *shared_pool, uint32_t *g)
+BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32_t *shared_pool,
+                           uint32_t *g)
 {
     const uint32_t F = (uint32_t)day.F;
     c.xdk = (float *)g; g += F; c.xak = (float *)g; g += F; c.atk = (float *)g; g += F;
     c.ct = (float *)g; g += F;
     c.wd = (float *)g; g += F; c.wa = (float *)g; g += F;
+    c.karr = g; g += F;
+    c.cal = g; g += 3 * F;
+    c.popkey = g; g += F; c.popseq = g; g += F;
     c.trl = c.tre = nullptr;
     if (day.any_track_t) { c.trl = (float *)g; g += F; c.tre = (float *)g; g += F; }
     c.qd = c.se = c.sw = nullptr;
@@ -238,14 +273,19 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, uint32_t *shared_pool
     }
     uint32_t *s = EXACT ? g : shared_pool;
     const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
-    const uint32_t bt = EXACT ? day.bag_total_x : day.bag_total_s;
     c.qf = s; s += qt; c.qs = (float *)s; s += qt; c.qw = (float *)s; s += qt;
     c.qx = (float *)s; s += qt; c.qy = (float *)s; s += qt; c.qz = (float *)s; s += qt;
-    c.bf = s; s += bt; c.ba = (float *)s; s += bt; c.bx = (float *)s; s += bt;
+    c.due_cap = EXACT ? F : (uint32_t)BA_DUE_CAP_S;
+    c.due_w = s; s += c.due_cap; c.due_key = s; s += c.due_cap; c.due_seq = s; s += c.due_cap;
+    c.due_av = (float *)s; s += c.due_cap; c.due_x = (float *)s; s += c.due_cap;
+    c.due_tgt = s; s += c.due_cap; c.due_cnt = s; s += c.due_cap;
+    c.cal_cap = EXACT ? (uint32_t)max_ticks + 2u : (uint32_t)BA_KCAL;
+    c.cal_cnt = s; s += c.cal_cap;
     if (EXACT) g = s;
     c.tt = (float *)g; g += day.turn_total; c.te = (float *)g; g += day.turn_total;
     c.at = (float *)g; g += day.av_total; c.ae = (float *)g; g += day.av_total;
     c.dl = g;
+    c.first_tick = day.first_tick;
 }
 
 BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
@@ -310,13 +350,11 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     c.q_asg[a] = NAN;
     c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
     c.acc_ln0[a] = 0.0f; c.acc_bc[a] = 0.0f;
-    c.next_dep[a] = 0; c.q_head[a] = 0; c.q_tail[a] = 0; c.bag_n[a] = 0; c.bag_sorted[a] = 0;
+    c.next_dep[a] = 0; c.q_head[a] = 0; c.q_tail[a] = 0; c.dep_pops[a] = 0;
     c.turn_n[a] = 0; c.av_head[a] = 0; c.av_tail[a] = 0; c.dl_head[a] = 0; c.dl_tail[a] = 0;
     c.s_flags[a] = A.flags;
     c.s_qoff[a] = EXACT ? A.q_off_x : A.q_off_s;
     c.s_qmask[a] = EXACT ? A.q_mask_x : A.q_mask_s;
-    c.s_bagoff[a] = EXACT ? A.bag_off_x : A.bag_off_s;
-    c.s_bagcap[a] = EXACT ? A.bag_cap_x : A.bag_cap_s;
     c.s_depoff[a] = (uint32_t)A.dep_off;
     c.s_depcnt[a] = (uint32_t)A.dep_cnt;
 }
@@ -343,8 +381,24 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
         y_dep = fl.sched_dep; y_arr = fl.sched_dep;
     }
     const int k = c.pos_dep[f];
-    c.xdk[k] = xd; c.xak[k] = xa;
-    c.atk[k] = BA_ADD(y_dep, tau);          // network.py:166-168 with the observed departure
+    const float at = BA_ADD(y_dep, tau);    // network.py:166-168 with the observed departure
+    c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at;
+    c.popkey[f] = BA_KEY_INVALID;
+    // arrival tick: the first tick whose clock reaches `at` (exact: same fp32 clock table
+    // the scan uses; network.py:186 `arrival_time <= time`)
+    uint32_t ka = 0xFFFFFFFFu;
+    if (cobs != 1u) {
+        const int kmax = (int)c.cal_cap - 1;
+        float guess = ceilf(at / c.tick_time[1]);
+        int kk = guess < 1.0f ? 1 : (guess > (float)kmax ? kmax : (int)guess);
+        while (kk > 1 && c.tick_time[kk - 1] >= at) --kk;
+        while (kk < kmax && c.tick_time[kk] < at) ++kk;
+        if (c.tick_time[kk] < at) acc.status |= BA_S_TICK_CAP;   // beyond the calendar
+        if (kk < c.first_tick) kk = c.first_tick;
+        ka = (uint32_t)kk;
+        BA_ATOMIC_INC(&c.cal_cnt[ka]);
+    }
+    c.karr[f] = ka;
     if (c.trl) {
         // Normal(m~, v_u m~).rsample (airport.py:217-221)
         const float mt = c.mt[d];
@@ -594,15 +648,24 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
             const float wait = c.qw[hi];
             if (word & BA_Q_DEP) {
                 c.wd[f] = wait;
-                // add_in_transit_flights (network.py:136-168): into the destination's bag
-                const int dst = (int)((word >> BA_Q_DST_SHIFT) & 0xFFFu);
-                const uint32_t slot = BA_ATOMIC_INC(&c.bag_n[dst]);
-                if (slot >= c.s_bagcap[dst]) acc.status |= BA_S_OVERFLOW;
-                else {
-                    const uint32_t bi = c.s_bagoff[dst] + slot;
-                    c.bf[bi] = ((uint32_t)a << BA_BAG_O_SHIFT) | (uint32_t)f;
-                    c.ba[bi] = c.qy[hi];
-                    c.bx[bi] = c.qz[hi];
+                // add_in_transit_flights (network.py:136-168).  The in-transit list is
+                // implicit: its order is the key (tick, origin, per-origin sequence).
+                const uint32_t key = ((uint32_t)tick << BA_KEY_TICK_SHIFT) | (uint32_t)a;
+                const uint32_t seq = c.dep_pops[a];
+                c.dep_pops[a] = seq + 1;
+                const float av = c.qy[hi];
+                if (av <= t) {
+                    // already past its arrival time: joins the destination queue at the
+                    // end of this very tick (update_in_transit_flights, network.py:186)
+                    const uint32_t slot = BA_ATOMIC_INC(&c.cta[0]);
+                    if (slot >= c.due_cap) acc.status |= BA_S_OVERFLOW;
+                    else {
+                        c.due_w[slot] = word & BA_DW_ENTRY_MASK; c.due_key[slot] = key;
+                        c.due_seq[slot] = seq; c.due_av[slot] = av; c.due_x[slot] = c.qz[hi];
+                    }
+                } else {
+                    c.popkey[f] = key; c.popseq[f] = seq;
+                    BA_ATOMIC_INC(&c.cta[1]);
                 }
                 if (c.pop_tick) c.pop_tick[2 * f] = tick;
             } else {
@@ -625,49 +688,98 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
 }
 
 // ---------------------------------------------------------------------------
-// SCAN, phase B: in-transit -> destination runway queue (network.py:178-198)
-// Returns whether this airport still has work (for the completion vote,
-// network.py:34-41).
+// PROLOGUE, calendar construction (after every flight's arrival tick is counted):
+//   ba_calendar_scan     exclusive prefix over the bucket counts (one thread)
+//   ba_calendar_scatter  one flight: write its record into its bucket
+// Afterwards cal_cnt[k] is the END offset of bucket k (= start of bucket k+1).
 // ---------------------------------------------------------------------------
-BA_DEV bool ba_phase_b(BaCtx &c, BaAcc &acc, int a, float t)
+BA_DEV void ba_calendar_scan(BaCtx &c)
 {
-    uint32_t n = c.bag_n[a];
-    const uint32_t cap = c.s_bagcap[a];
-    if (n > cap) n = cap;                     // overflow already flagged by the producer
-    if (n) {
-        const uint32_t off = c.s_bagoff[a];
-        const uint32_t ns = c.bag_sorted[a];
-        // entries [ns, n) were appended this tick by several origin lanes in arbitrary
-        // interleaving; entries of one origin are in service order.  A stable insertion
-        // sort by origin airport (day order) restores the reference's list order.
-        for (uint32_t i = ns + 1; i < n; ++i) {
-            const uint32_t w = c.bf[off + i];
-            const float av = c.ba[off + i], xv = c.bx[off + i];
-            const uint32_t key = w >> BA_BAG_O_SHIFT;
-            uint32_t j = i;
-            while (j > ns && (c.bf[off + j - 1] >> BA_BAG_O_SHIFT) > key) {
-                c.bf[off + j] = c.bf[off + j - 1];
-                c.ba[off + j] = c.ba[off + j - 1];
-                c.bx[off + j] = c.bx[off + j - 1];
-                --j;
-            }
-            if (j != i) { c.bf[off + j] = w; c.ba[off + j] = av; c.bx[off + j] = xv; }
-        }
-        uint32_t w = 0;
-        for (uint32_t i = 0; i < n; ++i) {
-            const float av = c.ba[off + i];
-            if (av <= t) {
-                ba_q_push(c, acc, a, c.bf[off + i] & BA_FID_MASK, av, c.bx[off + i], 0.0f, 0.0f);
-            } else {
-                if (w != i) { c.bf[off + w] = c.bf[off + i]; c.ba[off + w] = av; c.bx[off + w] = c.bx[off + i]; }
-                ++w;
-            }
-        }
-        c.bag_n[a] = w;
-        c.bag_sorted[a] = w;
-        n = w;
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < c.cal_cap; ++k) {
+        const uint32_t n = c.cal_cnt[k];
+        c.cal_cnt[k] = run;
+        run += n;
     }
-    return n != 0u || c.q_head[a] != c.q_tail[a] || c.next_dep[a] < c.s_depcnt[a] ||
+}
+
+BA_DEV void ba_calendar_scatter(BaCtx &c, int f)
+{
+    const uint32_t ka = c.karr[f];
+    if (ka == 0xFFFFFFFFu) return;
+    const uint32_t pos = BA_ATOMIC_INC(&c.cal_cnt[ka]);
+    const int k = c.pos_dep[f];
+    c.cal[3 * pos + 0] = c.dep_word[k] & BA_DW_ENTRY_MASK;      // dest << 18 | flight
+    c.cal[3 * pos + 1] = __float_as_uint_portable(c.atk[k]);
+    c.cal[3 * pos + 2] = __float_as_uint_portable(c.xak[k]);
+}
+
+// ---------------------------------------------------------------------------
+// SCAN, phase B: one calendar record (call for i in this tick's slice).  A flight whose
+// departure has been served moves to the due buffer; one whose departure is still
+// queued is skipped -- phase A will hand it over itself when it is served.
+// ---------------------------------------------------------------------------
+BA_DEV void ba_phase_b_record(BaCtx &c, BaAcc &acc, uint32_t i)
+{
+    const uint32_t word = c.cal[3 * i];
+    const int f = (int)(word & BA_FID_MASK);
+    const uint32_t key = c.popkey[f];
+    if (key == BA_KEY_INVALID) return;
+    const uint32_t slot = BA_ATOMIC_INC(&c.cta[0]);
+    if (slot >= c.due_cap) { acc.status |= BA_S_OVERFLOW; return; }
+    c.due_w[slot] = word; c.due_key[slot] = key; c.due_seq[slot] = c.popseq[f];
+    c.due_av[slot] = __uint_as_float_portable(c.cal[3 * i + 1]);
+    c.due_x[slot] = __uint_as_float_portable(c.cal[3 * i + 2]);
+    c.popkey[f] = BA_KEY_INVALID;          // consumed
+    BA_ATOMIC_DEC(&c.cta[1]);
+}
+
+// ---------------------------------------------------------------------------
+// SCAN, phase C: destination runway queues <- due buffer, in in-transit list order.
+//   step 1 (one thread per due entry): rank among the entries of the same destination
+//           by (tick, origin, sequence); remember the target slot.
+//   step 2 (after a barrier): write the entry; the last of each destination moves the tail.
+// ---------------------------------------------------------------------------
+BA_DEV void ba_phase_c_rank(BaCtx &c, BaAcc &acc, uint32_t i, uint32_t n_due)
+{
+    const uint32_t word = c.due_w[i];
+    const uint32_t dst = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
+    const uint32_t key = c.due_key[i], seq = c.due_seq[i];
+    uint32_t rank = 0, cnt = 0;
+    for (uint32_t j = 0; j < n_due; ++j) {
+        const uint32_t wj = c.due_w[j];
+        if (((wj >> BA_Q_DST_SHIFT) & 0xFFFu) != dst) continue;
+        ++cnt;
+        const uint32_t kj = c.due_key[j];
+        if (kj < key || (kj == key && c.due_seq[j] < seq)) ++rank;
+    }
+    const uint32_t head = c.q_head[dst], tail = c.q_tail[dst], mask = c.s_qmask[dst];
+    uint32_t target = 0xFFFFFFFFu;
+    if (tail + cnt - head > mask + 1u) acc.status |= BA_S_OVERFLOW;
+    else target = c.s_qoff[dst] + ((tail + rank) & mask);
+    c.due_tgt[i] = target;
+    c.due_cnt[i] = (rank + 1 == cnt) ? cnt : 0u;
+}
+
+BA_DEV void ba_phase_c_push(BaCtx &c, uint32_t i)
+{
+    const uint32_t target = c.due_tgt[i];
+    if (target == 0xFFFFFFFFu) return;
+    const uint32_t word = c.due_w[i];
+    c.qf[target] = word & BA_FID_MASK;            // arrival entry: no DEP flag
+    c.qs[target] = c.due_av[i]; c.qw[target] = 0.0f; c.qx[target] = c.due_x[i];
+    c.qy[target] = 0.0f; c.qz[target] = 0.0f;
+    const uint32_t cnt = c.due_cnt[i];
+    if (cnt) {
+        const uint32_t dst = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
+        c.q_tail[dst] = c.q_tail[dst] + cnt;
+    }
+}
+
+// Does this airport still hold work (completion vote, network.py:34-41)?
+BA_DEV bool ba_airport_busy(const BaCtx &c, int a)
+{
+    return c.q_head[a] != c.q_tail[a] || c.next_dep[a] < c.s_depcnt[a] ||
            c.dl_head[a] != c.dl_tail[a];
 }
 

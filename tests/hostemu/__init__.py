@@ -62,7 +62,7 @@ def day_tables(specs):
 
 class EmuPlan:
     def __init__(self, specs, n_airports, delta_t=0.2, max_t=30.0, include_cancellations=False,
-                 max_ticks=100000):
+                 max_ticks=20000):
         lib = _load()
         arr, self._keep = day_tables(specs)
         self.h = C.c_void_p()

@@ -51,8 +51,9 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     (void)P;
     const int N = plan.N, C = plan.C, R = plan.R, D = plan.D;
     std::vector<uint32_t> state((size_t)BA_NWORDS_STATE * N, 0);
-    std::vector<uint32_t> pool(6ull * day.q_total_s + 3ull * day.bag_total_s + 8, 0);
-    std::vector<uint32_t> gs(ba_scratch_words(day, true) + 8, 0);
+    std::vector<uint32_t> pool(ba_shared_list_words(day.q_total_s) + 8, 0);
+    std::vector<uint32_t> gs(ba_scratch_words(day, true, plan.max_ticks) + 8, 0);
+    uint32_t ctaw[BA_CTA_WORDS] = {0, 0, 0, 0};
     BaCtx c;
     memset(&c, 0, sizeof(c));
     ba_carve_state(c, state.data(), N);
@@ -65,6 +66,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     c.value_mode = value_mode; c.want_grad = want_grad && tape;
     c.cancel_mode = plan.include_cancellations; c.max_t = plan.max_t; c.seed = seed;
     c.route_base = C * N;
+    c.tick_time = plan.tick_time; c.cta = ctaw;
     const size_t pd = (size_t)p * D + d;
     c.N = N; c.F = day.F; c.flights = day.flights; c.route = day.route; c.ap = day.airports;
     c.dep_sched = day.dep_sched; c.dep_word = day.dep_word; c.pos_dep = day.pos_dep;
@@ -75,7 +77,8 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     c.particle = p; c.dayidx = d;
     c.grow = c.want_grad ? tape + pd * (size_t)plan.grad_stride : nullptr;
     c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
-    ba_carve_lists<EXACT>(c, day, pool.data(), gs.data());
+    ba_carve_lists<EXACT>(c, day, plan.max_ticks, pool.data(), gs.data());
+    for (uint32_t k = 0; k < c.cal_cap; ++k) c.cal_cnt[k] = 0;
 
     const float *la = lat_airport + (size_t)p * C * N;
     for (int a = 0; a < N; ++a) ba_init_airport<EXACT>(c, a, la, N);
@@ -84,28 +87,44 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
 
     // one accumulator per lane, reduced in lane order (as the kernel does per warp)
     std::vector<BaAcc> acc(N, BaAcc{0, 0, 0, 0, 0});
-    for (int f = 0; f < day.F; ++f) ba_prologue_flight(c, acc[f % N], f);
+    std::mt19937 rng(shuffle_seed + 977u * (unsigned)pd);
+    std::vector<int> forder(day.F);
+    for (int f = 0; f < day.F; ++f) forder[f] = f;
+    if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
+    for (int f : forder) ba_prologue_flight(c, acc[f % N], f);
+    ba_calendar_scan(c);
+    if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
+    for (int f : forder) ba_calendar_scatter(c, f);
     std::vector<int> order(N);
     for (int i = 0; i < N; ++i) order[i] = i;
-    std::mt19937 rng(shuffle_seed + 977u * (unsigned)pd);
     float t = day.t_before_first;
     int tick = day.first_tick - 1;
     bool busy = day.F > 0;
     uint32_t st = 0;
     while (busy) {
         if (tick >= plan.max_ticks) { st |= BA_S_TICK_CAP; break; }
-        t = BA_ADD(t, plan.delta_t);
         ++tick;
+        t = c.tick_time[tick];
         if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
-        for (int i = 0; i < N; ++i) {
-            int a = day.lane_airport[order[i]];
-            ba_phase_a<EXACT>(c, acc[order[i]], a, t, tick);
+        for (int i = 0; i < N; ++i)
+            ba_phase_a<EXACT>(c, acc[order[i]], day.lane_airport[order[i]], t, tick);
+        if ((uint32_t)tick < c.cal_cap) {
+            std::vector<uint32_t> slice;
+            for (uint32_t i = c.cal_cnt[tick - 1]; i < c.cal_cnt[tick]; ++i) slice.push_back(i);
+            if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
+            for (uint32_t i : slice) ba_phase_b_record(c, acc[i % N], i);
         }
-        bool more = false;
-        if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
-        for (int i = 0; i < N; ++i) {
-            int a = day.lane_airport[order[i]];
-            more |= ba_phase_b(c, acc[order[i]], a, t);
+        uint32_t n_due = c.cta[0];
+        if (n_due > c.due_cap) n_due = c.due_cap;
+        bool more = n_due != 0 || c.cta[1] != 0;
+        for (int a = 0; a < N; ++a) more |= ba_airport_busy(c, a);
+        if (n_due) {
+            for (uint32_t i = 0; i < n_due; ++i) ba_phase_c_rank(c, acc[i % N], i, n_due);
+            std::vector<uint32_t> dord(n_due);
+            for (uint32_t i = 0; i < n_due; ++i) dord[i] = i;
+            if (shuffle_seed) std::shuffle(dord.begin(), dord.end(), rng);
+            for (uint32_t i : dord) ba_phase_c_push(c, i);
+            c.cta[0] = 0;
         }
         busy = more;
     }

@@ -20,7 +20,7 @@ svcs = [float(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0.0
 N, Fs, _, svc, specs = build_workload("cfg3")
 specs = specs[:days]
 dev = torch.device("cuda:0")
-grid = [(16, 8, 0.4, 8), (16, 4, 0.25, 4), (32, 4, 0.2, 4), (32, 2, 0.15, 2)]
+grid = [(16, 8, 0, 0), (16, 4, 0, 0), (32, 4, 0, 0), (8, 8, 0, 0)]
 for spread, svc in itertools.product((0.3,), svcs):
     lat = synth_latents(N, P, seed=1, service_scale=svc, spread=spread)
     tl = {k: torch.tensor(v, device=dev) for k, v in lat.items()}
