@@ -236,6 +236,7 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
     prm.lat_airport = d_lat_airport; prm.lat_route = d_lat_route; prm.scales = d_scales;
     prm.noise = d_noise; prm.seed = o.seed;
     prm.value_mode = o.noise_is_value; prm.want_grad = o.want_grad;
+    prm.replay_waits = o.replay_waits;
     prm.logp = d_logp; prm.status = d_status; prm.ticks = d_ticks;
     prm.tape = (float *)d_tape; prm.pop_tick = o.d_pop_tick;
     prm.scratch = pl->d_scratch;

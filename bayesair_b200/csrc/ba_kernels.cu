@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
     c.c1_lp = ba_relaxed_bernoulli_lp(0.0f, 1.0f, nullptr);
     c.value_mode = prm.value_mode; c.want_grad = prm.want_grad && prm.tape != nullptr;
     c.cancel_mode = plan.include_cancellations;
+    c.replay_always = prm.replay_waits;
     c.max_t = plan.max_t;
     c.seed = prm.seed;
     c.route_base = C * N;

@@ -13,7 +13,7 @@ struct BaFwdParams {
     const float *scales;          // [3]
     const float *noise;           // [P, D, Fmax, 4] or nullptr
     uint64_t seed;
-    int32_t value_mode, want_grad;
+    int32_t value_mode, want_grad, replay_waits;
     float *logp;                  // [P, D]
     uint32_t *status;             // [P, D]
     int32_t *ticks;               // [P, D] or nullptr

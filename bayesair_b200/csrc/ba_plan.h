@@ -96,6 +96,7 @@ struct BaPlanView {
 //                                         dead after the scan and reused by the epilogue
 //                                         for per-flight gradient contributions
 //   ct              [F]                 : epilogue contributions to d/d mean_turnaround
+//   xaf             [F]                 : x_arr by flight (departures served after arrival)
 //   wd, wa          [F] each            : waits recorded by the scan ("tape")
 //   karr            [F]                 : arrival tick of every flight
 //   cal             [3F]                : arrival calendar records {flight|dest, arrival
@@ -109,7 +110,7 @@ struct BaPlanView {
 //   turnaround lists 2 x turn_total, aircraft FIFOs 2 x av_total, delayed deques dl_total
 static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_ticks)
 {
-    uint64_t w = 12ull * (uint64_t)d.F;
+    uint64_t w = 13ull * (uint64_t)d.F;
     if (d.any_track_t) w += 2ull * (uint64_t)d.F;
     if (d.any_track_a) w += 3ull * (uint64_t)d.F;
     if (exact) w += 6ull * d.q_total_x + (uint64_t)BA_DUE_WORDS * (uint64_t)d.F + (uint64_t)max_ticks + 2;

@@ -178,10 +178,13 @@ struct BaCtx {
     float inv_sigma2, inv_sigma3, inv_sigma, log_sigma;
     float inv_vt, inv_vu;
     float c0_lp, c1_lp;           // cancellation log-prob at p == 0 for v = 0 / 1
-    int value_mode, want_grad, cancel_mode;
+    int value_mode, want_grad, cancel_mode, replay_always;
     float max_t;
     // per-airport state (shared memory), indexed by day-local airport
-    float *m, *rate, *lograte, *mt, *tstd, *logtstd, *base, *n_avail, *n0, *q_asg, *next_sched;
+    float *m, *rate, *lograte, *mt, *tstd, *logtstd, *base, *n_avail, *n0, *next_sched;
+    float *asg_lo, *asg_hi, *w_head;  // head entry: interval holding its exact fp32 service
+                                      //   time (NaN = unassigned) and its total wait
+    double *psum;                     // running sum of all service draws assigned so far
     float *acc_ln0, *acc_bc;
     uint32_t *next_dep, *q_head, *q_tail, *dep_pops, *turn_n;
     uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail;
@@ -201,10 +204,12 @@ struct BaCtx {
     uint32_t due_cap;
     int first_tick;
     // list pools (shared memory in the fast variant, global scratch in the exact one)
-    uint32_t *qf; float *qs, *qw, *qx, *qy, *qz;   // runway queues: word, start, wait, x,
-                                                   //   arrival time, x at destination
+    uint32_t *qf, *ql; float *qs, *qp, *qx, *qy;   // runway queues: word, first service index
+                                                   //   that counts (lo), start, prefix sum at
+                                                   //   joining, own draw x, arrival time
     // per-flight global scratch
     float *xdk, *xak, *atk;       // prologue outputs, dep order (reused by the epilogue)
+    float *xaf;                   // x_arr by flight (for departures served after arrival)
     float *ct;                    // epilogue: per-flight d/d mean_turnaround contributions
     float *wd, *wa;               // tape: total wait of the departure / arrival entry
     float *trl, *tre;             // turnaround release time and its noise (tracked days)
@@ -225,7 +230,7 @@ struct BaAcc {
     uint32_t status;
 };
 
-#define BA_NWORDS_STATE 28        // per-airport words of shared state (see ba_carve_state)
+#define BA_NWORDS_STATE 32        // per-airport words of shared state (see ba_carve_state)
 #define BA_Q_WORDS 6              // words per runway-queue entry
 #define BA_CTA_WORDS 4            // CTA-wide scalars
 
@@ -235,7 +240,7 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N)
     float *f = (float *)w;
     c.m = f + 0 * N; c.rate = f + 1 * N; c.lograte = f + 2 * N; c.mt = f + 3 * N;
     c.tstd = f + 4 * N; c.logtstd = f + 5 * N; c.base = f + 6 * N; c.n_avail = f + 7 * N;
-    c.n0 = f + 8 * N; c.q_asg = f + 9 * N; c.next_sched = f + 10 * N;
+    c.n0 = f + 8 * N; c.w_head = f + 9 * N; c.next_sched = f + 10 * N;
     c.acc_ln0 = f + 11 * N; c.acc_bc = f + 12 * N;
     c.next_dep = w + 13 * N; c.q_head = w + 14 * N; c.q_tail = w + 15 * N;
     c.dep_pops = w + 16 * N; c.turn_n = w + 17 * N;
@@ -243,6 +248,8 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N)
     c.dl_head = w + 21 * N; c.dl_tail = w + 22 * N;
     c.s_flags = w + 23 * N; c.s_qoff = w + 24 * N; c.s_qmask = w + 25 * N;
     c.s_depoff = w + 26 * N; c.s_depcnt = w + 27 * N;
+    c.asg_lo = f + 28 * N; c.asg_hi = f + 29 * N;
+    c.psum = (double *)(w + 30 * N);       // needs N even or an 8-byte aligned base: see kernel
 }
 
 // Words of shared memory the list structures of the fast variant need.
@@ -260,7 +267,7 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32
 {
     const uint32_t F = (uint32_t)day.F;
     c.xdk = (float *)g; g += F; c.xak = (float *)g; g += F; c.atk = (float *)g; g += F;
-    c.ct = (float *)g; g += F;
+    c.ct = (float *)g; g += F; c.xaf = (float *)g; g += F;
     c.wd = (float *)g; g += F; c.wa = (float *)g; g += F;
     c.karr = g; g += F;
     c.cal = g; g += 3 * F;
@@ -273,8 +280,8 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32
     }
     uint32_t *s = EXACT ? g : shared_pool;
     const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
-    c.qf = s; s += qt; c.qs = (float *)s; s += qt; c.qw = (float *)s; s += qt;
-    c.qx = (float *)s; s += qt; c.qy = (float *)s; s += qt; c.qz = (float *)s; s += qt;
+    c.qf = s; s += qt; c.qs = (float *)s; s += qt; c.qp = (float *)s; s += qt;
+    c.qx = (float *)s; s += qt; c.qy = (float *)s; s += qt; c.ql = s; s += qt;
     c.due_cap = EXACT ? F : (uint32_t)BA_DUE_CAP_S;
     c.due_w = s; s += c.due_cap; c.due_key = s; s += c.due_cap; c.due_seq = s; s += c.due_cap;
     c.due_av = (float *)s; s += c.due_cap; c.due_x = (float *)s; s += c.due_cap;
@@ -347,7 +354,7 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
         nz = cz > 4.0e9f ? 4000000000u : (uint32_t)cz;
     }
     c.zeros_left[a] = nz;
-    c.q_asg[a] = NAN;
+    c.asg_lo[a] = NAN; c.asg_hi[a] = NAN; c.w_head[a] = 0.0f; c.psum[a] = 0.0;
     c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
     c.acc_ln0[a] = 0.0f; c.acc_bc[a] = 0.0f;
     c.next_dep[a] = 0; c.q_head[a] = 0; c.q_tail[a] = 0; c.dep_pops[a] = 0;
@@ -382,7 +389,7 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
     }
     const int k = c.pos_dep[f];
     const float at = BA_ADD(y_dep, tau);    // network.py:166-168 with the observed departure
-    c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at;
+    c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at; c.xaf[f] = xa;
     c.popkey[f] = BA_KEY_INVALID;
     // arrival tick: the first tick whose clock reaches `at` (exact: same fp32 clock table
     // the scan uses; network.py:186 `arrival_time <= time`)
@@ -411,13 +418,17 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
 // ---------------------------------------------------------------------------
 // runway-queue append (model.py:181-183 / network.py:186-191)
 // ---------------------------------------------------------------------------
-BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float x,
-                      float y, float z)
+// The entry remembers how much service had been handed out at this airport when it
+// joined (psum, rounded to fp32) and the index of the first later assignment (lo):
+// its total wait is the sum of the draws lo..own index (airport.py:150-153).
+BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float x, float y)
 {
     const uint32_t head = c.q_head[a], tail = c.q_tail[a], mask = c.s_qmask[a];
     if (tail - head > mask) { acc.status |= BA_S_OVERFLOW; return; }
     const uint32_t i = c.s_qoff[a] + (tail & mask);
-    c.qf[i] = word; c.qs[i] = qstart; c.qw[i] = 0.0f; c.qx[i] = x; c.qy[i] = y; c.qz[i] = z;
+    c.qf[i] = word; c.qs[i] = qstart; c.qx[i] = x; c.qy[i] = y;
+    c.qp[i] = (float)c.psum[a];
+    c.ql[i] = head + (isnan(c.asg_hi[a]) ? 0u : 1u);
     c.q_tail[a] = tail + 1;
 }
 
@@ -466,7 +477,7 @@ BA_DEV void ba_depart_tracked(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, u
     float weight, src_eps;
     const float ready = ba_take_aircraft(c, acc, a, A, sched, t, &weight, &src_eps);
     if (c.qd) { c.qd[f] = ready; c.se[f] = src_eps; c.sw[f] = weight; }
-    ba_q_push(c, acc, a, BA_Q_DEP | (w & BA_DW_ENTRY_MASK), ready, c.xdk[k], c.atk[k], c.xak[k]);
+    ba_q_push(c, acc, a, BA_Q_DEP | (w & BA_DW_ENTRY_MASK), ready, c.xdk[k], c.atk[k]);
 }
 
 // ---------------------------------------------------------------------------
@@ -555,7 +566,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 acc.lp += cobs ? c.c1_lp : c.c0_lp;
                 if (!cobs)
                     ba_q_push(c, acc, a, BA_Q_DEP | (w & BA_DW_ENTRY_MASK),
-                              fmaxf(0.0f, c.dep_sched[k]), c.xdk[k], c.atk[k], c.xak[k]);
+                              fmaxf(0.0f, c.dep_sched[k]), c.xdk[k], c.atk[k]);
             }
             c.next_dep[a] = nd + n_new;
         } else {
@@ -622,30 +633,52 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
         }
     }
 
-    // 5. update_runway_queue (airport.py:101-128): shared memory only
+    // 5. update_runway_queue (airport.py:101-128): shared memory only.
+    //
+    // The reference adds every service draw x to the wait of EVERY queued entry
+    // (airport.py:150-153), O(queue length) per assignment.  Here an entry's wait is
+    // psum(now) - psum(at joining), O(1).  That difference R (double) is not the fp32
+    // sequential sum W the reference forms, so the decision `queue_start + W <= t` is
+    // taken on an interval [asg_lo, asg_hi] that provably contains the reference's fp32
+    // value:  |W - R| <= (n-1) u R  (sequential fp32 sum of n non-negative terms),
+    // |fl32(psum) - psum| <= u psum,  |fl32(qs + W) - (qs + W)| <= u |qs + W|,
+    // u = 2^-24.  Only when the clock falls INSIDE the interval (probability ~1e-5 per
+    // check) is W replayed with the reference's sequential fp32 adds.
     {
         uint32_t head = c.q_head[a];
         const uint32_t tail = c.q_tail[a];
         if (head == tail) return;
         const uint32_t qoff = c.s_qoff[a], qmask = c.s_qmask[a];
-        float asg = c.q_asg[a];
+        float lo = c.asg_lo[a], hi = c.asg_hi[a], wait = c.w_head[a];
+        double psum = c.psum[a];
         while (head != tail) {
-            const uint32_t hi = qoff + (head & qmask);
-            if (isnan(asg)) {
-                // _assign_service_time (airport.py:130-158): the draw x joins the wait
-                // of every entry currently queued, head included
-                const float x = c.qx[hi];
-                for (uint32_t j = head; j != tail; ++j) {
-                    const uint32_t ji = qoff + (j & qmask);
-                    c.qw[ji] = BA_ADD(c.qw[ji], x);
-                }
-                asg = BA_ADD(c.qs[hi], c.qw[hi]);
+            const uint32_t hidx = qoff + (head & qmask);
+            if (isnan(hi)) {
+                // _assign_service_time (airport.py:130-158)
+                psum += (double)c.qx[hidx];
+                const float pj = c.qp[hidx];
+                const double R = psum - (double)pj;
+                const double A = (double)c.qs[hidx] + R;
+                const double n = (double)(head - c.ql[hidx] + 1u);
+                const double B = 3.0 * 5.9604644775390625e-08 * (n * R + (double)fabsf(pj) + fabs(A)) + 1e-30;
+                lo = (float)(A - B); hi = (float)(A + B);
+                wait = (float)R;
+                if (c.replay_always) lo = -INFINITY, hi = INFINITY;
             }
-            if (!(asg <= t)) break;
+            if (!(hi <= t)) {
+                if (lo > t || isnan(lo)) break;             // certainly still being served
+                // ambiguous: replay the reference's arithmetic exactly
+                const uint32_t first = c.ql[hidx];
+                if (tail - first > qmask + 1u) { acc.status |= BA_S_OVERFLOW; break; }
+                float w = 0.0f;
+                for (uint32_t j = first; j != head + 1u; ++j) w = BA_ADD(w, c.qx[qoff + (j & qmask)]);
+                wait = w;
+                lo = hi = BA_ADD(c.qs[hidx], w);
+                if (!(hi <= t)) break;
+            }
             // served (airport.py:111-126)
-            const uint32_t word = c.qf[hi];
+            const uint32_t word = c.qf[hidx];
             const int f = (int)(word & BA_FID_MASK);
-            const float wait = c.qw[hi];
             if (word & BA_Q_DEP) {
                 c.wd[f] = wait;
                 // add_in_transit_flights (network.py:136-168).  The in-transit list is
@@ -653,7 +686,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 const uint32_t key = ((uint32_t)tick << BA_KEY_TICK_SHIFT) | (uint32_t)a;
                 const uint32_t seq = c.dep_pops[a];
                 c.dep_pops[a] = seq + 1;
-                const float av = c.qy[hi];
+                const float av = c.qy[hidx];
                 if (av <= t) {
                     // already past its arrival time: joins the destination queue at the
                     // end of this very tick (update_in_transit_flights, network.py:186)
@@ -661,7 +694,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                     if (slot >= c.due_cap) acc.status |= BA_S_OVERFLOW;
                     else {
                         c.due_w[slot] = word & BA_DW_ENTRY_MASK; c.due_key[slot] = key;
-                        c.due_seq[slot] = seq; c.due_av[slot] = av; c.due_x[slot] = c.qz[hi];
+                        c.due_seq[slot] = seq; c.due_av[slot] = av; c.due_x[slot] = c.xaf[f];
                     }
                 } else {
                     c.popkey[f] = key; c.popseq[f] = seq;
@@ -680,10 +713,10 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 if (c.pop_tick) c.pop_tick[2 * f + 1] = tick;
             }
             ++head;
-            asg = NAN;
+            lo = hi = NAN;
         }
         c.q_head[a] = head;
-        c.q_asg[a] = asg;
+        c.asg_lo[a] = lo; c.asg_hi[a] = hi; c.w_head[a] = wait; c.psum[a] = psum;
     }
 }
 
@@ -766,9 +799,11 @@ BA_DEV void ba_phase_c_push(BaCtx &c, uint32_t i)
     const uint32_t target = c.due_tgt[i];
     if (target == 0xFFFFFFFFu) return;
     const uint32_t word = c.due_w[i];
+    const uint32_t dst0 = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
     c.qf[target] = word & BA_FID_MASK;            // arrival entry: no DEP flag
-    c.qs[target] = c.due_av[i]; c.qw[target] = 0.0f; c.qx[target] = c.due_x[i];
-    c.qy[target] = 0.0f; c.qz[target] = 0.0f;
+    c.qs[target] = c.due_av[i]; c.qx[target] = c.due_x[i]; c.qy[target] = 0.0f;
+    c.qp[target] = (float)c.psum[dst0];
+    c.ql[target] = c.q_head[dst0] + (isnan(c.asg_hi[dst0]) ? 0u : 1u);
     const uint32_t cnt = c.due_cnt[i];
     if (cnt) {
         const uint32_t dst = (word >> BA_Q_DST_SHIFT) & 0xFFFu;

@@ -94,7 +94,8 @@ class SimulationPlan:
                 noise: Optional[torch.Tensor] = None, *, seed: int = 0,
                 noise_is_value: bool = False, want_grad: bool = False,
                 force_exact_lists: bool = False, no_overflow_rerun: bool = False,
-                want_ticks: bool = False, want_pop_ticks: bool = False) -> Dict[str, torch.Tensor]:
+                want_ticks: bool = False, want_pop_ticks: bool = False,
+                replay_waits: bool = False) -> Dict[str, torch.Tensor]:
         """``lat_airport [P,C,N]``, ``lat_route [P,R]``, ``scales [3]``,
         ``noise [P,D,Fmax,4]`` or None (Philox from ``seed``).  Asynchronous."""
         P = int(lat_airport.shape[0])
@@ -113,7 +114,8 @@ class SimulationPlan:
             pop = (torch.empty((P, D, F, 2), dtype=torch.int32, device=self.device)
                    if want_pop_ticks else None)
             opts = _capi.BaForwardOpts(int(noise_is_value), int(want_grad), int(force_exact_lists),
-                                       int(no_overflow_rerun), int(seed) & (2**64 - 1),
+                                       int(no_overflow_rerun), int(replay_waits), 0,
+                                       int(seed) & (2**64 - 1),
                                        None if pop is None else pop.data_ptr())
             self._h.forward(P, _ptr(la), _ptr(lr), _ptr(sc), _ptr(nz), opts, _ptr(logp),
                             _ptr(status), _ptr(ticks), _ptr(tape), self._stream())
@@ -153,7 +155,7 @@ class SimulationPlan:
                 "g_scales": np.empty((P, 3), np.float32) if want_grad else None,
             }
         vp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)  # noqa: E731
-        opts = _capi.BaForwardOpts(int(noise_is_value), int(want_grad), 0, 0,
+        opts = _capi.BaForwardOpts(int(noise_is_value), int(want_grad), 0, 0, 0, 0,
                                    int(seed) & (2**64 - 1), None)
         self._h.logjoint_host(P, vp(lat_airport), vp(lat_route), vp(scales), vp(noise), opts,
                               vp(out["logp"]), vp(out["status"]), vp(out["g_airport"]),

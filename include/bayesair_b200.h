@@ -99,6 +99,10 @@ typedef struct BaForwardOpts {
     int32_t want_grad;          /* 1: also fill the gradient tape for ba_backward          */
     int32_t force_exact_lists;  /* 1: skip the shared-memory variant (testing)             */
     int32_t no_overflow_rerun;  /* 1: leave BA_PD_OVERFLOW particle-days unresolved (testing) */
+    int32_t replay_waits;       /* 1: always form queue waits with the reference's sequential
+                                      fp32 adds instead of only when a decision is within
+                                      rounding distance of the clock (testing; same results) */
+    int32_t reserved;
     uint64_t seed;              /* Philox seed, used when d_noise == NULL                  */
     int32_t *d_pop_tick;        /* nullable diagnostics [P, D, Fmax, 2]: tick at which each
                                    flight left its departure / arrival runway queue (-1 =

@@ -94,7 +94,8 @@ class EmuPlan:
         return la, lr
 
     def forward(self, latents, scales, noise, *, seed=0, value_mode=False, want_grad=True,
-                exact=False, rerun_overflow=True, shuffle_seed=1, want_pop=False):
+                exact=False, rerun_overflow=True, shuffle_seed=1, want_pop=False,
+                replay_waits=False):
         lib = _load()
         la, lr = self.pack_latents(latents)
         P = la.shape[0]
@@ -110,7 +111,7 @@ class EmuPlan:
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
         lib.ba_emu_forward(self.h, P, vp(la), vp(lr), vp(sc), vp(nz), C.c_uint64(seed),
                            int(value_mode), int(want_grad), int(exact), int(rerun_overflow),
-                           C.c_uint(shuffle_seed), vp(logp), vp(status), vp(ticks), vp(tape), vp(pop))
+                           int(replay_waits), C.c_uint(shuffle_seed), vp(logp), vp(status), vp(ticks), vp(tape), vp(pop))
         out = dict(logp=logp, status=status, ticks=ticks, pop_tick=pop)
         if want_grad:
             dl = np.ones((P, self.D), np.float32)

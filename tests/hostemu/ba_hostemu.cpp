@@ -45,7 +45,7 @@ template <bool EXACT>
 static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d, int P,
                      const float *lat_airport, const float *lat_route, const float *scales,
                      const float *noise, uint64_t seed, int value_mode, int want_grad,
-                     unsigned shuffle_seed, float *logp, uint32_t *status, int32_t *ticks,
+                     int replay_waits, unsigned shuffle_seed, float *logp, uint32_t *status, int32_t *ticks,
                      float *tape, int32_t *pop_tick)
 {
     (void)P;
@@ -65,6 +65,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     c.c1_lp = ba_relaxed_bernoulli_lp(0.0f, 1.0f, nullptr);
     c.value_mode = value_mode; c.want_grad = want_grad && tape;
     c.cancel_mode = plan.include_cancellations; c.max_t = plan.max_t; c.seed = seed;
+    c.replay_always = replay_waits;
     c.route_base = C * N;
     c.tick_time = plan.tick_time; c.cta = ctaw;
     const size_t pd = (size_t)p * D + d;
@@ -150,7 +151,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
 extern "C" int ba_emu_forward(const EmuPlan *pl, int P, const float *lat_airport,
                               const float *lat_route, const float *scales, const float *noise,
                               uint64_t seed, int value_mode, int want_grad, int exact,
-                              int rerun_overflow, unsigned shuffle_seed, float *logp,
+                              int rerun_overflow, int replay_waits, unsigned shuffle_seed, float *logp,
                               uint32_t *status, int32_t *ticks, float *tape, int32_t *pop_tick)
 {
     const BaPlanView &plan = pl->host.view;
@@ -159,13 +160,13 @@ extern "C" int ba_emu_forward(const EmuPlan *pl, int P, const float *lat_airport
             const BaDayView &day = plan.days[d];
             if (exact)
                 run_item<true>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
-                               value_mode, want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick);
+                               value_mode, want_grad, replay_waits, shuffle_seed, logp, status, ticks, tape, pop_tick);
             else {
                 run_item<false>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
-                                value_mode, want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick);
+                                value_mode, want_grad, replay_waits, shuffle_seed, logp, status, ticks, tape, pop_tick);
                 if (rerun_overflow && (status[(size_t)p * plan.D + d] & BA_S_OVERFLOW))
                     run_item<true>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
-                                   value_mode, want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick);
+                                   value_mode, want_grad, replay_waits, shuffle_seed, logp, status, ticks, tape, pop_tick);
             }
         }
     return 0;

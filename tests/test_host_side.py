@@ -146,7 +146,8 @@ def test_emulated_kernel_decisions_vs_oracle(canc):
     sc = (0.1, 0.1, 0.1)
     plan = EmuPlan(specs, N, 0.2, 30.0, canc)
     for shuffle in (1, 2):
-        o = plan.forward(lat, sc, noise, shuffle_seed=shuffle, want_pop=True)
+        o = plan.forward(lat, sc, noise, shuffle_seed=shuffle, want_pop=True,
+                         replay_waits=(shuffle == 2))
         assert (o["status"] == 0).all()
         for p in range(P):
             for d in range(2):
