@@ -242,6 +242,12 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
     prm.scratch = pl->d_scratch;
     prm.n_work = (int)n_work;
 
+    static unsigned long long *d_phase = nullptr;
+    if (std::getenv("BA_PHASE_PROFILE")) {
+        if (!d_phase) { BA_CUDA(cudaMalloc((void **)&d_phase, 8 * sizeof(unsigned long long))); }
+        BA_CUDA(cudaMemsetAsync(d_phase, 0, 8 * sizeof(unsigned long long), s));
+        prm.phase_cycles = d_phase;
+    }
     const bool use_fast = pl->fast_ok && !o.force_exact_lists;
     if (use_fast) {
         prm.scratch_stride = pl->stride_fast;
@@ -270,6 +276,20 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         int grid = (int)std::min<long long>(n_work, pl->grid_exact);
         BA_CUDA(ba_launch_forward(prm, true, grid, pl->block, pl->smem_exact, s));
         g_launches++;
+    }
+    if (prm.phase_cycles) {
+        unsigned long long h[8];
+        BA_CUDA(cudaStreamSynchronize(s));
+        BA_CUDA(cudaMemcpy(h, prm.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost));
+        const char *names[8] = {"init", "prologue", "calendar", "phaseA", "phaseB", "phaseC+vote",
+                                "epilogue", "-"};
+        double tot = 0;
+        for (int i = 0; i < 7; ++i) tot += (double)h[i];
+        fprintf(stderr, "[BA_PHASE_PROFILE] cycles per particle-day (thread 0 wall):");
+        for (int i = 0; i < 7; ++i)
+            fprintf(stderr, " %s=%.0f (%.0f%%)", names[i], (double)h[i] / (double)n_work,
+                    100.0 * (double)h[i] / tot);
+        fprintf(stderr, "\n");
     }
     return BA_OK;
 }

@@ -74,7 +74,14 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
     c.tick_time = plan.tick_time;
     c.cta = ctaw;
 
+    // optional phase timing (thread 0 reads the SM clock after each barrier)
+    long long pc_last = 0;
+    unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool prof = prm.phase_cycles != nullptr && tid == 0;
+#define BA_MARK(slot) do { if (prof) { long long now_ = clock64(); pc[slot] += (unsigned long long)(now_ - pc_last); pc_last = now_; } } while (0)
+
     for (;;) {
+        if (prof) pc_last = clock64();
         // ---- next work item ------------------------------------------------
         if (tid == 0) red[BA_RED_WORDS - 1] = atomicAdd(prm.work_counter, 1u);
         __syncthreads();
@@ -111,13 +118,16 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         if (tid < BA_CTA_WORDS) c.cta[tid] = 0;
         __syncthreads();
 
+        BA_MARK(0);
         // ---- prologue: flight-parallel, coalesced ------------------------------
         for (int f = tid; f < day.F; f += nthr) ba_prologue_flight(c, acc, f);
         __syncthreads();
+        BA_MARK(1);
         if (tid == 0) ba_calendar_scan(c);
         __syncthreads();
         for (int f = tid; f < day.F; f += nthr) ba_calendar_scatter(c, f);
         __syncthreads();
+        BA_MARK(2);
 
         // ---- tick loop (model.py:158-200) --------------------------------------
         int tick = day.first_tick - 1;
@@ -127,12 +137,17 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             ++tick;
             const float t = c.tick_time[tick];                  // model.py:161
             for (int s = tid; s < N; s += nthr) ba_phase_a<EXACT>(c, acc, day.lane_airport[s], t, tick);
+            if (!EXACT && (acc.status & BA_S_OVERFLOW)) c.cta[3] = 1u;
             __syncthreads();
+            BA_MARK(3);
             if ((uint32_t)tick < c.cal_cap) {
                 const uint32_t lo = c.cal_cnt[tick - 1], hi = c.cal_cnt[tick];
                 for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_record(c, acc, i);
             }
             __syncthreads();
+            BA_MARK(4);
+            if (!EXACT && c.cta[3]) break;                      // a ring overflowed: this
+                                                                // particle-day is re-run anyway
             uint32_t n_due = c.cta[0];
             if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
             int more = (n_due != 0u) || (c.cta[1] != 0u);
@@ -144,12 +159,15 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
                 if (tid == 0) c.cta[0] = 0;
             }
             busy = __syncthreads_or(more) != 0;
+            BA_MARK(5);
         }
 
         // ---- epilogue ----------------------------------------------------------
         __syncthreads();          // every wait of the tape is written
-        for (int f = tid; f < day.F; f += nthr) ba_epilogue_flight(c, acc, f);
-        if (c.grow) {
+        const bool aborted = !EXACT && c.cta[3] != 0u;
+        if (!aborted)
+            for (int f = tid; f < day.F; f += nthr) ba_epilogue_flight(c, acc, f);
+        if (c.grow && !aborted) {
             __syncthreads();
             for (int s = tid; s < N; s += nthr) ba_epilogue_airport(c, day.lane_airport[s], N);
             for (int r = tid; r < day.Rd; r += nthr) ba_epilogue_route(c, r);
@@ -191,7 +209,10 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             }
         }
         __syncthreads();     // red[] and the state arrays are reused by the next item
+        BA_MARK(6);
     }
+    if (prof)
+        for (int i = 0; i < 8; ++i) atomicAdd(prm.phase_cycles + i, pc[i]);
 }
 
 // g[p, j] = sum_d dlogp[p, d] * tape[p, d, j]

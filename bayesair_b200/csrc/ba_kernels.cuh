@@ -25,7 +25,7 @@ struct BaFwdParams {
     const int32_t *work_list;     // optional explicit list of pd = p*D + d
     int32_t n_work;
     const unsigned int *n_work_dev; // if set, overrides n_work (device-side count)
-    uint32_t smem_state_words;    // 35 * N
+    unsigned long long *phase_cycles; // optional [8] per-phase cycle totals (debug, BA_PHASE_PROFILE)
 };
 
 struct BaBwdParams {

@@ -29,11 +29,16 @@
 #define BA_AP_TRACK_T 1u              // turnaround list needed (n_avail can matter)
 #define BA_AP_TRACK_A 2u              // available-aircraft FIFO contents needed
 
-// no-cancellation mode: an airport with at most this many departures a day has
-// cancellation probability exactly 0 in fp32 at every tick (1000 reserves,
-// sigmoid(10*(n/nr - 1/4)) == 1.0f for n/nr >= 1.93), so neither the turnaround
-// list nor the aircraft FIFO can influence anything.
-#define BA_SIMPLE_MAX_DEPARTURES 340
+// No-cancellation mode (1000 reserve aircraft per airport, model.py:116-118): the
+// cancellation probability of a batch of n_ready flights is
+//   p = 1 - sigmoid(10 (n_avail / n_ready - 1/4)),
+// which is EXACTLY 0 in fp32 once n_avail / n_ready >= 1.93 (sigmoid rounds to 1.0f).
+// n_avail never drops below 1000 - (departures of the day) and n_ready never exceeds the
+// largest number of departures scheduled inside one tick, both known at plan time.  An
+// airport that satisfies (1000 - D_a) >= BA_SIMPLE_RATIO * max_batch_a can therefore
+// neither cancel nor delay anything and needs no aircraft bookkeeping at all
+// (SURVEY.md App. A.2 Q4).
+#define BA_SIMPLE_RATIO 1.95
 
 struct BaFlight {                     // 16 B, one LDG.128
     float sched_dep;

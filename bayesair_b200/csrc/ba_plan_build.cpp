@@ -7,7 +7,7 @@
 //     restricted to one origin the scan order is this list);
 //   * the compact route table (dense [N,N] travel times -> [R]);
 //   * which airports need aircraft bookkeeping at all (ba_plan.h:
-//     BA_SIMPLE_MAX_DEPARTURES);
+//     BA_SIMPLE_RATIO);
 //   * list capacities: a small shared-memory ring per airport sized from the
 //     airport's daily traffic (fast variant) and exact-capacity rings in global
 //     scratch (the variant a particle-day is re-run with if a ring overflows);
@@ -53,6 +53,9 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         return fail(BA_ERR_LIMIT, "ba_plan_create: max_ticks must be <= 65000");
 
     const int N = n_airports;
+    // the clock: t_k = fl32(t_{k-1} + fl32(delta_t))  (model.py:158-161)
+    out->tick_time.assign((size_t)max_ticks + 2, 0.0f);
+    for (int k = 1; k <= max_ticks + 1; ++k) out->tick_time[k] = out->tick_time[k - 1] + delta_t;
     out->days.clear();
     out->days.resize(n_days);
 
@@ -152,6 +155,19 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
                 H.rt_off.push_back((int32_t)H.rt_flt.size());
             }
         }
+        // largest number of departures of one airport that become ready in the same tick
+        std::vector<int> max_batch(N, 0);
+        {
+            std::vector<int> last_tick(N, -1), run(N, 0);
+            const std::vector<float> &tt = out->tick_time;
+            int k = 1;
+            for (int f = 0; f < F; ++f) {          // flights are sorted by scheduled departure
+                while (k < max_ticks + 1 && tt[k] < T.h_sched_dep[f]) ++k;
+                const int o = T.h_origin[f];
+                if (last_tick[o] == k) run[o]++; else { last_tick[o] = k; run[o] = 1; }
+                max_batch[o] = std::max(max_batch[o], run[o]);
+            }
+        }
         std::vector<int> dep_live(N, 0);
         for (int f = 0; f < F; ++f)
             if (((H.flights[f].od >> 24) & 3u) != 1u) dep_live[T.h_origin[f]]++;
@@ -166,7 +182,9 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             uint32_t flags = 0;
             if (include_cancellations) flags = BA_AP_TRACK_T | BA_AP_TRACK_A;
             else {
-                if (dep_cnt[a] > BA_SIMPLE_MAX_DEPARTURES) flags |= BA_AP_TRACK_T;
+                const bool simple = dep_cnt[a] < 1000 &&
+                    (double)(1000 - dep_cnt[a]) >= BA_SIMPLE_RATIO * (double)std::max(1, max_batch[a]);
+                if (!simple) flags |= BA_AP_TRACK_T;
                 if (dep_cnt[a] >= 1000) flags |= BA_AP_TRACK_T | BA_AP_TRACK_A;
             }
             A.flags = flags;
@@ -232,9 +250,6 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         smem_words = std::max(smem_words, 6u * q_s);
     }
 
-    // the clock: t_k = fl32(t_{k-1} + fl32(delta_t))  (model.py:158-161)
-    out->tick_time.assign((size_t)max_ticks + 2, 0.0f);
-    for (int k = 1; k <= max_ticks + 1; ++k) out->tick_time[k] = out->tick_time[k - 1] + delta_t;
     out->day_views.resize(n_days);
     for (int d = 0; d < n_days; ++d) out->day_views[d] = out->days[d].view;
     BaPlanView &P = out->view;
