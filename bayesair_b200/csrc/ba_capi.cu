@@ -121,6 +121,8 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         BA_PCUDA(upload(pl, H.rt_gid, &v.rt_gid));
         BA_PCUDA(upload(pl, H.rt_off, &v.rt_off));
         BA_PCUDA(upload(pl, H.rt_flt, &v.rt_flt));
+        BA_PCUDA(upload(pl, H.dcal_off, &v.dcal_off));
+        BA_PCUDA(upload(pl, H.dcal_rec, &v.dcal_rec));
         BA_PCUDA(upload(pl, H.airports, &v.airports));
         BA_PCUDA(upload(pl, H.lane_airport, &v.lane_airport));
         dviews[d] = v;
@@ -281,7 +283,7 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         unsigned long long h[8];
         BA_CUDA(cudaStreamSynchronize(s));
         BA_CUDA(cudaMemcpy(h, prm.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost));
-        const char *names[8] = {"init", "prologue", "calendar", "phaseA", "phaseB", "phaseC+vote",
+        const char *names[8] = {"init", "prologue", "calendar", "phaseC+A", "phaseB+vote", "-",
                                 "epilogue", "-"};
         double tot = 0;
         for (int i = 0; i < 7; ++i) tot += (double)h[i];

@@ -30,13 +30,13 @@ size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact)
 {
     size_t w = (((size_t)BA_NWORDS_STATE * n_airports + 3) & ~(size_t)3) + BA_RED_WORDS + BA_CTA_WORDS;
     // list_words = 6 words per queue entry; plus calendar counters and the due buffer
-    if (!exact) w += list_words + BA_KCAL + BA_DUE_WORDS * BA_DUE_CAP_S;
+    if (!exact) w += list_words + BA_KCAL + 2 * BA_DUE_WORDS * BA_DUE_CAP_S + 2 * (BA_DUE_CAP_S / 2);
     return w * 4;
 }
 
 // resident CTAs per SM the register allocation aims for, per block-size class
 #ifndef BA_MIN_BLOCKS_128
-#define BA_MIN_BLOCKS_128 6
+#define BA_MIN_BLOCKS_128 5
 #endif
 #define BA_MIN_BLOCKS(MAXT) ((MAXT) == 128 ? BA_MIN_BLOCKS_128 : ((MAXT) == 256 ? 3 : 1))
 
@@ -123,43 +123,50 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         for (int f = tid; f < day.F; f += nthr) ba_prologue_flight(c, acc, f);
         __syncthreads();
         BA_MARK(1);
-        if (tid == 0) ba_calendar_scan(c);
+        if (tid < 32) ba_calendar_scan(c, tid);
         __syncthreads();
         for (int f = tid; f < day.F; f += nthr) ba_calendar_scatter(c, f);
+        // departures that are ready at the very first tick
+        int tick = day.first_tick - 1;
+        if (tick + 1 <= day.last_ready_tick)
+            for (uint32_t i = day.dcal_off[tick + 1] + tid; i < (uint32_t)day.dcal_off[tick + 2]; i += nthr)
+                ba_phase_b_departure(c, acc, i, tick & 1);
         __syncthreads();
         BA_MARK(2);
 
-        // ---- tick loop (model.py:158-200) --------------------------------------
-        int tick = day.first_tick - 1;
+        // ---- tick loop (model.py:158-200): two barriers per tick ------------------
+        //   interval 1 (one lane per airport): phase C of the previous tick, then phase A
+        //   interval 2 (flight-parallel):      phase B, fills the due buffer of this tick
         bool busy = day.F > 0;
         while (busy) {
             if (tick >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
             ++tick;
             const float t = c.tick_time[tick];                  // model.py:161
-            for (int s = tid; s < N; s += nthr) ba_phase_a<EXACT>(c, acc, day.lane_airport[s], t, tick);
+            const int prev = (tick - 1) & 1, cur = tick & 1;
+            uint32_t n_due = c.cta[prev];
+            if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
+            int more = tick < day.last_ready_tick;
+            for (int s = tid; s < N; s += nthr) {
+                const int a = day.lane_airport[s];
+                if (n_due) ba_phase_c_pull(c, acc, a, prev, n_due);
+                ba_phase_a<EXACT>(c, acc, a, t, tick);
+                more |= ba_airport_busy(c, a) ? 1 : 0;
+            }
             if (!EXACT && (acc.status & BA_S_OVERFLOW)) c.cta[3] = 1u;
             __syncthreads();
             BA_MARK(3);
-            if ((uint32_t)tick < c.cal_cap) {
-                const uint32_t lo = c.cal_cnt[tick - 1], hi = c.cal_cnt[tick];
-                for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_record(c, acc, i);
-            }
-            __syncthreads();
-            BA_MARK(4);
             if (!EXACT && c.cta[3]) break;                      // a ring overflowed: this
                                                                 // particle-day is re-run anyway
-            uint32_t n_due = c.cta[0];
-            if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
-            int more = (n_due != 0u) || (c.cta[1] != 0u);
-            for (int s = tid; s < N; s += nthr) more |= ba_airport_busy(c, day.lane_airport[s]) ? 1 : 0;
-            if (n_due) {
-                for (uint32_t i = tid; i < n_due; i += nthr) ba_phase_c_rank(c, acc, i, n_due);
-                __syncthreads();
-                for (uint32_t i = tid; i < n_due; i += nthr) ba_phase_c_push(c, i);
-                if (tid == 0) c.cta[0] = 0;
+            if (tid == 0) c.cta[prev] = 0;                      // consumed by every lane
+            if ((uint32_t)tick < c.cal_cap) {
+                const uint32_t lo = c.cal_cnt[tick - 1], hi = c.cal_cnt[tick];
+                for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_arrival(c, acc, i, cur);
             }
+            if (tick + 1 <= day.last_ready_tick)
+                for (uint32_t i = day.dcal_off[tick + 1] + tid; i < (uint32_t)day.dcal_off[tick + 2]; i += nthr)
+                    ba_phase_b_departure(c, acc, i, cur);
             busy = __syncthreads_or(more) != 0;
-            BA_MARK(5);
+            BA_MARK(4);
         }
 
         // ---- epilogue ----------------------------------------------------------

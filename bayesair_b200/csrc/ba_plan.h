@@ -22,8 +22,11 @@
 #define BA_KEY_INVALID 0xFFFFFFFFu
 // arrival calendar: buckets (ticks) kept in shared memory by the fast variant
 #define BA_KCAL 1024
-#define BA_DUE_CAP_S 128              // due-buffer entries in shared memory (fast variant)
-#define BA_DUE_WORDS 7
+#ifndef BA_DUE_CAP_S
+#define BA_DUE_CAP_S 128              // entries per due buffer in shared memory (two buffers)
+#endif
+#define BA_KEY_DEPARTURE 0xF0000000u   // keys of newly ready departures sort after arrivals
+#define BA_DUE_WORDS 6               // word, key, owner<<16|seq, queue start, x, y
 
 // airport flags
 #define BA_AP_TRACK_T 1u              // turnaround list needed (n_avail can matter)
@@ -75,6 +78,11 @@ struct BaDayView {
     const int32_t *rt_off;            // [Rd+1] CSR offsets into rt_flt
     const int32_t *rt_flt;            // [sum arr_cnt] flights of each used route, ascending
     int32_t Rd;                       // routes used on this day
+    const int32_t *dcal_off;          // [last_ready_tick + 2] departure calendar: slice of tick k
+    const uint32_t *dcal_rec;         //   = flights of bookkeeping-free airports that become
+                                      //   ready at tick k; record = {batch rank << 18 | dep pos,
+                                      //   origin airport}
+    int32_t last_ready_tick;          // tick at which the day's last scheduled flight is ready
     const BaAirport *airports;        // [N] day order
     const int32_t *lane_airport;      // [N] airport handled by lane slot i (load-sorted)
     uint32_t q_total_s;               // queue pool size (entries) of the shared variant
@@ -110,7 +118,7 @@ struct BaPlanView {
 //   trl, tre        [F] each if any_track_t : turnaround release time / its noise
 //   qd, se, sw      [F] each if any_track_a : departure queue start, aircraft-source
 //                                         noise and branch weight (adjoint of max())
-//   exact variant only: runway queues 6 x q_total_x, due buffer 7 x F,
+//   exact variant only: runway queues 6 x q_total_x, two due buffers 6 x F each,
 //                       calendar counters max_ticks + 2
 //   turnaround lists 2 x turn_total, aircraft FIFOs 2 x av_total, delayed deques dl_total
 static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_ticks)
@@ -118,7 +126,8 @@ static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_
     uint64_t w = 13ull * (uint64_t)d.F;
     if (d.any_track_t) w += 2ull * (uint64_t)d.F;
     if (d.any_track_a) w += 3ull * (uint64_t)d.F;
-    if (exact) w += 6ull * d.q_total_x + (uint64_t)BA_DUE_WORDS * (uint64_t)d.F + (uint64_t)max_ticks + 2;
+    if (exact) w += 6ull * d.q_total_x + 2ull * (uint64_t)BA_DUE_WORDS * (uint64_t)d.F +
+                    2ull * (((uint64_t)d.F + 7) / 8 * 4) + (uint64_t)max_ticks + 2;
     w += 2ull * d.turn_total + 2ull * d.av_total + 1ull * d.dl_total;
     return w + 16;
 }

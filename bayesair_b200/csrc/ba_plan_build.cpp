@@ -157,6 +157,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         }
         // largest number of departures of one airport that become ready in the same tick
         std::vector<int> max_batch(N, 0);
+        std::vector<int> ready_tick(F, 1), batch_rank(F, 0);
+        int last_ready_tick = 0;
         {
             std::vector<int> last_tick(N, -1), run(N, 0);
             const std::vector<float> &tt = out->tick_time;
@@ -166,6 +168,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
                 const int o = T.h_origin[f];
                 if (last_tick[o] == k) run[o]++; else { last_tick[o] = k; run[o] = 1; }
                 max_batch[o] = std::max(max_batch[o], run[o]);
+                ready_tick[f] = k; batch_rank[f] = run[o] - 1;
+                last_ready_tick = std::max(last_ready_tick, k);
             }
         }
         std::vector<int> dep_live(N, 0);
@@ -212,6 +216,27 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
                 A.av_mask = ac - 1; av += ac;
             }
         }
+        // departure calendar: flights of bookkeeping-free airports, by ready tick
+        {
+            H.dcal_off.assign((size_t)last_ready_tick + 2, 0);
+            std::vector<int> cnt((size_t)last_ready_tick + 2, 0);
+            auto on_calendar = [&](int f) {
+                return !(H.airports[T.h_origin[f]].flags & BA_AP_TRACK_T) &&
+                       ((H.flights[f].od >> 24) & 3u) == 0u;
+            };
+            for (int f = 0; f < F; ++f) if (on_calendar(f)) cnt[ready_tick[f]]++;
+            for (int k = 0; k <= last_ready_tick; ++k) H.dcal_off[k + 1] = H.dcal_off[k] + cnt[k];
+            H.dcal_rec.assign(2 * (size_t)H.dcal_off[last_ready_tick + 1], 0u);
+            std::vector<int> cur(H.dcal_off.begin(), H.dcal_off.end() - 1);
+            for (int f = 0; f < F; ++f)
+                if (on_calendar(f)) {
+                    if (batch_rank[f] >= 4096)
+                        return fail(BA_ERR_LIMIT, "ba_plan_create: more than 4096 departures of one airport in one tick");
+                    const int pos = cur[ready_tick[f]]++;
+                    H.dcal_rec[2 * pos] = ((uint32_t)batch_rank[f] << 18) | (uint32_t)H.pos_dep[f];
+                    H.dcal_rec[2 * pos + 1] = (uint32_t)T.h_origin[f];
+                }
+        }
         // lane -> airport, heaviest first
         H.lane_airport.resize(N);
         std::iota(H.lane_airport.begin(), H.lane_airport.end(), 0);
@@ -240,6 +265,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         V.pos_dep = H.pos_dep.data(); V.pos_arr = H.pos_arr.data();
         V.rt_gid = H.rt_gid.data(); V.rt_off = H.rt_off.data(); V.rt_flt = H.rt_flt.data();
         V.Rd = (int32_t)H.rt_gid.size();
+        V.dcal_off = H.dcal_off.data(); V.dcal_rec = H.dcal_rec.data();
+        V.last_ready_tick = last_ready_tick;
         V.any_track_t = any_t; V.any_track_a = any_a;
         V.airports = H.airports.data(); V.lane_airport = H.lane_airport.data();
         V.q_total_s = q_s; V.q_total_x = q_x;

@@ -58,6 +58,7 @@
 #define BA_DIV(a, b) __fdiv_rn((a), (b))
 #define BA_ATOMIC_INC(p) atomicAdd((p), 1u)
 #define BA_ATOMIC_DEC(p) atomicSub((p), 1u)
+#define ba_ctz64(x) (__ffsll((long long)(x)) - 1)
 #define __float_as_uint_portable(x) __float_as_uint(x)
 #define __uint_as_float_portable(x) __uint_as_float(x)
 #define BA_LOG(x) logf(x)
@@ -75,6 +76,7 @@ static inline uint32_t __float_as_uint_portable(float x) { uint32_t u; memcpy(&u
 static inline float __uint_as_float_portable(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
 #define BA_ATOMIC_INC(p) ba_host_inc(p)
 #define BA_ATOMIC_DEC(p) ba_host_dec(p)
+#define ba_ctz64(x) __builtin_ctzll((unsigned long long)(x))
 #define BA_LOG(x) logf(x)
 #define BA_EXP(x) expf(x)
 #define BA_LOG1P(x) log1pf(x)
@@ -91,6 +93,20 @@ static inline float __uint_as_float_portable(uint32_t u) { float x; memcpy(&x, &
 #define BA_F32_TINY 1.17549435082228750797e-38f
 
 struct BaNoise4 { float e_dep, eps_travel, e_arr, eps_turn; };
+
+// 8-byte pair accesses (LDS.64 / STS.64 on the device)
+struct alignas(8) BaPairU { uint32_t a, b; };
+struct alignas(8) BaPairF { float a, b; };
+struct alignas(8) BaPairUF { uint32_t a; float b; };
+#if defined(__CUDA_ARCH__)
+#define BA_LD_PAIR(T, p) (*reinterpret_cast<const T *>(p))
+#define BA_ST_PAIR(T, p, v) (*reinterpret_cast<T *>(p) = (v))
+#else
+template <typename T> static inline T ba_ld_pair(const uint32_t *p) { T v; memcpy(&v, p, 8); return v; }
+template <typename T> static inline void ba_st_pair(uint32_t *p, T v) { memcpy(p, &v, 8); }
+#define BA_LD_PAIR(T, p) ba_ld_pair<T>(p)
+#define BA_ST_PAIR(T, p, v) ba_st_pair<T>(p, v)
+#endif
 
 // ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011): counter = (flight, day, particle lo, hi),
@@ -186,12 +202,15 @@ struct BaCtx {
                                       //   time (NaN = unassigned) and its total wait
     double *psum;                     // running sum of all service draws assigned so far
     float *acc_ln0, *acc_bc;
-    uint32_t *next_dep, *q_head, *q_tail, *dep_pops, *turn_n;
+    uint32_t *next_dep, *q_head, *q_tail, *dep_pops, *arr_pops, *turn_n;
     uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail;
-    uint32_t *s_flags, *s_qoff, *s_qmask, *s_depoff, *s_depcnt;
-    // CTA-wide scalars (shared memory): [0] entries in the due buffer, [1] flights in
-    // transit, [2] first calendar bucket not yet consumed
+    uint32_t *s_flags, *s_qoff, *s_qmask, *s_depoff, *s_depcnt, *s_arrcnt;
+    // CTA-wide scalars (shared memory): [0], [1] entries in the even / odd due buffer,
+    // [3] abort flag (a shared ring overflowed)
     uint32_t *cta;
+    const int32_t *dcal_off;      // static departure calendar (ba_plan.h)
+    const uint32_t *dcal_rec;
+    int last_ready_tick;
     // arrival calendar
     const float *tick_time;       // [max_ticks + 2]
     uint32_t *cal_cnt;            // [cal_cap] bucket end offsets (shared or global)
@@ -199,14 +218,16 @@ struct BaCtx {
     uint32_t *karr;               // [F] arrival tick of every flight (global scratch)
     uint32_t *cal;                // [3F] records {word, arrival time, x_arr} sorted by tick
     uint32_t *popkey, *popseq;    // [F] ordering key of served departures (global scratch)
-    // due buffer {word, key, seq, arrival time, x, target slot, count}: shared / global
-    uint32_t *due_w, *due_key, *due_seq, *due_tgt, *due_cnt; float *due_av, *due_x;
+    // two due buffers (even / odd ticks), 6 words per entry: {queue word, key}
+    // {owner << 16 | seq, queue start} {x, y}
+    uint32_t *due_base;           // buffer p at due_base + p * due_stride (no pointer arrays:
+    uint32_t due_stride;          //   a runtime-indexed member would push BaCtx to local memory)
     uint32_t due_cap;
     int first_tick;
     // list pools (shared memory in the fast variant, global scratch in the exact one)
-    uint32_t *qf, *ql; float *qs, *qp, *qx, *qy;   // runway queues: word, first service index
-                                                   //   that counts (lo), start, prefix sum at
-                                                   //   joining, own draw x, arrival time
+    // runway queues, 6 words per entry (three 8-byte pairs): {word, lo} {queue start,
+    // prefix sum at joining} {own service draw x, arrival time at the destination}
+    uint32_t *qe;
     // per-flight global scratch
     float *xdk, *xak, *atk;       // prologue outputs, dep order (reused by the epilogue)
     float *xaf;                   // x_arr by flight (for departures served after arrival)
@@ -230,7 +251,7 @@ struct BaAcc {
     uint32_t status;
 };
 
-#define BA_NWORDS_STATE 32        // per-airport words of shared state (see ba_carve_state)
+#define BA_NWORDS_STATE 34        // per-airport words of shared state (see ba_carve_state)
 #define BA_Q_WORDS 6              // words per runway-queue entry
 #define BA_CTA_WORDS 4            // CTA-wide scalars
 
@@ -249,13 +270,14 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N)
     c.s_flags = w + 23 * N; c.s_qoff = w + 24 * N; c.s_qmask = w + 25 * N;
     c.s_depoff = w + 26 * N; c.s_depcnt = w + 27 * N;
     c.asg_lo = f + 28 * N; c.asg_hi = f + 29 * N;
-    c.psum = (double *)(w + 30 * N);       // needs N even or an 8-byte aligned base: see kernel
+    c.psum = (double *)(w + 30 * N);       // 30 N words: always 8-byte aligned
+    c.arr_pops = w + 32 * N; c.s_arrcnt = w + 33 * N;
 }
 
 // Words of shared memory the list structures of the fast variant need.
 BA_DEV uint32_t ba_shared_list_words(uint32_t q_total_s)
 {
-    return BA_Q_WORDS * q_total_s + BA_KCAL + BA_DUE_WORDS * BA_DUE_CAP_S;
+    return BA_Q_WORDS * q_total_s + BA_KCAL + 2 * BA_DUE_WORDS * BA_DUE_CAP_S + 2 * (BA_DUE_CAP_S / 2);
 }
 
 // Carves the queue pool / calendar counters / due buffer (shared or global) and the
@@ -280,12 +302,11 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32
     }
     uint32_t *s = EXACT ? g : shared_pool;
     const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
-    c.qf = s; s += qt; c.qs = (float *)s; s += qt; c.qp = (float *)s; s += qt;
-    c.qx = (float *)s; s += qt; c.qy = (float *)s; s += qt; c.ql = s; s += qt;
+    c.qe = s; s += BA_Q_WORDS * qt;
     c.due_cap = EXACT ? F : (uint32_t)BA_DUE_CAP_S;
-    c.due_w = s; s += c.due_cap; c.due_key = s; s += c.due_cap; c.due_seq = s; s += c.due_cap;
-    c.due_av = (float *)s; s += c.due_cap; c.due_x = (float *)s; s += c.due_cap;
-    c.due_tgt = s; s += c.due_cap; c.due_cnt = s; s += c.due_cap;
+    const uint32_t own_words = (c.due_cap + 7u) / 8u * 4u;     // u16 per entry, 16-byte groups
+    c.due_base = s; c.due_stride = BA_DUE_WORDS * c.due_cap + own_words;
+    s += 2u * c.due_stride;
     c.cal_cap = EXACT ? (uint32_t)max_ticks + 2u : (uint32_t)BA_KCAL;
     c.cal_cnt = s; s += c.cal_cap;
     if (EXACT) g = s;
@@ -293,6 +314,7 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32
     c.at = (float *)g; g += day.av_total; c.ae = (float *)g; g += day.av_total;
     c.dl = g;
     c.first_tick = day.first_tick;
+    c.dcal_off = day.dcal_off; c.dcal_rec = day.dcal_rec; c.last_ready_tick = day.last_ready_tick;
 }
 
 BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
@@ -357,13 +379,14 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     c.asg_lo[a] = NAN; c.asg_hi[a] = NAN; c.w_head[a] = 0.0f; c.psum[a] = 0.0;
     c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
     c.acc_ln0[a] = 0.0f; c.acc_bc[a] = 0.0f;
-    c.next_dep[a] = 0; c.q_head[a] = 0; c.q_tail[a] = 0; c.dep_pops[a] = 0;
+    c.next_dep[a] = 0; c.q_head[a] = 0; c.q_tail[a] = 0; c.dep_pops[a] = 0; c.arr_pops[a] = 0;
     c.turn_n[a] = 0; c.av_head[a] = 0; c.av_tail[a] = 0; c.dl_head[a] = 0; c.dl_tail[a] = 0;
     c.s_flags[a] = A.flags;
     c.s_qoff[a] = EXACT ? A.q_off_x : A.q_off_s;
     c.s_qmask[a] = EXACT ? A.q_mask_x : A.q_mask_s;
     c.s_depoff[a] = (uint32_t)A.dep_off;
     c.s_depcnt[a] = (uint32_t)A.dep_cnt;
+    c.s_arrcnt[a] = (uint32_t)A.arr_cnt;
 }
 
 // ---------------------------------------------------------------------------
@@ -383,7 +406,7 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
     const float sc = BA_MUL(T, c.v_t);
     const float tau = c.value_mode ? nz.eps_travel : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
     float y_dep = fl.act_dep, y_arr = fl.act_arr;
-    if (cobs != 1u && (isnan(y_dep) || isnan(y_arr))) {
+    if (cobs == 3u || (cobs != 1u && (isnan(y_dep) || isnan(y_arr)))) {
         acc.status |= BA_S_UNOBSERVED;      // this entry point is the fully observed path
         y_dep = fl.sched_dep; y_arr = fl.sched_dep;
     }
@@ -424,12 +447,31 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
 BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float x, float y)
 {
     const uint32_t head = c.q_head[a], tail = c.q_tail[a], mask = c.s_qmask[a];
-    if (tail - head > mask) { acc.status |= BA_S_OVERFLOW; return; }
-    const uint32_t i = c.s_qoff[a] + (tail & mask);
-    c.qf[i] = word; c.qs[i] = qstart; c.qx[i] = x; c.qy[i] = y;
-    c.qp[i] = (float)c.psum[a];
-    c.ql[i] = head + (isnan(c.asg_hi[a]) ? 0u : 1u);
+    if (tail - head > mask) {
+#if defined(BA_EMU_DEBUG)
+        fprintf(stderr, "qpush overflow a=%d head=%u tail=%u mask=%u word=%08x\n", a, head, tail, mask, word);
+#endif
+        acc.status |= BA_S_OVERFLOW; return; }
+    uint32_t *e = c.qe + BA_Q_WORDS * (c.s_qoff[a] + (tail & mask));
+    BaPairU wl = {word, head + (isnan(c.asg_hi[a]) ? 0u : 1u)};
+    BaPairF sp = {qstart, (float)c.psum[a]};
+    BaPairF xy = {x, y};
+    BA_ST_PAIR(BaPairU, e, wl); BA_ST_PAIR(BaPairF, e + 2, sp); BA_ST_PAIR(BaPairF, e + 4, xy);
     c.q_tail[a] = tail + 1;
+}
+
+BA_DEV void ba_due_append(BaCtx &c, BaAcc &acc, int parity, uint32_t word, uint32_t key,
+                          uint32_t owner, uint32_t seq, float qstart, float x, float y)
+{
+    const uint32_t slot = BA_ATOMIC_INC(&c.cta[parity]);
+    if (slot >= c.due_cap) { acc.status |= BA_S_OVERFLOW; return; }
+    uint32_t *buf = c.due_base + (uint32_t)parity * c.due_stride;
+    uint32_t *de = buf + BA_DUE_WORDS * slot;
+    BaPairU wk = {word, key};
+    BaPairUF os = {(owner << 16) | (seq & 0xFFFFu), qstart};
+    BaPairF xy = {x, y};
+    BA_ST_PAIR(BaPairU, de, wk); BA_ST_PAIR(BaPairUF, de + 2, os); BA_ST_PAIR(BaPairF, de + 4, xy);
+    ((uint16_t *)(buf + BA_DUE_WORDS * c.due_cap))[slot] = (uint16_t)owner;
 }
 
 // available_aircraft.pop(0) for one departing flight (network.py:118-126).
@@ -537,9 +579,11 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
         }
     }
 
-    // 3. pop_ready_to_depart_flights restricted to this origin (network.py:57-134)
-    const bool due = c.next_sched[a] <= t;
-    if (due || (flags & BA_AP_TRACK_T)) {
+    // 3. pop_ready_to_depart_flights restricted to this origin (network.py:57-134).
+    //    Airports without aircraft bookkeeping never cancel or delay: their departures
+    //    arrive through the static departure calendar (phase B) instead.
+    if (flags & BA_AP_TRACK_T) {
+        const bool due = c.next_sched[a] <= t;
         const uint32_t dep_cnt = c.s_depcnt[a], dep_off = c.s_depoff[a];
         const uint32_t nd = c.next_dep[a];
         uint32_t n_new = 0;
@@ -556,80 +600,65 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
             c.next_sched[a] = nxt;
         }
         const uint32_t k0 = dep_off + nd;
-        if (!(flags & BA_AP_TRACK_T)) {
-            // cancellation probability is exactly 0 and aircraft are never scarce
+        const uint32_t n_old = c.dl_tail[a] - c.dl_head[a];
+        const uint32_t n_ready = n_new + n_old;
+        if (n_ready) {
+            const float n_start = c.n_avail[a];
+            const float base = c.base[a];
+            float lp0 = 0.0f, lp1 = 0.0f, dl0 = 0.0f, dl1 = 0.0f, sg = 1.0f, dp_dn = 0.0f;
+            if (n_new) {
+                // network.py:80-84, fp32 in the reference's operation order
+                const float ratio = BA_DIV(n_start, (float)n_ready);
+                const float z = BA_MUL(10.0f, BA_ADD(ratio, -0.25f));
+                sg = 1.0f / (1.0f + BA_EXP(-z));
+                const float p = 1.0f - (1.0f - base) * sg;
+                lp0 = ba_relaxed_bernoulli_lp(p, 0.0f, &dl0);
+                lp1 = ba_relaxed_bernoulli_lp(p, 1.0f, &dl1);
+                // d p / d base = sg ; d p / d n = -(1-base) sg (1-sg) * 10 / n_ready
+                dp_dn = -(1.0f - base) * sg * (1.0f - sg) * 10.0f / (float)n_ready;
+            }
+            float g_p = 0.0f;          // sum over newly scored flights of d lp / d p
+            uint32_t first_delayed = n_new;
             for (uint32_t i = 0; i < n_new; ++i) {
                 const uint32_t k = k0 + i;
-                const uint32_t w = c.dep_word[k];
-                const uint32_t cobs = (w >> BA_DW_CANCEL_SHIFT) & 3u;
+                const uint32_t cobs = (c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u;
                 if (cobs == 3u) { acc.status |= BA_S_UNOBSERVED; continue; }
-                acc.lp += cobs ? c.c1_lp : c.c0_lp;
-                if (!cobs)
-                    ba_q_push(c, acc, a, BA_Q_DEP | (w & BA_DW_ENTRY_MASK),
-                              fmaxf(0.0f, c.dep_sched[k]), c.xdk[k], c.atk[k]);
+                acc.lp += cobs ? lp1 : lp0;
+                g_p += cobs ? dl1 : dl0;
+                if (cobs) continue;                       // cancelled -> completed
+                if (c.n_avail[a] <= 0.0f) {               // delayed (network.py:112-114)
+                    if (first_delayed == n_new) first_delayed = i;
+                    continue;
+                }
+                ba_depart_tracked(c, acc, a, A, k, t);
+            }
+            if (c.cancel_mode && c.want_grad && n_new) {
+                c.acc_bc[a] += g_p * sg * base;           // b = exp(c)
+                // n = exp(l) + integers: d n / d l = exp(l); multiplied in the epilogue
+                c.acc_ln0[a] += g_p * dp_dn;
+            }
+            // newly delayed flights go IN FRONT of the previously delayed ones
+            // (they precede them in the re-built pending list, network.py:60-68,112-114)
+            if (first_delayed < n_new) {
+                uint32_t hd = c.dl_head[a];
+                for (uint32_t i = n_new; i-- > first_delayed;) {
+                    const uint32_t k = k0 + i;
+                    if (((c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u) != 0u) continue;
+                    hd -= 1;
+                    c.dl[A->dl_off + (hd & A->dl_mask)] = k;      // dep-order position
+                }
+                c.dl_head[a] = hd;
+            } else {
+                // previously delayed flights, oldest first, while aircraft remain
+                uint32_t hd = c.dl_head[a];
+                const uint32_t tl = c.dl_tail[a];
+                while (hd != tl && c.n_avail[a] > 0.0f) {
+                    ba_depart_tracked(c, acc, a, A, c.dl[A->dl_off + (hd & A->dl_mask)], t);
+                    ++hd;
+                }
+                c.dl_head[a] = hd;
             }
             c.next_dep[a] = nd + n_new;
-        } else {
-            const uint32_t n_old = c.dl_tail[a] - c.dl_head[a];
-            const uint32_t n_ready = n_new + n_old;
-            if (n_ready) {
-                const float n_start = c.n_avail[a];
-                const float base = c.base[a];
-                float lp0 = 0.0f, lp1 = 0.0f, dl0 = 0.0f, dl1 = 0.0f, sg = 1.0f, dp_dn = 0.0f;
-                if (n_new) {
-                    // network.py:80-84, fp32 in the reference's operation order
-                    const float ratio = BA_DIV(n_start, (float)n_ready);
-                    const float z = BA_MUL(10.0f, BA_ADD(ratio, -0.25f));
-                    sg = 1.0f / (1.0f + BA_EXP(-z));
-                    const float p = 1.0f - (1.0f - base) * sg;
-                    lp0 = ba_relaxed_bernoulli_lp(p, 0.0f, &dl0);
-                    lp1 = ba_relaxed_bernoulli_lp(p, 1.0f, &dl1);
-                    // d p / d base = sg ; d p / d n = -(1-base) sg (1-sg) * 10 / n_ready
-                    dp_dn = -(1.0f - base) * sg * (1.0f - sg) * 10.0f / (float)n_ready;
-                }
-                float g_p = 0.0f;          // sum over newly scored flights of d lp / d p
-                uint32_t first_delayed = n_new;
-                for (uint32_t i = 0; i < n_new; ++i) {
-                    const uint32_t k = k0 + i;
-                    const uint32_t cobs = (c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u;
-                    if (cobs == 3u) { acc.status |= BA_S_UNOBSERVED; continue; }
-                    acc.lp += cobs ? lp1 : lp0;
-                    g_p += cobs ? dl1 : dl0;
-                    if (cobs) continue;                       // cancelled -> completed
-                    if (c.n_avail[a] <= 0.0f) {               // delayed (network.py:112-114)
-                        if (first_delayed == n_new) first_delayed = i;
-                        continue;
-                    }
-                    ba_depart_tracked(c, acc, a, A, k, t);
-                }
-                if (c.cancel_mode && c.want_grad && n_new) {
-                    c.acc_bc[a] += g_p * sg * base;           // b = exp(c)
-                    // n = exp(l) + integers: d n / d l = exp(l); multiplied in the epilogue
-                    c.acc_ln0[a] += g_p * dp_dn;
-                }
-                // newly delayed flights go IN FRONT of the previously delayed ones
-                // (they precede them in the re-built pending list, network.py:60-68,112-114)
-                if (first_delayed < n_new) {
-                    uint32_t hd = c.dl_head[a];
-                    for (uint32_t i = n_new; i-- > first_delayed;) {
-                        const uint32_t k = k0 + i;
-                        if (((c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u) != 0u) continue;
-                        hd -= 1;
-                        c.dl[A->dl_off + (hd & A->dl_mask)] = k;      // dep-order position
-                    }
-                    c.dl_head[a] = hd;
-                } else {
-                    // previously delayed flights, oldest first, while aircraft remain
-                    uint32_t hd = c.dl_head[a];
-                    const uint32_t tl = c.dl_tail[a];
-                    while (hd != tl && c.n_avail[a] > 0.0f) {
-                        ba_depart_tracked(c, acc, a, A, c.dl[A->dl_off + (hd & A->dl_mask)], t);
-                        ++hd;
-                    }
-                    c.dl_head[a] = hd;
-                }
-                c.next_dep[a] = nd + n_new;
-            }
         }
     }
 
@@ -652,32 +681,33 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
         float lo = c.asg_lo[a], hi = c.asg_hi[a], wait = c.w_head[a];
         double psum = c.psum[a];
         while (head != tail) {
-            const uint32_t hidx = qoff + (head & qmask);
+            const uint32_t *e = c.qe + BA_Q_WORDS * (qoff + (head & qmask));
+            const BaPairU wl = BA_LD_PAIR(BaPairU, e);          // word, lo
             if (isnan(hi)) {
                 // _assign_service_time (airport.py:130-158)
-                psum += (double)c.qx[hidx];
-                const float pj = c.qp[hidx];
-                const double R = psum - (double)pj;
-                const double A = (double)c.qs[hidx] + R;
-                const double n = (double)(head - c.ql[hidx] + 1u);
-                const double B = 3.0 * 5.9604644775390625e-08 * (n * R + (double)fabsf(pj) + fabs(A)) + 1e-30;
-                lo = (float)(A - B); hi = (float)(A + B);
+                const BaPairF sp = BA_LD_PAIR(BaPairF, e + 2);  // queue start, psum at joining
+                psum += (double)BA_LD_PAIR(BaPairF, e + 4).a;
+                const double R = psum - (double)sp.b;
+                const double A_ = (double)sp.a + R;
+                const double n = (double)(head - wl.b + 1u);
+                const double B = 3.0 * 5.9604644775390625e-08 * (n * R + (double)fabsf(sp.b) + fabs(A_)) + 1e-30;
+                lo = (float)(A_ - B); hi = (float)(A_ + B);
                 wait = (float)R;
                 if (c.replay_always) lo = -INFINITY, hi = INFINITY;
             }
             if (!(hi <= t)) {
                 if (lo > t || isnan(lo)) break;             // certainly still being served
                 // ambiguous: replay the reference's arithmetic exactly
-                const uint32_t first = c.ql[hidx];
-                if (tail - first > qmask + 1u) { acc.status |= BA_S_OVERFLOW; break; }
+                if (tail - wl.b > qmask + 1u) { acc.status |= BA_S_OVERFLOW; break; }
                 float w = 0.0f;
-                for (uint32_t j = first; j != head + 1u; ++j) w = BA_ADD(w, c.qx[qoff + (j & qmask)]);
+                for (uint32_t j = wl.b; j != head + 1u; ++j)
+                    w = BA_ADD(w, BA_LD_PAIR(BaPairF, c.qe + BA_Q_WORDS * (qoff + (j & qmask)) + 4).a);
                 wait = w;
-                lo = hi = BA_ADD(c.qs[hidx], w);
+                lo = hi = BA_ADD(BA_LD_PAIR(BaPairF, e + 2).a, w);
                 if (!(hi <= t)) break;
             }
             // served (airport.py:111-126)
-            const uint32_t word = c.qf[hidx];
+            const uint32_t word = wl.a;
             const int f = (int)(word & BA_FID_MASK);
             if (word & BA_Q_DEP) {
                 c.wd[f] = wait;
@@ -686,23 +716,19 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 const uint32_t key = ((uint32_t)tick << BA_KEY_TICK_SHIFT) | (uint32_t)a;
                 const uint32_t seq = c.dep_pops[a];
                 c.dep_pops[a] = seq + 1;
-                const float av = c.qy[hidx];
+                const float av = BA_LD_PAIR(BaPairF, e + 4).b;
                 if (av <= t) {
                     // already past its arrival time: joins the destination queue at the
                     // end of this very tick (update_in_transit_flights, network.py:186)
-                    const uint32_t slot = BA_ATOMIC_INC(&c.cta[0]);
-                    if (slot >= c.due_cap) acc.status |= BA_S_OVERFLOW;
-                    else {
-                        c.due_w[slot] = word & BA_DW_ENTRY_MASK; c.due_key[slot] = key;
-                        c.due_seq[slot] = seq; c.due_av[slot] = av; c.due_x[slot] = c.xaf[f];
-                    }
+                    ba_due_append(c, acc, tick & 1, word & BA_FID_MASK, key,
+                                  (word >> BA_Q_DST_SHIFT) & 0xFFFu, seq, av, c.xaf[f], 0.0f);
                 } else {
                     c.popkey[f] = key; c.popseq[f] = seq;
-                    BA_ATOMIC_INC(&c.cta[1]);
                 }
                 if (c.pop_tick) c.pop_tick[2 * f] = tick;
             } else {
                 c.wa[f] = wait;
+                c.arr_pops[a] += 1;
                 // _assign_turnaround_time (airport.py:210-221)
                 if (flags & BA_AP_TRACK_T) {
                     const uint32_t n = c.turn_n[a];
@@ -721,19 +747,32 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
 }
 
 // ---------------------------------------------------------------------------
-// PROLOGUE, calendar construction (after every flight's arrival tick is counted):
-//   ba_calendar_scan     exclusive prefix over the bucket counts (one thread)
+// PROLOGUE, arrival-calendar construction (after every flight's arrival tick is counted):
+//   ba_calendar_scan     exclusive prefix over the bucket counts, by one warp
+//                        (`lane` = 0..31; the host emulation passes lane = -1: serial)
 //   ba_calendar_scatter  one flight: write its record into its bucket
 // Afterwards cal_cnt[k] is the END offset of bucket k (= start of bucket k+1).
 // ---------------------------------------------------------------------------
-BA_DEV void ba_calendar_scan(BaCtx &c)
+BA_DEV void ba_calendar_scan(BaCtx &c, int lane)
 {
-    uint32_t run = 0;
-    for (uint32_t k = 0; k < c.cal_cap; ++k) {
-        const uint32_t n = c.cal_cnt[k];
-        c.cal_cnt[k] = run;
-        run += n;
+#if defined(__CUDA_ARCH__)
+    const uint32_t per = (c.cal_cap + 31u) / 32u;
+    const uint32_t b = (uint32_t)lane * per, e = min(b + per, c.cal_cap);
+    uint32_t sum = 0;
+    for (uint32_t k = b; k < e; ++k) sum += c.cal_cnt[k];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
+    uint32_t run = incl - sum;
+    for (uint32_t k = b; k < e; ++k) { const uint32_t n = c.cal_cnt[k]; c.cal_cnt[k] = run; run += n; }
+#else
+    (void)lane;
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < c.cal_cap; ++k) { const uint32_t n = c.cal_cnt[k]; c.cal_cnt[k] = run; run += n; }
+#endif
 }
 
 BA_DEV void ba_calendar_scatter(BaCtx &c, int f)
@@ -748,74 +787,119 @@ BA_DEV void ba_calendar_scatter(BaCtx &c, int f)
 }
 
 // ---------------------------------------------------------------------------
-// SCAN, phase B: one calendar record (call for i in this tick's slice).  A flight whose
-// departure has been served moves to the due buffer; one whose departure is still
-// queued is skipped -- phase A will hand it over itself when it is served.
+// SCAN, phase B (flight-parallel).
+//   ba_phase_b_arrival    one record of this tick's arrival-calendar slice: a flight whose
+//       departure has been served moves to the due buffer; one whose departure is still
+//       queued is skipped -- phase A hands it over itself when it is served.
+//   ba_phase_b_departure  one record of NEXT tick's departure-calendar slice: the flight
+//       becomes ready at the next tick (network.py:60-68) at an airport that can neither
+//       cancel nor delay it; it joins its origin's runway queue behind this tick's
+//       arrivals (model.py:181-183), i.e. with a key above every arrival key.
 // ---------------------------------------------------------------------------
-BA_DEV void ba_phase_b_record(BaCtx &c, BaAcc &acc, uint32_t i)
+BA_DEV void ba_phase_b_arrival(BaCtx &c, BaAcc &acc, uint32_t i, int parity)
 {
     const uint32_t word = c.cal[3 * i];
     const int f = (int)(word & BA_FID_MASK);
     const uint32_t key = c.popkey[f];
     if (key == BA_KEY_INVALID) return;
-    const uint32_t slot = BA_ATOMIC_INC(&c.cta[0]);
-    if (slot >= c.due_cap) { acc.status |= BA_S_OVERFLOW; return; }
-    c.due_w[slot] = word; c.due_key[slot] = key; c.due_seq[slot] = c.popseq[f];
-    c.due_av[slot] = __uint_as_float_portable(c.cal[3 * i + 1]);
-    c.due_x[slot] = __uint_as_float_portable(c.cal[3 * i + 2]);
     c.popkey[f] = BA_KEY_INVALID;          // consumed
-    BA_ATOMIC_DEC(&c.cta[1]);
+    ba_due_append(c, acc, parity, word & BA_FID_MASK, key, (word >> BA_Q_DST_SHIFT) & 0xFFFu,
+                  c.popseq[f], __uint_as_float_portable(c.cal[3 * i + 1]),
+                  __uint_as_float_portable(c.cal[3 * i + 2]), 0.0f);
+}
+
+BA_DEV void ba_phase_b_departure(BaCtx &c, BaAcc &acc, uint32_t i, int parity)
+{
+    const uint32_t rec = c.dcal_rec[2 * i], origin = c.dcal_rec[2 * i + 1];
+    const uint32_t k = rec & BA_FID_MASK, rank = rec >> 18;
+    const uint32_t w = c.dep_word[k];
+    ba_due_append(c, acc, parity, BA_Q_DEP | (w & BA_DW_ENTRY_MASK), BA_KEY_DEPARTURE | rank,
+                  origin, 0u, fmaxf(0.0f, c.dep_sched[k]), c.xdk[k], c.atk[k]);
 }
 
 // ---------------------------------------------------------------------------
-// SCAN, phase C: destination runway queues <- due buffer, in in-transit list order.
-//   step 1 (one thread per due entry): rank among the entries of the same destination
-//           by (tick, origin, sequence); remember the target slot.
-//   step 2 (after a barrier): write the entry; the last of each destination moves the tail.
+// SCAN, phase C (owner pull): airport `a` appends the due entries addressed to it to its
+// runway queue, in key order = the reference's in-transit list order restricted to this
+// destination (model.py:186-196, network.py:186-191), then the newly ready departures in
+// pending order.  Runs at the start of the next tick's interval, before phase A.
 // ---------------------------------------------------------------------------
-BA_DEV void ba_phase_c_rank(BaCtx &c, BaAcc &acc, uint32_t i, uint32_t n_due)
+BA_DEV uint64_t ba_due_order(const uint32_t *de)
 {
-    const uint32_t word = c.due_w[i];
-    const uint32_t dst = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
-    const uint32_t key = c.due_key[i], seq = c.due_seq[i];
-    uint32_t rank = 0, cnt = 0;
-    for (uint32_t j = 0; j < n_due; ++j) {
-        const uint32_t wj = c.due_w[j];
-        if (((wj >> BA_Q_DST_SHIFT) & 0xFFFu) != dst) continue;
-        ++cnt;
-        const uint32_t kj = c.due_key[j];
-        if (kj < key || (kj == key && c.due_seq[j] < seq)) ++rank;
-    }
-    const uint32_t head = c.q_head[dst], tail = c.q_tail[dst], mask = c.s_qmask[dst];
-    uint32_t target = 0xFFFFFFFFu;
-    if (tail + cnt - head > mask + 1u) acc.status |= BA_S_OVERFLOW;
-    else target = c.s_qoff[dst] + ((tail + rank) & mask);
-    c.due_tgt[i] = target;
-    c.due_cnt[i] = (rank + 1 == cnt) ? cnt : 0u;
+    return ((uint64_t)de[1] << 16) | (uint64_t)(de[2] & 0xFFFFu);
 }
 
-BA_DEV void ba_phase_c_push(BaCtx &c, uint32_t i)
+BA_DEV void ba_due_push(BaCtx &c, BaAcc &acc, int a, const uint32_t *de)
 {
-    const uint32_t target = c.due_tgt[i];
-    if (target == 0xFFFFFFFFu) return;
-    const uint32_t word = c.due_w[i];
-    const uint32_t dst0 = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
-    c.qf[target] = word & BA_FID_MASK;            // arrival entry: no DEP flag
-    c.qs[target] = c.due_av[i]; c.qx[target] = c.due_x[i]; c.qy[target] = 0.0f;
-    c.qp[target] = (float)c.psum[dst0];
-    c.ql[target] = c.q_head[dst0] + (isnan(c.asg_hi[dst0]) ? 0u : 1u);
-    const uint32_t cnt = c.due_cnt[i];
-    if (cnt) {
-        const uint32_t dst = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
-        c.q_tail[dst] = c.q_tail[dst] + cnt;
+    const BaPairF xy = BA_LD_PAIR(BaPairF, de + 4);
+    ba_q_push(c, acc, a, de[0], __uint_as_float_portable(de[3]), xy.a, xy.b);
+}
+
+BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_due)
+{
+    const uint32_t *due = c.due_base + (uint32_t)parity * c.due_stride;
+    uint64_t m0 = 0, m1 = 0;
+    if (n_due <= 128u) {
+        // owners are packed u16, eight per 16-byte load (broadcast: every lane of the warp
+        // reads the same words)
+        const uint32_t *ow = due + BA_DUE_WORDS * c.due_cap;
+        const uint32_t aa = (uint32_t)a | ((uint32_t)a << 16);
+        const uint32_t groups = (n_due + 7u) >> 3;
+        for (uint32_t g = 0; g < groups; ++g) {
+            uint32_t w0 = ow[4 * g], w1 = ow[4 * g + 1], w2 = ow[4 * g + 2], w3 = ow[4 * g + 3];
+            // per-halfword equality -> one bit per entry
+            uint32_t bits = 0;
+            uint32_t x;
+            x = w0 ^ aa; bits |= ((x & 0xFFFFu) == 0u) | (((x >> 16) == 0u) << 1);
+            x = w1 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 2) | (((x >> 16) == 0u) << 3);
+            x = w2 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 4) | (((x >> 16) == 0u) << 5);
+            x = w3 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 6) | (((x >> 16) == 0u) << 7);
+            const uint32_t left = n_due - 8u * g;
+            if (left < 8u) bits &= (1u << left) - 1u;
+            if (g < 8u) m0 |= (uint64_t)bits << (8u * g); else m1 |= (uint64_t)bits << (8u * (g - 8u));
+        }
+    }
+    if (n_due <= 128u) {
+        while (m0 | m1) {
+            uint64_t best = ~0ull; uint32_t bj = 0;
+            for (uint64_t m = m0; m; m &= m - 1) {
+                const uint32_t j = (uint32_t)ba_ctz64(m);
+                const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
+                if (o < best) { best = o; bj = j; }
+            }
+            for (uint64_t m = m1; m; m &= m - 1) {
+                const uint32_t j = 64u + (uint32_t)ba_ctz64(m);
+                const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
+                if (o < best) { best = o; bj = j; }
+            }
+            ba_due_push(c, acc, a, due + BA_DUE_WORDS * bj);
+            if (bj < 64u) m0 &= ~(1ull << bj); else m1 &= ~(1ull << (bj - 64u));
+        }
+        return;
+    }
+    // general case (exact variant, pathological ticks): repeated selection
+    uint64_t last = 0; bool first = true;
+    for (;;) {
+        uint64_t best = ~0ull; uint32_t bj = 0xFFFFFFFFu;
+        for (uint32_t j = 0; j < n_due; ++j) {
+            const uint32_t *de = due + BA_DUE_WORDS * j;
+            if ((de[2] >> 16) != (uint32_t)a) continue;
+            const uint64_t o = ba_due_order(de);
+            if ((first || o > last) && o < best) { best = o; bj = j; }
+        }
+        if (bj == 0xFFFFFFFFu) break;
+        ba_due_push(c, acc, a, due + BA_DUE_WORDS * bj);
+        last = best; first = false;
     }
 }
 
-// Does this airport still hold work (completion vote, network.py:34-41)?
+// Does this airport still hold work (completion vote, network.py:34-41)?  Every flight
+// that is not observed as cancelled eventually lands here, so "in transit or queued
+// somewhere" is "not yet landed at its destination".
 BA_DEV bool ba_airport_busy(const BaCtx &c, int a)
 {
-    return c.q_head[a] != c.q_tail[a] || c.next_dep[a] < c.s_depcnt[a] ||
-           c.dl_head[a] != c.dl_tail[a];
+    return c.q_head[a] != c.q_tail[a] || c.arr_pops[a] < c.s_arrcnt[a] ||
+           ((c.s_flags[a] & BA_AP_TRACK_T) &&
+            (c.next_dep[a] < c.s_depcnt[a] || c.dl_head[a] != c.dl_tail[a]));
 }
 
 // ---------------------------------------------------------------------------
@@ -834,11 +918,14 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
     const BaFlight fl = ba_flight(c, f);
     const uint32_t cobs = (fl.od >> 24) & 3u;
     const int k = c.pos_dep[f];
+    const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
+    // *_cancelled (network.py:100-109) at an airport whose cancellation probability is
+    // exactly 0 (ba_plan.h: BA_SIMPLE_RATIO); other airports score it in the scan
+    if (!(c.s_flags[o] & BA_AP_TRACK_T)) acc.lp += (double)(cobs == 1u ? c.c1_lp : c.c0_lp);
     if (cobs == 1u) {                 // observed as cancelled: never queued anywhere
         if (c.want_grad) { c.xdk[k] = 0.0f; c.ct[k] = 0.0f; c.atk[f] = 0.0f; }
         return;
     }
-    const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
     const int j = c.pos_arr[f];
     const BaNoise4 nz = ba_noise(c, f);
     const int rid = c.route[f];

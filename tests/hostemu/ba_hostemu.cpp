@@ -93,40 +93,46 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     for (int f = 0; f < day.F; ++f) forder[f] = f;
     if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
     for (int f : forder) ba_prologue_flight(c, acc[f % N], f);
-    ba_calendar_scan(c);
+    ba_calendar_scan(c, -1);
     if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
     for (int f : forder) ba_calendar_scatter(c, f);
     std::vector<int> order(N);
     for (int i = 0; i < N; ++i) order[i] = i;
-    float t = day.t_before_first;
+    float t = 0.0f;
     int tick = day.first_tick - 1;
+    auto departures_of = [&](int k, int parity) {
+        if (k > day.last_ready_tick) return;
+        std::vector<uint32_t> sl;
+        for (int i = day.dcal_off[k]; i < day.dcal_off[k + 1]; ++i) sl.push_back((uint32_t)i);
+        if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
+        for (uint32_t i : sl) ba_phase_b_departure(c, acc[i % N], i, parity);
+    };
+    departures_of(tick + 1, tick & 1);
     bool busy = day.F > 0;
     uint32_t st = 0;
     while (busy) {
         if (tick >= plan.max_ticks) { st |= BA_S_TICK_CAP; break; }
         ++tick;
         t = c.tick_time[tick];
+        const int prev = (tick - 1) & 1, cur = tick & 1;
+        uint32_t n_due = c.cta[prev];
+        if (n_due > c.due_cap) n_due = c.due_cap;
+        bool more = tick < day.last_ready_tick;
         if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
-        for (int i = 0; i < N; ++i)
-            ba_phase_a<EXACT>(c, acc[order[i]], day.lane_airport[order[i]], t, tick);
+        for (int i = 0; i < N; ++i) {
+            const int a = day.lane_airport[order[i]];
+            if (n_due) ba_phase_c_pull(c, acc[order[i]], a, prev, n_due);
+            ba_phase_a<EXACT>(c, acc[order[i]], a, t, tick);
+            more |= ba_airport_busy(c, a);
+        }
+        c.cta[prev] = 0;
         if ((uint32_t)tick < c.cal_cap) {
             std::vector<uint32_t> slice;
             for (uint32_t i = c.cal_cnt[tick - 1]; i < c.cal_cnt[tick]; ++i) slice.push_back(i);
             if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
-            for (uint32_t i : slice) ba_phase_b_record(c, acc[i % N], i);
+            for (uint32_t i : slice) ba_phase_b_arrival(c, acc[i % N], i, cur);
         }
-        uint32_t n_due = c.cta[0];
-        if (n_due > c.due_cap) n_due = c.due_cap;
-        bool more = n_due != 0 || c.cta[1] != 0;
-        for (int a = 0; a < N; ++a) more |= ba_airport_busy(c, a);
-        if (n_due) {
-            for (uint32_t i = 0; i < n_due; ++i) ba_phase_c_rank(c, acc[i % N], i, n_due);
-            std::vector<uint32_t> dord(n_due);
-            for (uint32_t i = 0; i < n_due; ++i) dord[i] = i;
-            if (shuffle_seed) std::shuffle(dord.begin(), dord.end(), rng);
-            for (uint32_t i : dord) ba_phase_c_push(c, i);
-            c.cta[0] = 0;
-        }
+        departures_of(tick + 1, cur);
         busy = more;
     }
     for (int f = 0; f < day.F; ++f) ba_epilogue_flight(c, acc[f % N], f);
