@@ -141,8 +141,9 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         int b = std::atoi(e);
         if (b >= 32 && b <= 1024 && b % 32 == 0) pl->block = b;
     }
-    pl->smem_fast = ba_forward_smem_bytes(N, pl->host.smem_list_words, false);
-    pl->smem_exact = ba_forward_smem_bytes(N, 0, true);
+    const bool tracked = pl->host.view.any_track != 0;
+    pl->smem_fast = ba_forward_smem_bytes(N, pl->host.smem_list_words, false, tracked);
+    pl->smem_exact = ba_forward_smem_bytes(N, 0, true, tracked);
     int max_optin = 0;
     BA_PCUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (pl->smem_exact > (size_t)max_optin) {

@@ -26,9 +26,15 @@ int ba_forward_block_threads(int n_airports)
     return t;
 }
 
-size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact)
+static __host__ __device__ size_t ba_state_words(int n_airports, bool tracked)
 {
-    size_t w = (((size_t)BA_NWORDS_STATE * n_airports + 3) & ~(size_t)3) + BA_RED_WORDS + BA_CTA_WORDS;
+    const size_t per = tracked ? BA_NWORDS_STATE_TRACK : BA_NWORDS_STATE_SIMPLE;
+    return (per * (size_t)n_airports + 3) & ~(size_t)3;
+}
+
+size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bool tracked)
+{
+    size_t w = ba_state_words(n_airports, tracked) + BA_RED_WORDS + BA_CTA_WORDS;
     // list_words = 6 words per queue entry; plus calendar counters and the due buffer
     if (!exact) w += list_words + BA_KCAL + 2 * BA_DUE_WORDS * BA_DUE_CAP_S + 2 * (BA_DUE_CAP_S / 2);
     return w * 4;
@@ -50,13 +56,13 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
     const int N = plan.N, D = plan.D, C = plan.C, R = plan.R;
 
     uint32_t *state_w = smem;
-    uint32_t *red = smem + (((size_t)BA_NWORDS_STATE * N + 3) & ~(size_t)3);  // [BA_RED_WORDS], 16 B aligned
+    uint32_t *red = smem + ba_state_words(N, plan.any_track != 0);       // [BA_RED_WORDS], 16 B aligned
     uint32_t *ctaw = red + BA_RED_WORDS;                     // [BA_CTA_WORDS]
     uint32_t *pool = ctaw + BA_CTA_WORDS;                    // shared list structures (fast)
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
 
     BaCtx c;
-    ba_carve_state(c, state_w, N);
+    ba_carve_state(c, state_w, N, plan.any_track != 0);
     c.sigma = prm.scales[0]; c.v_t = prm.scales[1]; c.v_u = prm.scales[2];
     c.inv_sigma = 1.0f / c.sigma;
     c.inv_sigma2 = c.inv_sigma * c.inv_sigma;

@@ -96,6 +96,7 @@ struct BaDayView {
 struct BaPlanView {
     int32_t D, N, Fmax, R, C;         // days, airports, max flights, routes, latent rows
     int32_t include_cancellations;
+    int32_t any_track;                // some airport of some day tracks aircraft
     int32_t max_ticks;
     float delta_t, max_t;
     int32_t grad_stride;              // C*N + R + 3

@@ -283,6 +283,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
     P.D = n_days; P.N = N; P.Fmax = Fmax; P.R = R;
     P.C = include_cancellations ? 4 : 2;
     P.include_cancellations = include_cancellations ? 1 : 0;
+    P.any_track = 0;
+    for (int d = 0; d < n_days; ++d) P.any_track |= (int32_t)out->days[d].view.any_track_t;
     P.max_ticks = max_ticks; P.delta_t = delta_t; P.max_t = max_t;
     P.grad_stride = P.C * N + R + 3;
     P.days = out->day_views.data();

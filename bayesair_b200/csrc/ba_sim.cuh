@@ -251,27 +251,34 @@ struct BaAcc {
     uint32_t status;
 };
 
-#define BA_NWORDS_STATE 34        // per-airport words of shared state (see ba_carve_state)
+#define BA_NWORDS_STATE_SIMPLE 20 // per-airport words of shared state, no aircraft bookkeeping
+#define BA_NWORDS_STATE_TRACK 36  // ... when some airport of the plan tracks aircraft
 #define BA_Q_WORDS 6              // words per runway-queue entry
 #define BA_CTA_WORDS 4            // CTA-wide scalars
 
-// Assigns the per-airport arrays out of one contiguous word buffer.
-BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N)
+// Assigns the per-airport arrays out of one contiguous word buffer.  The arrays that only
+// airports with aircraft bookkeeping touch exist only when the plan has such airports.
+BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N, bool tracked)
 {
     float *f = (float *)w;
-    c.m = f + 0 * N; c.rate = f + 1 * N; c.lograte = f + 2 * N; c.mt = f + 3 * N;
-    c.tstd = f + 4 * N; c.logtstd = f + 5 * N; c.base = f + 6 * N; c.n_avail = f + 7 * N;
-    c.n0 = f + 8 * N; c.w_head = f + 9 * N; c.next_sched = f + 10 * N;
-    c.acc_ln0 = f + 11 * N; c.acc_bc = f + 12 * N;
-    c.next_dep = w + 13 * N; c.q_head = w + 14 * N; c.q_tail = w + 15 * N;
-    c.dep_pops = w + 16 * N; c.turn_n = w + 17 * N;
-    c.av_head = w + 18 * N; c.av_tail = w + 19 * N; c.zeros_left = w + 20 * N;
-    c.dl_head = w + 21 * N; c.dl_tail = w + 22 * N;
-    c.s_flags = w + 23 * N; c.s_qoff = w + 24 * N; c.s_qmask = w + 25 * N;
-    c.s_depoff = w + 26 * N; c.s_depcnt = w + 27 * N;
-    c.asg_lo = f + 28 * N; c.asg_hi = f + 29 * N;
-    c.psum = (double *)(w + 30 * N);       // 30 N words: always 8-byte aligned
-    c.arr_pops = w + 32 * N; c.s_arrcnt = w + 33 * N;
+    c.psum = (double *)w;                      // 2 N words, 8-byte aligned
+    c.m = f + 2 * N; c.rate = f + 3 * N; c.lograte = f + 4 * N; c.mt = f + 5 * N;
+    c.tstd = f + 6 * N; c.logtstd = f + 7 * N; c.w_head = f + 8 * N;
+    c.asg_lo = f + 9 * N; c.asg_hi = f + 10 * N;
+    c.q_head = w + 11 * N; c.q_tail = w + 12 * N; c.dep_pops = w + 13 * N;
+    c.arr_pops = w + 14 * N; c.s_flags = w + 15 * N; c.s_qoff = w + 16 * N;
+    c.s_qmask = w + 17 * N; c.s_arrcnt = w + 18 * N; c.next_sched = f + 19 * N;
+    if (tracked) {
+        c.base = f + 20 * N; c.n_avail = f + 21 * N; c.n0 = f + 22 * N;
+        c.acc_ln0 = f + 23 * N; c.acc_bc = f + 24 * N;
+        c.next_dep = w + 25 * N; c.turn_n = w + 26 * N; c.av_head = w + 27 * N;
+        c.av_tail = w + 28 * N; c.zeros_left = w + 29 * N; c.dl_head = w + 30 * N;
+        c.dl_tail = w + 31 * N; c.s_depoff = w + 32 * N; c.s_depcnt = w + 33 * N;
+    } else {
+        c.base = c.n_avail = c.n0 = c.acc_ln0 = c.acc_bc = nullptr;
+        c.next_dep = c.turn_n = c.av_head = c.av_tail = c.zeros_left = nullptr;
+        c.dl_head = c.dl_tail = c.s_depoff = c.s_depcnt = nullptr;
+    }
 }
 
 // Words of shared memory the list structures of the fast variant need.
@@ -361,31 +368,34 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     const float tstd = BA_MUL(c.v_u, mt);        // model.py:143-145
     c.rate[a] = rate; c.tstd[a] = tstd;
     c.lograte[a] = BA_LOG(rate); c.logtstd[a] = BA_LOG(tstd);
-    float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
-    if (c.cancel_mode) {
-        n0 = BA_EXP(lat_airport[2 * Ng + g]);    // model.py:91-99
-        base = BA_EXP(lat_airport[3 * Ng + g]);  // model.py:103-111
-    }
-    c.base[a] = base;
-    c.n_avail[a] = n0;
-    c.n0[a] = n0;
-    // while i < n0: append(0.0)  -> ceil(n0) zero-time aircraft (model.py:152-155)
-    uint32_t nz = 0;
-    if (n0 > 0.0f) {
-        float cz = ceilf(n0);
-        nz = cz > 4.0e9f ? 4000000000u : (uint32_t)cz;
-    }
-    c.zeros_left[a] = nz;
     c.asg_lo[a] = NAN; c.asg_hi[a] = NAN; c.w_head[a] = 0.0f; c.psum[a] = 0.0;
     c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
-    c.acc_ln0[a] = 0.0f; c.acc_bc[a] = 0.0f;
-    c.next_dep[a] = 0; c.q_head[a] = 0; c.q_tail[a] = 0; c.dep_pops[a] = 0; c.arr_pops[a] = 0;
-    c.turn_n[a] = 0; c.av_head[a] = 0; c.av_tail[a] = 0; c.dl_head[a] = 0; c.dl_tail[a] = 0;
+    c.q_head[a] = 0; c.q_tail[a] = 0; c.dep_pops[a] = 0; c.arr_pops[a] = 0;
+    if (c.n_avail) {
+        float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
+        if (c.cancel_mode) {
+            n0 = BA_EXP(lat_airport[2 * Ng + g]);    // model.py:91-99
+            base = BA_EXP(lat_airport[3 * Ng + g]);  // model.py:103-111
+        }
+        c.base[a] = base;
+        c.n_avail[a] = n0;
+        c.n0[a] = n0;
+        // while i < n0: append(0.0)  -> ceil(n0) zero-time aircraft (model.py:152-155)
+        uint32_t nz = 0;
+        if (n0 > 0.0f) {
+            float cz = ceilf(n0);
+            nz = cz > 4.0e9f ? 4000000000u : (uint32_t)cz;
+        }
+        c.zeros_left[a] = nz;
+        c.acc_ln0[a] = 0.0f; c.acc_bc[a] = 0.0f;
+        c.next_dep[a] = 0;
+        c.turn_n[a] = 0; c.av_head[a] = 0; c.av_tail[a] = 0; c.dl_head[a] = 0; c.dl_tail[a] = 0;
+        c.s_depoff[a] = (uint32_t)A.dep_off;
+        c.s_depcnt[a] = (uint32_t)A.dep_cnt;
+    }
     c.s_flags[a] = A.flags;
     c.s_qoff[a] = EXACT ? A.q_off_x : A.q_off_s;
     c.s_qmask[a] = EXACT ? A.q_mask_x : A.q_mask_s;
-    c.s_depoff[a] = (uint32_t)A.dep_off;
-    c.s_depcnt[a] = (uint32_t)A.dep_cnt;
     c.s_arrcnt[a] = (uint32_t)A.arr_cnt;
 }
 
@@ -689,10 +699,13 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 psum += (double)BA_LD_PAIR(BaPairF, e + 4).a;
                 const double R = psum - (double)sp.b;
                 const double A_ = (double)sp.a + R;
-                const double n = (double)(head - wl.b + 1u);
-                const double B = 3.0 * 5.9604644775390625e-08 * (n * R + (double)fabsf(sp.b) + fabs(A_)) + 1e-30;
-                lo = (float)(A_ - B); hi = (float)(A_ + B);
                 wait = (float)R;
+                // margin in fp32: 4u (n R + |pj| + |A|) covers the three bounds above plus the
+                // roundings of this very computation
+                const float Af = (float)A_;
+                const float Bf = 2.384185791015625e-07f *
+                    ((float)(head - wl.b + 1u) * wait + fabsf(sp.b) + fabsf(Af)) + 1e-30f;
+                lo = Af - Bf; hi = Af + Bf;
                 if (c.replay_always) lo = -INFINITY, hi = INFINITY;
             }
             if (!(hi <= t)) {

@@ -35,9 +35,9 @@ UNIT = "particle-days/s"
 WORKLOADS = {
     # BASELINE.json configs[2] (the north star's stated target size): full WN network,
     # Dec 21-30 2022 meltdown flight counts, 4096 particles x 10 days
-    "cfg3": (100, [3876, 3876, 3876, 3200, 3552, 3876, 3876, 3876, 3876, 3876], 4096, 0.02),
+    "cfg3": (100, [3876, 3876, 3876, 3200, 3552, 3876, 3876, 3876, 3876, 3876], 4096, 0.012),
     # configs[1]: full WN network, one day, 1024 particles
-    "cfg2": (100, [3876], 1024, 0.02),
+    "cfg2": (100, [3876], 1024, 0.012),
     # configs[0]: top-10 airports, one day (the reference's own CPU-runnable case)
     "cfg1": (10, [480], 1024, 0.03),
     # configs[4] scaled to fit a quick run: 500 airports, 20k flights/day, 4 days

@@ -50,13 +50,13 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
 {
     (void)P;
     const int N = plan.N, C = plan.C, R = plan.R, D = plan.D;
-    std::vector<uint32_t> state((size_t)BA_NWORDS_STATE * N, 0);
+    std::vector<uint32_t> state((size_t)BA_NWORDS_STATE_TRACK * N + 8, 0);
     std::vector<uint32_t> pool(ba_shared_list_words(day.q_total_s) + 8, 0);
     std::vector<uint32_t> gs(ba_scratch_words(day, true, plan.max_ticks) + 8, 0);
     uint32_t ctaw[BA_CTA_WORDS] = {0, 0, 0, 0};
     BaCtx c;
     memset(&c, 0, sizeof(c));
-    ba_carve_state(c, state.data(), N);
+    ba_carve_state(c, (uint32_t *)(((uintptr_t)state.data() + 7) & ~(uintptr_t)7), N, plan.any_track != 0);
     c.sigma = scales[0]; c.v_t = scales[1]; c.v_u = scales[2];
     c.inv_sigma = 1.0f / c.sigma; c.inv_sigma2 = c.inv_sigma * c.inv_sigma;
     c.inv_sigma3 = c.inv_sigma2 * c.inv_sigma; c.log_sigma = logf(c.sigma);
