@@ -1,0 +1,52 @@
+"""Multi-GPU plumbing: shard particles across ranks, all-reduce guide gradients.
+
+Particle-days are independent given a particle's latents (the reference re-initialises
+every airport per day, ``bayes_air/model.py:126-155``), so the simulation itself needs no
+collective: rank ``r`` runs a contiguous slice of the particles over all days.  The only
+exchange per optimisation step is one flat ``all_reduce(SUM)`` of the guide-parameter
+gradients (the reference has no distributed code at all; its only parallelism is one
+process per seed, ``scripts/wn/experiments.sh:3-13``).  One process per GPU, NCCL over
+NVLink/NVSwitch in production; the same code runs over gloo on CPU in the tests.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_particles(n_particles: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous, balanced slice ``(start, count)`` of ``n_particles`` for ``rank``."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(n_particles, world_size)
+    count = base + (1 if rank < extra else 0)
+    start = rank * base + min(rank, extra)
+    return start, count
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], extra: Optional[torch.Tensor] = None,
+                        group=None, average: bool = False) -> Optional[torch.Tensor]:
+    """Sums ``p.grad`` of every parameter (and ``extra``, e.g. the scalar loss or the three
+    noise-scale gradients) over all ranks with ONE collective on one flat fp32 buffer."""
+    plist: List[torch.nn.Parameter] = [p for p in params if p.grad is not None]
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return extra
+    chunks = [p.grad.reshape(-1) for p in plist]
+    if extra is not None:
+        chunks.append(extra.reshape(-1).to(chunks[0].dtype if chunks else extra.dtype))
+    flat = torch.cat(chunks) if chunks else None
+    if flat is None:
+        return extra
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat /= dist.get_world_size(group)
+    off = 0
+    for p in plist:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+    if extra is not None:
+        return flat[off:].view_as(extra).clone()
+    return None

@@ -183,3 +183,38 @@ def test_clock_matches_torch_inplace_add():
         c = np.float32(c + np.float32(0.2))
         assert float(t) == float(c)
     assert abs(float(c) - 80.0) > 1e-5     # i.e. NOT k * dt
+
+
+# ------------------------------------------------------ batched objective ---
+def test_latent_layout_and_priors_match_reference_sites():
+    """map_to_latents follows scripts/wn/train.py:244-297 and prior_log_prob equals the sum
+    of the model's global-site priors (bayes_air/model.py:58-113)."""
+    from bayesair_b200.objective import map_to_latents, n_latent, prior_log_prob
+    N, P = 5, 3
+    for canc in (False, True):
+        torch.manual_seed(1)
+        z = 0.3 * torch.randn(P, n_latent(N, canc)) - 1.0
+        lat = map_to_latents(z, N, canc)
+        assert torch.equal(lat["mean_turnaround"], torch.exp(z[:, :N]))
+        assert torch.equal(lat["mean_service"], torch.exp(z[:, N:2 * N]))
+        off = 4 * N if canc else 2 * N
+        assert torch.equal(lat["travel"][:, 1, 2], torch.exp(z[:, off + 1 * N + 2]))
+        td = torch.distributions
+        ref = td.Gamma(1.0, 2.0).log_prob(lat["mean_turnaround"]).sum(1)
+        ref = ref + td.Gamma(1.5, 10.0).log_prob(lat["mean_service"]).sum(1)
+        mask = ~torch.eye(N, dtype=torch.bool)
+        ref = ref + (td.Gamma(4.0, 1.25).log_prob(lat["travel"]) * mask).sum((1, 2))
+        if canc:
+            assert torch.equal(lat["log_initial_aircraft"], z[:, 2 * N:3 * N])
+            ref = ref + td.Normal(0.0, 1.0).log_prob(lat["log_initial_aircraft"]).sum(1)
+            ref = ref + td.Normal(-3.0, 1.0).log_prob(lat["base_cancel_logprob"]).sum(1)
+        assert torch.allclose(prior_log_prob(lat, canc), ref, rtol=1e-5, atol=1e-4)
+
+
+def test_mean_field_guide_surface():
+    from bayesair_b200.objective import MeanFieldGuide
+    g = MeanFieldGuide(7)
+    z, lp = g.rsample_and_log_prob((5,))
+    assert z.shape == (5, 7) and lp.shape == (5,)
+    assert torch.allclose(g.log_prob(z), lp, atol=1e-5)
+    assert g.sample((2,)).shape == (2, 7) and not g.sample((2,)).requires_grad
