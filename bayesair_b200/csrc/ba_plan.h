@@ -23,7 +23,7 @@
 // arrival calendar: buckets (ticks) kept in shared memory by the fast variant
 #define BA_KCAL 1024
 #ifndef BA_DUE_CAP_S
-#define BA_DUE_CAP_S 128              // entries per due buffer in shared memory (two buffers)
+#define BA_DUE_CAP_S 256              // entries per due buffer in shared memory (two buffers)
 #endif
 #define BA_KEY_DEPARTURE 0xF0000000u   // keys of newly ready departures sort after arrivals
 #define BA_DUE_WORDS 6               // word, key, owner<<16|seq, queue start, x, y
@@ -119,7 +119,8 @@ struct BaPlanView {
 //   trl, tre        [F] each if any_track_t : turnaround release time / its noise
 //   qd, se, sw      [F] each if any_track_a : departure queue start, aircraft-source
 //                                         noise and branch weight (adjoint of max())
-//   exact variant only: runway queues 6 x q_total_x, two due buffers 6 x F each,
+//   runway queues 6 x q_total_x (exact variant: the rings; fast variant: spill area)
+//   exact variant only: two due buffers 6 x F each,
 //                       calendar counters max_ticks + 2
 //   turnaround lists 2 x turn_total, aircraft FIFOs 2 x av_total, delayed deques dl_total
 static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_ticks)
@@ -127,7 +128,8 @@ static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_
     uint64_t w = 13ull * (uint64_t)d.F;
     if (d.any_track_t) w += 2ull * (uint64_t)d.F;
     if (d.any_track_a) w += 3ull * (uint64_t)d.F;
-    if (exact) w += 6ull * d.q_total_x + 2ull * (uint64_t)BA_DUE_WORDS * (uint64_t)d.F +
+    w += 7ull * d.q_total_x;          // draw history + exact rings (exact) / spill area (fast)
+    if (exact) w += 2ull * (uint64_t)BA_DUE_WORDS * (uint64_t)d.F +
                     2ull * (((uint64_t)d.F + 7) / 8 * 4) + (uint64_t)max_ticks + 2;
     w += 2ull * d.turn_total + 2ull * d.av_total + 1ull * d.dl_total;
     return w + 16;

@@ -202,9 +202,9 @@ struct BaCtx {
                                       //   time (NaN = unassigned) and its total wait
     double *psum;                     // running sum of all service draws assigned so far
     float *acc_ln0, *acc_bc;
-    uint32_t *next_dep, *q_head, *q_tail, *dep_pops, *arr_pops, *turn_n;
+    uint32_t *next_dep, *q_head, *q_tail, *q_fill, *dep_pops, *arr_pops, *turn_n;
     uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail;
-    uint32_t *s_flags, *s_qoff, *s_qmask, *s_depoff, *s_depcnt, *s_arrcnt;
+    uint32_t *s_flags, *s_qoff, *s_qmask, *s_goff, *s_depoff, *s_depcnt, *s_arrcnt;
     // CTA-wide scalars (shared memory): [0], [1] entries in the even / odd due buffer,
     // [3] abort flag (a shared ring overflowed)
     uint32_t *cta;
@@ -228,6 +228,12 @@ struct BaCtx {
     // runway queues, 6 words per entry (three 8-byte pairs): {word, lo} {queue start,
     // prefix sum at joining} {own service draw x, arrival time at the destination}
     uint32_t *qe;
+    // spill area (global scratch, fast variant): when an airport's shared ring is full, new
+    // entries go to gq at their absolute index and are refilled into the ring as the head
+    // advances.  q_fill[a] = first index not (yet) present in the shared ring.
+    uint32_t *gq;
+    float *gx;                    // service draw of every pushed entry at its absolute index
+                                  //   (global): the history the exact replay reads
     // per-flight global scratch
     float *xdk, *xak, *atk;       // prologue outputs, dep order (reused by the epilogue)
     float *xaf;                   // x_arr by flight (for departures served after arrival)
@@ -251,8 +257,8 @@ struct BaAcc {
     uint32_t status;
 };
 
-#define BA_NWORDS_STATE_SIMPLE 20 // per-airport words of shared state, no aircraft bookkeeping
-#define BA_NWORDS_STATE_TRACK 36  // ... when some airport of the plan tracks aircraft
+#define BA_NWORDS_STATE_SIMPLE 22 // per-airport words of shared state, no aircraft bookkeeping
+#define BA_NWORDS_STATE_TRACK 38  // ... when some airport of the plan tracks aircraft
 #define BA_Q_WORDS 6              // words per runway-queue entry
 #define BA_CTA_WORDS 4            // CTA-wide scalars
 
@@ -268,12 +274,13 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N, bool tracked)
     c.q_head = w + 11 * N; c.q_tail = w + 12 * N; c.dep_pops = w + 13 * N;
     c.arr_pops = w + 14 * N; c.s_flags = w + 15 * N; c.s_qoff = w + 16 * N;
     c.s_qmask = w + 17 * N; c.s_arrcnt = w + 18 * N; c.next_sched = f + 19 * N;
+    c.q_fill = w + 20 * N; c.s_goff = w + 21 * N;
     if (tracked) {
-        c.base = f + 20 * N; c.n_avail = f + 21 * N; c.n0 = f + 22 * N;
-        c.acc_ln0 = f + 23 * N; c.acc_bc = f + 24 * N;
-        c.next_dep = w + 25 * N; c.turn_n = w + 26 * N; c.av_head = w + 27 * N;
-        c.av_tail = w + 28 * N; c.zeros_left = w + 29 * N; c.dl_head = w + 30 * N;
-        c.dl_tail = w + 31 * N; c.s_depoff = w + 32 * N; c.s_depcnt = w + 33 * N;
+        c.base = f + 22 * N; c.n_avail = f + 23 * N; c.n0 = f + 24 * N;
+        c.acc_ln0 = f + 25 * N; c.acc_bc = f + 26 * N;
+        c.next_dep = w + 27 * N; c.turn_n = w + 28 * N; c.av_head = w + 29 * N;
+        c.av_tail = w + 30 * N; c.zeros_left = w + 31 * N; c.dl_head = w + 32 * N;
+        c.dl_tail = w + 33 * N; c.s_depoff = w + 34 * N; c.s_depcnt = w + 35 * N;
     } else {
         c.base = c.n_avail = c.n0 = c.acc_ln0 = c.acc_bc = nullptr;
         c.next_dep = c.turn_n = c.av_head = c.av_tail = c.zeros_left = nullptr;
@@ -307,6 +314,9 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32
     if (day.any_track_a) {
         c.qd = (float *)g; g += F; c.se = (float *)g; g += F; c.sw = (float *)g; g += F;
     }
+    c.gx = (float *)g; g += day.q_total_x;
+    c.gq = nullptr;
+    if (!EXACT) { c.gq = g; g += BA_Q_WORDS * day.q_total_x; }
     uint32_t *s = EXACT ? g : shared_pool;
     const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
     c.qe = s; s += BA_Q_WORDS * qt;
@@ -370,7 +380,8 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     c.lograte[a] = BA_LOG(rate); c.logtstd[a] = BA_LOG(tstd);
     c.asg_lo[a] = NAN; c.asg_hi[a] = NAN; c.w_head[a] = 0.0f; c.psum[a] = 0.0;
     c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
-    c.q_head[a] = 0; c.q_tail[a] = 0; c.dep_pops[a] = 0; c.arr_pops[a] = 0;
+    c.q_head[a] = 0; c.q_tail[a] = 0; c.q_fill[a] = 0; c.dep_pops[a] = 0; c.arr_pops[a] = 0;
+    c.s_goff[a] = A.q_off_x;
     if (c.n_avail) {
         float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
         if (c.cancel_mode) {
@@ -457,17 +468,38 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
 BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float x, float y)
 {
     const uint32_t head = c.q_head[a], tail = c.q_tail[a], mask = c.s_qmask[a];
-    if (tail - head > mask) {
-#if defined(BA_EMU_DEBUG)
-        fprintf(stderr, "qpush overflow a=%d head=%u tail=%u mask=%u word=%08x\n", a, head, tail, mask, word);
-#endif
-        acc.status |= BA_S_OVERFLOW; return; }
-    uint32_t *e = c.qe + BA_Q_WORDS * (c.s_qoff[a] + (tail & mask));
+    uint32_t *e;
+    if (c.q_fill[a] == tail && tail - head <= mask) {
+        e = c.qe + BA_Q_WORDS * (c.s_qoff[a] + (tail & mask));       // room in the ring
+        c.q_fill[a] = tail + 1;
+    } else if (c.gq) {
+        e = c.gq + BA_Q_WORDS * (c.s_goff[a] + tail);                // spill (absolute index)
+    } else {
+        acc.status |= BA_S_OVERFLOW; return;                          // cannot happen: exact ring
+    }
     BaPairU wl = {word, head + (isnan(c.asg_hi[a]) ? 0u : 1u)};
     BaPairF sp = {qstart, (float)c.psum[a]};
     BaPairF xy = {x, y};
     BA_ST_PAIR(BaPairU, e, wl); BA_ST_PAIR(BaPairF, e + 2, sp); BA_ST_PAIR(BaPairF, e + 4, xy);
+    c.gx[c.s_goff[a] + tail] = x;
     c.q_tail[a] = tail + 1;
+}
+
+// Moves spilled entries into the shared ring while there is room (owner lane only).
+BA_DEV void ba_q_refill(BaCtx &c, int a, uint32_t head, uint32_t tail)
+{
+    uint32_t fill = c.q_fill[a];
+    if (fill == tail) return;
+    const uint32_t mask = c.s_qmask[a], qoff = c.s_qoff[a], goff = c.s_goff[a];
+    while (fill != tail && fill - head <= mask) {
+        const uint32_t *src = c.gq + BA_Q_WORDS * (goff + fill);
+        uint32_t *dst = c.qe + BA_Q_WORDS * (qoff + (fill & mask));
+        BA_ST_PAIR(BaPairU, dst, BA_LD_PAIR(BaPairU, src));
+        BA_ST_PAIR(BaPairU, dst + 2, BA_LD_PAIR(BaPairU, src + 2));
+        BA_ST_PAIR(BaPairU, dst + 4, BA_LD_PAIR(BaPairU, src + 4));
+        ++fill;
+    }
+    c.q_fill[a] = fill;
 }
 
 BA_DEV void ba_due_append(BaCtx &c, BaAcc &acc, int parity, uint32_t word, uint32_t key,
@@ -690,7 +722,9 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
         const uint32_t qoff = c.s_qoff[a], qmask = c.s_qmask[a];
         float lo = c.asg_lo[a], hi = c.asg_hi[a], wait = c.w_head[a];
         double psum = c.psum[a];
+        if (c.gq) ba_q_refill(c, a, head, tail);
         while (head != tail) {
+            if (c.gq && head == c.q_fill[a]) { c.q_head[a] = head; ba_q_refill(c, a, head, tail); }
             const uint32_t *e = c.qe + BA_Q_WORDS * (qoff + (head & qmask));
             const BaPairU wl = BA_LD_PAIR(BaPairU, e);          // word, lo
             if (isnan(hi)) {
@@ -710,11 +744,11 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
             }
             if (!(hi <= t)) {
                 if (lo > t || isnan(lo)) break;             // certainly still being served
-                // ambiguous: replay the reference's arithmetic exactly
-                if (tail - wl.b > qmask + 1u) { acc.status |= BA_S_OVERFLOW; break; }
+                // ambiguous: replay the reference's arithmetic exactly from the history of
+                // service draws (global, absolute index: never overwritten)
                 float w = 0.0f;
-                for (uint32_t j = wl.b; j != head + 1u; ++j)
-                    w = BA_ADD(w, BA_LD_PAIR(BaPairF, c.qe + BA_Q_WORDS * (qoff + (j & qmask)) + 4).a);
+                const float *hx = c.gx + c.s_goff[a];
+                for (uint32_t j = wl.b; j != head + 1u; ++j) w = BA_ADD(w, hx[j]);
                 wait = w;
                 lo = hi = BA_ADD(BA_LD_PAIR(BaPairF, e + 2).a, w);
                 if (!(hi <= t)) break;

@@ -159,18 +159,59 @@ def test_emulated_kernel_decisions_vs_oracle(canc):
                 assert abs(r["logp"] - o["logp"][p, d]) <= 2e-6 * scale
 
 
-def test_emulated_overflow_rerun(monkeypatch):
+def test_emulated_ring_spill(monkeypatch):
+    """Starved shared-memory rings (capacity 1) spill to the global ring and refill:
+    same decisions and log-prob as the exact-capacity variant, no overflow."""
     from tests.hostemu import EmuPlan
     g = Golden("congested6")
     monkeypatch.setenv("BA_Q_MIN", "1"); monkeypatch.setenv("BA_Q_DIV", "1e9")
-    monkeypatch.setenv("BA_BAG_MIN", "1"); monkeypatch.setenv("BA_BAG_FRAC", "0")
     plan = EmuPlan(g.specs, len(g.global_codes), g.delta_t, g.max_t, False)
     lat = {k: v[None] for k, v in g.latents.items()}
-    flagged = plan.forward(lat, g.scales, g.noise[None], rerun_overflow=False)
+    spill = plan.forward(lat, g.scales, g.noise[None], rerun_overflow=False, want_pop=True)
+    exact = plan.forward(lat, g.scales, g.noise[None], exact=True, want_pop=True)
+    assert (spill["status"] == 0).all()
+    assert np.array_equal(spill["pop_tick"], exact["pop_tick"])
+    assert np.array_equal(spill["logp"], exact["logp"])
+    replay = plan.forward(lat, g.scales, g.noise[None], rerun_overflow=False, want_pop=True,
+                          replay_waits=True)
+    assert (replay["status"] == 0).all() and np.array_equal(replay["pop_tick"], exact["pop_tick"])
+
+
+def _burst_day(n_origins=20, per_origin=20):
+    """20 airports x 20 flights to one hub, all scheduled in the same minute: the 400
+    departures that become ready in one tick overflow the shared due buffer."""
+    from bayesair_b200.compiler import DaySpec
+    f32 = np.float32
+    n = n_origins * per_origin
+    origin = np.repeat(np.arange(1, n_origins + 1), per_origin).astype(np.int32)
+    order = np.argsort(np.tile(np.arange(per_origin), n_origins), kind="stable")
+    origin = origin[order]                      # interleave the origins
+    sched = np.full(n, 6.0, f32)
+    dep = (6.0 + 0.002 * np.arange(n)).astype(f32)
+    codes = ["HUB"] + [f"S{i:02d}" for i in range(n_origins)]
+    return DaySpec(codes, np.arange(n_origins + 1, dtype=np.int32), sched, dep,
+                   (dep + 2.0).astype(f32), np.zeros(n, np.int8), origin,
+                   np.zeros(n, np.int32), [f"{i}_{codes[o]}_HUB" for i, o in enumerate(origin)])
+
+
+def test_emulated_overflow_rerun():
+    """More flights due in one tick than the shared due buffer holds: the fast variant
+    flags BA_PD_OVERFLOW and the re-run with exact-capacity lists is transparent."""
+    from oracle import ba_oracle
+    from tests.hostemu import EmuPlan
+    spec = _burst_day()
+    N = spec.n_airports
+    plan = EmuPlan([spec], N, 0.2, 30.0, False)
+    lat = {"mean_turnaround": np.full((1, N), 0.5, np.float32),
+           "mean_service": np.full((1, N), 0.01, np.float32),
+           "travel": np.full((1, N, N), 2.0, np.float32)}
+    noise = std_noise(1, 1, spec.n_flights, seed=8)
+    flagged = plan.forward(lat, (0.1, 0.1, 0.1), noise, rerun_overflow=False)
     assert (flagged["status"] & 2).all()
-    fixed = plan.forward(lat, g.scales, g.noise[None])
-    exact = plan.forward(lat, g.scales, g.noise[None], exact=True)
-    assert (fixed["status"] == 0).all() and np.array_equal(fixed["logp"], exact["logp"])
+    fixed = plan.forward(lat, (0.1, 0.1, 0.1), noise)
+    ref = ba_oracle.run_batch([spec], lat, (0.1, 0.1, 0.1), noise, delta_t=0.2)
+    assert (fixed["status"] == 0).all()
+    np.testing.assert_allclose(fixed["logp"], ref["logp"], rtol=5e-6)
 
 
 def test_clock_matches_torch_inplace_add():
