@@ -44,7 +44,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("BA_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB_PATH] + [os.path.join(CSRC, f) for f in SOURCES]
     subprocess.check_call(cmd)
     return LIB_PATH
