@@ -284,12 +284,12 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         unsigned long long h[8];
         BA_CUDA(cudaStreamSynchronize(s));
         BA_CUDA(cudaMemcpy(h, prm.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost));
-        const char *names[8] = {"init", "prologue", "calendar", "phaseC+A", "phaseB+vote",
-                                "[busiest lane: pull]", "epilogue", "[busiest lane: phaseA]"};
+        const char *names[8] = {"init", "prologue", "calendar", "phaseC+A", "phaseB+vote", "-",
+                                "epilogue", "-"};
         double tot = 0;
-        for (int i = 0; i < 7; ++i) if (i != 5) tot += (double)h[i];
+        for (int i = 0; i < 7; ++i) tot += (double)h[i];
         fprintf(stderr, "[BA_PHASE_PROFILE] cycles per particle-day (thread 0 wall):");
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 7; ++i)
             fprintf(stderr, " %s=%.0f (%.0f%%)", names[i], (double)h[i] / (double)n_work,
                     100.0 * (double)h[i] / tot);
         fprintf(stderr, "\n");

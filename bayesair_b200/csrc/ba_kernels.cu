@@ -42,7 +42,7 @@ size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bo
 
 // resident CTAs per SM the register allocation aims for, per block-size class
 #ifndef BA_MIN_BLOCKS_128
-#define BA_MIN_BLOCKS_128 5
+#define BA_MIN_BLOCKS_128 7
 #endif
 #define BA_MIN_BLOCKS(MAXT) ((MAXT) == 128 ? BA_MIN_BLOCKS_128 : ((MAXT) == 256 ? 3 : 1))
 
@@ -144,15 +144,6 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         //   interval 1 (one lane per airport): phase C of the previous tick, then phase A
         //   interval 2 (flight-parallel):      phase B, fills the due buffer of this tick
         bool busy = day.F > 0;
-        // one airport per thread: its queue state stays in registers across ticks
-        const bool one = N <= nthr;
-        // Warp w of every CTA runs on SM sub-partition w % 4, and lane slots are sorted by
-        // traffic (warp 0 = the busiest airports).  Rotating the warp order by the CTA index
-        // spreads the busy warps of co-resident CTAs over all four schedulers.
-        const int vslot = (((warp + (int)blockIdx.x) % nwarp) << 5) | lane;
-        const int my_a = (one && vslot < N) ? day.lane_airport[vslot] : -1;
-        BaLane L;
-        if (my_a >= 0) ba_lane_load(c, my_a, L);
         while (busy) {
             if (tick >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
             ++tick;
@@ -161,30 +152,11 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             uint32_t n_due = c.cta[prev];
             if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
             int more = tick < day.last_ready_tick;
-            if (one) {
-                if (my_a >= 0) {
-                    const bool hubprof = prm.phase_cycles != nullptr && vslot == 0;
-                    long long h0 = 0, h1 = 0, h2 = 0;
-                    if (hubprof) h0 = clock64();
-                    if (n_due) ba_phase_c_pull(c, acc, L, my_a, prev, n_due);
-                    if (hubprof) h1 = clock64();
-                    ba_phase_a<EXACT>(c, acc, L, my_a, t, tick);
-                    if (hubprof) {
-                        h2 = clock64();
-                        atomicAdd(prm.phase_cycles + 5, (unsigned long long)(h1 - h0));
-                        atomicAdd(prm.phase_cycles + 7, (unsigned long long)(h2 - h1));
-                    }
-                    more |= ba_airport_busy(c, L, my_a) ? 1 : 0;
-                }
-            } else {
-                for (int s = tid; s < N; s += nthr) {
-                    const int a = day.lane_airport[s];
-                    ba_lane_load(c, a, L);
-                    if (n_due) ba_phase_c_pull(c, acc, L, a, prev, n_due);
-                    ba_phase_a<EXACT>(c, acc, L, a, t, tick);
-                    more |= ba_airport_busy(c, L, a) ? 1 : 0;
-                    ba_lane_store(c, a, L);
-                }
+            for (int s = tid; s < N; s += nthr) {
+                const int a = day.lane_airport[s];
+                if (n_due) ba_phase_c_pull(c, acc, a, prev, n_due);
+                ba_phase_a<EXACT>(c, acc, a, t, tick);
+                more |= ba_airport_busy(c, a) ? 1 : 0;
             }
             if (!EXACT && (acc.status & BA_S_OVERFLOW)) c.cta[3] = 1u;
             __syncthreads();

@@ -21,9 +21,11 @@
 #define BA_KEY_TICK_SHIFT 12
 #define BA_KEY_INVALID 0xFFFFFFFFu
 // arrival calendar: buckets (ticks) kept in shared memory by the fast variant
-#define BA_KCAL 1024
+#ifndef BA_KCAL
+#define BA_KCAL 512
+#endif
 #ifndef BA_DUE_CAP_S
-#define BA_DUE_CAP_S 256              // entries per due buffer in shared memory (two buffers)
+#define BA_DUE_CAP_S 192              // entries per due buffer in shared memory (two buffers)
 #endif
 #define BA_KEY_DEPARTURE 0xF0000000u   // keys of newly ready departures sort after arrivals
 #define BA_DUE_WORDS 6               // word, key, owner<<16|seq, queue start, x, y

@@ -47,7 +47,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         return fail(BA_ERR_LIMIT, "ba_plan_create: more than 4096 airports");
 
     // tunables of the shared-memory variant (documented in DESIGN.md)
-    const double q_div = env_double("BA_Q_DIV", 16.0);        // ring = traffic / q_div
+    const double q_div = env_double("BA_Q_DIV", 32.0);        // ring = traffic / q_div
     const double q_min = env_double("BA_Q_MIN", 4.0);
     if (max_ticks > 65000)
         return fail(BA_ERR_LIMIT, "ba_plan_create: max_ticks must be <= 65000");

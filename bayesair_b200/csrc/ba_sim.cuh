@@ -251,17 +251,6 @@ struct BaCtx {
     int route_base;               // C*N
 };
 
-// Dynamic state of one airport's runway queue.  When every thread owns exactly one airport
-// (N <= block size) it lives in registers for the whole tick loop; otherwise it is loaded
-// from / stored to the shared state arrays around each airport's turn.
-struct BaLane {
-    uint32_t head, tail, fill;        // ring counters (absolute indices)
-    uint32_t qoff, qmask, goff;       // ring slice, spill slice
-    uint32_t flags, dep_pops, arr_pops, arr_cnt;
-    float lo, hi, wait;               // head entry: service-time interval, total wait
-    double psum;                      // running sum of assigned service draws
-};
-
 struct BaAcc {
     double lp;                    // ~7F terms of mixed sign per particle-day: keep the sum exact-ish
     float g_sigma, g_vt, g_vu;
@@ -421,22 +410,6 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     c.s_arrcnt[a] = (uint32_t)A.arr_cnt;
 }
 
-BA_DEV void ba_lane_load(const BaCtx &c, int a, BaLane &L)
-{
-    L.head = c.q_head[a]; L.tail = c.q_tail[a]; L.fill = c.q_fill[a];
-    L.qoff = c.s_qoff[a]; L.qmask = c.s_qmask[a]; L.goff = c.s_goff[a];
-    L.flags = c.s_flags[a]; L.dep_pops = c.dep_pops[a]; L.arr_pops = c.arr_pops[a];
-    L.arr_cnt = c.s_arrcnt[a];
-    L.lo = c.asg_lo[a]; L.hi = c.asg_hi[a]; L.wait = c.w_head[a]; L.psum = c.psum[a];
-}
-
-BA_DEV void ba_lane_store(BaCtx &c, int a, const BaLane &L)
-{
-    c.q_head[a] = L.head; c.q_tail[a] = L.tail; c.q_fill[a] = L.fill;
-    c.dep_pops[a] = L.dep_pops; c.arr_pops[a] = L.arr_pops;
-    c.asg_lo[a] = L.lo; c.asg_hi[a] = L.hi; c.w_head[a] = L.wait; c.psum[a] = L.psum;
-}
-
 // ---------------------------------------------------------------------------
 // PROLOGUE: one flight (call for f = tid, tid + nthreads, ...)
 // ---------------------------------------------------------------------------
@@ -471,7 +444,8 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
         int kk = guess < 1.0f ? 1 : (guess > (float)kmax ? kmax : (int)guess);
         while (kk > 1 && c.tick_time[kk - 1] >= at) --kk;
         while (kk < kmax && c.tick_time[kk] < at) ++kk;
-        if (c.tick_time[kk] < at) acc.status |= BA_S_TICK_CAP;   // beyond the calendar
+        // beyond the calendar: the shared-memory variant hands the item to the exact one
+        if (c.tick_time[kk] < at) acc.status |= c.gq ? BA_S_OVERFLOW : BA_S_TICK_CAP;
         if (kk < c.first_tick) kk = c.first_tick;
         ka = (uint32_t)kk;
         BA_ATOMIC_INC(&c.cal_cnt[ka]);
@@ -492,37 +466,41 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
 // The entry remembers how much service had been handed out at this airport when it
 // joined (psum, rounded to fp32) and the index of the first later assignment (lo):
 // its total wait is the sum of the draws lo..own index (airport.py:150-153).
-BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, BaLane &L, uint32_t word, float qstart, float x,
-                      float y)
+BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float x, float y)
 {
+    const uint32_t head = c.q_head[a], tail = c.q_tail[a], mask = c.s_qmask[a];
     uint32_t *e;
-    if (L.fill == L.tail && L.tail - L.head <= L.qmask) {
-        e = c.qe + BA_Q_WORDS * (L.qoff + (L.tail & L.qmask));       // room in the ring
-        L.fill = L.tail + 1;
+    if (c.q_fill[a] == tail && tail - head <= mask) {
+        e = c.qe + BA_Q_WORDS * (c.s_qoff[a] + (tail & mask));       // room in the ring
+        c.q_fill[a] = tail + 1;
     } else if (c.gq) {
-        e = c.gq + BA_Q_WORDS * (L.goff + L.tail);                   // spill (absolute index)
+        e = c.gq + BA_Q_WORDS * (c.s_goff[a] + tail);                // spill (absolute index)
     } else {
         acc.status |= BA_S_OVERFLOW; return;                          // cannot happen: exact ring
     }
-    BaPairU wl = {word, L.head + (isnan(L.hi) ? 0u : 1u)};
-    BaPairF sp = {qstart, (float)L.psum};
+    BaPairU wl = {word, head + (isnan(c.asg_hi[a]) ? 0u : 1u)};
+    BaPairF sp = {qstart, (float)c.psum[a]};
     BaPairF xy = {x, y};
     BA_ST_PAIR(BaPairU, e, wl); BA_ST_PAIR(BaPairF, e + 2, sp); BA_ST_PAIR(BaPairF, e + 4, xy);
-    c.gx[L.goff + L.tail] = x;
-    L.tail += 1;
+    c.gx[c.s_goff[a] + tail] = x;
+    c.q_tail[a] = tail + 1;
 }
 
 // Moves spilled entries into the shared ring while there is room (owner lane only).
-BA_DEV void ba_q_refill(BaCtx &c, BaLane &L)
+BA_DEV void ba_q_refill(BaCtx &c, int a, uint32_t head, uint32_t tail)
 {
-    while (L.fill != L.tail && L.fill - L.head <= L.qmask) {
-        const uint32_t *src = c.gq + BA_Q_WORDS * (L.goff + L.fill);
-        uint32_t *dst = c.qe + BA_Q_WORDS * (L.qoff + (L.fill & L.qmask));
+    uint32_t fill = c.q_fill[a];
+    if (fill == tail) return;
+    const uint32_t mask = c.s_qmask[a], qoff = c.s_qoff[a], goff = c.s_goff[a];
+    while (fill != tail && fill - head <= mask) {
+        const uint32_t *src = c.gq + BA_Q_WORDS * (goff + fill);
+        uint32_t *dst = c.qe + BA_Q_WORDS * (qoff + (fill & mask));
         BA_ST_PAIR(BaPairU, dst, BA_LD_PAIR(BaPairU, src));
         BA_ST_PAIR(BaPairU, dst + 2, BA_LD_PAIR(BaPairU, src + 2));
         BA_ST_PAIR(BaPairU, dst + 4, BA_LD_PAIR(BaPairU, src + 4));
-        L.fill += 1;
+        ++fill;
     }
+    c.q_fill[a] = fill;
 }
 
 BA_DEV void ba_due_append(BaCtx &c, BaAcc &acc, int parity, uint32_t word, uint32_t key,
@@ -542,14 +520,14 @@ BA_DEV void ba_due_append(BaCtx &c, BaAcc &acc, int parity, uint32_t word, uint3
 // available_aircraft.pop(0) for one departing flight (network.py:118-126).
 // Returns the ready time max(aircraft, sched); *weight / *src_eps describe the
 // aircraft branch for the adjoint (0 none, 0.5 tie, 1 aircraft time strictly later).
-BA_DEV float ba_take_aircraft(BaCtx &c, BaAcc &acc, const BaLane &L, int a, const BaAirport *A,
-                              float sched, float t, float *weight, float *src_eps)
+BA_DEV float ba_take_aircraft(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, float sched,
+                              float t, float *weight, float *src_eps)
 {
     *weight = 0.0f; *src_eps = 0.0f;
     c.n_avail[a] = c.n_avail[a] - 1.0f;
     float ac_time = 0.0f;
     bool has_src = false;
-    if (L.flags & BA_AP_TRACK_A) {
+    if (c.s_flags[a] & BA_AP_TRACK_A) {
         if (c.zeros_left[a] > 0) {
             c.zeros_left[a] -= 1;
         } else {
@@ -575,25 +553,25 @@ BA_DEV float ba_take_aircraft(BaCtx &c, BaAcc &acc, const BaLane &L, int a, cons
 }
 
 // one ready departure of a tracked airport: take an aircraft, enqueue, record the branch
-BA_DEV void ba_depart_tracked(BaCtx &c, BaAcc &acc, BaLane &L, int a, const BaAirport *A,
-                              uint32_t k, float t)
+BA_DEV void ba_depart_tracked(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, uint32_t k,
+                              float t)
 {
     const uint32_t w = c.dep_word[k];
     const int f = (int)(w & BA_FID_MASK);
     const float sched = c.dep_sched[k];
     float weight, src_eps;
-    const float ready = ba_take_aircraft(c, acc, L, a, A, sched, t, &weight, &src_eps);
+    const float ready = ba_take_aircraft(c, acc, a, A, sched, t, &weight, &src_eps);
     if (c.qd) { c.qd[f] = ready; c.se[f] = src_eps; c.sw[f] = weight; }
-    ba_q_push(c, acc, L, BA_Q_DEP | (w & BA_DW_ENTRY_MASK), ready, c.xdk[k], c.atk[k]);
+    ba_q_push(c, acc, a, BA_Q_DEP | (w & BA_DW_ENTRY_MASK), ready, c.xdk[k], c.atk[k]);
 }
 
 // ---------------------------------------------------------------------------
 // SCAN, phase A
 // ---------------------------------------------------------------------------
 template <bool EXACT>
-BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, BaLane &L, int a, float t, int tick)
+BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
 {
-    const uint32_t flags = L.flags;
+    const uint32_t flags = c.s_flags[a];
     const BaAirport *A = &c.ap[a];      // only dereferenced on the tracked paths
 
     // 1. update_available_aircraft (airport.py:66-84)
@@ -695,7 +673,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, BaLane &L, int a, float t, int tick
                     if (first_delayed == n_new) first_delayed = i;
                     continue;
                 }
-                ba_depart_tracked(c, acc, L, a, A, k, t);
+                ba_depart_tracked(c, acc, a, A, k, t);
             }
             if (c.cancel_mode && c.want_grad && n_new) {
                 c.acc_bc[a] += g_p * sg * base;           // b = exp(c)
@@ -718,7 +696,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, BaLane &L, int a, float t, int tick
                 uint32_t hd = c.dl_head[a];
                 const uint32_t tl = c.dl_tail[a];
                 while (hd != tl && c.n_avail[a] > 0.0f) {
-                    ba_depart_tracked(c, acc, L, a, A, c.dl[A->dl_off + (hd & A->dl_mask)], t);
+                    ba_depart_tracked(c, acc, a, A, c.dl[A->dl_off + (hd & A->dl_mask)], t);
                     ++hd;
                 }
                 c.dl_head[a] = hd;
@@ -739,15 +717,15 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, BaLane &L, int a, float t, int tick
     // u = 2^-24.  Only when the clock falls INSIDE the interval (probability ~1e-5 per
     // check) is W replayed with the reference's sequential fp32 adds.
     {
-        uint32_t head = L.head;
-        const uint32_t tail = L.tail;
+        uint32_t head = c.q_head[a];
+        const uint32_t tail = c.q_tail[a];
         if (head == tail) return;
-        const uint32_t qoff = L.qoff, qmask = L.qmask;
-        float lo = L.lo, hi = L.hi, wait = L.wait;
-        double psum = L.psum;
-        if (c.gq && L.fill != tail) ba_q_refill(c, L);
+        const uint32_t qoff = c.s_qoff[a], qmask = c.s_qmask[a];
+        float lo = c.asg_lo[a], hi = c.asg_hi[a], wait = c.w_head[a];
+        double psum = c.psum[a];
+        if (c.gq) ba_q_refill(c, a, head, tail);
         while (head != tail) {
-            if (c.gq && head == L.fill) { L.head = head; ba_q_refill(c, L); }
+            if (c.gq && head == c.q_fill[a]) { c.q_head[a] = head; ba_q_refill(c, a, head, tail); }
             const uint32_t *e = c.qe + BA_Q_WORDS * (qoff + (head & qmask));
             const BaPairU wl = BA_LD_PAIR(BaPairU, e);          // word, lo
             if (isnan(hi)) {
@@ -770,7 +748,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, BaLane &L, int a, float t, int tick
                 // ambiguous: replay the reference's arithmetic exactly from the history of
                 // service draws (global, absolute index: never overwritten)
                 float w = 0.0f;
-                const float *hx = c.gx + L.goff;
+                const float *hx = c.gx + c.s_goff[a];
                 for (uint32_t j = wl.b; j != head + 1u; ++j) w = BA_ADD(w, hx[j]);
                 wait = w;
                 lo = hi = BA_ADD(BA_LD_PAIR(BaPairF, e + 2).a, w);
@@ -784,8 +762,8 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, BaLane &L, int a, float t, int tick
                 // add_in_transit_flights (network.py:136-168).  The in-transit list is
                 // implicit: its order is the key (tick, origin, per-origin sequence).
                 const uint32_t key = ((uint32_t)tick << BA_KEY_TICK_SHIFT) | (uint32_t)a;
-                const uint32_t seq = L.dep_pops;
-                L.dep_pops = seq + 1;
+                const uint32_t seq = c.dep_pops[a];
+                c.dep_pops[a] = seq + 1;
                 const float av = BA_LD_PAIR(BaPairF, e + 4).b;
                 if (av <= t) {
                     // already past its arrival time: joins the destination queue at the
@@ -798,7 +776,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, BaLane &L, int a, float t, int tick
                 if (c.pop_tick) c.pop_tick[2 * f] = tick;
             } else {
                 c.wa[f] = wait;
-                L.arr_pops += 1;
+                c.arr_pops[a] += 1;
                 // _assign_turnaround_time (airport.py:210-221)
                 if (flags & BA_AP_TRACK_T) {
                     const uint32_t n = c.turn_n[a];
@@ -811,8 +789,8 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, BaLane &L, int a, float t, int tick
             ++head;
             lo = hi = NAN;
         }
-        L.head = head;
-        L.lo = lo; L.hi = hi; L.wait = wait; L.psum = psum;
+        c.q_head[a] = head;
+        c.asg_lo[a] = lo; c.asg_hi[a] = hi; c.w_head[a] = wait; c.psum[a] = psum;
     }
 }
 
@@ -898,13 +876,13 @@ BA_DEV uint64_t ba_due_order(const uint32_t *de)
     return ((uint64_t)de[1] << 16) | (uint64_t)(de[2] & 0xFFFFu);
 }
 
-BA_DEV void ba_due_push(BaCtx &c, BaAcc &acc, BaLane &L, const uint32_t *de)
+BA_DEV void ba_due_push(BaCtx &c, BaAcc &acc, int a, const uint32_t *de)
 {
     const BaPairF xy = BA_LD_PAIR(BaPairF, de + 4);
-    ba_q_push(c, acc, L, de[0], __uint_as_float_portable(de[3]), xy.a, xy.b);
+    ba_q_push(c, acc, a, de[0], __uint_as_float_portable(de[3]), xy.a, xy.b);
 }
 
-BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, BaLane &L, int a, int parity, uint32_t n_due)
+BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_due)
 {
     const uint32_t *due = c.due_base + (uint32_t)parity * c.due_stride;
     uint64_t m0 = 0, m1 = 0;
@@ -941,7 +919,7 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, BaLane &L, int a, int parity, 
                 const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
                 if (o < best) { best = o; bj = j; }
             }
-            ba_due_push(c, acc, L, due + BA_DUE_WORDS * bj);
+            ba_due_push(c, acc, a, due + BA_DUE_WORDS * bj);
             if (bj < 64u) m0 &= ~(1ull << bj); else m1 &= ~(1ull << (bj - 64u));
         }
         return;
@@ -957,7 +935,7 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, BaLane &L, int a, int parity, 
             if ((first || o > last) && o < best) { best = o; bj = j; }
         }
         if (bj == 0xFFFFFFFFu) break;
-        ba_due_push(c, acc, L, due + BA_DUE_WORDS * bj);
+        ba_due_push(c, acc, a, due + BA_DUE_WORDS * bj);
         last = best; first = false;
     }
 }
@@ -965,10 +943,10 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, BaLane &L, int a, int parity, 
 // Does this airport still hold work (completion vote, network.py:34-41)?  Every flight
 // that is not observed as cancelled eventually lands here, so "in transit or queued
 // somewhere" is "not yet landed at its destination".
-BA_DEV bool ba_airport_busy(const BaCtx &c, const BaLane &L, int a)
+BA_DEV bool ba_airport_busy(const BaCtx &c, int a)
 {
-    return L.head != L.tail || L.arr_pops < L.arr_cnt ||
-           ((L.flags & BA_AP_TRACK_T) &&
+    return c.q_head[a] != c.q_tail[a] || c.arr_pops[a] < c.s_arrcnt[a] ||
+           ((c.s_flags[a] & BA_AP_TRACK_T) &&
             (c.next_dep[a] < c.s_depcnt[a] || c.dl_head[a] != c.dl_tail[a]));
 }
 

@@ -121,12 +121,9 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
         for (int i = 0; i < N; ++i) {
             const int a = day.lane_airport[order[i]];
-            BaLane L;
-            ba_lane_load(c, a, L);
-            if (n_due) ba_phase_c_pull(c, acc[order[i]], L, a, prev, n_due);
-            ba_phase_a<EXACT>(c, acc[order[i]], L, a, t, tick);
-            more |= ba_airport_busy(c, L, a);
-            ba_lane_store(c, a, L);
+            if (n_due) ba_phase_c_pull(c, acc[order[i]], a, prev, n_due);
+            ba_phase_a<EXACT>(c, acc[order[i]], a, t, tick);
+            more |= ba_airport_busy(c, a);
         }
         c.cta[prev] = 0;
         if ((uint32_t)tick < c.cal_cap) {
