@@ -279,15 +279,26 @@ __global__ void __launch_bounds__(256) ba_collect_kernel(const uint32_t *status,
         else { auto kfn = ba_forward_kernel<EX, 1024>; STMT; }                         \
     } while (0)
 
+// The dynamic-shared-memory limit is a property of the kernel function, shared by every plan
+// of the process: only ever raise it (a later, smaller plan must not lower it under an
+// earlier one).
 cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact)
 {
+    static size_t cur[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    const int cls = block <= 128 ? 0 : (block <= 256 ? 1 : (block <= 512 ? 2 : 3));
     cudaError_t e = cudaSuccess;
-    if (smem_fast)
+    if (smem_fast > cur[0][cls]) {
         BA_DISPATCH(false, block, e = cudaFuncSetAttribute(
             kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
-    if (e != cudaSuccess) return e;
-    BA_DISPATCH(true, block, e = cudaFuncSetAttribute(
-        kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact));
+        if (e != cudaSuccess) return e;
+        cur[0][cls] = smem_fast;
+    }
+    if (smem_exact > cur[1][cls]) {
+        BA_DISPATCH(true, block, e = cudaFuncSetAttribute(
+            kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact));
+        if (e != cudaSuccess) return e;
+        cur[1][cls] = smem_exact;
+    }
     return e;
 }
 

@@ -303,6 +303,41 @@ def run_native(args):
     torch.cuda.synchronize()
     philox_value = P * D * max(2, args.steps // 2) / (e0.elapsed_time(e1) * 1e-3)
 
+    # ---- "SVI step ms" (BASELINE metric, cfg2 shape): mean-field guide over the 2N+N^2
+    #      log-latents, 1024 particles, one day: guide sample -> model log-joint (kernel) ->
+    #      backward -> gradient all-reduce -> Adam step (scripts/wn/train.py:301-326 batched)
+    svi_ms = None
+    if not args.no_svi:
+        from bayesair_b200.objective import MeanFieldGuide, n_latent, objective_fn
+        from bayesair_b200.parallel import allreduce_gradients
+        plan1 = SimulationPlan(specs[:1], specs[0].codes, delta_t=0.2, device=dev)
+        init = torch.zeros(n_latent(N), device=dev)
+        init[:N] = float(np.log(0.5)); init[N:2 * N] = float(np.log(svc))
+        init[2 * N:] = torch.log(torch.tensor(np.maximum(lat["travel"][0], 0.5), device=dev)).reshape(-1)
+        guide = MeanFieldGuide(n_latent(N), init_loc=init, init_scale=0.05).to(dev)
+        opt = torch.optim.Adam(guide.parameters(), lr=1e-3)
+
+        def svi_step():
+            opt.zero_grad(set_to_none=True)
+            loss = objective_fn(guide, plan1, scales, 1024)
+            loss.backward()
+            allreduce_gradients(guide.parameters(), average=True)
+            opt.step()
+            return loss
+
+        for _ in range(3):
+            svi_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_svi = 10
+        for _ in range(n_svi):
+            svi_step()
+        e1.record()
+        torch.cuda.synchronize()
+        svi_ms = e0.elapsed_time(e1) / n_svi
+        plan1.close()
+
     # ---- end to end through the host-buffer C ABI --------------------------------
     h_la = torch.empty(la.shape, dtype=torch.float32, pin_memory=True).copy_(la.cpu())
     h_lr = torch.empty(lr.shape, dtype=torch.float32, pin_memory=True).copy_(lr.cpu())
@@ -361,6 +396,9 @@ def run_native(args):
                          if peaks else "fallback 6650 GB/s (of fallback)",
                          "note": "serial tick loop per particle-day: latency/issue bound by "
                                  "construction (SURVEY.md §8d); see profiles/ for issue-slot use"},
+            "svi_step_ms": {"value": svi_ms, "config": "cfg2: N=100, one day F=3876, 1024 particles per "
+                            "GPU, mean-field guide over 10200 log-latents, Adam; includes the status "
+                            "check (one host sync) per step"},
             "philox_value": philox_value,
             "congested_value": congested_value,
             "regimes": {"value": f"posterior-like latents: mean service {svc} h x LogNormal(0, 0.3); "
@@ -394,6 +432,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-svi", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
