@@ -172,8 +172,27 @@ typedef struct { int flight; float arrival_time; } Transit;
 
 static float flight_noise(const float *noise, int f, int col) { return noise[4 * f + col]; }
 
+/* RelaxedBernoulliStraightThrough(T=0.5, probs=p).rsample() driven by the uniform u
+ * (torch relaxed_bernoulli.py::LogitRelaxedBernoulli.rsample + SigmoidTransform._call,
+ * then Pyro's straight-through rounding).  Returns the hard 0/1 value, *soft = the
+ * relaxed value the site's log_prob is evaluated at. */
+static float relaxed_bernoulli_draw(float p, float u, float *soft)
+{
+    const float temp = 0.5f;
+    float q = p < kEps ? kEps : (p > 1.0f - kEps ? 1.0f - kEps : p);
+    float uu = u < kEps ? kEps : (u > 1.0f - kEps ? 1.0f - kEps : u);
+    float x = (logf(uu) - log1pf(-uu) + logf(q) - log1pf(-q)) / temp;
+    float y = sigmoid_f(x);
+    y = y < kTiny ? kTiny : (y > 1.0f - kEps ? 1.0f - kEps : y);   /* SigmoidTransform clamp */
+    y = y < kEps ? kEps : (y > 1.0f - kEps ? 1.0f - kEps : y);     /* clamp_probs            */
+    *soft = y;
+    return rintf(y);                                                /* torch.round: half-even */
+}
+
 int ba_oracle_run_day(const BaOracleDay *day, const BaOracleLatents *lat,
                       const float *noise,       /* [F,4] e_dep, eps_travel, e_arr, eps_turn */
+                      const float *obs_noise,   /* [F,4] u_cancel, eps_dep_obs, eps_arr_obs, -
+                                                   for flights with obs=None; nullable      */
                       int noise_is_value,       /* 1: columns are the site VALUES x,tau,x,u */
                       float delta_t, float max_t, int include_cancellations,
                       int max_ticks,
@@ -307,12 +326,17 @@ int ba_oracle_run_day(const BaOracleDay *day, const BaOracleLatents *lat,
                 int f = ready[i];
                 if (day->origin[f] != o) continue;
                 if (sim_cancelled[f] < 0) {               /* first time seen, :100-109 */
-                    if (day->cancel_obs[f] < 0) { status = BA_ORACLE_BAD_ARG; goto done; }
-                    float v = (float)day->cancel_obs[f];
+                    float v, v_hard;
+                    if (day->cancel_obs[f] < 0) {             /* obs=None: sampled */
+                        if (!obs_noise || grads) { status = BA_ORACLE_BAD_ARG; goto done; }
+                        v_hard = relaxed_bernoulli_draw(p_cancel, obs_noise[4 * f], &v);
+                    } else {
+                        v = v_hard = (float)day->cancel_obs[f];
+                    }
                     float dlp_dp = 0.0f;
                     float lpc = relaxed_bernoulli_logpdf(p_cancel, v, &dlp_dp);
                     lp_class[4] += (double)lpc;
-                    sim_cancelled[f] = day->cancel_obs[f];
+                    sim_cancelled[f] = v_hard != 0.0f ? 1 : 0;
                     if (grads && include_cancellations) {
                         /* p = 1 - (1-b) sigma(z), z = 10 (n/nr - 1/4),
                          * n = exp(l) + integers, b = exp(c) */
@@ -381,7 +405,10 @@ int ba_oracle_run_day(const BaOracleDay *day, const BaOracleLatents *lat,
                     if (departing) {
                         /* _assign_departure_time, airport.py:164-182 */
                         float y = day->act_dep[f];
-                        if (isnan(y)) { status = BA_ORACLE_BAD_ARG; goto done; }
+                        if (isnan(y)) {                        /* obs=None: Normal.rsample */
+                            if (!obs_noise || grads) { status = BA_ORACLE_BAD_ARG; goto done; }
+                            y = mu + obs_noise[4 * f + 1] * sigma_r;
+                        }
                         lp_class[5] += (double)normal_logpdf(y, mu, sigma_r);
                         sim_dep[f] = y;
                         if (pop_tick) pop_tick[2 * f] = tick;
@@ -417,7 +444,10 @@ int ba_oracle_run_day(const BaOracleDay *day, const BaOracleLatents *lat,
                     } else {
                         /* _assign_arrival_time, airport.py:188-204 */
                         float y = day->act_arr[f];
-                        if (isnan(y)) { status = BA_ORACLE_BAD_ARG; goto done; }
+                        if (isnan(y)) {
+                            if (!obs_noise || grads) { status = BA_ORACLE_BAD_ARG; goto done; }
+                            y = mu + obs_noise[4 * f + 2] * sigma_r;
+                        }
                         lp_class[6] += (double)normal_logpdf(y, mu, sigma_r);
                         sim_arr[f] = y;
                         if (pop_tick) pop_tick[2 * f + 1] = tick;
@@ -505,6 +535,7 @@ typedef struct {
     const BaOracleDay *days; int D; int P; int Ng; int Fmax;
     const float *mean_turnaround, *mean_service, *travel, *log_init, *base_cl; /* [P,...] */
     const float *scales; const float *noise; /* [P,D,Fmax,4] */
+    const float *obs_noise; float *sim; /* [P,D,Fmax,4] nullable; [P,D,Fmax,3] nullable */
     int noise_is_value; float delta_t, max_t; int include_cancellations, max_ticks;
     int want_grad;
     double *logp;      /* [P,D] */
@@ -543,8 +574,11 @@ static void *batch_worker(void *arg)
         for (int d = 0; d < b->D; ++d) {
             BaOracleResult r;
             const float *nz = b->noise + ((size_t)p * b->D + d) * (size_t)b->Fmax * 4;
-            ba_oracle_run_day(&b->days[d], &lat, nz, b->noise_is_value, b->delta_t, b->max_t,
-                              b->include_cancellations, b->max_ticks, &r, gp, NULL, NULL);
+            const size_t row = ((size_t)p * b->D + d) * (size_t)b->Fmax;
+            const float *on = b->obs_noise ? b->obs_noise + row * 4 : NULL;
+            float *so = b->sim ? b->sim + row * 3 : NULL;
+            ba_oracle_run_day(&b->days[d], &lat, nz, on, b->noise_is_value, b->delta_t, b->max_t,
+                              b->include_cancellations, b->max_ticks, &r, gp, so, NULL);
             b->logp[(size_t)p * b->D + d] = r.logp;
             b->status[(size_t)p * b->D + d] = r.status;
             b->n_ticks[(size_t)p * b->D + d] = r.n_ticks;
@@ -556,7 +590,8 @@ static void *batch_worker(void *arg)
 int ba_oracle_run_batch(const BaOracleDay *days, int D, int P, int Ng, int Fmax,
                         const float *mean_turnaround, const float *mean_service,
                         const float *travel, const float *log_init, const float *base_cl,
-                        const float *scales, const float *noise, int noise_is_value,
+                        const float *scales, const float *noise, const float *obs_noise,
+                        float *sim, int noise_is_value,
                         float delta_t, float max_t, int include_cancellations, int max_ticks,
                         int want_grad, int n_threads,
                         double *logp, int32_t *status, int32_t *n_ticks,
@@ -568,6 +603,7 @@ int ba_oracle_run_batch(const BaOracleDay *days, int D, int P, int Ng, int Fmax,
     b.days = days; b.D = D; b.P = P; b.Ng = Ng; b.Fmax = Fmax;
     b.mean_turnaround = mean_turnaround; b.mean_service = mean_service; b.travel = travel;
     b.log_init = log_init; b.base_cl = base_cl; b.scales = scales; b.noise = noise;
+    b.obs_noise = obs_noise; b.sim = sim;
     b.noise_is_value = noise_is_value; b.delta_t = delta_t; b.max_t = max_t;
     b.include_cancellations = include_cancellations; b.max_ticks = max_ticks;
     b.want_grad = want_grad; b.logp = logp; b.status = status; b.n_ticks = n_ticks;

@@ -103,7 +103,8 @@ class _DayHolder:
 def run_day(spec, latents: Dict[str, np.ndarray], scales: Sequence[float],
             noise: np.ndarray, *, delta_t: float = 0.2, max_t: float = 30.0,
             include_cancellations: bool = False, noise_is_value: bool = False,
-            want_grad: bool = True, max_ticks: int = 100000) -> Dict[str, object]:
+            want_grad: bool = True, max_ticks: int = 100000,
+            obs_noise: Optional[np.ndarray] = None) -> Dict[str, object]:
     """One particle-day.  ``latents``: 1-particle arrays in global airport order
     (``mean_turnaround [Ng]``, ``mean_service [Ng]``, ``travel [Ng,Ng]``
     [+ ``log_initial_aircraft``, ``base_cancel_logprob``]); ``noise``: ``[F,4]``."""
@@ -132,8 +133,10 @@ def run_day(spec, latents: Dict[str, np.ndarray], scales: Sequence[float],
                      ("turn", "serv", "travel", "logn0", "basecl", "scales")])
     sim = np.zeros((F, 3), np.float32)
     pop = np.zeros((F, 2), np.int32)
+    on = None if obs_noise is None else np.ascontiguousarray(obs_noise[:F], np.float32)
+    assert on is None or on.shape == (F, 4)
     rc = lib.ba_oracle_run_day(
-        C.byref(day), C.byref(lat), _ptr(nz), C.c_int(int(noise_is_value)),
+        C.byref(day), C.byref(lat), _ptr(nz), _ptr(on), C.c_int(int(noise_is_value)),
         C.c_float(delta_t), C.c_float(max_t), C.c_int(int(include_cancellations)),
         C.c_int(max_ticks), C.byref(res), C.byref(grads) if want_grad else None,
         _ptr(sim), _ptr(pop))
@@ -155,7 +158,8 @@ def run_batch(specs: Sequence, latents: Dict[str, np.ndarray], scales: Sequence[
               noise: np.ndarray, *, delta_t: float = 0.2, max_t: float = 30.0,
               include_cancellations: bool = False, noise_is_value: bool = False,
               want_grad: bool = True, n_threads: int = 1,
-              max_ticks: int = 100000) -> Dict[str, np.ndarray]:
+              max_ticks: int = 100000, obs_noise: Optional[np.ndarray] = None,
+              want_sim: bool = False) -> Dict[str, np.ndarray]:
     """``P x D`` particle-days.  ``latents``: ``[P,Ng]`` / ``[P,Ng,Ng]`` arrays;
     ``noise``: ``[P, D, Fmax, 4]``.  Gradients are summed over days (unit
     cotangent on every ``logp[p,d]``)."""
@@ -171,6 +175,9 @@ def run_batch(specs: Sequence, latents: Dict[str, np.ndarray], scales: Sequence[
     Fmax = nz.shape[2]
     assert nz.shape == (P, D, Fmax, 4) and Fmax >= max(s.n_flights for s in specs)
     sc = np.ascontiguousarray(np.asarray(scales, np.float32))
+    on = None if obs_noise is None else np.ascontiguousarray(obs_noise, np.float32)
+    assert on is None or on.shape == (P, D, Fmax, 4)
+    sim = np.full((P, D, Fmax, 3), np.nan, np.float32) if want_sim else None
     logp = np.zeros((P, D)); status = np.zeros((P, D), np.int32)
     n_ticks = np.zeros((P, D), np.int32)
     g = dict(turn=np.zeros((P, Ng)), serv=np.zeros((P, Ng)), travel=np.zeros((P, Ng, Ng)),
@@ -180,13 +187,13 @@ def run_batch(specs: Sequence, latents: Dict[str, np.ndarray], scales: Sequence[
         _ptr(keep["mean_turnaround"]), _ptr(keep["mean_service"]), _ptr(keep["travel"]),
         _ptr(keep.get("log_initial_aircraft")) if include_cancellations else None,
         _ptr(keep.get("base_cancel_logprob")) if include_cancellations else None,
-        _ptr(sc), _ptr(nz), C.c_int(int(noise_is_value)),
+        _ptr(sc), _ptr(nz), _ptr(on), _ptr(sim), C.c_int(int(noise_is_value)),
         C.c_float(delta_t), C.c_float(max_t), C.c_int(int(include_cancellations)),
         C.c_int(max_ticks), C.c_int(int(want_grad)), C.c_int(int(n_threads)),
         _ptr(logp), _ptr(status), _ptr(n_ticks),
         _ptr(g["turn"]), _ptr(g["serv"]), _ptr(g["travel"]),
         _ptr(g["logn0"]), _ptr(g["basecl"]), _ptr(g["scales"]))
-    out = {"logp": logp, "status": status, "n_ticks": n_ticks}
+    out = {"logp": logp, "status": status, "n_ticks": n_ticks, "sim": sim}
     if want_grad:
         out["grads"] = {
             "mean_turnaround": g["turn"], "mean_service": g["serv"], "travel": g["travel"],

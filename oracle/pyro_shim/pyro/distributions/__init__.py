@@ -60,3 +60,23 @@ class RelaxedBernoulliStraightThrough(_CallMixin, _td.RelaxedBernoulli):
     def log_prob(self, value):
         value = getattr(value, "_unquantize", value)
         return super().log_prob(value)
+
+    def draw_with(self, source, name):
+        """torch's LogitRelaxedBernoulli.rsample + SigmoidTransform with an externally
+        supplied uniform (relaxed_bernoulli.py::rsample, transforms.py::SigmoidTransform)."""
+        u = source(name, "uniform")
+        if u is None:
+            return self()
+        base = self.base_dist
+        shape = base._extended_shape()
+        probs = torch.distributions.utils.clamp_probs(base.probs.expand(shape))
+        uniforms = torch.distributions.utils.clamp_probs(
+            torch.as_tensor(u, dtype=probs.dtype).reshape(shape))
+        x = (uniforms.log() - (-uniforms).log1p() + probs.log() - (-probs).log1p()) / base.temperature
+        finfo = torch.finfo(x.dtype)
+        soft = torch.clamp(torch.sigmoid(x), min=finfo.tiny, max=1.0 - finfo.eps)
+        soft = torch.distributions.utils.clamp_probs(soft)
+        hard = soft.round()
+        out = (hard - soft).detach() + soft
+        out._unquantize = soft
+        return out

@@ -83,7 +83,11 @@ def run_reference(
         ``travel [N,N]`` (+ ``log_initial_aircraft [N]``, ``base_cancel_logprob [N]``),
         indexed in ``states[0].airports`` order.
     noise:   ``[D, Fmax, 4]`` standard draws (Exp(1), N(0,1), Exp(1), N(0,1)) per
-        flight in *sorted pending order*; None -> the global torch RNG is used.
+        flight in *sorted pending order*; None -> the global torch RNG is used.  With
+        ``strip_observations`` (posterior-predictive run: every ``obs=None``) pass
+        ``[D, Fmax, 8]``: columns 4-6 drive the three otherwise-observed sites
+        (U(0,1) for ``_cancelled``, N(0,1) for ``_simulated_departure_time`` and
+        ``_simulated_arrival_time``).
     Returns a dict of numpy values (see keys at the bottom).
     """
     pyro, model, _, _ = _import_reference()
@@ -131,9 +135,12 @@ def run_reference(
         for col, suffix in enumerate(SITE_KINDS):
             if rest.endswith("_" + suffix):
                 stem = rest[: -len(suffix) - 1]
-                # "_travel_time" is also a suffix of nothing else; but
-                # "..._departure_service_time" must not match "service_time" only
                 return float(noise[d, flight_index[d][stem], col])
+        if noise.shape[-1] >= 7:
+            for col, suffix in enumerate(OBS_KINDS):
+                if rest.endswith("_" + suffix):
+                    stem = rest[: -len(suffix) - 1]
+                    return float(noise[d, flight_index[d][stem], 4 + col])
         return None
 
     if hasattr(pyro, "set_noise_source"):
@@ -182,7 +189,10 @@ def run_reference(
                     class_sums[suffix] += float(site["fn"].log_prob(site["value"]).sum())
                     break
 
+    store = pyro.get_param_store()
     out = {
+        "scale_values": np.array([float(store.get(n)) if hasattr(store, "get") else float(pyro.param(n))
+                                  for n in names], np.float64),
         "codes": codes,
         "total": float(total),
         "per_flight": float(per_flight),
@@ -215,5 +225,4 @@ def run_reference(
         out["grad_scales_per_flight"] = np.array(
             [0.0 if g is None else float(g) / v for g, v in zip(g_pf[len(keys):], vals)],
             np.float64)
-        out["scale_values"] = np.array(vals, np.float64)
     return out

@@ -47,6 +47,50 @@ CASES = {
 }
 
 
+# posterior-predictive cases (every observation stripped: obs=None everywhere)
+# name: (N, [F per day], service_scale, include_cancellations, aircraft_mean, delta_t, seed)
+PREDICTIVE = {
+    "pred4c":  (4, [80], 0.03, True, 3.0, 0.2, 31),
+    "pred5":   (5, [120, 90], 0.05, False, 8.0, 0.2, 32),
+    "pred4s":  (4, [100], 0.04, True, 1.2, 0.2, 33),
+}
+
+
+def make_predictive(name):
+    N, Fs, svc, canc, nac, dt, seed = PREDICTIVE[name]
+    frames = [synth_day_frame(N, F, d, seed=seed) for d, F in enumerate(Fs)]
+    lat = {k: v[0] for k, v in synth_latents(
+        N, 1, seed=seed, service_scale=svc, include_cancellations=canc,
+        n_aircraft_mean=nac).items()}
+    D, Fmax = len(Fs), max(Fs)
+    rng = np.random.default_rng([seed, 271828])
+    noise = np.zeros((D, Fmax, 8), np.float32)
+    noise[..., :4] = flight_noise(D, Fmax, seed)
+    noise[..., 4] = rng.random((D, Fmax))
+    noise[..., 5] = rng.standard_normal((D, Fmax))
+    noise[..., 6] = rng.standard_normal((D, Fmax))
+    ref = run_reference(frames, lat, noise, delta_t=dt, include_cancellations=canc,
+                        want_grad=False, strip_observations=True)
+    codes, specs = compile_states(build_reference_states(frames))
+    out = {
+        "n_days": D, "global_codes": np.array(codes), "delta_t": dt, "max_t": 30.0,
+        "include_cancellations": int(canc), "scales": ref["scale_values"], "noise": noise,
+        "ref_sim": ref["sim"], "ref_per_flight": ref["per_flight"],
+    }
+    for k, v in lat.items():
+        out["lat_" + k] = v
+    for d, s in enumerate(specs):
+        out[f"day{d}_codes"] = np.array(s.codes)
+        out[f"day{d}_names"] = np.array(s.flight_names)
+        for f in ("airport_global", "sched_dep", "origin", "dest"):
+            out[f"day{d}_{f}"] = getattr(s, f)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    n_c = int(np.nansum(ref["sim"][..., 0] != 0))
+    print(f"{name}: predictive, {n_c} cancelled, per_flight={ref['per_flight']:.3f} -> "
+          f"{os.path.getsize(path)} B")
+
+
 def flight_noise(D, Fmax, seed):
     rng = np.random.default_rng([seed, 31337])
     z = np.empty((D, Fmax, 4), np.float32)
@@ -98,6 +142,6 @@ def make_case(name):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + list(PREDICTIVE))
     for n in names:
-        make_case(n)
+        make_predictive(n) if n in PREDICTIVE else make_case(n)

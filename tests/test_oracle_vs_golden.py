@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from oracle import ba_oracle
-from tests.util import Golden, golden_names, rel_err
+from tests.util import Golden, PredictiveGolden, golden_names, predictive_names, rel_err
 
 LOGP_RTOL = 2e-6      # observed <= 6e-7; the north-star gate for the kernel is 1e-4
 NORTH_STAR_LOGP_RTOL = 1e-4
@@ -64,3 +64,17 @@ def test_value_mode_logp(name):
     logp, _, _ = _run(g, noise_is_value=True)
     ref_sum = sum(g.ref_class.values())
     assert abs(logp - ref_sum) <= LOGP_RTOL * abs(ref_sum)
+
+
+@pytest.mark.parametrize("name", predictive_names())
+def test_posterior_predictive_outcomes(name):
+    """obs=None everywhere (posterior-predictive run): simulated
+    cancellations identical, simulated departure/arrival times within 2 ulp of the
+    reference driven by the same standard noise."""
+    g = PredictiveGolden(name)
+    for d, spec in enumerate(g.specs):
+        o = ba_oracle.run_day(spec, g.latents, g.scales, g.noise[d], delta_t=g.delta_t,
+                              max_t=g.max_t, include_cancellations=g.include_cancellations,
+                              want_grad=False, obs_noise=g.obs_noise[d])
+        assert o["status"] == 0
+        g.check(o["sim"], d)

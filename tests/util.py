@@ -13,8 +13,57 @@ LATENT_KEYS = ("mean_turnaround", "mean_service", "travel",
                "log_initial_aircraft", "base_cancel_logprob")
 
 
-def golden_names():
+def _all_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_names():
+    """Fully observed cases (log-prob + gradient fixtures)."""
+    return [n for n in _all_names() if not n.startswith("pred")]
+
+
+def predictive_names():
+    """Posterior-predictive cases (every obs=None; simulated outcomes fixtures)."""
+    return [n for n in _all_names() if n.startswith("pred")]
+
+
+class PredictiveGolden:
+    """One posterior-predictive fixture written by tests/golden/make_golden.py."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+        self.name = name
+        self.n_days = int(z["n_days"])
+        self.global_codes = [str(c) for c in z["global_codes"]]
+        self.delta_t, self.max_t = float(z["delta_t"]), float(z["max_t"])
+        self.include_cancellations = bool(int(z["include_cancellations"]))
+        self.scales = tuple(float(s) for s in z["scales"])
+        self.noise = z["noise"][..., :4]            # [D, Fmax, 4]
+        self.obs_noise = np.ascontiguousarray(z["noise"][..., 4:8])
+        self.latents = {k: z["lat_" + k] for k in LATENT_KEYS if "lat_" + k in z}
+        self.ref_sim = z["ref_sim"]                 # [D, Fmax, 3] cancelled, dep, arr
+        self.specs = []
+        for d in range(self.n_days):
+            F = z[f"day{d}_sched_dep"].shape[0]
+            nan = np.full(F, np.nan, np.float32)
+            self.specs.append(DaySpec(
+                codes=[str(c) for c in z[f"day{d}_codes"]],
+                airport_global=z[f"day{d}_airport_global"],
+                sched_dep=z[f"day{d}_sched_dep"], act_dep=nan.copy(), act_arr=nan.copy(),
+                cancel_obs=np.full(F, -1, np.int8),
+                origin=z[f"day{d}_origin"], dest=z[f"day{d}_dest"],
+                flight_names=[str(c) for c in z[f"day{d}_names"]]))
+
+    def check(self, sim, d):
+        """sim: [F(max), 3] of day d from an implementation driven by the same noise."""
+        F = self.specs[d].n_flights
+        ref = self.ref_sim[d, :F]
+        got = np.asarray(sim)[:F]
+        cancelled = ref[:, 0] != 0
+        assert np.array_equal(got[:, 0] != 0, cancelled)
+        ok = ~cancelled
+        np.testing.assert_allclose(got[ok, 1], ref[ok, 1], rtol=0, atol=4e-6)
+        np.testing.assert_allclose(got[ok, 2], ref[ok, 2], rtol=0, atol=4e-6)
 
 
 class Golden:
