@@ -21,7 +21,8 @@ PD_TICK_CAP, PD_OVERFLOW, PD_UNOBSERVED, PD_INTERNAL = 1, 2, 4, 8
 
 EXPORTS = (
     "ba_version", "ba_last_error", "ba_plan_create", "ba_plan_destroy", "ba_plan_info",
-    "ba_plan_routes", "ba_tape_bytes", "ba_forward", "ba_backward", "ba_generate_noise",
+    "ba_plan_routes", "ba_tape_bytes", "ba_forward", "ba_backward", "ba_predict",
+    "ba_generate_noise",
     "ba_logjoint_host", "ba_launch_count",
 )
 
@@ -84,7 +85,7 @@ def load_library(build_if_missing: bool = True):
     lib.ba_plan_destroy.restype = None
     lib.ba_plan_destroy.argtypes = [C.c_void_p]
     for name in ("ba_plan_create", "ba_plan_info", "ba_plan_routes", "ba_forward",
-                 "ba_backward", "ba_generate_noise", "ba_logjoint_host"):
+                 "ba_backward", "ba_predict", "ba_generate_noise", "ba_logjoint_host"):
         getattr(lib, name).restype = C.c_int
     lib.ba_plan_create.argtypes = [C.POINTER(BaDayTable), C.c_int32, C.c_int32, C.c_float,
                                    C.c_float, C.c_int32, C.c_int32, C.c_int32,
@@ -94,6 +95,8 @@ def load_library(build_if_missing: bool = True):
     lib.ba_forward.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + \
         [C.POINTER(BaForwardOpts)] + [C.c_void_p] * 5
     lib.ba_backward.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 6
+    lib.ba_predict.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5 + \
+        [C.POINTER(BaForwardOpts)] + [C.c_void_p] * 4
     lib.ba_generate_noise.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.ba_logjoint_host.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + \
         [C.POINTER(BaForwardOpts)] + [C.c_void_p] * 5
@@ -166,6 +169,12 @@ class PlanHandle:
         _check(load_library().ba_forward(self.handle, int(P), lat_airport, lat_route, scales,
                                          noise, C.byref(opts), logp, status, ticks, tape,
                                          stream), "ba_forward")
+
+    def predict(self, P, lat_airport, lat_route, scales, noise, noise2, opts: BaForwardOpts,
+                sim, status, ticks, stream):
+        _check(load_library().ba_predict(self.handle, int(P), lat_airport, lat_route, scales,
+                                         noise, noise2, C.byref(opts), sim, status, ticks,
+                                         stream), "ba_predict")
 
     def backward(self, P, dlogp, tape, g_airport, g_route, g_scales, stream):
         _check(load_library().ba_backward(self.handle, int(P), dlogp, tape, g_airport, g_route,

@@ -48,6 +48,19 @@ struct BaPlan {
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    // scratch log-prob output of ba_predict (the kernel writes one float per item)
+    float *d_plogp = nullptr;
+    size_t plogp_cap = 0;
+    float *d_predict_logp(size_t n)
+    {
+        if (plogp_cap < n) {
+            if (d_plogp) cudaFree(d_plogp);
+            d_plogp = nullptr; plogp_cap = 0;
+            if (cudaMalloc((void **)&d_plogp, n * sizeof(float)) != cudaSuccess) return nullptr;
+            plogp_cap = n;
+        }
+        return d_plogp;
+    }
 };
 
 template <typename T>
@@ -74,6 +87,7 @@ extern "C" void ba_plan_destroy(BaPlan *pl)
     for (void *p : pl->allocs) cudaFree(p);
     if (pl->d_worklist) cudaFree(pl->d_worklist);
     if (pl->d_stage) cudaFree(pl->d_stage);
+    if (pl->d_plogp) cudaFree(pl->d_plogp);
     if (pl->host_stream) cudaStreamDestroy(pl->host_stream);
     delete pl;
 }
@@ -294,6 +308,41 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
                     100.0 * (double)h[i] / tot);
         fprintf(stderr, "\n");
     }
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_predict(BaPlan *pl, int32_t P, const float *d_lat_airport,
+                               const float *d_lat_route, const float *d_scales,
+                               const float *d_noise, const float *d_noise2,
+                               const BaForwardOpts *opts, float *d_sim, uint32_t *d_status,
+                               int32_t *d_ticks, void *stream)
+{
+    if (!pl || P <= 0 || !d_lat_airport || !d_lat_route || !d_scales || !d_sim || !d_status)
+        return set_err(BA_ERR_BAD_ARG, "ba_predict: null / empty argument");
+    BaForwardOpts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) o = *opts;
+    cudaStream_t s = (cudaStream_t)stream;
+    BA_CUDA(cudaSetDevice(pl->device));
+    const long long n_work = (long long)P * pl->host.view.D;
+    if (n_work > 0x7fffffffLL) return set_err(BA_ERR_LIMIT, "ba_predict: P*D too large");
+    BA_CUDA(cudaMemsetAsync(pl->d_counters, 0, 4 * sizeof(unsigned int), s));
+    BaFwdParams prm;
+    std::memset(&prm, 0, sizeof(prm));
+    prm.plan = pl->dev_view;
+    prm.P = P;
+    prm.lat_airport = d_lat_airport; prm.lat_route = d_lat_route; prm.scales = d_scales;
+    prm.noise = d_noise; prm.noise2 = d_noise2; prm.sim = d_sim; prm.seed = o.seed;
+    prm.value_mode = o.noise_is_value;
+    prm.logp = pl->d_predict_logp(P * pl->host.view.D);
+    if (!prm.logp) return set_err(BA_ERR_CUDA, "ba_predict: out of device memory");
+    prm.status = d_status; prm.ticks = d_ticks; prm.pop_tick = o.d_pop_tick;
+    prm.scratch = pl->d_scratch; prm.scratch_stride = pl->stride_exact;
+    prm.work_counter = pl->d_counters + 1;
+    prm.n_work = (int)n_work;
+    int grid = (int)std::min<long long>(n_work, pl->grid_exact);
+    BA_CUDA(ba_launch_predict(prm, grid, pl->block, pl->smem_exact, s));
+    g_launches++;
     return BA_OK;
 }
 

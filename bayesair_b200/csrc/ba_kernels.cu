@@ -46,7 +46,7 @@ size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bo
 #endif
 #define BA_MIN_BLOCKS(MAXT) ((MAXT) == 128 ? BA_MIN_BLOCKS_128 : ((MAXT) == 256 ? 3 : 1))
 
-template <bool EXACT, int MAXT>
+template <bool EXACT, int MAXT, bool PREDICT>
 __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(const BaFwdParams prm)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         c.rt_flt = day.rt_flt; c.Rd = day.Rd;
         c.lat_route = prm.lat_route + (size_t)p * R;
         c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
+        c.noise2 = (PREDICT && prm.noise2) ? prm.noise2 + pd * (size_t)plan.Fmax * 4 : nullptr;
+        c.sim = PREDICT ? prm.sim + pd * (size_t)plan.Fmax * 3 : nullptr;
         c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
@@ -126,12 +128,14 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
 
         BA_MARK(0);
         // ---- prologue: flight-parallel, coalesced ------------------------------
-        for (int f = tid; f < day.F; f += nthr) ba_prologue_flight(c, acc, f);
+        for (int f = tid; f < day.F; f += nthr) ba_prologue_flight<PREDICT>(c, acc, f);
         __syncthreads();
         BA_MARK(1);
-        if (tid < 32) ba_calendar_scan(c, tid);
-        __syncthreads();
-        for (int f = tid; f < day.F; f += nthr) ba_calendar_scatter(c, f);
+        if (!PREDICT) {
+            if (tid < 32) ba_calendar_scan(c, tid);
+            __syncthreads();
+            for (int f = tid; f < day.F; f += nthr) ba_calendar_scatter(c, f);
+        }
         // departures that are ready at the very first tick
         int tick = day.first_tick - 1;
         if (tick + 1 <= day.last_ready_tick)
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             for (int s = tid; s < N; s += nthr) {
                 const int a = day.lane_airport[s];
                 if (n_due) ba_phase_c_pull(c, acc, a, prev, n_due);
-                ba_phase_a<EXACT>(c, acc, a, t, tick);
+                ba_phase_a<EXACT, PREDICT>(c, acc, a, t, tick);
                 more |= ba_airport_busy(c, a) ? 1 : 0;
             }
             if (!EXACT && (acc.status & BA_S_OVERFLOW)) c.cta[3] = 1u;
@@ -164,7 +168,10 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             if (!EXACT && c.cta[3]) break;                      // a ring overflowed: this
                                                                 // particle-day is re-run anyway
             if (tid == 0) c.cta[prev] = 0;                      // consumed by every lane
-            if ((uint32_t)tick < c.cal_cap) {
+            if (PREDICT) {
+                const uint32_t lo = c.cta[4], hi = c.cta[2];
+                for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_pool(c, acc, i, t, cur);
+            } else if ((uint32_t)tick < c.cal_cap) {
                 const uint32_t lo = c.cal_cnt[tick - 1], hi = c.cal_cnt[tick];
                 for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_arrival(c, acc, i, cur);
             }
@@ -172,12 +179,13 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
                 for (uint32_t i = day.dcal_off[tick + 1] + tid; i < (uint32_t)day.dcal_off[tick + 2]; i += nthr)
                     ba_phase_b_departure(c, acc, i, cur);
             busy = __syncthreads_or(more) != 0;
+            if (PREDICT && tid == 0) ba_pool_advance(c, 64u);   // next reader: phase B, after a barrier
             BA_MARK(4);
         }
 
         // ---- epilogue ----------------------------------------------------------
         __syncthreads();          // every wait of the tape is written
-        const bool aborted = !EXACT && c.cta[3] != 0u;
+        const bool aborted = PREDICT || (!EXACT && c.cta[3] != 0u);   // predictive: outcomes only
         if (!aborted)
             for (int f = tid; f < day.F; f += nthr) ba_epilogue_flight(c, acc, f);
         if (c.grow && !aborted) {
@@ -273,10 +281,10 @@ __global__ void __launch_bounds__(256) ba_collect_kernel(const uint32_t *status,
 // block-size classes: the register budget follows the CTA size actually used
 #define BA_DISPATCH(EX, BLOCK, STMT)                                                   \
     do {                                                                               \
-        if ((BLOCK) <= 128) { auto kfn = ba_forward_kernel<EX, 128>; STMT; }           \
-        else if ((BLOCK) <= 256) { auto kfn = ba_forward_kernel<EX, 256>; STMT; }      \
-        else if ((BLOCK) <= 512) { auto kfn = ba_forward_kernel<EX, 512>; STMT; }      \
-        else { auto kfn = ba_forward_kernel<EX, 1024>; STMT; }                         \
+        if ((BLOCK) <= 128) { auto kfn = ba_forward_kernel<EX, 128, false>; STMT; }      \
+        else if ((BLOCK) <= 256) { auto kfn = ba_forward_kernel<EX, 256, false>; STMT; } \
+        else if ((BLOCK) <= 512) { auto kfn = ba_forward_kernel<EX, 512, false>; STMT; } \
+        else { auto kfn = ba_forward_kernel<EX, 1024, false>; STMT; }                    \
     } while (0)
 
 // The dynamic-shared-memory limit is a property of the kernel function, shared by every plan
@@ -323,6 +331,31 @@ cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, int grid, int bl
 {
     if (exact) BA_DISPATCH(true, block, (kfn<<<grid, block, smem, s>>>(p)));
     else BA_DISPATCH(false, block, (kfn<<<grid, block, smem, s>>>(p)));
+    return cudaGetLastError();
+}
+
+// posterior-predictive variant: exact-capacity lists only
+#define BA_DISPATCH_PREDICT(BLOCK, STMT)                                                 \
+    do {                                                                                 \
+        if ((BLOCK) <= 128) { auto kfn = ba_forward_kernel<true, 128, true>; STMT; }     \
+        else if ((BLOCK) <= 256) { auto kfn = ba_forward_kernel<true, 256, true>; STMT; } \
+        else if ((BLOCK) <= 512) { auto kfn = ba_forward_kernel<true, 512, true>; STMT; } \
+        else { auto kfn = ba_forward_kernel<true, 1024, true>; STMT; }                   \
+    } while (0)
+
+cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
+                              cudaStream_t s)
+{
+    static size_t cur[4] = {0, 0, 0, 0};
+    const int cls = block <= 128 ? 0 : (block <= 256 ? 1 : (block <= 512 ? 2 : 3));
+    if (smem > cur[cls]) {
+        cudaError_t e = cudaSuccess;
+        BA_DISPATCH_PREDICT(block, e = cudaFuncSetAttribute(
+            kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (e != cudaSuccess) return e;
+        cur[cls] = smem;
+    }
+    BA_DISPATCH_PREDICT(block, (kfn<<<grid, block, smem, s>>>(p)));
     return cudaGetLastError();
 }
 

@@ -12,6 +12,8 @@ struct BaFwdParams {
     const float *lat_route;       // [P, R]
     const float *scales;          // [3]
     const float *noise;           // [P, D, Fmax, 4] or nullptr
+    const float *noise2;          // predictive: [P, D, Fmax, 4] or nullptr (Philox)
+    float *sim;                   // predictive: [P, D, Fmax, 3] out
     uint64_t seed;
     int32_t value_mode, want_grad, replay_waits;
     float *logp;                  // [P, D]
@@ -44,6 +46,8 @@ int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, in
 
 cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, int grid, int block,
                               size_t smem, cudaStream_t s);
+cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
+                              cudaStream_t s);
 cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s);
 cudaError_t ba_launch_noise(const BaPlanView &plan, int P, uint64_t seed, float *noise,
                             cudaStream_t s);

@@ -221,8 +221,10 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             H.dcal_off.assign((size_t)last_ready_tick + 2, 0);
             std::vector<int> cnt((size_t)last_ready_tick + 2, 0);
             auto on_calendar = [&](int f) {
+                // (an unobserved cancellation at such an airport can only come out "not
+                //  cancelled": its probability is exactly 0, see BA_SIMPLE_RATIO)
                 return !(H.airports[T.h_origin[f]].flags & BA_AP_TRACK_T) &&
-                       ((H.flights[f].od >> 24) & 3u) == 0u;
+                       ((H.flights[f].od >> 24) & 3u) != 1u;
             };
             for (int f = 0; f < F; ++f) if (on_calendar(f)) cnt[ready_tick[f]]++;
             for (int k = 0; k <= last_ready_tick; ++k) H.dcal_off[k + 1] = H.dcal_off[k] + cnt[k];

@@ -188,6 +188,11 @@ struct BaCtx {
     // particle inputs
     const float *lat_route;       // [R]
     const float *noise;           // [Fmax*4] of this (particle, day) or nullptr
+    // posterior-predictive mode only (flights with obs=None are sampled):
+    const float *noise2;          // [Fmax*4] U(0,1) cancel, N(0,1) departure, N(0,1) arrival, -
+    float *sim;                   // [Fmax*3] out: cancelled, simulated departure, arrival
+    uint32_t *pool;               // in-transit pool {word, key, seq, arrival, x} x F (aliases
+                                  //   the calendar arrays, unused in this mode)
     uint64_t seed;
     uint32_t particle, dayidx;
     float sigma, v_t, v_u;        // the three scales
@@ -206,7 +211,8 @@ struct BaCtx {
     uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail;
     uint32_t *s_flags, *s_qoff, *s_qmask, *s_goff, *s_depoff, *s_depcnt, *s_arrcnt;
     // CTA-wide scalars (shared memory): [0], [1] entries in the even / odd due buffer,
-    // [3] abort flag (a shared ring overflowed)
+    // [3] abort flag (a shared ring overflowed), [2] / [4] entries in / first live entry of
+    // the predictive in-transit pool
     uint32_t *cta;
     const int32_t *dcal_off;      // static departure calendar (ba_plan.h)
     const uint32_t *dcal_rec;
@@ -260,7 +266,7 @@ struct BaAcc {
 #define BA_NWORDS_STATE_SIMPLE 22 // per-airport words of shared state, no aircraft bookkeeping
 #define BA_NWORDS_STATE_TRACK 38  // ... when some airport of the plan tracks aircraft
 #define BA_Q_WORDS 6              // words per runway-queue entry
-#define BA_CTA_WORDS 4            // CTA-wide scalars
+#define BA_CTA_WORDS 8            // CTA-wide scalars
 
 // Assigns the per-airport arrays out of one contiguous word buffer.  The arrays that only
 // airports with aircraft bookkeeping touch exist only when the plan has such airports.
@@ -308,6 +314,7 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32
     c.karr = g; g += F;
     c.cal = g; g += 3 * F;
     c.popkey = g; g += F; c.popseq = g; g += F;
+    c.pool = c.cal;                           // cal (3F) + popkey + popseq = 5F words
     c.trl = c.tre = nullptr;
     if (day.any_track_t) { c.trl = (float *)g; g += F; c.tre = (float *)g; g += F; }
     c.qd = c.se = c.sw = nullptr;
@@ -347,6 +354,39 @@ BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
 #endif
     }
     return ba_philox_noise(c.seed, c.particle, c.dayidx, (uint32_t)f);
+}
+
+struct BaObsNoise { float u_cancel, eps_dep, eps_arr; };
+
+BA_DEV BaObsNoise ba_noise2(const BaCtx &c, int f)
+{
+    BaObsNoise z;
+    if (c.noise2) {
+        z.u_cancel = c.noise2[4 * f]; z.eps_dep = c.noise2[4 * f + 1]; z.eps_arr = c.noise2[4 * f + 2];
+        return z;
+    }
+    uint32_t r[4];
+    ba_philox((uint32_t)f, c.dayidx, c.particle, 0x42413231u, (uint32_t)c.seed,
+              (uint32_t)(c.seed >> 32), r);
+    z.u_cancel = ba_u01(r[0]);
+    const float rad = sqrtf(-2.0f * BA_LOG(ba_u01(r[1])));
+    const float ang = 6.283185307179586f * ba_u01(r[2]);
+    z.eps_dep = rad * cosf(ang); z.eps_arr = rad * sinf(ang);
+    return z;
+}
+
+// RelaxedBernoulliStraightThrough(T = 0.5, probs = p) sample driven by the uniform u: hard 0/1
+// (torch LogitRelaxedBernoulli.rsample + SigmoidTransform + Pyro's straight-through round;
+// bayes_air/network.py:100-109 with obs=None)
+BA_DEV float ba_relaxed_bernoulli_draw(float p, float u)
+{
+    const float q = fminf(fmaxf(p, BA_F32_EPS), 1.0f - BA_F32_EPS);
+    const float uu = fminf(fmaxf(u, BA_F32_EPS), 1.0f - BA_F32_EPS);
+    const float x = (BA_LOG(uu) - BA_LOG1P(-uu) + BA_LOG(q) - BA_LOG1P(-q)) / 0.5f;
+    float y = 1.0f / (1.0f + BA_EXP(-x));
+    y = fminf(fmaxf(y, BA_F32_TINY), 1.0f - BA_F32_EPS);
+    y = fminf(fmaxf(y, BA_F32_EPS), 1.0f - BA_F32_EPS);
+    return rintf(y);
 }
 
 BA_DEV BaFlight ba_flight(const BaCtx &c, int f)
@@ -413,6 +453,7 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
 // ---------------------------------------------------------------------------
 // PROLOGUE: one flight (call for f = tid, tid + nthreads, ...)
 // ---------------------------------------------------------------------------
+template <bool PREDICT>
 BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
 {
     const BaFlight fl = ba_flight(c, f);
@@ -427,11 +468,23 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
     const float sc = BA_MUL(T, c.v_t);
     const float tau = c.value_mode ? nz.eps_travel : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
     float y_dep = fl.act_dep, y_arr = fl.act_arr;
+    const int k = c.pos_dep[f];
+    if (PREDICT) {
+        // departure / arrival times may be sampled: the arrival time is only known when the
+        // departure is served.  Stage the travel time and the turnaround duration instead.
+        c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = tau; c.xaf[f] = xa;
+        c.sim[3 * f] = cobs == 1u ? 1.0f : 0.0f; c.sim[3 * f + 1] = NAN; c.sim[3 * f + 2] = NAN;
+        if (c.trl) {
+            const float mt = c.mt[d];
+            c.trl[f] = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, c.tstd[d]));
+            c.tre[f] = nz.eps_turn;
+        }
+        return;
+    }
     if (cobs == 3u || (cobs != 1u && (isnan(y_dep) || isnan(y_arr)))) {
         acc.status |= BA_S_UNOBSERVED;      // this entry point is the fully observed path
         y_dep = fl.sched_dep; y_arr = fl.sched_dep;
     }
-    const int k = c.pos_dep[f];
     const float at = BA_ADD(y_dep, tau);    // network.py:166-168 with the observed departure
     c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at; c.xaf[f] = xa;
     c.popkey[f] = BA_KEY_INVALID;
@@ -568,7 +621,7 @@ BA_DEV void ba_depart_tracked(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, u
 // ---------------------------------------------------------------------------
 // SCAN, phase A
 // ---------------------------------------------------------------------------
-template <bool EXACT>
+template <bool EXACT, bool PREDICT>
 BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
 {
     const uint32_t flags = c.s_flags[a];
@@ -664,8 +717,18 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
             uint32_t first_delayed = n_new;
             for (uint32_t i = 0; i < n_new; ++i) {
                 const uint32_t k = k0 + i;
-                const uint32_t cobs = (c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u;
-                if (cobs == 3u) { acc.status |= BA_S_UNOBSERVED; continue; }
+                uint32_t cobs = (c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u;
+                if (cobs == 3u) {
+                    if (!PREDICT) { acc.status |= BA_S_UNOBSERVED; continue; }
+                    // obs=None: the site is sampled (network.py:100-109)
+                    const uint32_t w = c.dep_word[k];
+                    const int f = (int)(w & BA_FID_MASK);
+                    const float pp = 1.0f - (1.0f - base) * sg;
+                    cobs = ba_relaxed_bernoulli_draw(pp, ba_noise2(c, f).u_cancel) != 0.0f ? 1u : 0u;
+                    c.sim[3 * f] = (float)cobs;
+                    if (cobs)   // it will never land: one arrival less to wait for
+                        BA_ATOMIC_DEC(&c.s_arrcnt[(w >> BA_Q_DST_SHIFT) & 0xFFFu]);
+                }
                 acc.lp += cobs ? lp1 : lp0;
                 g_p += cobs ? dl1 : dl0;
                 if (cobs) continue;                       // cancelled -> completed
@@ -686,7 +749,9 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 uint32_t hd = c.dl_head[a];
                 for (uint32_t i = n_new; i-- > first_delayed;) {
                     const uint32_t k = k0 + i;
-                    if (((c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u) != 0u) continue;
+                    uint32_t cobs = (c.dep_word[k] >> BA_DW_CANCEL_SHIFT) & 3u;
+                    if (PREDICT && cobs == 3u) cobs = c.sim[3 * (c.dep_word[k] & BA_FID_MASK)] != 0.0f;
+                    if (cobs != 0u) continue;
                     hd -= 1;
                     c.dl[A->dl_off + (hd & A->dl_mask)] = k;      // dep-order position
                 }
@@ -741,7 +806,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 const float Bf = 2.384185791015625e-07f *
                     ((float)(head - wl.b + 1u) * wait + fabsf(sp.b) + fabsf(Af)) + 1e-30f;
                 lo = Af - Bf; hi = Af + Bf;
-                if (c.replay_always) lo = -INFINITY, hi = INFINITY;
+                if (PREDICT || c.replay_always) lo = -INFINITY, hi = INFINITY;
             }
             if (!(hi <= t)) {
                 if (lo > t || isnan(lo)) break;             // certainly still being served
@@ -757,7 +822,45 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
             // served (airport.py:111-126)
             const uint32_t word = wl.a;
             const int f = (int)(word & BA_FID_MASK);
-            if (word & BA_Q_DEP) {
+            if (PREDICT) {
+                // outcomes: observed values where present, else Normal(mu, sigma_r).rsample
+                // (airport.py:175-182,197-204); hi == lo == the exact fp32 queue_start + wait
+                const BaFlight fl = ba_flight(c, f);
+                const BaObsNoise on = ba_noise2(c, f);
+                if (word & BA_Q_DEP) {
+                    float y = fl.act_dep;
+                    if (isnan(y)) y = BA_ADD(hi, BA_MUL(on.eps_dep, c.sigma));
+                    c.sim[3 * f + 1] = y;
+                    const uint32_t key = ((uint32_t)tick << BA_KEY_TICK_SHIFT) | (uint32_t)a;
+                    const uint32_t seq = c.dep_pops[a];
+                    c.dep_pops[a] = seq + 1;
+                    const float av = BA_ADD(y, BA_LD_PAIR(BaPairF, e + 4).b);   // + travel time
+                    const uint32_t dst = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
+                    if (av <= t) {
+                        ba_due_append(c, acc, tick & 1, word & BA_FID_MASK, key, dst, seq, av,
+                                      c.xaf[f], 0.0f);
+                    } else {
+                        const uint32_t slot = BA_ATOMIC_INC(&c.cta[2]);
+                        uint32_t *pe = c.pool + 5u * slot;
+                        pe[0] = word & BA_DW_ENTRY_MASK; pe[1] = key; pe[2] = seq;
+                        pe[3] = __float_as_uint_portable(av);
+                        pe[4] = __float_as_uint_portable(c.xaf[f]);
+                    }
+                    if (c.pop_tick) c.pop_tick[2 * f] = tick;
+                } else {
+                    float y = fl.act_arr;
+                    if (isnan(y)) y = BA_ADD(hi, BA_MUL(on.eps_arr, c.sigma));
+                    c.sim[3 * f + 2] = y;
+                    c.arr_pops[a] += 1;
+                    if (flags & BA_AP_TRACK_T) {
+                        const uint32_t n = c.turn_n[a];
+                        c.tt[A->turn_off + n] = BA_ADD(y, c.trl[f]);
+                        c.te[A->turn_off + n] = c.tre[f];
+                        c.turn_n[a] = n + 1;
+                    }
+                    if (c.pop_tick) c.pop_tick[2 * f + 1] = tick;
+                }
+            } else if (word & BA_Q_DEP) {
                 c.wd[f] = wait;
                 // add_in_transit_flights (network.py:136-168).  The in-transit list is
                 // implicit: its order is the key (tick, origin, per-origin sequence).
@@ -863,6 +966,29 @@ BA_DEV void ba_phase_b_departure(BaCtx &c, BaAcc &acc, uint32_t i, int parity)
     const uint32_t w = c.dep_word[k];
     ba_due_append(c, acc, parity, BA_Q_DEP | (w & BA_DW_ENTRY_MASK), BA_KEY_DEPARTURE | rank,
                   origin, 0u, fmaxf(0.0f, c.dep_sched[k]), c.xdk[k], c.atk[k]);
+}
+
+// Posterior-predictive mode: arrival times are only known once a departure is served, so
+// in-transit flights sit in an append-only pool that all threads scan each tick
+// (update_in_transit_flights, network.py:178-198); consumed entries are tombstoned.
+BA_DEV void ba_phase_b_pool(BaCtx &c, BaAcc &acc, uint32_t i, float t, int parity)
+{
+    uint32_t *pe = c.pool + 5u * i;
+    const float av = __uint_as_float_portable(pe[3]);
+    if (!(av <= t)) return;                        // not yet arrived, or tombstone (NaN)
+    const uint32_t word = pe[0];
+    ba_due_append(c, acc, parity, word & BA_FID_MASK, pe[1], (word >> BA_Q_DST_SHIFT) & 0xFFFu,
+                  pe[2], av, __uint_as_float_portable(pe[4]), 0.0f);
+    pe[3] = __float_as_uint_portable(NAN);
+}
+
+// advances the first-live pointer over leading tombstones (one thread; up to `budget`)
+BA_DEV void ba_pool_advance(BaCtx &c, uint32_t budget)
+{
+    uint32_t lo = c.cta[4];
+    const uint32_t n = c.cta[2];
+    while (lo < n && budget-- && isnan(__uint_as_float_portable(c.pool[5u * lo + 3]))) ++lo;
+    c.cta[4] = lo;
 }
 
 // ---------------------------------------------------------------------------

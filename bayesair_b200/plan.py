@@ -122,6 +122,34 @@ class SimulationPlan:
         return {"logp": logp, "status": status, "ticks": ticks, "tape": tape, "pop_tick": pop,
                 "_keep": (la, lr, sc, nz)}
 
+    def predict(self, lat_airport: torch.Tensor, lat_route: torch.Tensor, scales: torch.Tensor,
+                noise: Optional[torch.Tensor] = None, obs_noise: Optional[torch.Tensor] = None,
+                *, seed: int = 0, want_ticks: bool = False,
+                want_pop_ticks: bool = False) -> Dict[str, torch.Tensor]:
+        """Posterior-predictive forward simulation (``ba_predict``): flights without
+        observations are sampled.  Returns ``sim [P, D, Fmax, 3]`` = (cancelled 0/1,
+        simulated departure time, simulated arrival time; NaN where cancelled / padded)."""
+        P = int(lat_airport.shape[0])
+        D, N, Cn, R, F = (self.n_days, self.n_airports, self.n_airport_latents, self.n_routes,
+                          self.max_flights)
+        la = self._chk(lat_airport, (P, Cn, N), "lat_airport")
+        lr = self._chk(lat_route, (P, R), "lat_route")
+        sc = self._chk(scales, (3,), "scales")
+        nz = None if noise is None else self._chk(noise, (P, D, F, 4), "noise")
+        n2 = None if obs_noise is None else self._chk(obs_noise, (P, D, F, 4), "obs_noise")
+        with torch.cuda.device(self.device):
+            sim = torch.full((P, D, F, 3), float("nan"), dtype=torch.float32, device=self.device)
+            status = torch.empty((P, D), dtype=torch.int32, device=self.device)
+            ticks = torch.empty((P, D), dtype=torch.int32, device=self.device) if want_ticks else None
+            pop = (torch.empty((P, D, F, 2), dtype=torch.int32, device=self.device)
+                   if want_pop_ticks else None)
+            opts = _capi.BaForwardOpts(0, 0, 1, 0, 1, 0, int(seed) & (2**64 - 1),
+                                       None if pop is None else pop.data_ptr())
+            self._h.predict(P, _ptr(la), _ptr(lr), _ptr(sc), _ptr(nz), _ptr(n2), opts, _ptr(sim),
+                            _ptr(status), _ptr(ticks), self._stream())
+        return {"sim": sim, "status": status, "ticks": ticks, "pop_tick": pop,
+                "_keep": (la, lr, sc, nz, n2)}
+
     def backward(self, dlogp: torch.Tensor, tape: torch.Tensor):
         P = int(tape.shape[0])
         dl = self._chk(dlogp, (P, self.n_days), "dlogp")

@@ -160,6 +160,22 @@ BaStatus ba_backward(BaPlan *plan, int32_t n_particles, const float *d_dlogp,
                      const void *d_tape, float *d_g_airport, float *d_g_route,
                      float *d_g_scales, void *stream);
 
+/* Posterior-predictive forward simulation: flights whose observations are
+ * missing (h_act_dep / h_act_arr NaN, h_cancel_obs -1, i.e. obs=None at
+ * bayes_air/network.py:100-109 and bayes_air/types/airport.py:175-204) are SAMPLED; their
+ * sampled departure time drives the downstream arrival like in the reference.  No
+ * log-prob, no gradient.
+ *   d_noise  [P, D, Fmax, 4] as in ba_forward, or NULL (Philox from opts->seed)
+ *   d_noise2 [P, D, Fmax, 4] U(0,1) for `_cancelled`, N(0,1) for `_simulated_departure_time`,
+ *            N(0,1) for `_simulated_arrival_time`, unused; or NULL (Philox)
+ *   d_sim    [P, D, Fmax, 3] out: cancelled (0/1), departure time, arrival time (NaN where
+ *            the flight was cancelled) */
+BaStatus ba_predict(BaPlan *plan, int32_t n_particles,
+                    const float *d_lat_airport, const float *d_lat_route,
+                    const float *d_scales, const float *d_noise, const float *d_noise2,
+                    const BaForwardOpts *opts, float *d_sim, uint32_t *d_status,
+                    int32_t *d_ticks, void *stream);
+
 /* Writes the standard per-flight noise the kernel would draw from `seed`
  * ([P, D, Fmax, 4]); for tests and for callers that want to keep the draws. */
 BaStatus ba_generate_noise(BaPlan *plan, int32_t n_particles, uint64_t seed,

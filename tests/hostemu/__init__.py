@@ -132,3 +132,24 @@ class EmuPlan:
         nz = np.zeros((P, self.D, self.Fmax, 4), np.float32)
         _load().ba_emu_noise(self.h, P, C.c_uint64(seed), nz.ctypes.data_as(C.c_void_p))
         return nz
+
+
+def _predict(self, latents, scales, noise, noise2, *, seed=0, shuffle_seed=1, want_pop=False):
+    """Posterior-predictive run: returns dict(sim [P,D,Fmax,3], status, ticks, pop_tick)."""
+    lib = _load()
+    la, lr = self.pack_latents(latents)
+    P = la.shape[0]
+    sc = np.ascontiguousarray(scales, np.float32)
+    nz = None if noise is None else np.ascontiguousarray(noise, np.float32)
+    n2 = None if noise2 is None else np.ascontiguousarray(noise2, np.float32)
+    sim = np.zeros((P, self.D, self.Fmax, 3), np.float32)
+    status = np.zeros((P, self.D), np.uint32)
+    ticks = np.zeros((P, self.D), np.int32)
+    pop = np.zeros((P, self.D, self.Fmax, 2), np.int32) if want_pop else None
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    lib.ba_emu_predict(self.h, P, vp(la), vp(lr), vp(sc), vp(nz), vp(n2), C.c_uint64(seed),
+                       C.c_uint(shuffle_seed), vp(sim), vp(status), vp(ticks), vp(pop))
+    return dict(sim=sim, status=status, ticks=ticks, pop_tick=pop)
+
+
+EmuPlan.predict = _predict

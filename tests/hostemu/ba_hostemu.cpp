@@ -41,12 +41,13 @@ extern "C" void ba_emu_plan_routes(const EmuPlan *p, int32_t *o, int32_t *d)
     memcpy(d, p->host.route_dest.data(), p->host.route_dest.size() * 4);
 }
 
-template <bool EXACT>
+template <bool EXACT, bool PREDICT = false>
 static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d, int P,
                      const float *lat_airport, const float *lat_route, const float *scales,
                      const float *noise, uint64_t seed, int value_mode, int want_grad,
                      int replay_waits, unsigned shuffle_seed, float *logp, uint32_t *status, int32_t *ticks,
-                     float *tape, int32_t *pop_tick)
+                     float *tape, int32_t *pop_tick, const float *noise2 = nullptr,
+                     float *sim = nullptr)
 {
     (void)P;
     const int N = plan.N, C = plan.C, R = plan.R, D = plan.D;
@@ -75,6 +76,8 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     c.rt_flt = day.rt_flt; c.Rd = day.Rd;
     c.lat_route = lat_route + (size_t)p * R;
     c.noise = noise ? noise + pd * (size_t)plan.Fmax * 4 : nullptr;
+    c.noise2 = (PREDICT && noise2) ? noise2 + pd * (size_t)plan.Fmax * 4 : nullptr;
+    c.sim = PREDICT ? sim + pd * (size_t)plan.Fmax * 3 : nullptr;
     c.particle = p; c.dayidx = d;
     c.grow = c.want_grad ? tape + pd * (size_t)plan.grad_stride : nullptr;
     c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
@@ -92,10 +95,12 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     std::vector<int> forder(day.F);
     for (int f = 0; f < day.F; ++f) forder[f] = f;
     if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
-    for (int f : forder) ba_prologue_flight(c, acc[f % N], f);
-    ba_calendar_scan(c, -1);
-    if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
-    for (int f : forder) ba_calendar_scatter(c, f);
+    for (int f : forder) ba_prologue_flight<PREDICT>(c, acc[f % N], f);
+    if (!PREDICT) {
+        ba_calendar_scan(c, -1);
+        if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
+        for (int f : forder) ba_calendar_scatter(c, f);
+    }
     std::vector<int> order(N);
     for (int i = 0; i < N; ++i) order[i] = i;
     float t = 0.0f;
@@ -122,11 +127,17 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         for (int i = 0; i < N; ++i) {
             const int a = day.lane_airport[order[i]];
             if (n_due) ba_phase_c_pull(c, acc[order[i]], a, prev, n_due);
-            ba_phase_a<EXACT>(c, acc[order[i]], a, t, tick);
+            ba_phase_a<EXACT, PREDICT>(c, acc[order[i]], a, t, tick);
             more |= ba_airport_busy(c, a);
         }
         c.cta[prev] = 0;
-        if ((uint32_t)tick < c.cal_cap) {
+        if (PREDICT) {
+            std::vector<uint32_t> slice;
+            for (uint32_t i = c.cta[4]; i < c.cta[2]; ++i) slice.push_back(i);
+            if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
+            for (uint32_t i : slice) ba_phase_b_pool(c, acc[i % N], i, t, cur);
+            ba_pool_advance(c, 7u);
+        } else if ((uint32_t)tick < c.cal_cap) {
             std::vector<uint32_t> slice;
             for (uint32_t i = c.cal_cnt[tick - 1]; i < c.cal_cnt[tick]; ++i) slice.push_back(i);
             if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
@@ -135,8 +146,8 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         departures_of(tick + 1, cur);
         busy = more;
     }
-    for (int f = 0; f < day.F; ++f) ba_epilogue_flight(c, acc[f % N], f);
-    if (c.grow) {
+    if (!PREDICT) for (int f = 0; f < day.F; ++f) ba_epilogue_flight(c, acc[f % N], f);
+    if (c.grow && !PREDICT) {
         for (int i = 0; i < N; ++i) ba_epilogue_airport(c, day.lane_airport[i], N);
         for (int r = 0; r < day.Rd; ++r) ba_epilogue_route(c, r);
     }
@@ -204,4 +215,19 @@ extern "C" void ba_emu_noise(const EmuPlan *pl, int P, uint64_t seed, float *noi
                 float *o = noise + (((size_t)p * v.D + d) * v.Fmax + f) * 4;
                 o[0] = z.e_dep; o[1] = z.eps_travel; o[2] = z.e_arr; o[3] = z.eps_turn;
             }
+}
+
+extern "C" int ba_emu_predict(const EmuPlan *pl, int P, const float *lat_airport,
+                              const float *lat_route, const float *scales, const float *noise,
+                              const float *noise2, uint64_t seed, unsigned shuffle_seed,
+                              float *sim, uint32_t *status, int32_t *ticks, int32_t *pop_tick)
+{
+    const BaPlanView &plan = pl->host.view;
+    std::vector<float> logp((size_t)P * plan.D);
+    for (int d = 0; d < plan.D; ++d)
+        for (int p = 0; p < P; ++p)
+            run_item<true, true>(plan, plan.days[d], p, d, P, lat_airport, lat_route, scales, noise,
+                                 seed, 0, 0, 0, shuffle_seed, logp.data(), status, ticks, nullptr,
+                                 pop_tick, noise2, sim);
+    return 0;
 }

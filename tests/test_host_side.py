@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import Golden, golden_names, rel_err, std_noise
+from tests.util import (Golden, PredictiveGolden, golden_names, predictive_names, rel_err,
+                        std_noise)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -259,3 +260,46 @@ def test_mean_field_guide_surface():
     assert z.shape == (5, 7) and lp.shape == (5,)
     assert torch.allclose(g.log_prob(z), lp, atol=1e-5)
     assert g.sample((2,)).shape == (2, 7) and not g.sample((2,)).requires_grad
+
+
+# ------------------------------------------------ posterior-predictive mode --
+@pytest.mark.parametrize("name", predictive_names())
+def test_emulated_predictive_vs_golden(name):
+    """obs=None everywhere: the emulated kernel reproduces the reference's simulated
+    cancellations exactly and its simulated times within 2 ulp, for two interleavings."""
+    from tests.hostemu import EmuPlan
+    g = PredictiveGolden(name)
+    plan = EmuPlan(g.specs, len(g.global_codes), g.delta_t, g.max_t, g.include_cancellations)
+    lat = {k: v[None] for k, v in g.latents.items()}
+    for shuffle in (1, 4):
+        o = plan.predict(lat, g.scales, g.noise[None], g.obs_noise[None], shuffle_seed=shuffle)
+        assert (o["status"] == 0).all()
+        for d in range(g.n_days):
+            g.check(o["sim"][0, d], d)
+
+
+def test_emulated_predictive_vs_oracle_batch():
+    from bayesair_b200.compiler import day_spec_from_frame
+    from bayesair_b200.synth import synth_day_frame, synth_latents
+    from oracle import ba_oracle
+    from tests.hostemu import EmuPlan
+    N, F, P = 7, 260, 5
+    spec = day_spec_from_frame(synth_day_frame(N, F, 0, seed=55))
+    spec.act_dep[::2] = np.nan          # half the flights keep their observations
+    spec.act_arr[::3] = np.nan
+    spec.cancel_obs[:] = -1
+    lat = synth_latents(N, P, seed=6, service_scale=0.05, spread=0.5, include_cancellations=True,
+                        n_aircraft_mean=3.0)
+    noise = std_noise(P, 1, F, seed=1)
+    rng = np.random.default_rng(2)
+    n2 = np.zeros((P, 1, F, 4), np.float32)
+    n2[..., 0] = rng.random((P, 1, F)); n2[..., 1:3] = rng.standard_normal((P, 1, F, 2))
+    sc = (0.1, 0.1, 0.1)
+    ref = ba_oracle.run_batch([spec], lat, sc, noise, delta_t=0.2, include_cancellations=True,
+                              want_grad=False, obs_noise=n2, want_sim=True)
+    plan = EmuPlan([spec], N, 0.2, 30.0, True)
+    o = plan.predict(lat, sc, noise, n2, shuffle_seed=3)
+    assert (o["status"] == 0).all() and (ref["status"] == 0).all()
+    assert np.array_equal(o["ticks"], ref["n_ticks"])
+    assert np.array_equal(o["sim"][..., 0], ref["sim"][..., 0])
+    np.testing.assert_array_equal(np.nan_to_num(o["sim"], nan=-1.0), np.nan_to_num(ref["sim"], nan=-1.0))
