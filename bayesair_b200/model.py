@@ -74,7 +74,10 @@ def air_traffic_network_model(
 ):
     """See the module docstring.  ``device`` must be a CUDA device (``None`` ->
     the current one); the simulation has no CPU path.  Returns ``states``
-    unmodified (every caller of the reference ignores the return value)."""
+    unmodified (every caller of the reference ignores the return value); if some
+    flight has no observations (``obs=None``) the call is a posterior-predictive
+    simulation instead and returns ``[P, D, Fmax, 3]`` (cancelled, departure time,
+    arrival time) -- the reference returns the mutated state objects there."""
     plan = plan_for_states(states, delta_t, max_t, include_cancellations, device)
     device = plan.device
 
@@ -122,6 +125,16 @@ def air_traffic_network_model(
     noise, seed, is_value = getattr(_tls, "override", None) or (None, None, False)
     if noise is None and seed is None:
         seed = int(torch.randint(0, 2**62, (1,), dtype=torch.int64))
+    if plan.has_unobserved:
+        # obs=None somewhere: posterior-predictive run.  Like the reference, the observed
+        # sites of such flights are sampled; there is no log-joint to report.  The outcomes
+        # are exposed as a deterministic site and returned.
+        out = plan.predict(lat_airport.detach(), lat_route.detach(), scales.detach(), noise, None,
+                           seed=seed or 0)
+        plan.check_status(out["status"])
+        sim = out["sim"] if batched else out["sim"][0]
+        pyro.deterministic("air_traffic_simulated", sim)
+        return sim
     logp = simulate_log_joint(plan, lat_airport, lat_route, scales, noise,
                               seed=seed or 0, noise_is_value=is_value)
     log_joint = logp.sum(dim=1)               # sum over days -> [P]

@@ -120,3 +120,22 @@ def objective_fn(guide, plan: SimulationPlan, scales: torch.Tensor, n_particles:
                  seed: Optional[int] = None) -> torch.Tensor:
     """The reference's loss: ``-mean ELBO / number of flights`` (``train.py:318-326``)."""
     return -batched_elbo(guide, plan, scales, n_particles, seed).mean() / plan.n_flights_total
+
+
+def posterior_predictive(plan: SimulationPlan, sample: torch.Tensor, scales: torch.Tensor,
+                         seed: Optional[int] = None, check_status: bool = True) -> torch.Tensor:
+    """Forward-simulates the network for every row of ``sample`` (``[P, n_latent]``
+    log-latents, e.g. draws from a trained guide): ``[P, D, Fmax, 3]`` = (cancelled, simulated
+    departure time, simulated arrival time).  Flights that carry observations keep them
+    (teacher forcing, like the reference with ``obs=`` set); flights without are sampled --
+    BASELINE config 4 (delay / cancellation distributions)."""
+    lat = map_to_latents(sample, plan.n_airports, plan.include_cancellations)
+    lat_airport, lat_route = plan.pack_latents(
+        lat["mean_turnaround"], lat["mean_service"], lat["travel"],
+        lat.get("log_initial_aircraft"), lat.get("base_cancel_logprob"))
+    if seed is None:
+        seed = int(torch.randint(0, 2**62, (1,), dtype=torch.int64))
+    out = plan.predict(lat_airport.detach(), lat_route.detach(), scales.detach(), None, None, seed=seed)
+    if check_status:
+        plan.check_status(out["status"])
+    return out["sim"]

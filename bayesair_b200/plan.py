@@ -72,6 +72,11 @@ class SimulationPlan:
         self.route_origin = torch.from_numpy(self._h.route_origin.astype(np.int64)).to(self.device)
         self.route_dest = torch.from_numpy(self._h.route_dest.astype(np.int64)).to(self.device)
         self.n_flights_total = int(sum(s.n_flights for s in self.specs))
+        # any flight with obs=None (not counting the measured times of cancelled flights)
+        self.has_unobserved = any(
+            bool(np.any(s.cancel_obs < 0)) or
+            bool(np.any((np.isnan(s.act_dep) | np.isnan(s.act_arr)) & (s.cancel_obs != 1)))
+            for s in self.specs)
 
     @classmethod
     def from_states(cls, states, delta_t=0.1, max_t=30.0, include_cancellations=False,

@@ -59,3 +59,36 @@ for name, P, days in (("cfg1", 1024, 1), ("cfg2", 1024, 1), ("cfg5s", 256, 2)):
           f"ticks_equal={ticks_ok} | {ms:.2f} ms/step {P * days / ms * 1e3:.0f} pd/s bad_status={bad}",
           flush=True)
     plan.close()
+
+# BASELINE config 4: posterior-predictive forward simulation (all observations stripped,
+# cancellations on) of the 10-day network
+N, Fs, _, svc, specs = build_workload("cfg3")
+import copy
+pspecs = []
+for sp in specs[:4]:
+    q = copy.deepcopy(sp)
+    q.act_dep[:] = np.nan; q.act_arr[:] = np.nan; q.cancel_obs[:] = -1
+    pspecs.append(q)
+P = 2048
+plan = SimulationPlan(pspecs, pspecs[0].codes, delta_t=0.2, include_cancellations=True, device=dev)
+lat = synth_latents(N, P, seed=4, service_scale=svc, include_cancellations=True, n_aircraft_mean=8.0)
+tl = {k: torch.tensor(v, device=dev) for k, v in lat.items()}
+la, lr = plan.pack_latents(tl["mean_turnaround"], tl["mean_service"], tl["travel"],
+                           tl["log_initial_aircraft"], tl["base_cancel_logprob"])
+sc = torch.tensor([0.1, 0.1, 0.1], device=dev)
+for _ in range(2):
+    o = plan.predict(la, lr, sc, None, None, seed=3)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3):
+    o = plan.predict(la, lr, sc, None, None, seed=3)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 3
+sim = o["sim"]
+canc = float((sim[..., 0] == 1).float().mean())
+delay = float(torch.nanmean(sim[..., 1] - torch.tensor(np.stack([np.pad(s.sched_dep, (0, plan.max_flights - s.n_flights)) for s in pspecs]), device=dev)[None]))
+print(f"cfg4 (predictive, cancellations on): P={P} days={len(pspecs)} {ms:.1f} ms/step "
+      f"{P * len(pspecs) / ms * 1e3:.0f} pd/s bad_status={int(o['status'].ne(0).sum())} "
+      f"cancelled fraction {canc:.3f} mean departure delay {delay:.2f} h", flush=True)
