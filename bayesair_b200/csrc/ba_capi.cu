@@ -137,6 +137,8 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         BA_PCUDA(upload(pl, H.rt_flt, &v.rt_flt));
         BA_PCUDA(upload(pl, H.dcal_off, &v.dcal_off));
         BA_PCUDA(upload(pl, H.dcal_rec, &v.dcal_rec));
+        BA_PCUDA(upload(pl, H.drun_off, &v.drun_off));
+        BA_PCUDA(upload(pl, H.drun, &v.drun));
         BA_PCUDA(upload(pl, H.airports, &v.airports));
         BA_PCUDA(upload(pl, H.lane_airport, &v.lane_airport));
         dviews[d] = v;
@@ -156,8 +158,9 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         if (b >= 32 && b <= 1024 && b % 32 == 0) pl->block = b;
     }
     const bool tracked = pl->host.view.any_track != 0;
-    pl->smem_fast = ba_forward_smem_bytes(N, pl->host.smem_list_words, false, tracked);
-    pl->smem_exact = ba_forward_smem_bytes(N, 0, true, tracked);
+    pl->smem_fast = ba_forward_smem_bytes(N, pl->host.smem_list_words, false, tracked,
+                                          pl->host.max_dslice);
+    pl->smem_exact = ba_forward_smem_bytes(N, 0, true, tracked, pl->host.max_dslice);
     int max_optin = 0;
     BA_PCUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (pl->smem_exact > (size_t)max_optin) {

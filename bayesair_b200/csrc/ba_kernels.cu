@@ -32,11 +32,13 @@ static __host__ __device__ size_t ba_state_words(int n_airports, bool tracked)
     return (per * (size_t)n_airports + 3) & ~(size_t)3;
 }
 
-size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bool tracked)
+size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bool tracked,
+                             int max_dslice)
 {
     size_t w = ba_state_words(n_airports, tracked) + BA_RED_WORDS + BA_CTA_WORDS;
     // list_words = 6 words per queue entry; plus calendar counters and the due buffer
-    if (!exact) w += list_words + BA_KCAL + 2 * BA_DUE_WORDS * BA_DUE_CAP_S + 2 * (BA_DUE_CAP_S / 2);
+    if (!exact) w += list_words + BA_KCAL + 2 * BA_DUE_WORDS * BA_DUE_CAP_S + 2 * (BA_DUE_CAP_S / 2) +
+                     2 * BA_DSTAGE_WORDS * (size_t)((max_dslice + 1) & ~1);
     return w * 4;
 }
 
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
-        ba_carve_lists<EXACT>(c, day, plan.max_ticks, pool, gscr);
+        ba_carve_lists<EXACT>(c, day, plan.max_ticks, plan.max_dslice, pool, gscr);
 
         // ---- setup -----------------------------------------------------------
         const float *lat_airport = prm.lat_airport + (size_t)p * C * N;
@@ -138,9 +140,11 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         }
         // departures that are ready at the very first tick
         int tick = day.first_tick - 1;
-        if (tick + 1 <= day.last_ready_tick)
-            for (uint32_t i = day.dcal_off[tick + 1] + tid; i < (uint32_t)day.dcal_off[tick + 2]; i += nthr)
-                ba_phase_b_departure(c, acc, i, tick & 1);
+        if (tick + 1 <= day.last_ready_tick) {
+            const uint32_t lo = (uint32_t)day.dcal_off[tick + 1], hi = (uint32_t)day.dcal_off[tick + 2];
+            if (tid == 0) c.cta[6 + (tick & 1)] = lo;
+            for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_departure(c, acc, i, lo, tick & 1);
+        }
         __syncthreads();
         BA_MARK(2);
 
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             int more = tick < day.last_ready_tick;
             for (int s = tid; s < N; s += nthr) {
                 const int a = day.lane_airport[s];
-                if (n_due) ba_phase_c_pull(c, acc, a, prev, n_due);
+                ba_phase_c_pull(c, acc, a, prev, n_due, tick);
                 ba_phase_a<EXACT, PREDICT>(c, acc, a, t, tick);
                 more |= ba_airport_busy(c, a) ? 1 : 0;
             }
@@ -175,9 +179,11 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
                 const uint32_t lo = c.cal_cnt[tick - 1], hi = c.cal_cnt[tick];
                 for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_arrival(c, acc, i, cur);
             }
-            if (tick + 1 <= day.last_ready_tick)
-                for (uint32_t i = day.dcal_off[tick + 1] + tid; i < (uint32_t)day.dcal_off[tick + 2]; i += nthr)
-                    ba_phase_b_departure(c, acc, i, cur);
+            if (tick + 1 <= day.last_ready_tick) {
+                const uint32_t lo = (uint32_t)day.dcal_off[tick + 1], hi = (uint32_t)day.dcal_off[tick + 2];
+                if (tid == 0) c.cta[6 + cur] = lo;
+                for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_departure(c, acc, i, lo, cur);
+            }
             busy = __syncthreads_or(more) != 0;
             if (PREDICT && tid == 0) ba_pool_advance(c, 64u);   // next reader: phase B, after a barrier
             BA_MARK(4);

@@ -40,7 +40,8 @@ struct BaBwdParams {
 };
 
 int ba_forward_block_threads(int n_airports);
-size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bool tracked);
+size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bool tracked,
+                             int max_dslice);
 cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact);
 int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, int device);
 

@@ -22,13 +22,14 @@
 #define BA_KEY_INVALID 0xFFFFFFFFu
 // arrival calendar: buckets (ticks) kept in shared memory by the fast variant
 #ifndef BA_KCAL
-#define BA_KCAL 512
+#define BA_KCAL 384
 #endif
 #ifndef BA_DUE_CAP_S
-#define BA_DUE_CAP_S 192              // entries per due buffer in shared memory (two buffers)
+#define BA_DUE_CAP_S 128              // entries per due buffer in shared memory (two buffers)
 #endif
 #define BA_KEY_DEPARTURE 0xF0000000u   // keys of newly ready departures sort after arrivals
 #define BA_DUE_WORDS 6               // word, key, owner<<16|seq, queue start, x, y
+#define BA_DSTAGE_WORDS 4            // staged departure: queue word, queue start, x, arrival time
 
 // airport flags
 #define BA_AP_TRACK_T 1u              // turnaround list needed (n_avail can matter)
@@ -82,9 +83,14 @@ struct BaDayView {
     int32_t Rd;                       // routes used on this day
     const int32_t *dcal_off;          // [last_ready_tick + 2] departure calendar: slice of tick k
     const uint32_t *dcal_rec;         //   = flights of bookkeeping-free airports that become
-                                      //   ready at tick k; record = {batch rank << 18 | dep pos,
-                                      //   origin airport}
+                                      //   ready at tick k, grouped by origin airport, pending
+                                      //   order inside a group; record = {dep pos, origin}
     int32_t last_ready_tick;          // tick at which the day's last scheduled flight is ready
+    const int32_t *drun_off;          // [N+1] per-airport slices of drun (in units of runs)
+    const uint32_t *drun;             // runs {tick, first record, count}: the contiguous part of
+                                      //   a tick's calendar slice that belongs to one airport;
+                                      //   every airport's list ends with a sentinel run
+    int32_t max_dslice;               // largest calendar slice of any tick of the day
     const BaAirport *airports;        // [N] day order
     const int32_t *lane_airport;      // [N] airport handled by lane slot i (load-sorted)
     uint32_t q_total_s;               // queue pool size (entries) of the shared variant
@@ -99,6 +105,7 @@ struct BaPlanView {
     int32_t D, N, Fmax, R, C;         // days, airports, max flights, routes, latent rows
     int32_t include_cancellations;
     int32_t any_track;                // some airport of some day tracks aircraft
+    int32_t max_dslice;               // largest departure-calendar slice over days and ticks
     int32_t max_ticks;
     float delta_t, max_t;
     int32_t grad_stride;              // C*N + R + 3
@@ -131,7 +138,8 @@ static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_
     if (d.any_track_t) w += 2ull * (uint64_t)d.F;
     if (d.any_track_a) w += 3ull * (uint64_t)d.F;
     w += 7ull * d.q_total_x;          // draw history + exact rings (exact) / spill area (fast)
-    if (exact) w += 2ull * (uint64_t)BA_DUE_WORDS * (uint64_t)d.F +
+    if (exact) w += 2ull * BA_DSTAGE_WORDS * ((uint64_t)d.max_dslice + 2) +
+                    2ull * (uint64_t)BA_DUE_WORDS * (uint64_t)d.F +
                     2ull * (((uint64_t)d.F + 7) / 8 * 4) + (uint64_t)max_ticks + 2;
     w += 2ull * d.turn_total + 2ull * d.av_total + 1ull * d.dl_total;
     return w + 16;

@@ -58,6 +58,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
     for (int k = 1; k <= max_ticks + 1; ++k) out->tick_time[k] = out->tick_time[k - 1] + delta_t;
     out->days.clear();
     out->days.resize(n_days);
+    out->max_dslice = 0;
 
     // ---- route table over all days ----------------------------------------
     std::map<int64_t, int32_t> route_id;
@@ -229,15 +230,39 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             for (int f = 0; f < F; ++f) if (on_calendar(f)) cnt[ready_tick[f]]++;
             for (int k = 0; k <= last_ready_tick; ++k) H.dcal_off[k + 1] = H.dcal_off[k] + cnt[k];
             H.dcal_rec.assign(2 * (size_t)H.dcal_off[last_ready_tick + 1], 0u);
-            std::vector<int> cur(H.dcal_off.begin(), H.dcal_off.end() - 1);
-            for (int f = 0; f < F; ++f)
-                if (on_calendar(f)) {
-                    if (batch_rank[f] >= 4096)
-                        return fail(BA_ERR_LIMIT, "ba_plan_create: more than 4096 departures of one airport in one tick");
-                    const int pos = cur[ready_tick[f]]++;
-                    H.dcal_rec[2 * pos] = ((uint32_t)batch_rank[f] << 18) | (uint32_t)H.pos_dep[f];
-                    H.dcal_rec[2 * pos + 1] = (uint32_t)T.h_origin[f];
+            // within a tick: grouped by origin (day order), pending order inside a group
+            std::vector<std::vector<int>> per_tick((size_t)last_ready_tick + 1);
+            for (int f = 0; f < F; ++f) if (on_calendar(f)) per_tick[ready_tick[f]].push_back(f);
+            std::vector<std::vector<uint32_t>> runs(N);
+            int max_slice = 0;
+            for (int k = 0; k <= last_ready_tick; ++k) {
+                std::vector<int> &v = per_tick[k];
+                std::stable_sort(v.begin(), v.end(),
+                                 [&](int x, int y) { return T.h_origin[x] < T.h_origin[y]; });
+                max_slice = std::max(max_slice, (int)v.size());
+                int pos = H.dcal_off[k];
+                for (size_t i = 0; i < v.size(); ++i, ++pos) {
+                    const int f = v[i], o = T.h_origin[f];
+                    H.dcal_rec[2 * pos] = (uint32_t)H.pos_dep[f];
+                    H.dcal_rec[2 * pos + 1] = (uint32_t)o;
+                    if (i == 0 || T.h_origin[v[i - 1]] != o) {
+                        runs[o].push_back((uint32_t)k); runs[o].push_back((uint32_t)pos);
+                        runs[o].push_back(1u);
+                    } else {
+                        runs[o].back() += 1u;
+                    }
                 }
+            }
+            H.drun_off.assign(N + 1, 0);
+            H.drun.clear();
+            for (int a = 0; a < N; ++a) {
+                H.drun.insert(H.drun.end(), runs[a].begin(), runs[a].end());
+                // sentinel run: never matches a tick
+                H.drun.push_back(0xFFFFFFFFu); H.drun.push_back(0u); H.drun.push_back(0u);
+                H.drun_off[a + 1] = (int32_t)(H.drun.size() / 3);
+            }
+            H.view.max_dslice = max_slice;
+            out->max_dslice = std::max(out->max_dslice, max_slice);
         }
         // lane -> airport, heaviest first
         H.lane_airport.resize(N);
@@ -269,6 +294,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         V.Rd = (int32_t)H.rt_gid.size();
         V.dcal_off = H.dcal_off.data(); V.dcal_rec = H.dcal_rec.data();
         V.last_ready_tick = last_ready_tick;
+        V.drun_off = H.drun_off.data(); V.drun = H.drun.data();
         V.any_track_t = any_t; V.any_track_a = any_a;
         V.airports = H.airports.data(); V.lane_airport = H.lane_airport.data();
         V.q_total_s = q_s; V.q_total_x = q_x;
@@ -285,6 +311,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
     P.D = n_days; P.N = N; P.Fmax = Fmax; P.R = R;
     P.C = include_cancellations ? 4 : 2;
     P.include_cancellations = include_cancellations ? 1 : 0;
+    P.max_dslice = out->max_dslice;
     P.any_track = 0;
     for (int d = 0; d < n_days; ++d) P.any_track |= (int32_t)out->days[d].view.any_track_t;
     P.max_ticks = max_ticks; P.delta_t = delta_t; P.max_t = max_t;

@@ -11,7 +11,8 @@ struct BaHostDay {
     std::vector<int32_t> route, dep_fid, lane_airport, pos_dep, pos_arr, rt_gid, rt_off, rt_flt;
     std::vector<float> dep_sched;
     std::vector<uint32_t> dep_word, dcal_rec;
-    std::vector<int32_t> dcal_off;
+    std::vector<int32_t> dcal_off, drun_off;
+    std::vector<uint32_t> drun;
     std::vector<BaAirport> airports;
     BaDayView view;   // pointers into the vectors above (host view)
 };
@@ -24,6 +25,7 @@ struct BaHostPlan {
     uint64_t scratch_words_fast = 0;    // per-CTA scratch, shared-memory variant
     uint64_t scratch_words_exact = 0;   // per-CTA scratch, exact variant
     uint32_t smem_list_words = 0;       // max over days: 6*q_total_s
+    int32_t max_dslice = 0;             // max over days and ticks of the departure slice
     std::vector<float> tick_time;       // [max_ticks + 2]
 };
 

@@ -202,21 +202,29 @@ struct BaCtx {
     int value_mode, want_grad, cancel_mode, replay_always;
     float max_t;
     // per-airport state (shared memory), indexed by day-local airport
-    float *m, *rate, *lograte, *mt, *tstd, *logtstd, *base, *n_avail, *n0, *next_sched;
+    float *m, *rate, *mt, *tstd, *base, *n_avail, *n0, *next_sched;
     float *asg_lo, *asg_hi, *w_head;  // head entry: interval holding its exact fp32 service
                                       //   time (NaN = unassigned) and its total wait
     double *psum;                     // running sum of all service draws assigned so far
     float *acc_ln0, *acc_bc;
     uint32_t *next_dep, *q_head, *q_tail, *q_fill, *dep_pops, *arr_pops, *turn_n;
+    uint32_t *run_ptr, *run_tick;         // next run of the departure calendar, its tick
     uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail;
     uint32_t *s_flags, *s_qoff, *s_qmask, *s_goff, *s_depoff, *s_depcnt, *s_arrcnt;
     // CTA-wide scalars (shared memory): [0], [1] entries in the even / odd due buffer,
     // [3] abort flag (a shared ring overflowed), [2] / [4] entries in / first live entry of
-    // the predictive in-transit pool
+    // the predictive in-transit pool, [6], [7] first calendar record staged in the even / odd
+    // departure buffer
     uint32_t *cta;
     const int32_t *dcal_off;      // static departure calendar (ba_plan.h)
     const uint32_t *dcal_rec;
+    const int32_t *drun_off;      // per-airport runs of the departure calendar
+    const uint32_t *drun;
     int last_ready_tick;
+    // staged departures of the next tick (two buffers, 4 words per record, in calendar-slice
+    // order): shared (fast variant) or global (exact variant)
+    uint32_t *dstage_base;
+    uint32_t dstage_stride, dstage_cap;
     // arrival calendar
     const float *tick_time;       // [max_ticks + 2]
     uint32_t *cal_cnt;            // [cal_cap] bucket end offsets (shared or global)
@@ -274,13 +282,12 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N, bool tracked)
 {
     float *f = (float *)w;
     c.psum = (double *)w;                      // 2 N words, 8-byte aligned
-    c.m = f + 2 * N; c.rate = f + 3 * N; c.lograte = f + 4 * N; c.mt = f + 5 * N;
-    c.tstd = f + 6 * N; c.logtstd = f + 7 * N; c.w_head = f + 8 * N;
-    c.asg_lo = f + 9 * N; c.asg_hi = f + 10 * N;
-    c.q_head = w + 11 * N; c.q_tail = w + 12 * N; c.dep_pops = w + 13 * N;
-    c.arr_pops = w + 14 * N; c.s_flags = w + 15 * N; c.s_qoff = w + 16 * N;
-    c.s_qmask = w + 17 * N; c.s_arrcnt = w + 18 * N; c.next_sched = f + 19 * N;
-    c.q_fill = w + 20 * N; c.s_goff = w + 21 * N;
+    c.m = f + 2 * N; c.rate = f + 3 * N; c.mt = f + 4 * N; c.tstd = f + 5 * N;
+    c.w_head = f + 6 * N; c.asg_lo = f + 7 * N; c.asg_hi = f + 8 * N;
+    c.q_head = w + 9 * N; c.q_tail = w + 10 * N; c.dep_pops = w + 11 * N;
+    c.arr_pops = w + 12 * N; c.s_flags = w + 13 * N; c.s_qoff = w + 14 * N;
+    c.s_qmask = w + 15 * N; c.s_arrcnt = w + 16 * N; c.next_sched = f + 17 * N;
+    c.q_fill = w + 18 * N; c.s_goff = w + 19 * N; c.run_ptr = w + 20 * N; c.run_tick = w + 21 * N;
     if (tracked) {
         c.base = f + 22 * N; c.n_avail = f + 23 * N; c.n0 = f + 24 * N;
         c.acc_ln0 = f + 25 * N; c.acc_bc = f + 26 * N;
@@ -304,8 +311,8 @@ BA_DEV uint32_t ba_shared_list_words(uint32_t q_total_s)
 // per-flight scratch.  `shared_pool` = shared memory after the state arrays,
 // `g` = start of this CTA's global scratch.
 template <bool EXACT>
-BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32_t *shared_pool,
-                           uint32_t *g)
+BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int max_dslice_plan,
+                           uint32_t *shared_pool, uint32_t *g)
 {
     const uint32_t F = (uint32_t)day.F;
     c.xdk = (float *)g; g += F; c.xak = (float *)g; g += F; c.atk = (float *)g; g += F;
@@ -331,6 +338,9 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32
     const uint32_t own_words = (c.due_cap + 7u) / 8u * 4u;     // u16 per entry, 16-byte groups
     c.due_base = s; c.due_stride = BA_DUE_WORDS * c.due_cap + own_words;
     s += 2u * c.due_stride;
+    c.dstage_cap = (uint32_t)day.max_dslice;
+    c.dstage_stride = BA_DSTAGE_WORDS * (((uint32_t)max_dslice_plan + 1u) & ~1u);
+    c.dstage_base = s; s += 2u * c.dstage_stride;
     c.cal_cap = EXACT ? (uint32_t)max_ticks + 2u : (uint32_t)BA_KCAL;
     c.cal_cnt = s; s += c.cal_cap;
     if (EXACT) g = s;
@@ -339,6 +349,7 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, uint32
     c.dl = g;
     c.first_tick = day.first_tick;
     c.dcal_off = day.dcal_off; c.dcal_rec = day.dcal_rec; c.last_ready_tick = day.last_ready_tick;
+    c.drun_off = day.drun_off; c.drun = day.drun;
 }
 
 BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
@@ -417,11 +428,12 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     const float rate = BA_DIV(1.0f, m);          // airport.py:146
     const float tstd = BA_MUL(c.v_u, mt);        // model.py:143-145
     c.rate[a] = rate; c.tstd[a] = tstd;
-    c.lograte[a] = BA_LOG(rate); c.logtstd[a] = BA_LOG(tstd);
     c.asg_lo[a] = NAN; c.asg_hi[a] = NAN; c.w_head[a] = 0.0f; c.psum[a] = 0.0;
     c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
     c.q_head[a] = 0; c.q_tail[a] = 0; c.q_fill[a] = 0; c.dep_pops[a] = 0; c.arr_pops[a] = 0;
     c.s_goff[a] = A.q_off_x;
+    c.run_ptr[a] = (uint32_t)c.drun_off[a];
+    c.run_tick[a] = c.drun[3 * c.drun_off[a]];
     if (c.n_avail) {
         float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
         if (c.cancel_mode) {
@@ -944,8 +956,9 @@ BA_DEV void ba_calendar_scatter(BaCtx &c, int f)
 //       queued is skipped -- phase A hands it over itself when it is served.
 //   ba_phase_b_departure  one record of NEXT tick's departure-calendar slice: the flight
 //       becomes ready at the next tick (network.py:60-68) at an airport that can neither
-//       cancel nor delay it; it joins its origin's runway queue behind this tick's
-//       arrivals (model.py:181-183), i.e. with a key above every arrival key.
+//       cancel nor delay it.  Its queue entry is staged at the record's position in the
+//       slice; the origin lane knows (static runs) where its records are and appends them
+//       behind this tick's arrivals (model.py:181-183).
 // ---------------------------------------------------------------------------
 BA_DEV void ba_phase_b_arrival(BaCtx &c, BaAcc &acc, uint32_t i, int parity)
 {
@@ -959,13 +972,15 @@ BA_DEV void ba_phase_b_arrival(BaCtx &c, BaAcc &acc, uint32_t i, int parity)
                   __uint_as_float_portable(c.cal[3 * i + 2]), 0.0f);
 }
 
-BA_DEV void ba_phase_b_departure(BaCtx &c, BaAcc &acc, uint32_t i, int parity)
+BA_DEV void ba_phase_b_departure(BaCtx &c, BaAcc &acc, uint32_t i, uint32_t slice_lo, int parity)
 {
-    const uint32_t rec = c.dcal_rec[2 * i], origin = c.dcal_rec[2 * i + 1];
-    const uint32_t k = rec & BA_FID_MASK, rank = rec >> 18;
+    const uint32_t k = c.dcal_rec[2 * i];
     const uint32_t w = c.dep_word[k];
-    ba_due_append(c, acc, parity, BA_Q_DEP | (w & BA_DW_ENTRY_MASK), BA_KEY_DEPARTURE | rank,
-                  origin, 0u, fmaxf(0.0f, c.dep_sched[k]), c.xdk[k], c.atk[k]);
+    if (i - slice_lo >= c.dstage_cap) { acc.status |= BA_S_INTERNAL; return; }
+    uint32_t *d = c.dstage_base + (uint32_t)parity * c.dstage_stride + BA_DSTAGE_WORDS * (i - slice_lo);
+    BaPairUF wq = {BA_Q_DEP | (w & BA_DW_ENTRY_MASK), fmaxf(0.0f, c.dep_sched[k])};
+    BaPairF xy = {c.xdk[k], c.atk[k]};
+    BA_ST_PAIR(BaPairUF, d, wq); BA_ST_PAIR(BaPairF, d + 2, xy);
 }
 
 // Posterior-predictive mode: arrival times are only known once a departure is served, so
@@ -1002,17 +1017,51 @@ BA_DEV uint64_t ba_due_order(const uint32_t *de)
     return ((uint64_t)de[1] << 16) | (uint64_t)(de[2] & 0xFFFFu);
 }
 
-BA_DEV void ba_due_push(BaCtx &c, BaAcc &acc, int a, const uint32_t *de)
+// Ring counters of one airport held in registers while a batch of entries is appended.
+// Every entry appended between two service loops shares lo and the prefix sum at joining.
+struct BaPush {
+    uint32_t head, tail, fill, qoff, qmask, goff, lo;
+    float pj;
+};
+
+BA_DEV void ba_push_begin(const BaCtx &c, int a, BaPush &P)
 {
-    const BaPairF xy = BA_LD_PAIR(BaPairF, de + 4);
-    ba_q_push(c, acc, a, de[0], __uint_as_float_portable(de[3]), xy.a, xy.b);
+    P.head = c.q_head[a]; P.tail = c.q_tail[a]; P.fill = c.q_fill[a];
+    P.qoff = c.s_qoff[a]; P.qmask = c.s_qmask[a]; P.goff = c.s_goff[a];
+    P.lo = P.head + (isnan(c.asg_hi[a]) ? 0u : 1u);
+    P.pj = (float)c.psum[a];
 }
 
-BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_due)
+BA_DEV void ba_push_one(BaCtx &c, BaAcc &acc, BaPush &P, uint32_t word, float qstart, float x, float y)
 {
-    const uint32_t *due = c.due_base + (uint32_t)parity * c.due_stride;
+    uint32_t *e;
+    if (P.fill == P.tail && P.tail - P.head <= P.qmask) {
+        e = c.qe + BA_Q_WORDS * (P.qoff + (P.tail & P.qmask));
+        P.fill = P.tail + 1;
+    } else if (c.gq) {
+        e = c.gq + BA_Q_WORDS * (P.goff + P.tail);
+    } else {
+        acc.status |= BA_S_OVERFLOW; return;
+    }
+    BaPairU wl = {word, P.lo};
+    BaPairF sp = {qstart, P.pj};
+    BaPairF xy = {x, y};
+    BA_ST_PAIR(BaPairU, e, wl); BA_ST_PAIR(BaPairF, e + 2, sp); BA_ST_PAIR(BaPairF, e + 4, xy);
+    c.gx[P.goff + P.tail] = x;
+    P.tail += 1;
+}
+
+BA_DEV void ba_push_end(BaCtx &c, int a, const BaPush &P)
+{
+    c.q_tail[a] = P.tail; c.q_fill[a] = P.fill;
+}
+
+BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_due, int tick)
+{
+    const bool has_run = c.run_tick[a] == (uint32_t)tick;
     uint64_t m0 = 0, m1 = 0;
-    if (n_due <= 128u) {
+    const uint32_t *due = c.due_base + (uint32_t)parity * c.due_stride;
+    if (n_due && n_due <= 128u) {
         // owners are packed u16, eight per 16-byte load (broadcast: every lane of the warp
         // reads the same words)
         const uint32_t *ow = due + BA_DUE_WORDS * c.due_cap;
@@ -1020,7 +1069,6 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
         const uint32_t groups = (n_due + 7u) >> 3;
         for (uint32_t g = 0; g < groups; ++g) {
             uint32_t w0 = ow[4 * g], w1 = ow[4 * g + 1], w2 = ow[4 * g + 2], w3 = ow[4 * g + 3];
-            // per-halfword equality -> one bit per entry
             uint32_t bits = 0;
             uint32_t x;
             x = w0 ^ aa; bits |= ((x & 0xFFFFu) == 0u) | (((x >> 16) == 0u) << 1);
@@ -1032,38 +1080,59 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
             if (g < 8u) m0 |= (uint64_t)bits << (8u * g); else m1 |= (uint64_t)bits << (8u * (g - 8u));
         }
     }
-    if (n_due <= 128u) {
-        while (m0 | m1) {
-            uint64_t best = ~0ull; uint32_t bj = 0;
-            for (uint64_t m = m0; m; m &= m - 1) {
-                const uint32_t j = (uint32_t)ba_ctz64(m);
-                const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
-                if (o < best) { best = o; bj = j; }
-            }
-            for (uint64_t m = m1; m; m &= m - 1) {
-                const uint32_t j = 64u + (uint32_t)ba_ctz64(m);
-                const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
-                if (o < best) { best = o; bj = j; }
-            }
-            ba_due_push(c, acc, a, due + BA_DUE_WORDS * bj);
-            if (bj < 64u) m0 &= ~(1ull << bj); else m1 &= ~(1ull << (bj - 64u));
+    const bool general = n_due > 128u;
+    if (!(m0 | m1) && !has_run && !general) return;
+    BaPush P;
+    ba_push_begin(c, a, P);
+    // ---- arrivals addressed to this airport, in in-transit list order ------------------
+    while (m0 | m1) {
+        uint64_t best = ~0ull; uint32_t bj = 0;
+        for (uint64_t m = m0; m; m &= m - 1) {
+            const uint32_t j = (uint32_t)ba_ctz64(m);
+            const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
+            if (o < best) { best = o; bj = j; }
         }
-        return;
-    }
-    // general case (exact variant, pathological ticks): repeated selection
-    uint64_t last = 0; bool first = true;
-    for (;;) {
-        uint64_t best = ~0ull; uint32_t bj = 0xFFFFFFFFu;
-        for (uint32_t j = 0; j < n_due; ++j) {
-            const uint32_t *de = due + BA_DUE_WORDS * j;
-            if ((de[2] >> 16) != (uint32_t)a) continue;
-            const uint64_t o = ba_due_order(de);
-            if ((first || o > last) && o < best) { best = o; bj = j; }
+        for (uint64_t m = m1; m; m &= m - 1) {
+            const uint32_t j = 64u + (uint32_t)ba_ctz64(m);
+            const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
+            if (o < best) { best = o; bj = j; }
         }
-        if (bj == 0xFFFFFFFFu) break;
-        ba_due_push(c, acc, a, due + BA_DUE_WORDS * bj);
-        last = best; first = false;
+        const uint32_t *de = due + BA_DUE_WORDS * bj;
+        ba_push_one(c, acc, P, de[0], __uint_as_float_portable(de[3]), BA_LD_PAIR(BaPairF, de + 4).a, 0.0f);
+        if (bj < 64u) m0 &= ~(1ull << bj); else m1 &= ~(1ull << (bj - 64u));
     }
+    if (general) {
+        // very busy ticks (exact variant): repeated selection over the whole buffer
+        uint64_t last = 0; bool first = true;
+        for (;;) {
+            uint64_t best = ~0ull; uint32_t bj = 0xFFFFFFFFu;
+            for (uint32_t j = 0; j < n_due; ++j) {
+                const uint32_t *de = due + BA_DUE_WORDS * j;
+                if ((de[2] >> 16) != (uint32_t)a) continue;
+                const uint64_t o = ba_due_order(de);
+                if ((first || o > last) && o < best) { best = o; bj = j; }
+            }
+            if (bj == 0xFFFFFFFFu) break;
+            const uint32_t *de = due + BA_DUE_WORDS * bj;
+            ba_push_one(c, acc, P, de[0], __uint_as_float_portable(de[3]), BA_LD_PAIR(BaPairF, de + 4).a, 0.0f);
+            last = best; first = false;
+        }
+    }
+    // ---- this airport's newly ready departures: a static run of the staged slice ---------
+    if (has_run) {
+        const uint32_t rp = c.run_ptr[a];
+        const uint32_t start = c.drun[3 * rp + 1], cnt = c.drun[3 * rp + 2];
+        const uint32_t *d = c.dstage_base + (uint32_t)parity * c.dstage_stride +
+                            BA_DSTAGE_WORDS * (start - c.cta[6 + parity]);
+        for (uint32_t i = 0; i < cnt; ++i, d += BA_DSTAGE_WORDS) {
+            const BaPairUF wq = BA_LD_PAIR(BaPairUF, d);
+            const BaPairF xy = BA_LD_PAIR(BaPairF, d + 2);
+            ba_push_one(c, acc, P, wq.a, wq.b, xy.a, xy.b);
+        }
+        c.run_ptr[a] = rp + 1;
+        c.run_tick[a] = c.drun[3 * (rp + 1)];
+    }
+    ba_push_end(c, a, P);
 }
 
 // Does this airport still hold work (completion vote, network.py:34-41)?  Every flight
@@ -1117,7 +1186,7 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
     const float qstart_d = track_a ? c.qd[f] : fmaxf(0.0f, fl.sched_dep);
     const float mu_d = BA_ADD(qstart_d, wdep);              // queue_start + total_wait
     const float dy_d = fl.act_dep - mu_d;
-    float lp = (c.lograte[o] - rate_o * xd) + (lp_const - dy_d * dy_d * half_inv_var);
+    float lp = (BA_LOG(rate_o) - rate_o * xd) + (lp_const - dy_d * dy_d * half_inv_var);
 
     // ---- arrival side: *_travel_time, *_arrival_service_time,
     //      *_simulated_arrival_time, *_turnaround_time
@@ -1133,9 +1202,9 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
     const float u = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, tstd));
     const float dz = (tau - T) / sc;
     const float du = (u - mt) / tstd;
-    lp += (c.lograte[d] - rate_d * xa) + (lp_const - dy_a * dy_a * half_inv_var);
+    lp += (BA_LOG(rate_d) - rate_d * xa) + (lp_const - dy_a * dy_a * half_inv_var);
     float lp2 = (-0.5f * dz * dz - BA_LOG(sc) - BA_LOG_SQRT_2PI)
-              + (-0.5f * du * du - c.logtstd[d] - BA_LOG_SQRT_2PI);
+              + (-0.5f * du * du - BA_LOG(tstd) - BA_LOG_SQRT_2PI);
     acc.lp += (double)lp + (double)lp2;
 
     if (grad) {

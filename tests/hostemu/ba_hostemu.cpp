@@ -52,7 +52,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     (void)P;
     const int N = plan.N, C = plan.C, R = plan.R, D = plan.D;
     std::vector<uint32_t> state((size_t)BA_NWORDS_STATE_TRACK * N + 8, 0);
-    std::vector<uint32_t> pool(ba_shared_list_words(day.q_total_s) + 8, 0);
+    std::vector<uint32_t> pool(ba_shared_list_words(day.q_total_s) + 2 * BA_DSTAGE_WORDS * (plan.max_dslice + 2) + 8, 0);
     std::vector<uint32_t> gs(ba_scratch_words(day, true, plan.max_ticks) + 8, 0);
     uint32_t ctaw[BA_CTA_WORDS] = {0, 0, 0, 0};
     BaCtx c;
@@ -81,7 +81,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     c.particle = p; c.dayidx = d;
     c.grow = c.want_grad ? tape + pd * (size_t)plan.grad_stride : nullptr;
     c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
-    ba_carve_lists<EXACT>(c, day, plan.max_ticks, pool.data(), gs.data());
+    ba_carve_lists<EXACT>(c, day, plan.max_ticks, plan.max_dslice, pool.data(), gs.data());
     for (uint32_t k = 0; k < c.cal_cap; ++k) c.cal_cnt[k] = 0;
 
     const float *la = lat_airport + (size_t)p * C * N;
@@ -107,10 +107,11 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     int tick = day.first_tick - 1;
     auto departures_of = [&](int k, int parity) {
         if (k > day.last_ready_tick) return;
+        c.cta[6 + parity] = (uint32_t)day.dcal_off[k];
         std::vector<uint32_t> sl;
         for (int i = day.dcal_off[k]; i < day.dcal_off[k + 1]; ++i) sl.push_back((uint32_t)i);
         if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
-        for (uint32_t i : sl) ba_phase_b_departure(c, acc[i % N], i, parity);
+        for (uint32_t i : sl) ba_phase_b_departure(c, acc[i % N], i, (uint32_t)day.dcal_off[k], parity);
     };
     departures_of(tick + 1, tick & 1);
     bool busy = day.F > 0;
@@ -126,7 +127,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
         for (int i = 0; i < N; ++i) {
             const int a = day.lane_airport[order[i]];
-            if (n_due) ba_phase_c_pull(c, acc[order[i]], a, prev, n_due);
+            ba_phase_c_pull(c, acc[order[i]], a, prev, n_due, tick);
             ba_phase_a<EXACT, PREDICT>(c, acc[order[i]], a, t, tick);
             more |= ba_airport_busy(c, a);
         }

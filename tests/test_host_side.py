@@ -179,8 +179,9 @@ def test_emulated_ring_spill(monkeypatch):
 
 
 def _burst_day(n_origins=20, per_origin=20):
-    """20 airports x 20 flights to one hub, all scheduled in the same minute: the 400
-    departures that become ready in one tick overflow the shared due buffer."""
+    """20 airports x 20 flights to one hub, all departing within seconds of each other: with a
+    tight travel-time scale the ~400 arrivals fall into one or two ticks and overflow the
+    shared due buffer."""
     from bayesair_b200.compiler import DaySpec
     f32 = np.float32
     n = n_origins * per_origin
@@ -188,7 +189,7 @@ def _burst_day(n_origins=20, per_origin=20):
     order = np.argsort(np.tile(np.arange(per_origin), n_origins), kind="stable")
     origin = origin[order]                      # interleave the origins
     sched = np.full(n, 6.0, f32)
-    dep = (6.0 + 0.002 * np.arange(n)).astype(f32)
+    dep = (6.0 + 0.0001 * np.arange(n)).astype(f32)
     codes = ["HUB"] + [f"S{i:02d}" for i in range(n_origins)]
     return DaySpec(codes, np.arange(n_origins + 1, dtype=np.int32), sched, dep,
                    (dep + 2.0).astype(f32), np.zeros(n, np.int8), origin,
@@ -207,10 +208,11 @@ def test_emulated_overflow_rerun():
            "mean_service": np.full((1, N), 0.01, np.float32),
            "travel": np.full((1, N, N), 2.0, np.float32)}
     noise = std_noise(1, 1, spec.n_flights, seed=8)
-    flagged = plan.forward(lat, (0.1, 0.1, 0.1), noise, rerun_overflow=False)
+    sc = (0.1, 0.004, 0.1)
+    flagged = plan.forward(lat, sc, noise, rerun_overflow=False)
     assert (flagged["status"] & 2).all()
-    fixed = plan.forward(lat, (0.1, 0.1, 0.1), noise)
-    ref = ba_oracle.run_batch([spec], lat, (0.1, 0.1, 0.1), noise, delta_t=0.2)
+    fixed = plan.forward(lat, sc, noise)
+    ref = ba_oracle.run_batch([spec], lat, sc, noise, delta_t=0.2)
     assert (fixed["status"] == 0).all()
     np.testing.assert_allclose(fixed["logp"], ref["logp"], rtol=5e-6)
 
