@@ -35,7 +35,7 @@ for f in sorted(os.listdir(tmp)):
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             lines.append(cur)
     if lines:
         break
