@@ -51,6 +51,11 @@
 #else
 #define BA_DEV static inline
 #endif
+#if defined(__CUDACC__)
+#define BA_MEMBER __device__ __forceinline__
+#else
+#define BA_MEMBER inline
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define BA_ADD(a, b) __fadd_rn((a), (b))
@@ -174,6 +179,14 @@ BA_DEV float ba_relaxed_bernoulli_lp(float p, float v, float *dlp_dp)
 // ---------------------------------------------------------------------------
 // per-CTA context
 // ---------------------------------------------------------------------------
+// One field of the per-airport records (see ba_carve_state): indexed by airport.
+template <typename T> struct BaCol {
+    T *p;
+    uint32_t s;
+    BA_MEMBER T &operator[](int a) const { return p[(uint32_t)a * s]; }
+    BA_MEMBER T &operator[](uint32_t a) const { return p[a * s]; }
+};
+
 struct BaCtx {
     // static day tables
     int N, F;
@@ -202,15 +215,15 @@ struct BaCtx {
     int value_mode, want_grad, cancel_mode, replay_always;
     float max_t;
     // per-airport state (shared memory), indexed by day-local airport
-    float *m, *rate, *mt, *tstd, *base, *n_avail, *n0, *next_sched;
-    float *asg_lo, *asg_hi, *w_head;  // head entry: interval holding its exact fp32 service
-                                      //   time (NaN = unassigned) and its total wait
+    BaCol<float> m, rate, mt, tstd, base, n_avail, n0, next_sched;
+    BaCol<float> asg_lo, asg_hi, w_head;  // head entry: interval holding its exact fp32
+                                      //   service time (NaN = unassigned) and its total wait
     double *psum;                     // running sum of all service draws assigned so far
-    float *acc_ln0, *acc_bc;
-    uint32_t *next_dep, *q_head, *q_tail, *q_fill, *dep_pops, *arr_pops, *turn_n;
-    uint32_t *run_ptr, *run_tick;         // next run of the departure calendar, its tick
-    uint32_t *av_head, *av_tail, *zeros_left, *dl_head, *dl_tail;
-    uint32_t *s_flags, *s_qoff, *s_qmask, *s_goff, *s_depoff, *s_depcnt, *s_arrcnt;
+    BaCol<float> acc_ln0, acc_bc;
+    BaCol<uint32_t> next_dep, q_head, q_tail, q_fill, dep_pops, arr_pops, turn_n;
+    BaCol<uint32_t> run_ptr, run_tick;    // next run of the departure calendar, its tick
+    BaCol<uint32_t> av_head, av_tail, zeros_left, dl_head, dl_tail;
+    BaCol<uint32_t> s_flags, s_qw, s_goff, s_depoff, s_depcnt, s_arrcnt;
     // CTA-wide scalars (shared memory): [0], [1] entries in the even / odd due buffer,
     // [3] abort flag (a shared ring overflowed), [2] / [4] entries in / first live entry of
     // the predictive in-transit pool, [6], [7] first calendar record staged in the even / odd
@@ -271,34 +284,61 @@ struct BaAcc {
     uint32_t status;
 };
 
-#define BA_NWORDS_STATE_SIMPLE 22 // per-airport words of shared state, no aircraft bookkeeping
-#define BA_NWORDS_STATE_TRACK 38  // ... when some airport of the plan tracks aircraft
+// Per-airport shared state is an array of records (one per airport, odd word stride so
+// that consecutive lanes hit different banks): every field of an airport is then the
+// airport's record address plus a compile-time offset, which costs no address arithmetic
+// per access.  Only psum (8-byte) lives in its own array in front of the records.
+#define BA_REC_WORDS_SIMPLE 19    // 19 fields, no aircraft bookkeeping
+#define BA_REC_WORDS_TRACK 33     // 33 fields, some airport of the plan tracks aircraft
+#define BA_NWORDS_STATE_SIMPLE (2 + BA_REC_WORDS_SIMPLE)
+#define BA_NWORDS_STATE_TRACK (2 + BA_REC_WORDS_TRACK)
 #define BA_Q_WORDS 6              // words per runway-queue entry
 #define BA_CTA_WORDS 8            // CTA-wide scalars
 
-// Assigns the per-airport arrays out of one contiguous word buffer.  The arrays that only
+// Ring placement of an airport in one word: first entry of its ring in the pool (27 bits)
+// and log2 of the ring's power-of-two capacity (5 bits).
+BA_DEV uint32_t ba_qw_pack(uint32_t off, uint32_t mask)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t lg = (uint32_t)__popc(mask);          // mask = 2^lg - 1
+#else
+    uint32_t lg = 0;
+    while ((1u << lg) <= mask && lg < 31u) ++lg;
+#endif
+    return off | (lg << 27);
+}
+BA_DEV uint32_t ba_qw_off(uint32_t qw) { return qw & 0x07FFFFFFu; }
+BA_DEV uint32_t ba_qw_mask(uint32_t qw) { return (1u << (qw >> 27)) - 1u; }
+
+// Assigns the per-airport fields out of one contiguous word buffer.  The fields that only
 // airports with aircraft bookkeeping touch exist only when the plan has such airports.
 BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N, bool tracked)
 {
-    float *f = (float *)w;
     c.psum = (double *)w;                      // 2 N words, 8-byte aligned
-    c.m = f + 2 * N; c.rate = f + 3 * N; c.mt = f + 4 * N; c.tstd = f + 5 * N;
-    c.w_head = f + 6 * N; c.asg_lo = f + 7 * N; c.asg_hi = f + 8 * N;
-    c.q_head = w + 9 * N; c.q_tail = w + 10 * N; c.dep_pops = w + 11 * N;
-    c.arr_pops = w + 12 * N; c.s_flags = w + 13 * N; c.s_qoff = w + 14 * N;
-    c.s_qmask = w + 15 * N; c.s_arrcnt = w + 16 * N; c.next_sched = f + 17 * N;
-    c.q_fill = w + 18 * N; c.s_goff = w + 19 * N; c.run_ptr = w + 20 * N; c.run_tick = w + 21 * N;
+    w += 2 * N;
+    float *f = (float *)w;
+    const uint32_t s = tracked ? BA_REC_WORDS_TRACK : BA_REC_WORDS_SIMPLE;
+#define BA_COLF(name, k) c.name.p = f + (k); c.name.s = s
+#define BA_COLU(name, k) c.name.p = w + (k); c.name.s = s
+    BA_COLF(m, 0); BA_COLF(rate, 1); BA_COLF(mt, 2); BA_COLF(tstd, 3);
+    BA_COLF(w_head, 4); BA_COLF(asg_lo, 5); BA_COLF(asg_hi, 6);
+    BA_COLU(q_head, 7); BA_COLU(q_tail, 8); BA_COLU(dep_pops, 9);
+    BA_COLU(arr_pops, 10); BA_COLU(s_flags, 11); BA_COLU(s_qw, 12);
+    BA_COLU(s_arrcnt, 13); BA_COLF(next_sched, 14);
+    BA_COLU(q_fill, 15); BA_COLU(s_goff, 16); BA_COLU(run_ptr, 17); BA_COLU(run_tick, 18);
     if (tracked) {
-        c.base = f + 22 * N; c.n_avail = f + 23 * N; c.n0 = f + 24 * N;
-        c.acc_ln0 = f + 25 * N; c.acc_bc = f + 26 * N;
-        c.next_dep = w + 27 * N; c.turn_n = w + 28 * N; c.av_head = w + 29 * N;
-        c.av_tail = w + 30 * N; c.zeros_left = w + 31 * N; c.dl_head = w + 32 * N;
-        c.dl_tail = w + 33 * N; c.s_depoff = w + 34 * N; c.s_depcnt = w + 35 * N;
+        BA_COLF(base, 19); BA_COLF(n_avail, 20); BA_COLF(n0, 21);
+        BA_COLF(acc_ln0, 22); BA_COLF(acc_bc, 23);
+        BA_COLU(next_dep, 24); BA_COLU(turn_n, 25); BA_COLU(av_head, 26);
+        BA_COLU(av_tail, 27); BA_COLU(zeros_left, 28); BA_COLU(dl_head, 29);
+        BA_COLU(dl_tail, 30); BA_COLU(s_depoff, 31); BA_COLU(s_depcnt, 32);
     } else {
-        c.base = c.n_avail = c.n0 = c.acc_ln0 = c.acc_bc = nullptr;
-        c.next_dep = c.turn_n = c.av_head = c.av_tail = c.zeros_left = nullptr;
-        c.dl_head = c.dl_tail = c.s_depoff = c.s_depcnt = nullptr;
+        c.base.p = c.n_avail.p = c.n0.p = c.acc_ln0.p = c.acc_bc.p = nullptr;
+        c.next_dep.p = c.turn_n.p = c.av_head.p = c.av_tail.p = c.zeros_left.p = nullptr;
+        c.dl_head.p = c.dl_tail.p = c.s_depoff.p = c.s_depcnt.p = nullptr;
     }
+#undef BA_COLF
+#undef BA_COLU
 }
 
 // Words of shared memory the list structures of the fast variant need.
@@ -434,7 +474,7 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     c.s_goff[a] = A.q_off_x;
     c.run_ptr[a] = (uint32_t)c.drun_off[a];
     c.run_tick[a] = c.drun[3 * c.drun_off[a]];
-    if (c.n_avail) {
+    if (c.n_avail.p) {
         float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
         if (c.cancel_mode) {
             n0 = BA_EXP(lat_airport[2 * Ng + g]);    // model.py:91-99
@@ -457,8 +497,7 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
         c.s_depcnt[a] = (uint32_t)A.dep_cnt;
     }
     c.s_flags[a] = A.flags;
-    c.s_qoff[a] = EXACT ? A.q_off_x : A.q_off_s;
-    c.s_qmask[a] = EXACT ? A.q_mask_x : A.q_mask_s;
+    c.s_qw[a] = ba_qw_pack(EXACT ? A.q_off_x : A.q_off_s, EXACT ? A.q_mask_x : A.q_mask_s);
     c.s_arrcnt[a] = (uint32_t)A.arr_cnt;
 }
 
@@ -533,10 +572,10 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
 // its total wait is the sum of the draws lo..own index (airport.py:150-153).
 BA_DEV void ba_q_push(BaCtx &c, BaAcc &acc, int a, uint32_t word, float qstart, float x, float y)
 {
-    const uint32_t head = c.q_head[a], tail = c.q_tail[a], mask = c.s_qmask[a];
+    const uint32_t head = c.q_head[a], tail = c.q_tail[a], mask = ba_qw_mask(c.s_qw[a]);
     uint32_t *e;
     if (c.q_fill[a] == tail && tail - head <= mask) {
-        e = c.qe + BA_Q_WORDS * (c.s_qoff[a] + (tail & mask));       // room in the ring
+        e = c.qe + BA_Q_WORDS * (ba_qw_off(c.s_qw[a]) + (tail & mask));       // room in the ring
         c.q_fill[a] = tail + 1;
     } else if (c.gq) {
         e = c.gq + BA_Q_WORDS * (c.s_goff[a] + tail);                // spill (absolute index)
@@ -556,7 +595,7 @@ BA_DEV void ba_q_refill(BaCtx &c, int a, uint32_t head, uint32_t tail)
 {
     uint32_t fill = c.q_fill[a];
     if (fill == tail) return;
-    const uint32_t mask = c.s_qmask[a], qoff = c.s_qoff[a], goff = c.s_goff[a];
+    const uint32_t qw = c.s_qw[a], mask = ba_qw_mask(qw), qoff = ba_qw_off(qw), goff = c.s_goff[a];
     while (fill != tail && fill - head <= mask) {
         const uint32_t *src = c.gq + BA_Q_WORDS * (goff + fill);
         uint32_t *dst = c.qe + BA_Q_WORDS * (qoff + (fill & mask));
@@ -797,7 +836,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
         uint32_t head = c.q_head[a];
         const uint32_t tail = c.q_tail[a];
         if (head == tail) return;
-        const uint32_t qoff = c.s_qoff[a], qmask = c.s_qmask[a];
+        const uint32_t qw = c.s_qw[a], qoff = ba_qw_off(qw), qmask = ba_qw_mask(qw);
         float lo = c.asg_lo[a], hi = c.asg_hi[a], wait = c.w_head[a];
         double psum = c.psum[a];
         if (c.gq) ba_q_refill(c, a, head, tail);
@@ -1027,7 +1066,8 @@ struct BaPush {
 BA_DEV void ba_push_begin(const BaCtx &c, int a, BaPush &P)
 {
     P.head = c.q_head[a]; P.tail = c.q_tail[a]; P.fill = c.q_fill[a];
-    P.qoff = c.s_qoff[a]; P.qmask = c.s_qmask[a]; P.goff = c.s_goff[a];
+    { const uint32_t qw = c.s_qw[a]; P.qoff = ba_qw_off(qw); P.qmask = ba_qw_mask(qw); }
+    P.goff = c.s_goff[a];
     P.lo = P.head + (isnan(c.asg_hi[a]) ? 0u : 1u);
     P.pj = (float)c.psum[a];
 }

@@ -1,5 +1,8 @@
 """Attribute ncu per-SASS-instruction samples to CUDA source lines.
-    python tools/ncu_lines.py <report.ncu-rep> <lib.so> <kernel-substring> [top]
+    python tools/ncu_lines.py <report.ncu-rep> <lib.so> <kernel-substring> [top] [column]
+`column` ranks by one stall column of the source page (e.g. stall_long_sb); the
+pseudo-column `busy` = all samples minus stall_barrier (where the warps that are NOT
+parked at a barrier spend their time, i.e. the critical path of a tick).
 Joins `ncu --page source --csv` (SASS rows, in address order) with the line table
 `nvdisasm -g` prints for the same function (needs -lineinfo at compile time).
 """
@@ -14,6 +17,7 @@ import tempfile
 
 rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+col = sys.argv[5] if len(sys.argv) > 5 else None
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
@@ -48,8 +52,15 @@ body = [r for r in rows[2:] if len(r) > ce]
 if len(body) != len(lines):
     print(f"warning: {len(body)} SASS rows vs {len(lines)} disassembled instructions", file=sys.stderr)
 samp, inst = collections.Counter(), collections.Counter()
+cb = hdr.index("stall_barrier")
+cc = hdr.index(col) if col and col != "busy" else None
 for r, loc in zip(body, lines):
-    samp[loc] += float(r[ci] or 0)
+    if col == "busy":
+        samp[loc] += float(r[ci] or 0) - float(r[cb] or 0)
+    elif cc is not None:
+        samp[loc] += float(r[cc] or 0)
+    else:
+        samp[loc] += float(r[ci] or 0)
     inst[loc] += float(r[ce] or 0)
 ts, ti = sum(samp.values()) or 1, sum(inst.values()) or 1
 src_cache = {}
