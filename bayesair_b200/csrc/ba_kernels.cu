@@ -36,8 +36,8 @@ size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bo
                              int max_dslice)
 {
     size_t w = ba_state_words(n_airports, tracked) + BA_RED_WORDS + BA_CTA_WORDS;
-    // list_words = 6 words per queue entry; plus calendar counters and the due buffer
-    if (!exact) w += list_words + BA_KCAL + 2 * BA_DUE_WORDS * BA_DUE_CAP_S + 2 * (BA_DUE_CAP_S / 2) +
+    // list_words = 6 words per queue entry; plus calendar counters, due buffers, staged departures
+    if (!exact) w += list_words + BA_SHARED_FIXED_WORDS +
                      2 * BA_DSTAGE_WORDS * (size_t)((max_dslice + 1) & ~1);
     return w * 4;
 }
@@ -57,10 +57,13 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
     const BaPlanView &plan = prm.plan;
     const int N = plan.N, D = plan.D, C = plan.C, R = plan.R;
 
-    uint32_t *state_w = smem;
-    uint32_t *red = smem + ba_state_words(N, plan.any_track != 0);       // [BA_RED_WORDS], 16 B aligned
+    // shared memory: everything of fixed size first (immediate addresses), then the
+    // per-airport records, then the size-dependent lists of the fast variant
+    uint32_t *red = smem;                                    // [BA_RED_WORDS], 16 B aligned
     uint32_t *ctaw = red + BA_RED_WORDS;                     // [BA_CTA_WORDS]
-    uint32_t *pool = ctaw + BA_CTA_WORDS;                    // shared list structures (fast)
+    uint32_t *fixed = ctaw + BA_CTA_WORDS;                   // [BA_SHARED_FIXED_WORDS] (fast)
+    uint32_t *state_w = fixed + (EXACT ? 0 : BA_SHARED_FIXED_WORDS);
+    uint32_t *pool = state_w + ba_state_words(N, plan.any_track != 0);
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
 
     BaCtx c;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
-        ba_carve_lists<EXACT>(c, day, plan.max_ticks, plan.max_dslice, pool, gscr);
+        ba_carve_lists<EXACT>(c, day, plan.max_ticks, plan.max_dslice, fixed, pool, gscr);
 
         // ---- setup -----------------------------------------------------------
         const float *lat_airport = prm.lat_airport + (size_t)p * C * N;

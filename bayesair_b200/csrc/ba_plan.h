@@ -132,13 +132,14 @@ struct BaPlanView {
 //   exact variant only: two due buffers 6 x F each,
 //                       calendar counters max_ticks + 2
 //   turnaround lists 2 x turn_total, aircraft FIFOs 2 x av_total, delayed deques dl_total
-static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_ticks)
+static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_ticks,
+                                        int max_dslice_plan)
 {
     uint64_t w = 13ull * (uint64_t)d.F;
     if (d.any_track_t) w += 2ull * (uint64_t)d.F;
     if (d.any_track_a) w += 3ull * (uint64_t)d.F;
     w += 7ull * d.q_total_x;          // draw history + exact rings (exact) / spill area (fast)
-    if (exact) w += 2ull * BA_DSTAGE_WORDS * ((uint64_t)d.max_dslice + 2) +
+    if (exact) w += 2ull * BA_DSTAGE_WORDS * ((uint64_t)max_dslice_plan + 2) + 4 +
                     2ull * (uint64_t)BA_DUE_WORDS * (uint64_t)d.F +
                     2ull * (((uint64_t)d.F + 7) / 8 * 4) + (uint64_t)max_ticks + 2;
     w += 2ull * d.turn_total + 2ull * d.av_total + 1ull * d.dl_total;

@@ -300,13 +300,17 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         V.q_total_s = q_s; V.q_total_x = q_x;
         V.turn_total = turn; V.av_total = av; V.dl_total = dl;
         V.first_tick = first_tick; V.t_before_first = t_before;
-        scratch_fast = std::max(scratch_fast, ba_scratch_words(V, false, max_ticks));
-        scratch_exact = std::max(scratch_exact, ba_scratch_words(V, true, max_ticks));
         smem_words = std::max(smem_words, 6u * q_s);
     }
 
     out->day_views.resize(n_days);
-    for (int d = 0; d < n_days; ++d) out->day_views[d] = out->days[d].view;
+    for (int d = 0; d < n_days; ++d) {
+        const BaDayView &V = out->days[d].view;
+        out->day_views[d] = V;
+        // the staged-departure buffers are strided by the plan-wide largest calendar slice
+        scratch_fast = std::max(scratch_fast, ba_scratch_words(V, false, max_ticks, out->max_dslice));
+        scratch_exact = std::max(scratch_exact, ba_scratch_words(V, true, max_ticks, out->max_dslice));
+    }
     BaPlanView &P = out->view;
     P.D = n_days; P.N = N; P.Fmax = Fmax; P.R = R;
     P.C = include_cancellations ? 4 : 2;

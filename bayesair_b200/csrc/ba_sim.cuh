@@ -341,18 +341,26 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N, bool tracked)
 #undef BA_COLU
 }
 
-// Words of shared memory the list structures of the fast variant need.
+// Fixed-size shared structures of the fast variant (calendar counters + two due buffers):
+// they sit at compile-time offsets in front of the per-airport state, so every access to
+// them is a shared load with an immediate address.
+#define BA_DUE_STRIDE_S (BA_DUE_WORDS * BA_DUE_CAP_S + BA_DUE_CAP_S / 2)
+#define BA_SHARED_FIXED_WORDS (BA_KCAL + 2 * BA_DUE_STRIDE_S)
+
+// Words of shared memory the size-dependent list structures of the fast variant need
+// (runway rings; the staged departures are added by the caller).
 BA_DEV uint32_t ba_shared_list_words(uint32_t q_total_s)
 {
-    return BA_Q_WORDS * q_total_s + BA_KCAL + 2 * BA_DUE_WORDS * BA_DUE_CAP_S + 2 * (BA_DUE_CAP_S / 2);
+    return BA_Q_WORDS * q_total_s;
 }
 
 // Carves the queue pool / calendar counters / due buffer (shared or global) and the
-// per-flight scratch.  `shared_pool` = shared memory after the state arrays,
-// `g` = start of this CTA's global scratch.
+// per-flight scratch.  `shared_fixed` = BA_SHARED_FIXED_WORDS of shared memory (fast
+// variant), `shared_pool` = shared memory after the state records, `g` = start of this
+// CTA's global scratch.
 template <bool EXACT>
 BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int max_dslice_plan,
-                           uint32_t *shared_pool, uint32_t *g)
+                           uint32_t *shared_fixed, uint32_t *shared_pool, uint32_t *g)
 {
     const uint32_t F = (uint32_t)day.F;
     c.xdk = (float *)g; g += F; c.xak = (float *)g; g += F; c.atk = (float *)g; g += F;
@@ -372,18 +380,26 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int ma
     c.gq = nullptr;
     if (!EXACT) { c.gq = g; g += BA_Q_WORDS * day.q_total_x; }
     uint32_t *s = EXACT ? g : shared_pool;
-    const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
-    c.qe = s; s += BA_Q_WORDS * qt;
-    c.due_cap = EXACT ? F : (uint32_t)BA_DUE_CAP_S;
-    const uint32_t own_words = (c.due_cap + 7u) / 8u * 4u;     // u16 per entry, 16-byte groups
-    c.due_base = s; c.due_stride = BA_DUE_WORDS * c.due_cap + own_words;
-    s += 2u * c.due_stride;
     c.dstage_cap = (uint32_t)day.max_dslice;
     c.dstage_stride = BA_DSTAGE_WORDS * (((uint32_t)max_dslice_plan + 1u) & ~1u);
     c.dstage_base = s; s += 2u * c.dstage_stride;
-    c.cal_cap = EXACT ? (uint32_t)max_ticks + 2u : (uint32_t)BA_KCAL;
-    c.cal_cnt = s; s += c.cal_cap;
-    if (EXACT) g = s;
+    const uint32_t qt = EXACT ? day.q_total_x : day.q_total_s;
+    c.qe = s; s += BA_Q_WORDS * qt;
+    if (EXACT) {
+        c.due_cap = F;
+        const uint32_t own_words = (c.due_cap + 7u) / 8u * 4u; // u16 per entry, 16-byte groups
+        s += (4u - ((uint32_t)(s - g) & 3u)) & 3u;             // g is 16-byte aligned
+        c.due_base = s; c.due_stride = BA_DUE_WORDS * c.due_cap + own_words;
+        s += 2u * c.due_stride;
+        c.cal_cap = (uint32_t)max_ticks + 2u;
+        c.cal_cnt = s; s += c.cal_cap;
+        g = s;
+    } else {
+        c.due_cap = (uint32_t)BA_DUE_CAP_S;
+        c.cal_cap = (uint32_t)BA_KCAL;
+        c.cal_cnt = shared_fixed;
+        c.due_base = shared_fixed + BA_KCAL; c.due_stride = (uint32_t)BA_DUE_STRIDE_S;
+    }
     c.tt = (float *)g; g += day.turn_total; c.te = (float *)g; g += day.turn_total;
     c.at = (float *)g; g += day.av_total; c.ae = (float *)g; g += day.av_total;
     c.dl = g;

@@ -53,7 +53,8 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     const int N = plan.N, C = plan.C, R = plan.R, D = plan.D;
     std::vector<uint32_t> state((size_t)BA_NWORDS_STATE_TRACK * N + 8, 0);
     std::vector<uint32_t> pool(ba_shared_list_words(day.q_total_s) + 2 * BA_DSTAGE_WORDS * (plan.max_dslice + 2) + 8, 0);
-    std::vector<uint32_t> gs(ba_scratch_words(day, true, plan.max_ticks) + 8, 0);
+    std::vector<uint32_t> fixed(BA_SHARED_FIXED_WORDS + 8, 0);
+    std::vector<uint32_t> gs(ba_scratch_words(day, true, plan.max_ticks, plan.max_dslice) + 8, 0);
     uint32_t ctaw[BA_CTA_WORDS] = {0, 0, 0, 0};
     BaCtx c;
     memset(&c, 0, sizeof(c));
@@ -81,7 +82,8 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     c.particle = p; c.dayidx = d;
     c.grow = c.want_grad ? tape + pd * (size_t)plan.grad_stride : nullptr;
     c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
-    ba_carve_lists<EXACT>(c, day, plan.max_ticks, plan.max_dslice, pool.data(), gs.data());
+    ba_carve_lists<EXACT>(c, day, plan.max_ticks, plan.max_dslice,
+                          (uint32_t *)(((uintptr_t)fixed.data() + 15) & ~(uintptr_t)15), pool.data(), gs.data());
     for (uint32_t k = 0; k < c.cal_cap; ++k) c.cal_cnt[k] = 0;
 
     const float *la = lat_airport + (size_t)p * C * N;
