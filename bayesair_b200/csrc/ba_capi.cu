@@ -137,6 +137,7 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         BA_PCUDA(upload(pl, H.rt_flt, &v.rt_flt));
         BA_PCUDA(upload(pl, H.dcal_off, &v.dcal_off));
         BA_PCUDA(upload(pl, H.dcal_rec, &v.dcal_rec));
+        BA_PCUDA(upload(pl, H.dep_cpos, &v.dep_cpos));
         BA_PCUDA(upload(pl, H.drun_off, &v.drun_off));
         BA_PCUDA(upload(pl, H.drun, &v.drun));
         BA_PCUDA(upload(pl, H.airports, &v.airports));

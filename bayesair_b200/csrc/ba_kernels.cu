@@ -141,24 +141,44 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             __syncthreads();
             for (int f = tid; f < day.F; f += nthr) ba_calendar_scatter(c, f);
         }
-        // departures that are ready at the very first tick
+        // Staging runs ahead of the scan (the records are static once the prologue is done):
+        // arrival-calendar slice k -> due buffer k & 1 during tick k - 1, departure-calendar
+        // slice k -> staging buffer (k - 1) & 1 during tick k - 2.
         int tick = day.first_tick - 1;
-        if (tick + 1 <= day.last_ready_tick) {
-            const uint32_t lo = (uint32_t)day.dcal_off[tick + 1], hi = (uint32_t)day.dcal_off[tick + 2];
-            if (tid == 0) c.cta[6 + (tick & 1)] = lo;
-            for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_departure(c, acc, i, lo, tick & 1);
-        }
+        __syncthreads();                                        // calendar records are written
+        auto stage_departures = [&](int k) {
+            if (k > day.last_ready_tick) return;
+            const uint32_t lo = (uint32_t)day.dcal_off[k], hi = (uint32_t)day.dcal_off[k + 1];
+            for (uint32_t i = lo + tid; i < hi; i += nthr)
+                ba_stage_departure<EXACT>(c, acc, i, lo, (k - 1) & 1);
+        };
+        auto stage_arrivals = [&](int k) {                      // returns nothing; counter by tid 0
+            uint32_t n = 0;
+            if (!PREDICT && (uint32_t)k < c.cal_cap) {
+                const uint32_t lo = c.cal_cnt[k - 1], hi = c.cal_cnt[k];
+                n = hi - lo;
+                if (n > c.due_cap) { n = c.due_cap; acc.status |= BA_S_OVERFLOW; }
+                for (uint32_t i = lo + tid; i < lo + n; i += nthr) ba_stage_arrival<EXACT>(c, i, lo, k & 1);
+            }
+            if (tid == 0) c.cta[k & 1] = n;                     // late entries go behind the slice
+        };
+        stage_departures(tick + 1);
+        stage_departures(tick + 2);
+        stage_arrivals(tick + 1);
+        ba_copy_wait();
         __syncthreads();
         BA_MARK(2);
 
         // ---- tick loop (model.py:158-200): two barriers per tick ------------------
         //   interval 1 (one lane per airport): phase C of the previous tick, then phase A
-        //   interval 2 (flight-parallel):      phase B, fills the due buffer of this tick
+        //   interval 2 (flight-parallel):      phase B, completes the due buffer of this tick
         bool busy = day.F > 0;
+        float t_next = c.tick_time[tick + 1];
         while (busy) {
             if (tick >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
             ++tick;
-            const float t = c.tick_time[tick];                  // model.py:161
+            const float t = t_next;                             // model.py:161
+            t_next = c.tick_time[tick + 1];
             const int prev = (tick - 1) & 1, cur = tick & 1;
             uint32_t n_due = c.cta[prev];
             if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
@@ -170,27 +190,27 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
                 more |= ba_airport_busy(c, a) ? 1 : 0;
             }
             if (!EXACT && (acc.status & BA_S_OVERFLOW)) c.cta[3] = 1u;
+            ba_copy_wait();                                     // copies issued a tick ago
             __syncthreads();
             BA_MARK(3);
             if (!EXACT && c.cta[3]) break;                      // a ring overflowed: this
                                                                 // particle-day is re-run anyway
-            if (tid == 0) c.cta[prev] = 0;                      // consumed by every lane
+            for (int s = tid; s < N; s += nthr) ba_run_advance(c, day.lane_airport[s], tick);
             if (PREDICT) {
                 const uint32_t lo = c.cta[4], hi = c.cta[2];
                 for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_pool(c, acc, i, t, cur);
             } else if ((uint32_t)tick < c.cal_cap) {
-                const uint32_t lo = c.cal_cnt[tick - 1], hi = c.cal_cnt[tick];
-                for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_arrival(c, acc, i, cur);
+                uint32_t n = c.cal_cnt[tick] - c.cal_cnt[tick - 1];
+                if (n > c.due_cap) n = c.due_cap;
+                for (uint32_t i = tid; i < n; i += nthr) ba_phase_b_arrival(c, i, cur);
             }
-            if (tick + 1 <= day.last_ready_tick) {
-                const uint32_t lo = (uint32_t)day.dcal_off[tick + 1], hi = (uint32_t)day.dcal_off[tick + 2];
-                if (tid == 0) c.cta[6 + cur] = lo;
-                for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_departure(c, acc, i, lo, cur);
-            }
+            stage_arrivals(tick + 1);                           // due buffer `prev`: consumed
+            stage_departures(tick + 2);                         // staging buffer `prev`: consumed
             busy = __syncthreads_or(more) != 0;
             if (PREDICT && tid == 0) ba_pool_advance(c, 64u);   // next reader: phase B, after a barrier
             BA_MARK(4);
         }
+        ba_copy_wait();
 
         // ---- epilogue ----------------------------------------------------------
         __syncthreads();          // every wait of the tape is written

@@ -84,11 +84,14 @@ struct BaDayView {
     const int32_t *dcal_off;          // [last_ready_tick + 2] departure calendar: slice of tick k
     const uint32_t *dcal_rec;         //   = flights of bookkeeping-free airports that become
                                       //   ready at tick k, grouped by origin airport, pending
-                                      //   order inside a group; record = {dep pos, origin}
+                                      //   order inside a group; record = the static half of the
+                                      //   flight's queue entry {queue word, queue start (fp32)}
+    const int32_t *dep_cpos;          // [F] dep order -> calendar record (-1: not on the calendar)
     int32_t last_ready_tick;          // tick at which the day's last scheduled flight is ready
     const int32_t *drun_off;          // [N+1] per-airport slices of drun (in units of runs)
-    const uint32_t *drun;             // runs {tick, first record, count}: the contiguous part of
-                                      //   a tick's calendar slice that belongs to one airport;
+    const uint32_t *drun;             // runs {tick, first record relative to the tick's slice,
+                                      //   count}: the contiguous part of a tick's calendar
+                                      //   slice that belongs to one airport;
                                       //   every airport's list ends with a sentinel run
     int32_t max_dslice;               // largest calendar slice of any tick of the day
     const BaAirport *airports;        // [N] day order
@@ -135,7 +138,7 @@ struct BaPlanView {
 static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_ticks,
                                         int max_dslice_plan)
 {
-    uint64_t w = 13ull * (uint64_t)d.F;
+    uint64_t w = 15ull * (uint64_t)d.F + 2;   // incl. the calendar-ordered {x_dep, arrival} pairs
     if (d.any_track_t) w += 2ull * (uint64_t)d.F;
     if (d.any_track_a) w += 3ull * (uint64_t)d.F;
     w += 7ull * d.q_total_x;          // draw history + exact rings (exact) / spill area (fast)

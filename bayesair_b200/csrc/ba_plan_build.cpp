@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <numeric>
 
@@ -230,6 +231,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             for (int f = 0; f < F; ++f) if (on_calendar(f)) cnt[ready_tick[f]]++;
             for (int k = 0; k <= last_ready_tick; ++k) H.dcal_off[k + 1] = H.dcal_off[k] + cnt[k];
             H.dcal_rec.assign(2 * (size_t)H.dcal_off[last_ready_tick + 1], 0u);
+            H.dep_cpos.assign((size_t)F, -1);
             // within a tick: grouped by origin (day order), pending order inside a group
             std::vector<std::vector<int>> per_tick((size_t)last_ready_tick + 1);
             for (int f = 0; f < F; ++f) if (on_calendar(f)) per_tick[ready_tick[f]].push_back(f);
@@ -243,10 +245,16 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
                 int pos = H.dcal_off[k];
                 for (size_t i = 0; i < v.size(); ++i, ++pos) {
                     const int f = v[i], o = T.h_origin[f];
-                    H.dcal_rec[2 * pos] = (uint32_t)H.pos_dep[f];
-                    H.dcal_rec[2 * pos + 1] = (uint32_t)o;
+                    const int kd = H.pos_dep[f];
+                    const float ready = std::max(0.0f, H.dep_sched[kd]);     // network.py:60-68
+                    uint32_t ready_bits;
+                    memcpy(&ready_bits, &ready, 4);
+                    H.dcal_rec[2 * pos] = BA_Q_DEP | (H.dep_word[kd] & BA_DW_ENTRY_MASK);
+                    H.dcal_rec[2 * pos + 1] = ready_bits;
+                    H.dep_cpos[kd] = pos;
                     if (i == 0 || T.h_origin[v[i - 1]] != o) {
-                        runs[o].push_back((uint32_t)k); runs[o].push_back((uint32_t)pos);
+                        runs[o].push_back((uint32_t)k);
+                        runs[o].push_back((uint32_t)(pos - H.dcal_off[k]));
                         runs[o].push_back(1u);
                     } else {
                         runs[o].back() += 1u;
@@ -293,6 +301,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         V.rt_gid = H.rt_gid.data(); V.rt_off = H.rt_off.data(); V.rt_flt = H.rt_flt.data();
         V.Rd = (int32_t)H.rt_gid.size();
         V.dcal_off = H.dcal_off.data(); V.dcal_rec = H.dcal_rec.data();
+        V.dep_cpos = H.dep_cpos.data();
         V.last_ready_tick = last_ready_tick;
         V.drun_off = H.drun_off.data(); V.drun = H.drun.data();
         V.any_track_t = any_t; V.any_track_a = any_a;

@@ -11,7 +11,7 @@ struct BaHostDay {
     std::vector<int32_t> route, dep_fid, lane_airport, pos_dep, pos_arr, rt_gid, rt_off, rt_flt;
     std::vector<float> dep_sched;
     std::vector<uint32_t> dep_word, dcal_rec;
-    std::vector<int32_t> dcal_off, drun_off;
+    std::vector<int32_t> dcal_off, drun_off, dep_cpos;
     std::vector<uint32_t> drun;
     std::vector<BaAirport> airports;
     BaDayView view;   // pointers into the vectors above (host view)

@@ -220,10 +220,12 @@ struct BaCtx {
                                       //   service time (NaN = unassigned) and its total wait
     double *psum;                     // running sum of all service draws assigned so far
     BaCol<float> acc_ln0, acc_bc;
-    BaCol<uint32_t> next_dep, q_head, q_tail, q_fill, dep_pops, arr_pops, turn_n;
-    BaCol<uint32_t> run_ptr, run_tick;    // next run of the departure calendar, its tick
+    BaCol<uint32_t> next_dep, q_head, q_tail, q_fill, dep_pops, turn_n;
+    BaCol<uint32_t> arr_left;             // arrivals this airport still waits for
+    BaCol<uint32_t> run_ptr, run_tick;    // next run of the departure calendar, its tick,
+    BaCol<uint32_t> run_info;             //   first staged record << 16 | records
     BaCol<uint32_t> av_head, av_tail, zeros_left, dl_head, dl_tail;
-    BaCol<uint32_t> s_flags, s_qw, s_goff, s_depoff, s_depcnt, s_arrcnt;
+    BaCol<uint32_t> s_flags, s_qw, s_goff, s_depoff, s_depcnt;
     // CTA-wide scalars (shared memory): [0], [1] entries in the even / odd due buffer,
     // [3] abort flag (a shared ring overflowed), [2] / [4] entries in / first live entry of
     // the predictive in-transit pool, [6], [7] first calendar record staged in the even / odd
@@ -231,6 +233,9 @@ struct BaCtx {
     uint32_t *cta;
     const int32_t *dcal_off;      // static departure calendar (ba_plan.h)
     const uint32_t *dcal_rec;
+    const int32_t *dep_cpos;      // dep order -> calendar record
+    uint32_t *dpair;              // [2 F] {x_dep, arrival time} in calendar-record order
+                                  //   (global scratch): the per-particle half of a staged entry
     const int32_t *drun_off;      // per-airport runs of the departure calendar
     const uint32_t *drun;
     int last_ready_tick;
@@ -323,8 +328,8 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N, bool tracked)
     BA_COLF(m, 0); BA_COLF(rate, 1); BA_COLF(mt, 2); BA_COLF(tstd, 3);
     BA_COLF(w_head, 4); BA_COLF(asg_lo, 5); BA_COLF(asg_hi, 6);
     BA_COLU(q_head, 7); BA_COLU(q_tail, 8); BA_COLU(dep_pops, 9);
-    BA_COLU(arr_pops, 10); BA_COLU(s_flags, 11); BA_COLU(s_qw, 12);
-    BA_COLU(s_arrcnt, 13); BA_COLF(next_sched, 14);
+    BA_COLU(arr_left, 10); BA_COLU(s_flags, 11); BA_COLU(s_qw, 12);
+    BA_COLU(run_info, 13); BA_COLF(next_sched, 14);
     BA_COLU(q_fill, 15); BA_COLU(s_goff, 16); BA_COLU(run_ptr, 17); BA_COLU(run_tick, 18);
     if (tracked) {
         BA_COLF(base, 19); BA_COLF(n_avail, 20); BA_COLF(n0, 21);
@@ -363,6 +368,7 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int ma
                            uint32_t *shared_fixed, uint32_t *shared_pool, uint32_t *g)
 {
     const uint32_t F = (uint32_t)day.F;
+    c.dpair = g; g += 2 * F;                  // first: 8-byte aligned
     c.xdk = (float *)g; g += F; c.xak = (float *)g; g += F; c.atk = (float *)g; g += F;
     c.ct = (float *)g; g += F; c.xaf = (float *)g; g += F;
     c.wd = (float *)g; g += F; c.wa = (float *)g; g += F;
@@ -406,6 +412,7 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int ma
     c.first_tick = day.first_tick;
     c.dcal_off = day.dcal_off; c.dcal_rec = day.dcal_rec; c.last_ready_tick = day.last_ready_tick;
     c.drun_off = day.drun_off; c.drun = day.drun;
+    c.dep_cpos = day.dep_cpos;
 }
 
 BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
@@ -486,10 +493,15 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     c.rate[a] = rate; c.tstd[a] = tstd;
     c.asg_lo[a] = NAN; c.asg_hi[a] = NAN; c.w_head[a] = 0.0f; c.psum[a] = 0.0;
     c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
-    c.q_head[a] = 0; c.q_tail[a] = 0; c.q_fill[a] = 0; c.dep_pops[a] = 0; c.arr_pops[a] = 0;
+    c.q_head[a] = 0; c.q_tail[a] = 0; c.q_fill[a] = 0; c.dep_pops[a] = 0;
+    c.arr_left[a] = (uint32_t)A.arr_cnt;
     c.s_goff[a] = A.q_off_x;
-    c.run_ptr[a] = (uint32_t)c.drun_off[a];
-    c.run_tick[a] = c.drun[3 * c.drun_off[a]];
+    {
+        const uint32_t rp = (uint32_t)c.drun_off[a];
+        c.run_ptr[a] = rp;
+        c.run_tick[a] = c.drun[3 * rp];
+        c.run_info[a] = (c.drun[3 * rp + 1] << 16) | c.drun[3 * rp + 2];
+    }
     if (c.n_avail.p) {
         float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
         if (c.cancel_mode) {
@@ -514,12 +526,21 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     }
     c.s_flags[a] = A.flags;
     c.s_qw[a] = ba_qw_pack(EXACT ? A.q_off_x : A.q_off_s, EXACT ? A.q_mask_x : A.q_mask_s);
-    c.s_arrcnt[a] = (uint32_t)A.arr_cnt;
 }
 
 // ---------------------------------------------------------------------------
 // PROLOGUE: one flight (call for f = tid, tid + nthreads, ...)
 // ---------------------------------------------------------------------------
+// The per-particle half {x_dep, arrival time} of the flight's departure-queue entry, stored
+// where the static half lies in the departure calendar (ba_stage_departure copies both).
+BA_DEV void ba_store_dpair(BaCtx &c, int k, float xd, float at)
+{
+    const int cp = c.dep_cpos[k];
+    if (cp < 0) return;
+    BaPairF xy = {xd, at};
+    BA_ST_PAIR(BaPairF, c.dpair + 2 * cp, xy);
+}
+
 template <bool PREDICT>
 BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
 {
@@ -540,6 +561,7 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
         // departure / arrival times may be sampled: the arrival time is only known when the
         // departure is served.  Stage the travel time and the turnaround duration instead.
         c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = tau; c.xaf[f] = xa;
+        ba_store_dpair(c, k, xd, tau);
         c.sim[3 * f] = cobs == 1u ? 1.0f : 0.0f; c.sim[3 * f + 1] = NAN; c.sim[3 * f + 2] = NAN;
         if (c.trl) {
             const float mt = c.mt[d];
@@ -554,6 +576,7 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
     }
     const float at = BA_ADD(y_dep, tau);    // network.py:166-168 with the observed departure
     c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at; c.xaf[f] = xa;
+    ba_store_dpair(c, k, xd, at);
     c.popkey[f] = BA_KEY_INVALID;
     // arrival tick: the first tick whose clock reaches `at` (exact: same fp32 clock table
     // the scan uses; network.py:186 `arrival_time <= time`)
@@ -794,7 +817,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                     cobs = ba_relaxed_bernoulli_draw(pp, ba_noise2(c, f).u_cancel) != 0.0f ? 1u : 0u;
                     c.sim[3 * f] = (float)cobs;
                     if (cobs)   // it will never land: one arrival less to wait for
-                        BA_ATOMIC_DEC(&c.s_arrcnt[(w >> BA_Q_DST_SHIFT) & 0xFFFu]);
+                        BA_ATOMIC_DEC(&c.arr_left[(w >> BA_Q_DST_SHIFT) & 0xFFFu]);
                 }
                 acc.lp += cobs ? lp1 : lp0;
                 g_p += cobs ? dl1 : dl0;
@@ -918,7 +941,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                     float y = fl.act_arr;
                     if (isnan(y)) y = BA_ADD(hi, BA_MUL(on.eps_arr, c.sigma));
                     c.sim[3 * f + 2] = y;
-                    c.arr_pops[a] += 1;
+                    BA_ATOMIC_DEC(&c.arr_left[a]);     // origin lanes may decrement it too (sampled cancellation)
                     if (flags & BA_AP_TRACK_T) {
                         const uint32_t n = c.turn_n[a];
                         c.tt[A->turn_off + n] = BA_ADD(y, c.trl[f]);
@@ -946,7 +969,7 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 if (c.pop_tick) c.pop_tick[2 * f] = tick;
             } else {
                 c.wa[f] = wait;
-                c.arr_pops[a] += 1;
+                c.arr_left[a] -= 1;
                 // _assign_turnaround_time (airport.py:210-221)
                 if (flags & BA_AP_TRACK_T) {
                     const uint32_t n = c.turn_n[a];
@@ -1006,36 +1029,108 @@ BA_DEV void ba_calendar_scatter(BaCtx &c, int f)
 
 // ---------------------------------------------------------------------------
 // SCAN, phase B (flight-parallel).
-//   ba_phase_b_arrival    one record of this tick's arrival-calendar slice: a flight whose
-//       departure has been served moves to the due buffer; one whose departure is still
-//       queued is skipped -- phase A hands it over itself when it is served.
-//   ba_phase_b_departure  one record of NEXT tick's departure-calendar slice: the flight
-//       becomes ready at the next tick (network.py:60-68) at an airport that can neither
-//       cancel nor delay it.  Its queue entry is staged at the record's position in the
-//       slice; the origin lane knows (static runs) where its records are and appends them
-//       behind this tick's arrivals (model.py:181-183).
+//   ba_stage_arrival      (one tick ahead) the static part of one record of an
+//       arrival-calendar slice goes to its slot of that tick's due buffer
+//   ba_phase_b_arrival    one slot of this tick's slice: a flight whose departure has been
+//       served gets its place in the in-transit order; one whose departure is still queued
+//       leaves its slot empty -- phase A hands it over itself when it is served
+//   ba_stage_departure    (two ticks ahead) one record of a departure-calendar slice
+//   ba_run_advance        per airport: the next run of the departure calendar
 // ---------------------------------------------------------------------------
-BA_DEV void ba_phase_b_arrival(BaCtx &c, BaAcc &acc, uint32_t i, int parity)
+// Copies of static records into the staging areas.  Fast variant: asynchronous global ->
+// shared copies (cp.async), issued one or two ticks before the data is read, so that no
+// thread ever waits for them; ba_copy_wait() before the next barrier makes them visible.
+// Exact variant / host: plain copies at the same place.
+template <bool EXACT>
+BA_DEV void ba_copy8(uint32_t *dst, const uint32_t *src)
 {
-    const uint32_t word = c.cal[3 * i];
-    const int f = (int)(word & BA_FID_MASK);
-    const uint32_t key = c.popkey[f];
-    if (key == BA_KEY_INVALID) return;
-    c.popkey[f] = BA_KEY_INVALID;          // consumed
-    ba_due_append(c, acc, parity, word & BA_FID_MASK, key, (word >> BA_Q_DST_SHIFT) & 0xFFFu,
-                  c.popseq[f], __uint_as_float_portable(c.cal[3 * i + 1]),
-                  __uint_as_float_portable(c.cal[3 * i + 2]), 0.0f);
+#if defined(__CUDA_ARCH__)
+    if (!EXACT) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::
+                     "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        return;
+    }
+#endif
+    BA_ST_PAIR(BaPairU, dst, BA_LD_PAIR(BaPairU, src));
 }
 
-BA_DEV void ba_phase_b_departure(BaCtx &c, BaAcc &acc, uint32_t i, uint32_t slice_lo, int parity)
+template <bool EXACT>
+BA_DEV void ba_copy4(uint32_t *dst, const uint32_t *src)
 {
-    const uint32_t k = c.dcal_rec[2 * i];
-    const uint32_t w = c.dep_word[k];
+#if defined(__CUDA_ARCH__)
+    if (!EXACT) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::
+                     "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+        return;
+    }
+#endif
+    *dst = *src;
+}
+
+BA_DEV void ba_copy_wait()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
+// Stage record i of an arrival-calendar slice into its slot of a due buffer: {queue word,
+// arrival time (= queue start), service draw}.  The slot is completed (ordering key,
+// owner) by ba_phase_b_arrival at the slice's tick.
+template <bool EXACT>
+BA_DEV void ba_stage_arrival(BaCtx &c, uint32_t i, uint32_t slice_lo, int parity)
+{
+    const uint32_t slot = i - slice_lo;
+    if (slot >= c.due_cap) return;                  // flagged by the caller
+    uint32_t *de = c.due_base + (uint32_t)parity * c.due_stride + BA_DUE_WORDS * slot;
+    const uint32_t *r = c.cal + 3 * i;
+    ba_copy4<EXACT>(de, r); ba_copy4<EXACT>(de + 3, r + 1); ba_copy4<EXACT>(de + 4, r + 2);
+}
+
+BA_DEV void ba_phase_b_arrival(BaCtx &c, uint32_t slot, int parity)
+{
+    uint32_t *buf = c.due_base + (uint32_t)parity * c.due_stride;
+    uint32_t *de = buf + BA_DUE_WORDS * slot;
+    uint16_t *own = (uint16_t *)(buf + BA_DUE_WORDS * c.due_cap);
+    const uint32_t word = de[0];
+    const int f = (int)(word & BA_FID_MASK);
+    const uint32_t key = c.popkey[f];
+    if (key == BA_KEY_INVALID) {
+        // departure still queued (phase A hands the flight over itself when it is served):
+        // the slot stays empty
+        own[slot] = (uint16_t)0xFFFFu; de[2] = 0xFFFF0000u;
+        return;
+    }
+    c.popkey[f] = BA_KEY_INVALID;          // consumed
+    const uint32_t owner = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
+    de[1] = key; de[2] = (owner << 16) | (c.popseq[f] & 0xFFFFu);
+    own[slot] = (uint16_t)owner;
+}
+
+// Stage record i of a departure-calendar slice: the flight becomes ready at the slice's
+// tick (network.py:60-68) at an airport that can neither cancel nor delay it.  Its queue
+// entry {queue word, queue start} {x, arrival time} lands at the record's position in the
+// slice; the origin lane knows (static runs) where its records are and appends them behind
+// the arrivals of the tick before (model.py:181-183).
+template <bool EXACT>
+BA_DEV void ba_stage_departure(BaCtx &c, BaAcc &acc, uint32_t i, uint32_t slice_lo, int parity)
+{
     if (i - slice_lo >= c.dstage_cap) { acc.status |= BA_S_INTERNAL; return; }
     uint32_t *d = c.dstage_base + (uint32_t)parity * c.dstage_stride + BA_DSTAGE_WORDS * (i - slice_lo);
-    BaPairUF wq = {BA_Q_DEP | (w & BA_DW_ENTRY_MASK), fmaxf(0.0f, c.dep_sched[k])};
-    BaPairF xy = {c.xdk[k], c.atk[k]};
-    BA_ST_PAIR(BaPairUF, d, wq); BA_ST_PAIR(BaPairF, d + 2, xy);
+    ba_copy8<EXACT>(d, c.dcal_rec + 2 * i);
+    ba_copy8<EXACT>(d + 2, c.dpair + 2 * i);
+}
+
+// The run of the departure calendar this airport consumed at `tick` is done: fetch its next
+// one (interval 2: off the lanes' critical path).
+BA_DEV void ba_run_advance(BaCtx &c, int a, int tick)
+{
+    if (c.run_tick[a] != (uint32_t)tick) return;
+    const uint32_t rp = c.run_ptr[a] + 1u;
+    const uint32_t *r = c.drun + 3 * rp;
+    c.run_ptr[a] = rp;
+    c.run_tick[a] = r[0];
+    c.run_info[a] = (r[1] << 16) | r[2];
 }
 
 // Posterior-predictive mode: arrival times are only known once a departure is served, so
@@ -1154,7 +1249,7 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
             if (o < best) { best = o; bj = j; }
         }
         const uint32_t *de = due + BA_DUE_WORDS * bj;
-        ba_push_one(c, acc, P, de[0], __uint_as_float_portable(de[3]), BA_LD_PAIR(BaPairF, de + 4).a, 0.0f);
+        ba_push_one(c, acc, P, de[0] & BA_FID_MASK, __uint_as_float_portable(de[3]), BA_LD_PAIR(BaPairF, de + 4).a, 0.0f);
         if (bj < 64u) m0 &= ~(1ull << bj); else m1 &= ~(1ull << (bj - 64u));
     }
     if (general) {
@@ -1170,23 +1265,21 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
             }
             if (bj == 0xFFFFFFFFu) break;
             const uint32_t *de = due + BA_DUE_WORDS * bj;
-            ba_push_one(c, acc, P, de[0], __uint_as_float_portable(de[3]), BA_LD_PAIR(BaPairF, de + 4).a, 0.0f);
+            ba_push_one(c, acc, P, de[0] & BA_FID_MASK, __uint_as_float_portable(de[3]), BA_LD_PAIR(BaPairF, de + 4).a, 0.0f);
             last = best; first = false;
         }
     }
     // ---- this airport's newly ready departures: a static run of the staged slice ---------
     if (has_run) {
-        const uint32_t rp = c.run_ptr[a];
-        const uint32_t start = c.drun[3 * rp + 1], cnt = c.drun[3 * rp + 2];
+        const uint32_t ri = c.run_info[a];
+        const uint32_t cnt = ri & 0xFFFFu;
         const uint32_t *d = c.dstage_base + (uint32_t)parity * c.dstage_stride +
-                            BA_DSTAGE_WORDS * (start - c.cta[6 + parity]);
+                            BA_DSTAGE_WORDS * (ri >> 16);
         for (uint32_t i = 0; i < cnt; ++i, d += BA_DSTAGE_WORDS) {
             const BaPairUF wq = BA_LD_PAIR(BaPairUF, d);
             const BaPairF xy = BA_LD_PAIR(BaPairF, d + 2);
             ba_push_one(c, acc, P, wq.a, wq.b, xy.a, xy.b);
         }
-        c.run_ptr[a] = rp + 1;
-        c.run_tick[a] = c.drun[3 * (rp + 1)];
     }
     ba_push_end(c, a, P);
 }
@@ -1196,7 +1289,7 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
 // somewhere" is "not yet landed at its destination".
 BA_DEV bool ba_airport_busy(const BaCtx &c, int a)
 {
-    return c.q_head[a] != c.q_tail[a] || c.arr_pops[a] < c.s_arrcnt[a] ||
+    return c.q_head[a] != c.q_tail[a] || c.arr_left[a] != 0u ||
            ((c.s_flags[a] & BA_AP_TRACK_T) &&
             (c.next_dep[a] < c.s_depcnt[a] || c.dl_head[a] != c.dl_tail[a]));
 }

@@ -107,15 +107,31 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     for (int i = 0; i < N; ++i) order[i] = i;
     float t = 0.0f;
     int tick = day.first_tick - 1;
-    auto departures_of = [&](int k, int parity) {
+    // staging runs ahead of the scan exactly as in the kernel (ba_kernels.cu)
+    auto stage_departures = [&](int k) {
         if (k > day.last_ready_tick) return;
-        c.cta[6 + parity] = (uint32_t)day.dcal_off[k];
         std::vector<uint32_t> sl;
         for (int i = day.dcal_off[k]; i < day.dcal_off[k + 1]; ++i) sl.push_back((uint32_t)i);
         if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
-        for (uint32_t i : sl) ba_phase_b_departure(c, acc[i % N], i, (uint32_t)day.dcal_off[k], parity);
+        for (uint32_t i : sl)
+            ba_stage_departure<true>(c, acc[i % N], i, (uint32_t)day.dcal_off[k], (k - 1) & 1);
     };
-    departures_of(tick + 1, tick & 1);
+    auto stage_arrivals = [&](int k) {
+        uint32_t n = 0;
+        if (!PREDICT && (uint32_t)k < c.cal_cap) {
+            const uint32_t lo = c.cal_cnt[k - 1], hi = c.cal_cnt[k];
+            n = hi - lo;
+            if (n > c.due_cap) { n = c.due_cap; acc[0].status |= BA_S_OVERFLOW; }
+            std::vector<uint32_t> sl;
+            for (uint32_t i = lo; i < lo + n; ++i) sl.push_back(i);
+            if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
+            for (uint32_t i : sl) ba_stage_arrival<true>(c, i, lo, k & 1);
+        }
+        c.cta[k & 1] = n;
+    };
+    stage_departures(tick + 1);
+    stage_departures(tick + 2);
+    stage_arrivals(tick + 1);
     bool busy = day.F > 0;
     uint32_t st = 0;
     while (busy) {
@@ -133,7 +149,12 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
             ba_phase_a<EXACT, PREDICT>(c, acc[order[i]], a, t, tick);
             more |= ba_airport_busy(c, a);
         }
-        c.cta[prev] = 0;
+        if (!EXACT) {
+            bool ovf = false;
+            for (int i = 0; i < N; ++i) ovf |= (acc[i].status & BA_S_OVERFLOW) != 0;
+            if (ovf) break;                      // the kernel aborts: the item is re-run exactly
+        }
+        for (int i = 0; i < N; ++i) ba_run_advance(c, day.lane_airport[order[i]], tick);
         if (PREDICT) {
             std::vector<uint32_t> slice;
             for (uint32_t i = c.cta[4]; i < c.cta[2]; ++i) slice.push_back(i);
@@ -141,12 +162,15 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
             for (uint32_t i : slice) ba_phase_b_pool(c, acc[i % N], i, t, cur);
             ba_pool_advance(c, 7u);
         } else if ((uint32_t)tick < c.cal_cap) {
+            uint32_t n = c.cal_cnt[tick] - c.cal_cnt[tick - 1];
+            if (n > c.due_cap) n = c.due_cap;
             std::vector<uint32_t> slice;
-            for (uint32_t i = c.cal_cnt[tick - 1]; i < c.cal_cnt[tick]; ++i) slice.push_back(i);
+            for (uint32_t i = 0; i < n; ++i) slice.push_back(i);
             if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
-            for (uint32_t i : slice) ba_phase_b_arrival(c, acc[i % N], i, cur);
+            for (uint32_t i : slice) ba_phase_b_arrival(c, i, cur);
         }
-        departures_of(tick + 1, cur);
+        stage_arrivals(tick + 1);
+        stage_departures(tick + 2);
         busy = more;
     }
     if (!PREDICT) for (int f = 0; f < day.F; ++f) ba_epilogue_flight(c, acc[f % N], f);
