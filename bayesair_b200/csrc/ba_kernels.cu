@@ -146,11 +146,13 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         // slice k -> staging buffer (k - 1) & 1 during tick k - 2.
         int tick = day.first_tick - 1;
         __syncthreads();                                        // calendar records are written
-        auto stage_departures = [&](int k) {
-            if (k > day.last_ready_tick) return;
-            const uint32_t lo = (uint32_t)day.dcal_off[k], hi = (uint32_t)day.dcal_off[k + 1];
+        auto stage_departures = [&](int k, uint32_t lo, uint32_t hi) {
             for (uint32_t i = lo + tid; i < hi; i += nthr)
                 ba_stage_departure<EXACT>(c, acc, i, lo, (k - 1) & 1);
+        };
+        // calendar offsets are fetched a tick before they are needed (no load on the path)
+        auto dcal_at = [&](int k) {
+            return (uint32_t)day.dcal_off[k <= day.last_ready_tick + 1 ? k : day.last_ready_tick + 1];
         };
         auto stage_arrivals = [&](int k) {                      // returns nothing; counter by tid 0
             uint32_t n = 0;
@@ -162,9 +164,11 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             }
             if (tid == 0) c.cta[k & 1] = n;                     // late entries go behind the slice
         };
-        stage_departures(tick + 1);
-        stage_departures(tick + 2);
+        uint32_t d_lo = dcal_at(tick + 1), d_mid = dcal_at(tick + 2), d_hi = dcal_at(tick + 3);
+        stage_departures(tick + 1, d_lo, d_mid);
+        stage_departures(tick + 2, d_mid, d_hi);
         stage_arrivals(tick + 1);
+        const int a0 = tid < N ? day.lane_airport[tid] : 0;     // this thread's first airport
         ba_copy_wait();
         __syncthreads();
         BA_MARK(2);
@@ -179,12 +183,13 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             ++tick;
             const float t = t_next;                             // model.py:161
             t_next = c.tick_time[tick + 1];
+            d_lo = d_hi; d_hi = dcal_at(tick + 3);              // slice tick + 2, used in interval 2
             const int prev = (tick - 1) & 1, cur = tick & 1;
             uint32_t n_due = c.cta[prev];
             if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
             int more = tick < day.last_ready_tick;
             for (int s = tid; s < N; s += nthr) {
-                const int a = day.lane_airport[s];
+                const int a = s == tid ? a0 : day.lane_airport[s];
                 ba_phase_c_pull(c, acc, a, prev, n_due, tick);
                 ba_phase_a<EXACT, PREDICT>(c, acc, a, t, tick);
                 more |= ba_airport_busy(c, a) ? 1 : 0;
@@ -195,7 +200,8 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             BA_MARK(3);
             if (!EXACT && c.cta[3]) break;                      // a ring overflowed: this
                                                                 // particle-day is re-run anyway
-            for (int s = tid; s < N; s += nthr) ba_run_advance(c, day.lane_airport[s], tick);
+            for (int s = tid; s < N; s += nthr)
+                ba_run_advance(c, s == tid ? a0 : day.lane_airport[s], tick);
             if (PREDICT) {
                 const uint32_t lo = c.cta[4], hi = c.cta[2];
                 for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_pool(c, acc, i, t, cur);
@@ -205,7 +211,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
                 for (uint32_t i = tid; i < n; i += nthr) ba_phase_b_arrival(c, i, cur);
             }
             stage_arrivals(tick + 1);                           // due buffer `prev`: consumed
-            stage_departures(tick + 2);                         // staging buffer `prev`: consumed
+            stage_departures(tick + 2, d_lo, d_hi);             // staging buffer `prev`: consumed
             busy = __syncthreads_or(more) != 0;
             if (PREDICT && tid == 0) ba_pool_advance(c, 64u);   // next reader: phase B, after a barrier
             BA_MARK(4);
