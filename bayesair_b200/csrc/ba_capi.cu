@@ -302,8 +302,8 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         unsigned long long h[8];
         BA_CUDA(cudaStreamSynchronize(s));
         BA_CUDA(cudaMemcpy(h, prm.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost));
-        const char *names[8] = {"init", "prologue", "calendar", "phaseC+A", "phaseB+vote", "-",
-                                "epilogue", "-"};
+        const char *names[8] = {"init", "prologue", "calendar", "phaseC+A", "phaseB+vote", "epilogue1",
+                                "epilogue2", "-"};
         double tot = 0;
         for (int i = 0; i < 7; ++i) tot += (double)h[i];
         fprintf(stderr, "[BA_PHASE_PROFILE] cycles per particle-day (thread 0 wall):");

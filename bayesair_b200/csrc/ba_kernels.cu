@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         const bool aborted = PREDICT || (!EXACT && c.cta[3] != 0u);   // predictive: outcomes only
         if (!aborted)
             for (int f = tid; f < day.F; f += nthr) ba_epilogue_flight(c, acc, f);
+        BA_MARK(5);
         if (c.grow && !aborted) {
             __syncthreads();
             for (int s = tid; s < N; s += nthr) ba_epilogue_airport(c, day.lane_airport[s], N);
@@ -330,6 +331,15 @@ cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact)
     static size_t cur[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
     const int cls = block <= 128 ? 0 : (block <= 256 ? 1 : (block <= 512 ? 2 : 3));
     cudaError_t e = cudaSuccess;
+    // tuning knob: share of the SM's L1/shared array given to shared memory (percent); the
+    // rest caches the per-CTA scratch.  Default: the driver's choice for full occupancy.
+    static int carve = -2;
+    if (carve == -2) { const char *v = getenv("BA_CARVEOUT"); carve = v ? atoi(v) : -1; }
+    if (carve >= 0) {
+        BA_DISPATCH(false, block, e = cudaFuncSetAttribute(
+            kfn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        if (e != cudaSuccess) return e;
+    }
     if (smem_fast > cur[0][cls]) {
         BA_DISPATCH(false, block, e = cudaFuncSetAttribute(
             kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
@@ -358,6 +368,7 @@ int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, in
     if (e != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
         return -1;
+    if (const char *v = getenv("BA_MAX_CTAS_PER_SM")) { const int cap = atoi(v); if (cap > 0 && cap < per_sm) per_sm = cap; }
     return per_sm * sms;
 }
 
