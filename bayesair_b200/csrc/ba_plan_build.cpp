@@ -37,7 +37,7 @@ static double env_double(const char *name, double dflt)
 
 int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float delta_t,
                        float max_t, int include_cancellations, int max_ticks,
-                       BaHostPlan *out, std::string *err)
+                       BaHostPlan *out, std::string *err, double q_div_arg, double q_min_arg)
 {
     auto fail = [&](int code, const std::string &m) { if (err) *err = m; return code; };
     if (!days || n_days <= 0 || n_airports <= 0 || !out)
@@ -48,8 +48,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         return fail(BA_ERR_LIMIT, "ba_plan_create: more than 4096 airports");
 
     // tunables of the shared-memory variant (documented in DESIGN.md)
-    const double q_div = env_double("BA_Q_DIV", 32.0);        // ring = traffic / q_div
-    const double q_min = env_double("BA_Q_MIN", 4.0);
+    const double q_div = q_div_arg > 0.0 ? q_div_arg : env_double("BA_Q_DIV", 32.0);   // ring = traffic / q_div
+    const double q_min = q_min_arg > 0.0 ? q_min_arg : env_double("BA_Q_MIN", 4.0);
     if (max_ticks > 65000)
         return fail(BA_ERR_LIMIT, "ba_plan_create: max_ticks must be <= 65000");
 

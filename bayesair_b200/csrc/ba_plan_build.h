@@ -32,4 +32,4 @@ struct BaHostPlan {
 // Returns BA_OK or an error status with *err filled.
 int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float delta_t,
                        float max_t, int include_cancellations, int max_ticks,
-                       BaHostPlan *out, std::string *err);
+                       BaHostPlan *out, std::string *err, double q_div = 0.0, double q_min = 0.0);
