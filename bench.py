@@ -402,9 +402,10 @@ def run_native(args):
             "philox_value": philox_value,
             "congested_value": congested_value,
             "regimes": {"value": f"posterior-like latents: mean service {svc} h x LogNormal(0, 0.3); "
-                                 "~15% of particle-days saturate the hub and take the exact-list re-run",
-                        "congested_value": "prior-like latents: mean service 0.05 h; every "
-                                           "particle-day takes the exact-list variant"},
+                                 "shared rings spill on demand, no particle-day is re-run",
+                        "congested_value": "prior-like latents: mean service 0.05 h, every hub "
+                                           "queue saturates (long spilled rings); still the "
+                                           "shared-memory variant, no re-runs"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
