@@ -234,6 +234,7 @@ struct BaCtx {
     const int32_t *dcal_off;      // static departure calendar (ba_plan.h)
     const uint32_t *dcal_rec;
     const int32_t *dep_cpos;      // dep order -> calendar record
+    float *nzs;                   // [4 F] generated noise kept for the epilogue (Philox mode)
     uint32_t *dpair;              // [2 F] {x_dep, arrival time} in calendar-record order
                                   //   (global scratch): the per-particle half of a staged entry
     const int32_t *drun_off;      // per-airport runs of the departure calendar
@@ -368,7 +369,8 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int ma
                            uint32_t *shared_fixed, uint32_t *shared_pool, uint32_t *g)
 {
     const uint32_t F = (uint32_t)day.F;
-    c.dpair = g; g += 2 * F;                  // first: 8-byte aligned
+    c.nzs = (float *)g; g += 4 * F;           // first: 16-byte aligned
+    c.dpair = g; g += 2 * F;                  // 8-byte aligned
     c.xdk = (float *)g; g += F; c.xak = (float *)g; g += F; c.atk = (float *)g; g += F;
     c.ct = (float *)g; g += F; c.xaf = (float *)g; g += F;
     c.wd = (float *)g; g += F; c.wa = (float *)g; g += F;
@@ -428,6 +430,30 @@ BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
 #endif
     }
     return ba_philox_noise(c.seed, c.particle, c.dayidx, (uint32_t)f);
+}
+
+// The epilogue needs the same four draws again.  Generated noise is kept in scratch by the
+// prologue (16 bytes per flight) instead of running Philox + the four transforms twice.
+BA_DEV void ba_noise_keep(BaCtx &c, int f, const BaNoise4 &z)
+{
+    if (c.noise) return;
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<float4 *>(c.nzs)[f] = make_float4(z.e_dep, z.eps_travel, z.e_arr, z.eps_turn);
+#else
+    c.nzs[4 * f] = z.e_dep; c.nzs[4 * f + 1] = z.eps_travel; c.nzs[4 * f + 2] = z.e_arr; c.nzs[4 * f + 3] = z.eps_turn;
+#endif
+}
+
+BA_DEV BaNoise4 ba_noise_again(const BaCtx &c, int f)
+{
+    if (c.noise) return ba_noise(c, f);
+#if defined(__CUDA_ARCH__)
+    const float4 v = reinterpret_cast<const float4 *>(c.nzs)[f];
+    BaNoise4 z = {v.x, v.y, v.z, v.w};
+#else
+    BaNoise4 z = {c.nzs[4 * f], c.nzs[4 * f + 1], c.nzs[4 * f + 2], c.nzs[4 * f + 3]};
+#endif
+    return z;
 }
 
 struct BaObsNoise { float u_cancel, eps_dep, eps_arr; };
@@ -548,6 +574,7 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
     const uint32_t cobs = (fl.od >> 24) & 3u;
     const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
     const BaNoise4 nz = ba_noise(c, f);
+    ba_noise_keep(c, f, nz);
     const float T = c.lat_route[c.route[f]];
     // Exponential(1/m).rsample = e / rate  (airport.py:144-147)
     const float xd = c.value_mode ? nz.e_dep : BA_DIV(nz.e_dep, c.rate[o]);
@@ -1319,7 +1346,7 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
         return;
     }
     const int j = c.pos_arr[f];
-    const BaNoise4 nz = ba_noise(c, f);
+    const BaNoise4 nz = ba_noise_again(c, f);
     const int rid = c.route[f];
     const float T = c.lat_route[rid];
     const bool grad = c.want_grad != 0;
