@@ -278,6 +278,21 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         std::stable_sort(H.lane_airport.begin(), H.lane_airport.end(), [&](int x, int y) {
             return dep_cnt[x] + arr_cnt[x] > dep_cnt[y] + arr_cnt[y];
         });
+        {
+            // ... and dealt round-robin over the full warps: a warp's time per tick is the sum
+            // over its loops of the longest trip count among its lanes, and the maxima over
+            // 1/k of the hubs are smaller than over all of them (measured: +6 % with
+            // saturated hubs, neutral otherwise)
+            const int full = N / 32;
+            if (full > 1) {
+                const std::vector<int32_t> srt = H.lane_airport;
+                std::vector<int32_t> lanes;
+                for (int w = 0; w < full; ++w)
+                    for (int l = 0; l < 32; ++l) lanes.push_back(srt[(size_t)l * full + w]);
+                for (int r = 32 * full; r < N; ++r) lanes.push_back(srt[r]);
+                H.lane_airport = lanes;
+            }
+        }
         // idle prefix of the day: ticks before the first scheduled departure do nothing
         // (no pending flight is ready, nothing is queued or in transit) as long as the
         // reserve injection (t >= max_t, model.py:170-174) has not started.
