@@ -256,8 +256,6 @@ struct BaCtx {
     uint32_t *due_base;           // buffer p at due_base + p * due_stride (no pointer arrays:
     uint32_t due_stride;          //   a runtime-indexed member would push BaCtx to local memory)
     uint32_t due_cap;
-    uint32_t own8;                // owner list of a due buffer: one byte per slot (N < 255)
-                                  //   instead of two
     int first_tick;
     // list pools (shared memory in the fast variant, global scratch in the exact one)
     // runway queues, 6 words per entry (three 8-byte pairs): {word, lo} {queue start,
@@ -417,7 +415,6 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int ma
     c.dcal_off = day.dcal_off; c.dcal_rec = day.dcal_rec; c.last_ready_tick = day.last_ready_tick;
     c.drun_off = day.drun_off; c.drun = day.drun;
     c.dep_cpos = day.dep_cpos;
-    c.own8 = day.N < 255 ? 1u : 0u;
 }
 
 BA_DEV BaNoise4 ba_noise(const BaCtx &c, int f)
@@ -676,15 +673,6 @@ BA_DEV void ba_q_refill(BaCtx &c, int a, uint32_t head, uint32_t tail)
     c.q_fill[a] = fill;
 }
 
-// Owner list behind the entries of a due buffer (what ba_phase_c_pull scans): the
-// destination airport of every slot, 0xFF / 0xFFFF for an empty slot.
-BA_DEV void ba_own_store(const BaCtx &c, uint32_t *buf, uint32_t slot, uint32_t owner)
-{
-    uint32_t *own = buf + BA_DUE_WORDS * c.due_cap;
-    if (c.own8) ((uint8_t *)own)[slot] = (uint8_t)owner;
-    else ((uint16_t *)own)[slot] = (uint16_t)owner;
-}
-
 BA_DEV void ba_due_append(BaCtx &c, BaAcc &acc, int parity, uint32_t word, uint32_t key,
                           uint32_t owner, uint32_t seq, float qstart, float x, float y)
 {
@@ -696,7 +684,7 @@ BA_DEV void ba_due_append(BaCtx &c, BaAcc &acc, int parity, uint32_t word, uint3
     BaPairUF os = {(owner << 16) | (seq & 0xFFFFu), qstart};
     BaPairF xy = {x, y};
     BA_ST_PAIR(BaPairU, de, wk); BA_ST_PAIR(BaPairUF, de + 2, os); BA_ST_PAIR(BaPairF, de + 4, xy);
-    ba_own_store(c, buf, slot, owner);
+    ((uint16_t *)(buf + BA_DUE_WORDS * c.due_cap))[slot] = (uint16_t)owner;
 }
 
 // available_aircraft.pop(0) for one departing flight (network.py:118-126).
@@ -1130,19 +1118,20 @@ BA_DEV void ba_phase_b_arrival(BaCtx &c, uint32_t slot, int parity)
 {
     uint32_t *buf = c.due_base + (uint32_t)parity * c.due_stride;
     uint32_t *de = buf + BA_DUE_WORDS * slot;
+    uint16_t *own = (uint16_t *)(buf + BA_DUE_WORDS * c.due_cap);
     const uint32_t word = de[0];
     const int f = (int)(word & BA_FID_MASK);
     const uint32_t key = c.popkey[f];
     if (key == BA_KEY_INVALID) {
         // departure still queued (phase A hands the flight over itself when it is served):
         // the slot stays empty
-        ba_own_store(c, buf, slot, 0xFFFFu); de[2] = 0xFFFF0000u;
+        own[slot] = (uint16_t)0xFFFFu; de[2] = 0xFFFF0000u;
         return;
     }
     c.popkey[f] = BA_KEY_INVALID;          // consumed
     const uint32_t owner = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
     de[1] = key; de[2] = (owner << 16) | (c.popseq[f] & 0xFFFFu);
-    ba_own_store(c, buf, slot, owner);
+    own[slot] = (uint16_t)owner;
 }
 
 // Stage record i of a departure-calendar slice: the flight becomes ready at the slice's
@@ -1251,44 +1240,22 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
     uint64_t m0 = 0, m1 = 0;
     const uint32_t *due = c.due_base + (uint32_t)parity * c.due_stride;
     if (n_due && n_due <= 128u) {
+        // owners are packed u16, eight per 16-byte load (broadcast: every lane of the warp
+        // reads the same words)
         const uint32_t *ow = due + BA_DUE_WORDS * c.due_cap;
-        if (c.own8) {
-            // owners are packed u8, sixteen per 16-byte load (broadcast: every lane of the
-            // warp reads the same words).  Exact zero-byte test of w ^ aaaa, then the four
-            // flag bits of a word are gathered by one multiply.
-            const uint32_t aa = (uint32_t)a * 0x01010101u;
-            const uint32_t groups = (n_due + 15u) >> 4;
-#define BA_NIB(w) ((((~((((w) ^ aa) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | ((w) ^ aa)) & 0x80808080u) >> 7) * 0x01020408u) >> 24)
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-            for (uint32_t g = 0; g < 8u; ++g) {
-                if (g < groups) {
-                    const uint32_t w0 = ow[4 * g], w1 = ow[4 * g + 1], w2 = ow[4 * g + 2], w3 = ow[4 * g + 3];
-                    const uint32_t b = BA_NIB(w0) | (BA_NIB(w1) << 4) | (BA_NIB(w2) << 8) | (BA_NIB(w3) << 12);
-                    if (g < 4u) m0 |= (uint64_t)b << (16u * g); else m1 |= (uint64_t)b << (16u * (g - 4u));
-                }
-            }
-#undef BA_NIB
-            // slots at and beyond n_due hold stale owners
-            if (n_due < 64u) { m0 &= (1ull << n_due) - 1ull; m1 = 0; }
-            else if (n_due < 128u) m1 &= (1ull << (n_due - 64u)) - 1ull;
-        } else {
-            // u16 owners, eight per 16-byte load
-            const uint32_t aa = (uint32_t)a | ((uint32_t)a << 16);
-            const uint32_t groups = (n_due + 7u) >> 3;
-            for (uint32_t g = 0; g < groups; ++g) {
-                uint32_t w0 = ow[4 * g], w1 = ow[4 * g + 1], w2 = ow[4 * g + 2], w3 = ow[4 * g + 3];
-                uint32_t bits = 0;
-                uint32_t x;
-                x = w0 ^ aa; bits |= ((x & 0xFFFFu) == 0u) | (((x >> 16) == 0u) << 1);
-                x = w1 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 2) | (((x >> 16) == 0u) << 3);
-                x = w2 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 4) | (((x >> 16) == 0u) << 5);
-                x = w3 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 6) | (((x >> 16) == 0u) << 7);
-                const uint32_t left = n_due - 8u * g;
-                if (left < 8u) bits &= (1u << left) - 1u;
-                if (g < 8u) m0 |= (uint64_t)bits << (8u * g); else m1 |= (uint64_t)bits << (8u * (g - 8u));
-            }
+        const uint32_t aa = (uint32_t)a | ((uint32_t)a << 16);
+        const uint32_t groups = (n_due + 7u) >> 3;
+        for (uint32_t g = 0; g < groups; ++g) {
+            uint32_t w0 = ow[4 * g], w1 = ow[4 * g + 1], w2 = ow[4 * g + 2], w3 = ow[4 * g + 3];
+            uint32_t bits = 0;
+            uint32_t x;
+            x = w0 ^ aa; bits |= ((x & 0xFFFFu) == 0u) | (((x >> 16) == 0u) << 1);
+            x = w1 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 2) | (((x >> 16) == 0u) << 3);
+            x = w2 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 4) | (((x >> 16) == 0u) << 5);
+            x = w3 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 6) | (((x >> 16) == 0u) << 7);
+            const uint32_t left = n_due - 8u * g;
+            if (left < 8u) bits &= (1u << left) - 1u;
+            if (g < 8u) m0 |= (uint64_t)bits << (8u * g); else m1 |= (uint64_t)bits << (8u * (g - 8u));
         }
     }
     const bool general = n_due > 128u;
