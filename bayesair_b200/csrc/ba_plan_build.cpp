@@ -281,10 +281,11 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         {
             // ... and dealt round-robin over the full warps: a warp's time per tick is the sum
             // over its loops of the longest trip count among its lanes, and the maxima over
-            // 1/k of the hubs are smaller than over all of them (measured: +6 % with
-            // saturated hubs, neutral otherwise)
+            // 1/k of the hubs are smaller than over all of them (measured: +8 % with
+            // saturated hubs, +2 % otherwise)
             const int full = N / 32;
-            if (full > 1) {
+            const char *lo = std::getenv("BA_LANE_ORDER");        // "0": keep the sorted order
+            if (full > 1 && !(lo && std::atoi(lo) == 0)) {
                 const std::vector<int32_t> srt = H.lane_airport;
                 std::vector<int32_t> lanes;
                 for (int w = 0; w < full; ++w)
