@@ -109,14 +109,16 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     // Shared rings are sized so that the SM holds as many CTAs as the kernel's register
     // budget allows (ba_kernels.cu: BA_MIN_BLOCKS): smaller rings spill to global memory a
     // little more often, one more resident CTA is worth ~10 %.  BA_Q_DIV / BA_Q_MIN pin them.
-    static const double ladder[][2] = {{32, 4}, {40, 4}, {48, 4}, {48, 2}, {64, 2}, {64, 1}};
+    static const double ladder[][2] = {{32, 4}, {40, 4}, {48, 4}, {48, 2}, {64, 2}, {64, 1},
+                                       {96, 1}, {128, 1}};
+    const int n_ladder = (int)(sizeof(ladder) / sizeof(ladder[0]));
     const bool pinned = std::getenv("BA_Q_DIV") || std::getenv("BA_Q_MIN");
     int smem_sm = 0;
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
     const int blk = ba_forward_block_threads(n_airports);
-    const int want_ctas = blk <= 128 ? 7 : (blk <= 256 ? 3 : 1);
+    const int want_ctas = ba_forward_target_ctas(blk);
     int rc = BA_OK;
-    for (int step = 0; step < 6; ++step) {
+    for (int step = 0; step < n_ladder; ++step) {
         rc = ba_build_host_plan(days, n_days, n_airports, delta_t, max_t, include_cancellations,
                                 max_ticks, &pl->host, &err, pinned ? 0.0 : ladder[step][0],
                                 pinned ? 0.0 : ladder[step][1]);
@@ -124,7 +126,7 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         const size_t smem = ba_forward_smem_bytes(n_airports, pl->host.smem_list_words, false,
                                                   pl->host.view.any_track != 0, pl->host.max_dslice);
         if ((smem + 1024) * (size_t)want_ctas <= (size_t)smem_sm) break;
-        if (step == 5)          // nothing fits: keep the roomiest rings
+        if (step == n_ladder - 1)   // nothing fits: keep the roomiest rings
             rc = ba_build_host_plan(days, n_days, n_airports, delta_t, max_t, include_cancellations,
                                     max_ticks, &pl->host, &err, ladder[0][0], ladder[0][1]);
     }

@@ -43,10 +43,18 @@ size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bo
 }
 
 // resident CTAs per SM the register allocation aims for, per block-size class
+// (measured on the bench workload: 7 CTAs/SM at 72 registers 7.4e5, 8 at 64 registers 7.8e5,
+//  9 at 56 registers 7.5e5 particle-days/s; the plan sizes its shared rings to match)
 #ifndef BA_MIN_BLOCKS_128
-#define BA_MIN_BLOCKS_128 7
+#define BA_MIN_BLOCKS_128 8
 #endif
 #define BA_MIN_BLOCKS(MAXT) ((MAXT) == 128 ? BA_MIN_BLOCKS_128 : ((MAXT) == 256 ? 3 : 1))
+
+// resident CTAs per SM the plan should size its shared memory for
+int ba_forward_target_ctas(int block_threads)
+{
+    return block_threads <= 128 ? BA_MIN_BLOCKS(128) : (block_threads <= 256 ? BA_MIN_BLOCKS(256) : 1);
+}
 
 template <bool EXACT, int MAXT, bool PREDICT>
 __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(const BaFwdParams prm)

@@ -40,6 +40,7 @@ struct BaBwdParams {
 };
 
 int ba_forward_block_threads(int n_airports);
+int ba_forward_target_ctas(int block_threads);
 size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bool tracked,
                              int max_dslice);
 cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact);
