@@ -191,9 +191,9 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         return set_err(BA_ERR_LIMIT, "ba_plan_create: too many airports for one CTA's shared memory");
     }
     pl->fast_ok = pl->smem_fast <= (size_t)max_optin;
-    BA_PCUDA(ba_forward_configure(pl->block, pl->fast_ok ? pl->smem_fast : 0, pl->smem_exact));
-    pl->grid_exact = ba_forward_max_resident(pl->block, pl->smem_exact, true, device);
-    pl->grid_fast = pl->fast_ok ? ba_forward_max_resident(pl->block, pl->smem_fast, false, device) : 0;
+    BA_PCUDA(ba_forward_configure(pl->block, pl->fast_ok ? pl->smem_fast : 0, pl->smem_exact, tracked));
+    pl->grid_exact = ba_forward_max_resident(pl->block, pl->smem_exact, true, tracked, device);
+    pl->grid_fast = pl->fast_ok ? ba_forward_max_resident(pl->block, pl->smem_fast, false, tracked, device) : 0;
     if (pl->grid_exact <= 0 || (pl->fast_ok && pl->grid_fast <= 0)) {
         ba_plan_destroy(pl);
         return set_err(BA_ERR_CUDA, "ba_plan_create: occupancy query failed");
@@ -292,11 +292,12 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         prm.phase_cycles = d_phase;
     }
     const bool use_fast = pl->fast_ok && !o.force_exact_lists;
+    const bool trk = pl->host.view.any_track != 0;
     if (use_fast) {
         prm.scratch_stride = pl->stride_fast;
         prm.work_counter = pl->d_counters + 0;
         int grid = (int)std::min<long long>(n_work, pl->grid_fast);
-        BA_CUDA(ba_launch_forward(prm, false, grid, pl->block, pl->smem_fast, s));
+        BA_CUDA(ba_launch_forward(prm, false, trk, grid, pl->block, pl->smem_fast, s));
         g_launches++;
         if (!o.no_overflow_rerun) {
             // particle-days whose shared-memory lists overflowed are re-run with
@@ -310,14 +311,14 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
             rr.work_list = pl->d_worklist;
             rr.n_work_dev = pl->d_counters + 2;
             int rgrid = (int)std::min<long long>(n_work, pl->grid_exact);
-            BA_CUDA(ba_launch_forward(rr, true, rgrid, pl->block, pl->smem_exact, s));
+            BA_CUDA(ba_launch_forward(rr, true, trk, rgrid, pl->block, pl->smem_exact, s));
             g_launches++;
         }
     } else {
         prm.scratch_stride = pl->stride_exact;
         prm.work_counter = pl->d_counters + 1;
         int grid = (int)std::min<long long>(n_work, pl->grid_exact);
-        BA_CUDA(ba_launch_forward(prm, true, grid, pl->block, pl->smem_exact, s));
+        BA_CUDA(ba_launch_forward(prm, true, trk, grid, pl->block, pl->smem_exact, s));
         g_launches++;
     }
     if (prm.phase_cycles) {

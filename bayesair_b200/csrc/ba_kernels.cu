@@ -56,7 +56,7 @@ int ba_forward_target_ctas(int block_threads)
     return block_threads <= 128 ? BA_MIN_BLOCKS(128) : (block_threads <= 256 ? BA_MIN_BLOCKS(256) : 1);
 }
 
-template <bool EXACT, int MAXT, bool PREDICT>
+template <bool EXACT, int MAXT, bool PREDICT, bool TRK>
 __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(const BaFwdParams prm)
 {
     extern __shared__ __align__(16) uint32_t smem[];
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
 
         // ---- setup -----------------------------------------------------------
         const float *lat_airport = prm.lat_airport + (size_t)p * C * N;
-        for (int a = tid; a < N; a += nthr) ba_init_airport<EXACT>(c, a, lat_airport, N);
+        for (int a = tid; a < N; a += nthr) ba_init_airport<EXACT, TRK>(c, a, lat_airport, N);
         if (c.grow)
             for (int i = tid; i < plan.grad_stride; i += nthr) c.grow[i] = 0.0f;
         if (c.pop_tick)
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
 
         BA_MARK(0);
         // ---- prologue: flight-parallel, coalesced ------------------------------
-        for (int f = tid; f < day.F; f += nthr) ba_prologue_flight<PREDICT>(c, acc, f);
+        for (int f = tid; f < day.F; f += nthr) ba_prologue_flight<PREDICT, TRK>(c, acc, f);
         __syncthreads();
         BA_MARK(1);
         if (!PREDICT) {
@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             for (int s = tid; s < N; s += nthr) {
                 const int a = s == tid ? a0 : day.lane_airport[s];
                 ba_phase_c_pull(c, acc, a, prev, n_due, tick);
-                ba_phase_a<EXACT, PREDICT>(c, acc, a, t, tick);
-                more |= ba_airport_busy(c, a) ? 1 : 0;
+                ba_phase_a<EXACT, PREDICT, TRK>(c, acc, a, t, tick);
+                more |= ba_airport_busy<TRK>(c, a) ? 1 : 0;
             }
             if (!EXACT && (acc.status & BA_S_OVERFLOW)) c.cta[3] = 1u;
             ba_copy_wait();                                     // copies issued a tick ago
@@ -230,11 +230,11 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         __syncthreads();          // every wait of the tape is written
         const bool aborted = PREDICT || (!EXACT && c.cta[3] != 0u);   // predictive: outcomes only
         if (!aborted)
-            for (int f = tid; f < day.F; f += nthr) ba_epilogue_flight(c, acc, f);
+            for (int f = tid; f < day.F; f += nthr) ba_epilogue_flight<TRK>(c, acc, f);
         BA_MARK(5);
         if (c.grow && !aborted) {
             __syncthreads();
-            for (int s = tid; s < N; s += nthr) ba_epilogue_airport(c, day.lane_airport[s], N);
+            for (int s = tid; s < N; s += nthr) ba_epilogue_airport<TRK>(c, day.lane_airport[s], N);
             for (int r = tid; r < day.Rd; r += nthr) ba_epilogue_route(c, r);
         }
         // deterministic block reduction: lanes -> warp (shuffle tree) -> warps in order
@@ -323,20 +323,26 @@ __global__ void __launch_bounds__(256) ba_collect_kernel(const uint32_t *status,
 // launch wrappers
 // ---------------------------------------------------------------------------
 // block-size classes: the register budget follows the CTA size actually used
-#define BA_DISPATCH(EX, BLOCK, STMT)                                                   \
-    do {                                                                               \
-        if ((BLOCK) <= 128) { auto kfn = ba_forward_kernel<EX, 128, false>; STMT; }      \
-        else if ((BLOCK) <= 256) { auto kfn = ba_forward_kernel<EX, 256, false>; STMT; } \
-        else if ((BLOCK) <= 512) { auto kfn = ba_forward_kernel<EX, 512, false>; STMT; } \
-        else { auto kfn = ba_forward_kernel<EX, 1024, false>; STMT; }                    \
+#define BA_DISPATCH_T(EX, TRK, BLOCK, STMT)                                                 \
+    do {                                                                                    \
+        if ((BLOCK) <= 128) { auto kfn = ba_forward_kernel<EX, 128, false, TRK>; STMT; }      \
+        else if ((BLOCK) <= 256) { auto kfn = ba_forward_kernel<EX, 256, false, TRK>; STMT; } \
+        else if ((BLOCK) <= 512) { auto kfn = ba_forward_kernel<EX, 512, false, TRK>; STMT; } \
+        else { auto kfn = ba_forward_kernel<EX, 1024, false, TRK>; STMT; }                    \
+    } while (0)
+// TRKV (runtime): does any airport of the plan keep aircraft books (ba_sim.cuh: ba_ap_flags)
+#define BA_DISPATCH(EX, TRKV, BLOCK, STMT)                                                  \
+    do {                                                                                    \
+        if (TRKV) BA_DISPATCH_T(EX, true, BLOCK, STMT); else BA_DISPATCH_T(EX, false, BLOCK, STMT); \
     } while (0)
 
 // The dynamic-shared-memory limit is a property of the kernel function, shared by every plan
 // of the process: only ever raise it (a later, smaller plan must not lower it under an
 // earlier one).
-cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact)
+cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact, bool tracked)
 {
-    static size_t cur[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    static size_t cur_all[2][2][4] = {{{0, 0, 0, 0}, {0, 0, 0, 0}}, {{0, 0, 0, 0}, {0, 0, 0, 0}}};
+    size_t (*cur)[4] = cur_all[tracked ? 1 : 0];
     const int cls = block <= 128 ? 0 : (block <= 256 ? 1 : (block <= 512 ? 2 : 3));
     cudaError_t e = cudaSuccess;
     // tuning knob: share of the SM's L1/shared array given to shared memory (percent); the
@@ -344,18 +350,18 @@ cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact)
     static int carve = -2;
     if (carve == -2) { const char *v = getenv("BA_CARVEOUT"); carve = v ? atoi(v) : -1; }
     if (carve >= 0) {
-        BA_DISPATCH(false, block, e = cudaFuncSetAttribute(
+        BA_DISPATCH(false, tracked, block, e = cudaFuncSetAttribute(
             kfn, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         if (e != cudaSuccess) return e;
     }
     if (smem_fast > cur[0][cls]) {
-        BA_DISPATCH(false, block, e = cudaFuncSetAttribute(
+        BA_DISPATCH(false, tracked, block, e = cudaFuncSetAttribute(
             kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast));
         if (e != cudaSuccess) return e;
         cur[0][cls] = smem_fast;
     }
     if (smem_exact > cur[1][cls]) {
-        BA_DISPATCH(true, block, e = cudaFuncSetAttribute(
+        BA_DISPATCH(true, tracked, block, e = cudaFuncSetAttribute(
             kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact));
         if (e != cudaSuccess) return e;
         cur[1][cls] = smem_exact;
@@ -363,15 +369,15 @@ cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact)
     return e;
 }
 
-int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, int device)
+int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, bool tracked, int device)
 {
     int per_sm = 0, sms = 0;
     cudaError_t e;
     if (exact)
-        BA_DISPATCH(true, block_threads, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        BA_DISPATCH(true, tracked, block_threads, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &per_sm, kfn, block_threads, smem_bytes));
     else
-        BA_DISPATCH(false, block_threads, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        BA_DISPATCH(false, tracked, block_threads, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &per_sm, kfn, block_threads, smem_bytes));
     if (e != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
@@ -380,21 +386,21 @@ int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, in
     return per_sm * sms;
 }
 
-cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, int grid, int block,
+cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, bool tracked, int grid, int block,
                               size_t smem, cudaStream_t s)
 {
-    if (exact) BA_DISPATCH(true, block, (kfn<<<grid, block, smem, s>>>(p)));
-    else BA_DISPATCH(false, block, (kfn<<<grid, block, smem, s>>>(p)));
+    if (exact) BA_DISPATCH(true, tracked, block, (kfn<<<grid, block, smem, s>>>(p)));
+    else BA_DISPATCH(false, tracked, block, (kfn<<<grid, block, smem, s>>>(p)));
     return cudaGetLastError();
 }
 
 // posterior-predictive variant: exact-capacity lists only
 #define BA_DISPATCH_PREDICT(BLOCK, STMT)                                                 \
     do {                                                                                 \
-        if ((BLOCK) <= 128) { auto kfn = ba_forward_kernel<true, 128, true>; STMT; }     \
-        else if ((BLOCK) <= 256) { auto kfn = ba_forward_kernel<true, 256, true>; STMT; } \
-        else if ((BLOCK) <= 512) { auto kfn = ba_forward_kernel<true, 512, true>; STMT; } \
-        else { auto kfn = ba_forward_kernel<true, 1024, true>; STMT; }                   \
+        if ((BLOCK) <= 128) { auto kfn = ba_forward_kernel<true, 128, true, true>; STMT; }     \
+        else if ((BLOCK) <= 256) { auto kfn = ba_forward_kernel<true, 256, true, true>; STMT; } \
+        else if ((BLOCK) <= 512) { auto kfn = ba_forward_kernel<true, 512, true, true>; STMT; } \
+        else { auto kfn = ba_forward_kernel<true, 1024, true, true>; STMT; }                   \
     } while (0)
 
 cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,

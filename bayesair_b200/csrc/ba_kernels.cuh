@@ -43,10 +43,10 @@ int ba_forward_block_threads(int n_airports);
 int ba_forward_target_ctas(int block_threads);
 size_t ba_forward_smem_bytes(int n_airports, uint32_t list_words, bool exact, bool tracked,
                              int max_dslice);
-cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact);
-int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, int device);
+cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact, bool tracked);
+int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, bool tracked, int device);
 
-cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, int grid, int block,
+cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, bool tracked, int grid, int block,
                               size_t smem, cudaStream_t s);
 cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
                               cudaStream_t s);

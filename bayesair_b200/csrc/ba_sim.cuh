@@ -505,7 +505,18 @@ BA_DEV BaFlight ba_flight(const BaCtx &c, int f)
 // ---------------------------------------------------------------------------
 // per-airport initialisation (model.py:139-155)
 // ---------------------------------------------------------------------------
-template <bool EXACT>
+// Plans without aircraft bookkeeping (no cancellations, every airport "simple") run kernels
+// built with TRK = false: the tracking flags read as clear at compile time, so all of that
+// code (and its registers) drops out.
+#define BA_AP_TRACK_ANY (BA_AP_TRACK_T | BA_AP_TRACK_A)
+template <bool TRK>
+BA_DEV uint32_t ba_ap_flags(const BaCtx &c, int a)
+{
+    const uint32_t f = c.s_flags[a];
+    return TRK ? f : (f & ~(uint32_t)BA_AP_TRACK_ANY);
+}
+
+template <bool EXACT, bool TRK = true>
 BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] */, int Ng)
 {
     const BaAirport A = c.ap[a];
@@ -528,7 +539,7 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
         c.run_tick[a] = c.drun[3 * rp];
         c.run_info[a] = (c.drun[3 * rp + 1] << 16) | c.drun[3 * rp + 2];
     }
-    if (c.n_avail.p) {
+    if (TRK && c.n_avail.p) {
         float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
         if (c.cancel_mode) {
             n0 = BA_EXP(lat_airport[2 * Ng + g]);    // model.py:91-99
@@ -567,7 +578,7 @@ BA_DEV void ba_store_dpair(BaCtx &c, int k, float xd, float at)
     BA_ST_PAIR(BaPairF, c.dpair + 2 * cp, xy);
 }
 
-template <bool PREDICT>
+template <bool PREDICT, bool TRK = true>
 BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
 {
     const BaFlight fl = ba_flight(c, f);
@@ -590,7 +601,7 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
         c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = tau; c.xaf[f] = xa;
         ba_store_dpair(c, k, xd, tau);
         c.sim[3 * f] = cobs == 1u ? 1.0f : 0.0f; c.sim[3 * f + 1] = NAN; c.sim[3 * f + 2] = NAN;
-        if (c.trl) {
+        if (TRK && c.trl) {
             const float mt = c.mt[d];
             c.trl[f] = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, c.tstd[d]));
             c.tre[f] = nz.eps_turn;
@@ -621,7 +632,7 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
         BA_ATOMIC_INC(&c.cal_cnt[ka]);
     }
     c.karr[f] = ka;
-    if (c.trl) {
+    if (TRK && c.trl) {
         // Normal(m~, v_u m~).rsample (airport.py:217-221)
         const float mt = c.mt[d];
         const float u = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, c.tstd[d]));
@@ -738,10 +749,10 @@ BA_DEV void ba_depart_tracked(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, u
 // ---------------------------------------------------------------------------
 // SCAN, phase A
 // ---------------------------------------------------------------------------
-template <bool EXACT, bool PREDICT>
+template <bool EXACT, bool PREDICT, bool TRK = true>
 BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
 {
-    const uint32_t flags = c.s_flags[a];
+    const uint32_t flags = ba_ap_flags<TRK>(c, a);
     const BaAirport *A = &c.ap[a];      // only dereferenced on the tracked paths
 
     // 1. update_available_aircraft (airport.py:66-84)
@@ -1314,10 +1325,11 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
 // Does this airport still hold work (completion vote, network.py:34-41)?  Every flight
 // that is not observed as cancelled eventually lands here, so "in transit or queued
 // somewhere" is "not yet landed at its destination".
+template <bool TRK = true>
 BA_DEV bool ba_airport_busy(const BaCtx &c, int a)
 {
     return c.q_head[a] != c.q_tail[a] || c.arr_left[a] != 0u ||
-           ((c.s_flags[a] & BA_AP_TRACK_T) &&
+           ((ba_ap_flags<TRK>(c, a) & BA_AP_TRACK_T) &&
             (c.next_dep[a] < c.s_depcnt[a] || c.dl_head[a] != c.dl_tail[a]));
 }
 
@@ -1332,6 +1344,7 @@ BA_DEV bool ba_airport_busy(const BaCtx &c, int a)
 //   ct[k|j]                  d/d mean_turnaround term (noise mode: aircraft branch of the
 //                            departure, dep order; value mode: landing term, arrival order)
 // ---------------------------------------------------------------------------
+template <bool TRK = true>
 BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
 {
     const BaFlight fl = ba_flight(c, f);
@@ -1340,7 +1353,7 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
     const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
     // *_cancelled (network.py:100-109) at an airport whose cancellation probability is
     // exactly 0 (ba_plan.h: BA_SIMPLE_RATIO); other airports score it in the scan
-    if (!(c.s_flags[o] & BA_AP_TRACK_T)) acc.lp += (double)(cobs == 1u ? c.c1_lp : c.c0_lp);
+    if (!(ba_ap_flags<TRK>(c, o) & BA_AP_TRACK_T)) acc.lp += (double)(cobs == 1u ? c.c1_lp : c.c0_lp);
     if (cobs == 1u) {                 // observed as cancelled: never queued anywhere
         if (c.want_grad) { c.xdk[k] = 0.0f; c.ct[k] = 0.0f; c.atk[f] = 0.0f; }
         return;
@@ -1358,7 +1371,7 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
     const float rate_o = c.rate[o];
     const float xd = c.value_mode ? nz.e_dep : BA_DIV(nz.e_dep, rate_o);
     const float wdep = c.wd[f];
-    const bool track_a = (c.s_flags[o] & BA_AP_TRACK_A) != 0u;
+    const bool track_a = (ba_ap_flags<TRK>(c, o) & BA_AP_TRACK_A) != 0u;
     const float qstart_d = track_a ? c.qd[f] : fmaxf(0.0f, fl.sched_dep);
     const float mu_d = BA_ADD(qstart_d, wdep);              // queue_start + total_wait
     const float dy_d = fl.act_dep - mu_d;
@@ -1418,6 +1431,7 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
 // ---------------------------------------------------------------------------
 // EPILOGUE, stage 2: owner sums over contiguous slices, fixed order, no atomics.
 // ---------------------------------------------------------------------------
+template <bool TRK = true>
 BA_DEV void ba_epilogue_airport(BaCtx &c, int a, int Ng)
 {
     const BaAirport A = c.ap[a];
@@ -1428,7 +1442,7 @@ BA_DEV void ba_epilogue_airport(BaCtx &c, int a, int Ng)
     const float n_ent = (float)(A.dep_live + A.arr_cnt), n_land = (float)A.arr_cnt;
     float g_serv, g_turn;
     if (!c.value_mode) {
-        if (A.flags & BA_AP_TRACK_A)
+        if (TRK && (A.flags & BA_AP_TRACK_A))
             for (int i = 0; i < A.dep_cnt; ++i) s_turn += c.ct[A.dep_off + i];
         // x = e m  =>  d/dm = sum r W / m - (#entries)/m ;  u = m~ (1 + v_u eps)
         g_serv = (s_dep + s_arr) / m - n_ent / m;

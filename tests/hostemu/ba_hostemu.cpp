@@ -41,7 +41,7 @@ extern "C" void ba_emu_plan_routes(const EmuPlan *p, int32_t *o, int32_t *d)
     memcpy(d, p->host.route_dest.data(), p->host.route_dest.size() * 4);
 }
 
-template <bool EXACT, bool PREDICT = false>
+template <bool EXACT, bool PREDICT = false, bool TRK = true>
 static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d, int P,
                      const float *lat_airport, const float *lat_route, const float *scales,
                      const float *noise, uint64_t seed, int value_mode, int want_grad,
@@ -87,7 +87,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     for (uint32_t k = 0; k < c.cal_cap; ++k) c.cal_cnt[k] = 0;
 
     const float *la = lat_airport + (size_t)p * C * N;
-    for (int a = 0; a < N; ++a) ba_init_airport<EXACT>(c, a, la, N);
+    for (int a = 0; a < N; ++a) ba_init_airport<EXACT, TRK>(c, a, la, N);
     if (c.grow) for (int i = 0; i < plan.grad_stride; ++i) c.grow[i] = 0.0f;
     if (c.pop_tick) for (int i = 0; i < 2 * plan.Fmax; ++i) c.pop_tick[i] = -1;
 
@@ -97,7 +97,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
     std::vector<int> forder(day.F);
     for (int f = 0; f < day.F; ++f) forder[f] = f;
     if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
-    for (int f : forder) ba_prologue_flight<PREDICT>(c, acc[f % N], f);
+    for (int f : forder) ba_prologue_flight<PREDICT, TRK>(c, acc[f % N], f);
     if (!PREDICT) {
         ba_calendar_scan(c, -1);
         if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
@@ -146,8 +146,8 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         for (int i = 0; i < N; ++i) {
             const int a = day.lane_airport[order[i]];
             ba_phase_c_pull(c, acc[order[i]], a, prev, n_due, tick);
-            ba_phase_a<EXACT, PREDICT>(c, acc[order[i]], a, t, tick);
-            more |= ba_airport_busy(c, a);
+            ba_phase_a<EXACT, PREDICT, TRK>(c, acc[order[i]], a, t, tick);
+            more |= ba_airport_busy<TRK>(c, a);
         }
         if (!EXACT) {
             bool ovf = false;
@@ -173,9 +173,9 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         stage_departures(tick + 2);
         busy = more;
     }
-    if (!PREDICT) for (int f = 0; f < day.F; ++f) ba_epilogue_flight(c, acc[f % N], f);
+    if (!PREDICT) for (int f = 0; f < day.F; ++f) ba_epilogue_flight<TRK>(c, acc[f % N], f);
     if (c.grow && !PREDICT) {
-        for (int i = 0; i < N; ++i) ba_epilogue_airport(c, day.lane_airport[i], N);
+        for (int i = 0; i < N; ++i) ba_epilogue_airport<TRK>(c, day.lane_airport[i], N);
         for (int r = 0; r < day.Rd; ++r) ba_epilogue_route(c, r);
     }
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -202,16 +202,20 @@ extern "C" int ba_emu_forward(const EmuPlan *pl, int P, const float *lat_airport
     for (int d = 0; d < plan.D; ++d)
         for (int p = 0; p < P; ++p) {
             const BaDayView &day = plan.days[d];
-            if (exact)
-                run_item<true>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
-                               value_mode, want_grad, replay_waits, shuffle_seed, logp, status, ticks, tape, pop_tick);
-            else {
-                run_item<false>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
-                                value_mode, want_grad, replay_waits, shuffle_seed, logp, status, ticks, tape, pop_tick);
-                if (rerun_overflow && (status[(size_t)p * plan.D + d] & BA_S_OVERFLOW))
-                    run_item<true>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed,
-                                   value_mode, want_grad, replay_waits, shuffle_seed, logp, status, ticks, tape, pop_tick);
+            // same kernel selection as ba_forward: built without the aircraft-bookkeeping code
+            // when no airport of the plan needs it
+#define BA_EMU_RUN(EX, TRK) run_item<EX, false, TRK>(plan, day, p, d, P, lat_airport, lat_route, scales, noise, seed, \
+                               value_mode, want_grad, replay_waits, shuffle_seed, logp, status, ticks, tape, pop_tick)
+            const bool trk = plan.any_track != 0;
+            if (exact) {
+                if (trk) BA_EMU_RUN(true, true); else BA_EMU_RUN(true, false);
+            } else {
+                if (trk) BA_EMU_RUN(false, true); else BA_EMU_RUN(false, false);
+                if (rerun_overflow && (status[(size_t)p * plan.D + d] & BA_S_OVERFLOW)) {
+                    if (trk) BA_EMU_RUN(true, true); else BA_EMU_RUN(true, false);
+                }
             }
+#undef BA_EMU_RUN
         }
     return 0;
 }
