@@ -110,7 +110,7 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     // budget allows (ba_kernels.cu: BA_MIN_BLOCKS): smaller rings spill to global memory a
     // little more often, one more resident CTA is worth ~10 %.  BA_Q_DIV / BA_Q_MIN pin them.
     static const double ladder[][2] = {{32, 4}, {40, 4}, {48, 4}, {48, 2}, {64, 2}, {64, 1},
-                                       {96, 1}, {128, 1}};
+                                       {96, 1}, {128, 1}, {192, 1}, {256, 1}};
     const int n_ladder = (int)(sizeof(ladder) / sizeof(ladder[0]));
     const bool pinned = std::getenv("BA_Q_DIV") || std::getenv("BA_Q_MIN");
     int smem_sm = 0;
