@@ -95,9 +95,9 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
 
     // optional phase timing (thread 0 reads the SM clock after each barrier)
     long long pc_last = 0;
-    unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const bool prof = prm.phase_cycles != nullptr && tid == 0;
-#define BA_MARK(slot) do { if (prof) { long long now_ = clock64(); pc[slot] += (unsigned long long)(now_ - pc_last); pc_last = now_; } } while (0)
+    // (accumulated straight into global memory: no per-thread counters held in registers)
+#define BA_MARK(slot) do { if (prof) { long long now_ = clock64(); atomicAdd(prm.phase_cycles + (slot), (unsigned long long)(now_ - pc_last)); pc_last = now_; } } while (0)
 
     for (;;) {
         if (prof) pc_last = clock64();
@@ -276,8 +276,6 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         __syncthreads();     // red[] and the state arrays are reused by the next item
         BA_MARK(6);
     }
-    if (prof)
-        for (int i = 0; i < 8; ++i) atomicAdd(prm.phase_cycles + i, pc[i]);
 }
 
 // g[p, j] = sum_d dlogp[p, d] * tape[p, d, j]
