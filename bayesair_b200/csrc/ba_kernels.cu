@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             int more = tick < day.last_ready_tick;
             for (int s = tid; s < N; s += nthr) {
                 const int a = s == tid ? a0 : day.lane_airport[s];
-                ba_phase_c_pull(c, acc, a, prev, n_due, tick);
+                ba_phase_c_pull<EXACT>(c, acc, a, prev, n_due, tick);
                 ba_phase_a<EXACT, PREDICT, TRK>(c, acc, a, t, tick);
                 more |= ba_airport_busy<TRK>(c, a) ? 1 : 0;
             }

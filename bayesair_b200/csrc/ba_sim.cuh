@@ -1245,6 +1245,8 @@ BA_DEV void ba_push_end(BaCtx &c, int a, const BaPush &P)
     c.q_tail[a] = P.tail; c.q_fill[a] = P.fill;
 }
 
+static_assert(BA_DUE_CAP_S <= 128, "the owner scan of the shared due buffer uses two 64-bit masks");
+template <bool EXACT = true>
 BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_due, int tick)
 {
     const bool has_run = c.run_tick[a] == (uint32_t)tick;
@@ -1269,7 +1271,7 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
             if (g < 8u) m0 |= (uint64_t)bits << (8u * g); else m1 |= (uint64_t)bits << (8u * (g - 8u));
         }
     }
-    const bool general = n_due > 128u;
+    const bool general = EXACT && n_due > 128u;     // the shared due buffer holds 128 entries
     if (!(m0 | m1) && !has_run && !general) return;
     BaPush P;
     ba_push_begin(c, a, P);

@@ -145,7 +145,7 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
         for (int i = 0; i < N; ++i) {
             const int a = day.lane_airport[order[i]];
-            ba_phase_c_pull(c, acc[order[i]], a, prev, n_due, tick);
+            ba_phase_c_pull<EXACT>(c, acc[order[i]], a, prev, n_due, tick);
             ba_phase_a<EXACT, PREDICT, TRK>(c, acc[order[i]], a, t, tick);
             more |= ba_airport_busy<TRK>(c, a);
         }
