@@ -72,8 +72,36 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.rows, self._stop = index, [], threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:                                   # set up before the timed region starts
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self._nvml = (pynvml, h, reasons, mx)
+        except Exception:
+            self._nvml = None
 
     def _run(self):
+        # NVML in-process (a sample every 20 ms); nvidia-smi (a few per second) if it is absent
+        if self._nvml is not None:
+            pynvml, h, get_reasons, mx = self._nvml
+            bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40),
+                    ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+            try:
+                while True:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    r = int(get_reasons(h))
+                    self.rows.append([str(sm), str(mx), "0"] +
+                                     ["Active" if r & b else "Not Active" for _, b in bits])
+                    if self._stop.wait(0.02):
+                        break
+                return
+            except Exception:
+                pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(

@@ -5,7 +5,7 @@
 set -e
 cd "$(dirname "$0")/.."
 LIB=bayesair_b200/_lib/libbayesair_b200.so
-K=ba_forward_kernelILb0ELi128ELb0
+K=ba_forward_kernelILb0ELi128ELb0ELb0
 REP=gpurun_out/prof_r1_forward.ncu-rep
 python tools/launch_list.py gpurun_out/launches_r1.csv > profiles/r1_launch_list.csv
 {
