@@ -162,69 +162,132 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         auto dcal_at = [&](int k) {
             return (uint32_t)day.dcal_off[k <= day.last_ready_tick + 1 ? k : day.last_ready_tick + 1];
         };
-        auto stage_arrivals = [&](int k) {                      // returns nothing; counter by tid 0
-            uint32_t n = 0;
-            if (!PREDICT && (uint32_t)k < c.cal_cap) {
-                const uint32_t lo = c.cal_cnt[k - 1], hi = c.cal_cnt[k];
-                n = hi - lo;
-                if (n > c.due_cap) { n = c.due_cap; acc.status |= BA_S_OVERFLOW; }
-                for (uint32_t i = lo + tid; i < lo + n; i += nthr) ba_stage_arrival<EXACT>(c, i, lo, k & 1);
-            }
-            if (tid == 0) c.cta[k & 1] = n;                     // late entries go behind the slice
-        };
-        uint32_t d_lo = dcal_at(tick + 1), d_mid = dcal_at(tick + 2), d_hi = dcal_at(tick + 3);
-        stage_departures(tick + 1, d_lo, d_mid);
-        stage_departures(tick + 2, d_mid, d_hi);
-        stage_arrivals(tick + 1);
         const int a0 = tid < N ? day.lane_airport[tid] : 0;     // this thread's first airport
-        ba_copy_wait();
-        __syncthreads();
-        BA_MARK(2);
-
-        // ---- tick loop (model.py:158-200): two barriers per tick ------------------
-        //   interval 1 (one lane per airport): phase C of the previous tick, then phase A
-        //   interval 2 (flight-parallel):      phase B, completes the due buffer of this tick
         bool busy = day.F > 0;
-        float t_next = c.tick_time[tick + 1];
-        while (busy) {
-            if (tick >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
-            ++tick;
-            const float t = t_next;                             // model.py:161
-            t_next = c.tick_time[tick + 1];
-            d_lo = d_hi; d_hi = dcal_at(tick + 3);              // slice tick + 2, used in interval 2
-            const int prev = (tick - 1) & 1, cur = tick & 1;
-            uint32_t n_due = c.cta[prev];
-            if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
-            int more = tick < day.last_ready_tick;
-            for (int s = tid; s < N; s += nthr) {
-                const int a = s == tid ? a0 : day.lane_airport[s];
-                ba_phase_c_pull<EXACT>(c, acc, a, prev, n_due, tick);
-                ba_phase_a<EXACT, PREDICT, TRK>(c, acc, a, t, tick);
-                more |= ba_airport_busy<TRK>(c, a) ? 1 : 0;
-            }
-            if (!EXACT && (acc.status & BA_S_OVERFLOW)) c.cta[3] = 1u;
-            ba_copy_wait();                                     // copies issued a tick ago
+        if (!EXACT && !PREDICT) {
+            // ---- tick loop (model.py:158-200), ONE barrier per tick (ba_sim.cuh: single-
+            //      barrier scan).  During tick j every thread first issues the asynchronous
+            //      copies that assemble the due buffer of tick j and stage what tick j + 1
+            //      will read, then runs its airport lane: phase C of tick j - 1, phase A of
+            //      tick j.  Nothing a thread reads in tick j is written in tick j. ----------
+            const uint32_t cap = (uint32_t)BA_DUE_CAP_S;
+            auto slice_lo = [&](int k) { return k >= 1 && (uint32_t)k < c.cal_cap ? c.cal_cnt[k - 1] : 0u; };
+            auto slice_n = [&](int k) {
+                if (k < 1 || (uint32_t)k >= c.cal_cap) return 0u;
+                const uint32_t n = c.cal_cnt[k] - c.cal_cnt[k - 1];
+                return n > cap ? cap : n;
+            };
+            auto stage_words = [&](int k) {
+                if (k < 1 || (uint32_t)k >= c.cal_cap) return;
+                const uint32_t lo = c.cal_cnt[k - 1], n = c.cal_cnt[k] - lo;
+                if (n > cap) acc.status |= BA_S_OVERFLOW;       // more arrivals in one tick than slots
+                for (uint32_t i = lo + tid; i < lo + (n > cap ? cap : n); i += nthr) ba_stage_word(c, i, lo, k & 1);
+            };
+            uint32_t d_lo = dcal_at(tick + 1), d_hi = dcal_at(tick + 2), d_nx = dcal_at(tick + 3);
+            stage_departures(tick + 1, d_lo, d_hi);             // slice tick + 1 -> buffer tick & 1
+            stage_words(tick + 1);
+            ba_copy_wait();
             __syncthreads();
-            BA_MARK(3);
-            if (!EXACT && c.cta[3]) break;                      // a ring overflowed: this
-                                                                // particle-day is re-run anyway
-            for (int s = tid; s < N; s += nthr)
-                ba_run_advance(c, s == tid ? a0 : day.lane_airport[s], tick);
-            if (PREDICT) {
-                const uint32_t lo = c.cta[4], hi = c.cta[2];
-                for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_pool(c, acc, i, t, cur);
-            } else if ((uint32_t)tick < c.cal_cap) {
-                uint32_t n = c.cal_cnt[tick] - c.cal_cnt[tick - 1];
-                if (n > c.due_cap) n = c.due_cap;
-                for (uint32_t i = tid; i < n; i += nthr) ba_phase_b_arrival(c, i, cur);
+            BA_MARK(2);
+            float t_next = c.tick_time[tick + 1];
+            while (busy) {
+                if (tick >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
+                ++tick;
+                const float t = t_next;                         // model.py:161
+                t_next = c.tick_time[tick + 1];
+                d_lo = d_hi; d_hi = d_nx; d_nx = dcal_at(tick + 3);   // slice tick + 1 = [d_lo, d_hi)
+                const int prev = (tick - 1) & 1, cur = tick & 1;
+                const uint32_t n_cur = slice_n(tick), n_prev = slice_n(tick - 1);
+                uint32_t n_late = c.cta[8 + (tick - 1) % 3];
+                if (n_late > cap - n_prev) n_late = cap - n_prev;   // overflow already flagged
+                if (tid == 0) c.cta[8 + (tick + 1) % 3] = 0;    // read two ticks ago, next used next tick
+                // (1) this tick's arrival slice -> due buffer `cur` (read next tick)
+                {
+                    const uint32_t lo = slice_lo(tick);
+                    for (uint32_t i = tid; i < n_cur; i += nthr) ba_complete_arrival(c, i, lo, cur);
+                }
+                // (2) what the next tick reads: its slice's queue words, its departures
+                stage_words(tick + 1);
+                stage_departures(tick + 1, d_lo, d_hi);         // slice tick + 1 -> buffer `cur`
+                // (3) the airport lanes
+                int more = tick < day.last_ready_tick;
+                for (int s = tid; s < N; s += nthr) {
+                    const int a = s == tid ? a0 : day.lane_airport[s];
+                    ba_phase_c_pull_fast(c, acc, a, prev, n_prev, n_late, tick);
+                    ba_phase_a<EXACT, PREDICT, TRK>(c, acc, a, t, tick, n_cur);
+                    more |= ba_airport_busy<TRK>(c, a) ? 1 : 0;
+                }
+                if (acc.status & BA_S_OVERFLOW) c.cta[3] = 1u;
+                ba_copy_wait();
+                busy = __syncthreads_or(more) != 0;
+                BA_MARK(3);
+                if (c.cta[3]) break;                            // re-run with exact lists anyway
             }
-            stage_arrivals(tick + 1);                           // due buffer `prev`: consumed
-            stage_departures(tick + 2, d_lo, d_hi);             // staging buffer `prev`: consumed
-            busy = __syncthreads_or(more) != 0;
-            if (PREDICT && tid == 0) ba_pool_advance(c, 64u);   // next reader: phase B, after a barrier
-            BA_MARK(4);
+            ba_copy_wait();
+        } else {
+            auto stage_arrivals = [&](int k) {                      // returns nothing; counter by tid 0
+                uint32_t n = 0;
+                if (!PREDICT && (uint32_t)k < c.cal_cap) {
+                    const uint32_t lo = c.cal_cnt[k - 1], hi = c.cal_cnt[k];
+                    n = hi - lo;
+                    if (n > c.due_cap) { n = c.due_cap; acc.status |= BA_S_OVERFLOW; }
+                    for (uint32_t i = lo + tid; i < lo + n; i += nthr) ba_stage_arrival<EXACT>(c, i, lo, k & 1);
+                }
+                if (tid == 0) c.cta[k & 1] = n;                     // late entries go behind the slice
+            };
+            uint32_t d_lo = dcal_at(tick + 1), d_mid = dcal_at(tick + 2), d_hi = dcal_at(tick + 3);
+            stage_departures(tick + 1, d_lo, d_mid);
+            stage_departures(tick + 2, d_mid, d_hi);
+            stage_arrivals(tick + 1);
+            ba_copy_wait();
+            __syncthreads();
+            BA_MARK(2);
+
+            // ---- tick loop (model.py:158-200): two barriers per tick ------------------
+            //   interval 1 (one lane per airport): phase C of the previous tick, then phase A
+            //   interval 2 (flight-parallel):      phase B, completes the due buffer of this tick
+            float t_next = c.tick_time[tick + 1];
+            while (busy) {
+                if (tick >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
+                ++tick;
+                const float t = t_next;                             // model.py:161
+                t_next = c.tick_time[tick + 1];
+                d_lo = d_hi; d_hi = dcal_at(tick + 3);              // slice tick + 2, used in interval 2
+                const int prev = (tick - 1) & 1, cur = tick & 1;
+                uint32_t n_due = c.cta[prev];
+                if (n_due > c.due_cap) n_due = c.due_cap;           // overflow already flagged
+                int more = tick < day.last_ready_tick;
+                for (int s = tid; s < N; s += nthr) {
+                    const int a = s == tid ? a0 : day.lane_airport[s];
+                    ba_phase_c_pull<EXACT>(c, acc, a, prev, n_due, tick);
+                    ba_phase_a<EXACT, PREDICT, TRK>(c, acc, a, t, tick);
+                    more |= ba_airport_busy<TRK>(c, a) ? 1 : 0;
+                }
+                if (!EXACT && (acc.status & BA_S_OVERFLOW)) c.cta[3] = 1u;
+                ba_copy_wait();                                     // copies issued a tick ago
+                __syncthreads();
+                BA_MARK(3);
+                if (!EXACT && c.cta[3]) break;                      // a ring overflowed: this
+                                                                    // particle-day is re-run anyway
+                for (int s = tid; s < N; s += nthr)
+                    ba_run_advance(c, s == tid ? a0 : day.lane_airport[s], tick);
+                if (PREDICT) {
+                    const uint32_t lo = c.cta[4], hi = c.cta[2];
+                    for (uint32_t i = lo + tid; i < hi; i += nthr) ba_phase_b_pool(c, acc, i, t, cur);
+                } else if ((uint32_t)tick < c.cal_cap) {
+                    uint32_t n = c.cal_cnt[tick] - c.cal_cnt[tick - 1];
+                    if (n > c.due_cap) n = c.due_cap;
+                    for (uint32_t i = tid; i < n; i += nthr) ba_phase_b_arrival(c, i, cur);
+                }
+                stage_arrivals(tick + 1);                           // due buffer `prev`: consumed
+                stage_departures(tick + 2, d_lo, d_hi);             // staging buffer `prev`: consumed
+                busy = __syncthreads_or(more) != 0;
+                if (PREDICT && tid == 0) ba_pool_advance(c, 64u);   // next reader: phase B, after a barrier
+                BA_MARK(4);
+            }
+            ba_copy_wait();
+
         }
-        ba_copy_wait();
 
         // ---- epilogue ----------------------------------------------------------
         __syncthreads();          // every wait of the tape is written

@@ -89,9 +89,9 @@ struct BaDayView {
     const int32_t *dep_cpos;          // [F] dep order -> calendar record (-1: not on the calendar)
     int32_t last_ready_tick;          // tick at which the day's last scheduled flight is ready
     const int32_t *drun_off;          // [N+1] per-airport slices of drun (in units of runs)
-    const uint32_t *drun;             // runs {tick, first record relative to the tick's slice,
-                                      //   count}: the contiguous part of a tick's calendar
-                                      //   slice that belongs to one airport;
+    const uint32_t *drun;             // runs {tick, first record relative to the tick's slice
+                                      //   << 16 | count}: the contiguous part of a tick's
+                                      //   calendar slice that belongs to one airport;
                                       //   every airport's list ends with a sentinel run
     int32_t max_dslice;               // largest calendar slice of any tick of the day
     const BaAirport *airports;        // [N] day order

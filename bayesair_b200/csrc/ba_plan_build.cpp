@@ -264,10 +264,14 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             H.drun_off.assign(N + 1, 0);
             H.drun.clear();
             for (int a = 0; a < N; ++a) {
-                H.drun.insert(H.drun.end(), runs[a].begin(), runs[a].end());
+                // two words per run: tick, first record relative to the slice << 16 | records
+                for (size_t r = 0; r + 2 < runs[a].size(); r += 3) {
+                    H.drun.push_back(runs[a][r]);
+                    H.drun.push_back((runs[a][r + 1] << 16) | (runs[a][r + 2] & 0xFFFFu));
+                }
                 // sentinel run: never matches a tick
-                H.drun.push_back(0xFFFFFFFFu); H.drun.push_back(0u); H.drun.push_back(0u);
-                H.drun_off[a + 1] = (int32_t)(H.drun.size() / 3);
+                H.drun.push_back(0xFFFFFFFFu); H.drun.push_back(0u);
+                H.drun_off[a + 1] = (int32_t)(H.drun.size() / 2);
             }
             H.view.max_dslice = max_slice;
             out->max_dslice = std::max(out->max_dslice, max_slice);

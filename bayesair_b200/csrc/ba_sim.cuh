@@ -43,6 +43,9 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#if !defined(__CUDACC__)
+#include <vector>
+#endif
 
 #include "ba_plan.h"
 
@@ -228,8 +231,8 @@ struct BaCtx {
     BaCol<uint32_t> s_flags, s_qw, s_goff, s_depoff, s_depcnt;
     // CTA-wide scalars (shared memory): [0], [1] entries in the even / odd due buffer,
     // [3] abort flag (a shared ring overflowed), [2] / [4] entries in / first live entry of
-    // the predictive in-transit pool, [6], [7] first calendar record staged in the even / odd
-    // departure buffer
+    // the predictive in-transit pool; single-barrier scan: [8], [9], [10] late entries of the
+    // due buffer of tick j at [8 + j % 3]
     uint32_t *cta;
     const int32_t *dcal_off;      // static departure calendar (ba_plan.h)
     const uint32_t *dcal_rec;
@@ -256,6 +259,9 @@ struct BaCtx {
     uint32_t *due_base;           // buffer p at due_base + p * due_stride (no pointer arrays:
     uint32_t due_stride;          //   a runtime-indexed member would push BaCtx to local memory)
     uint32_t due_cap;
+    // single-barrier scan (shared-list variant): queue words of the next arrival slice, two
+    // buffers of BA_DUE_CAP_S words, staged a tick ahead
+    uint32_t *wbuf;
     int first_tick;
     // list pools (shared memory in the fast variant, global scratch in the exact one)
     // runway queues, 6 words per entry (three 8-byte pairs): {word, lo} {queue start,
@@ -299,7 +305,7 @@ struct BaAcc {
 #define BA_NWORDS_STATE_SIMPLE (2 + BA_REC_WORDS_SIMPLE)
 #define BA_NWORDS_STATE_TRACK (2 + BA_REC_WORDS_TRACK)
 #define BA_Q_WORDS 6              // words per runway-queue entry
-#define BA_CTA_WORDS 8            // CTA-wide scalars
+#define BA_CTA_WORDS 12           // CTA-wide scalars
 
 // Ring placement of an airport in one word: first entry of its ring in the pool (27 bits)
 // and log2 of the ring's power-of-two capacity (5 bits).
@@ -351,7 +357,7 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N, bool tracked)
 // they sit at compile-time offsets in front of the per-airport state, so every access to
 // them is a shared load with an immediate address.
 #define BA_DUE_STRIDE_S (BA_DUE_WORDS * BA_DUE_CAP_S + BA_DUE_CAP_S / 2)
-#define BA_SHARED_FIXED_WORDS (BA_KCAL + 2 * BA_DUE_STRIDE_S)
+#define BA_SHARED_FIXED_WORDS (BA_KCAL + 2 * BA_DUE_STRIDE_S + 2 * BA_DUE_CAP_S)
 
 // Words of shared memory the size-dependent list structures of the fast variant need
 // (runway rings; the staged departures are added by the caller).
@@ -407,6 +413,7 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int ma
         c.cal_cap = (uint32_t)BA_KCAL;
         c.cal_cnt = shared_fixed;
         c.due_base = shared_fixed + BA_KCAL; c.due_stride = (uint32_t)BA_DUE_STRIDE_S;
+        c.wbuf = c.due_base + 2 * BA_DUE_STRIDE_S;
     }
     c.tt = (float *)g; g += day.turn_total; c.te = (float *)g; g += day.turn_total;
     c.at = (float *)g; g += day.av_total; c.ae = (float *)g; g += day.av_total;
@@ -536,8 +543,8 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     {
         const uint32_t rp = (uint32_t)c.drun_off[a];
         c.run_ptr[a] = rp;
-        c.run_tick[a] = c.drun[3 * rp];
-        c.run_info[a] = (c.drun[3 * rp + 1] << 16) | c.drun[3 * rp + 2];
+        c.run_tick[a] = c.drun[2 * rp];
+        c.run_info[a] = c.drun[2 * rp + 1];
     }
     if (TRK && c.n_avail.p) {
         float n0 = 1000.0f, base = 0.0f;             // model.py:116-121
@@ -749,8 +756,11 @@ BA_DEV void ba_depart_tracked(BaCtx &c, BaAcc &acc, int a, const BaAirport *A, u
 // ---------------------------------------------------------------------------
 // SCAN, phase A
 // ---------------------------------------------------------------------------
+BA_DEV void ba_late_append(BaCtx &c, BaAcc &acc, int tick, uint32_t n_slice, uint32_t word,
+                           uint32_t key, uint32_t owner, uint32_t seq, float qstart, float x);
+
 template <bool EXACT, bool PREDICT, bool TRK = true>
-BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
+BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick, uint32_t n_slice_cur = 0)
 {
     const uint32_t flags = ba_ap_flags<TRK>(c, a);
     const BaAirport *A = &c.ap[a];      // only dereferenced on the tracked paths
@@ -999,8 +1009,12 @@ BA_DEV void ba_phase_a(BaCtx &c, BaAcc &acc, int a, float t, int tick)
                 if (av <= t) {
                     // already past its arrival time: joins the destination queue at the
                     // end of this very tick (update_in_transit_flights, network.py:186)
-                    ba_due_append(c, acc, tick & 1, word & BA_FID_MASK, key,
-                                  (word >> BA_Q_DST_SHIFT) & 0xFFFu, seq, av, c.xaf[f], 0.0f);
+                    if (!EXACT)     // single-barrier scan: slots from the top of this tick's buffer
+                        ba_late_append(c, acc, tick, n_slice_cur, word & BA_FID_MASK, key,
+                                       (word >> BA_Q_DST_SHIFT) & 0xFFFu, seq, av, c.xaf[f]);
+                    else
+                        ba_due_append(c, acc, tick & 1, word & BA_FID_MASK, key,
+                                      (word >> BA_Q_DST_SHIFT) & 0xFFFu, seq, av, c.xaf[f], 0.0f);
                 } else {
                     c.popkey[f] = key; c.popseq[f] = seq;
                 }
@@ -1079,6 +1093,14 @@ BA_DEV void ba_calendar_scatter(BaCtx &c, int f)
 // shared copies (cp.async), issued one or two ticks before the data is read, so that no
 // thread ever waits for them; ba_copy_wait() before the next barrier makes them visible.
 // Exact variant / host: plain copies at the same place.
+#if !defined(__CUDACC__)
+// Host emulation of the asynchronous copies: with a hook installed they are queued and land
+// when the emulated barrier is reached (tests/hostemu), otherwise they land at once -- the
+// two extremes of what cp.async may do.
+struct BaEmuCopy { uint32_t *dst; const uint32_t *src; int words; };
+static thread_local std::vector<BaEmuCopy> *ba_emu_defer = nullptr;
+#endif
+
 template <bool EXACT>
 BA_DEV void ba_copy8(uint32_t *dst, const uint32_t *src)
 {
@@ -1088,6 +1110,9 @@ BA_DEV void ba_copy8(uint32_t *dst, const uint32_t *src)
                      "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
         return;
     }
+#endif
+#if !defined(__CUDACC__)
+    if (!EXACT && ba_emu_defer) { ba_emu_defer->push_back({dst, src, 2}); return; }
 #endif
     BA_ST_PAIR(BaPairU, dst, BA_LD_PAIR(BaPairU, src));
 }
@@ -1101,6 +1126,9 @@ BA_DEV void ba_copy4(uint32_t *dst, const uint32_t *src)
                      "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
         return;
     }
+#endif
+#if !defined(__CUDACC__)
+    if (!EXACT && ba_emu_defer) { ba_emu_defer->push_back({dst, src, 1}); return; }
 #endif
     *dst = *src;
 }
@@ -1165,10 +1193,10 @@ BA_DEV void ba_run_advance(BaCtx &c, int a, int tick)
 {
     if (c.run_tick[a] != (uint32_t)tick) return;
     const uint32_t rp = c.run_ptr[a] + 1u;
-    const uint32_t *r = c.drun + 3 * rp;
+    const uint32_t *r = c.drun + 2 * rp;
     c.run_ptr[a] = rp;
     c.run_tick[a] = r[0];
-    c.run_info[a] = (r[1] << 16) | r[2];
+    c.run_info[a] = r[1];
 }
 
 // Posterior-predictive mode: arrival times are only known once a departure is served, so
@@ -1192,6 +1220,66 @@ BA_DEV void ba_pool_advance(BaCtx &c, uint32_t budget)
     const uint32_t n = c.cta[2];
     while (lo < n && budget-- && isnan(__uint_as_float_portable(c.pool[5u * lo + 3]))) ++lo;
     c.cta[4] = lo;
+}
+
+// ---------------------------------------------------------------------------
+// SINGLE-BARRIER SCAN (shared-list variant, observed flights).  Which flights of the arrival
+// slice of tick j have left their origin is settled when tick j - 1 ends (a departure served
+// in tick j itself at or after its arrival time takes the late path), so the slice's due
+// buffer can be assembled DURING tick j, next to the lanes' work, by asynchronous copies that
+// nobody waits for until the tick's only barrier:
+//   ba_stage_word        (tick j - 1) queue word of record i of slice j -> word buffer j & 1
+//   ba_complete_arrival  (tick j) slot s of slice j: {word} by a plain store, {ordering key,
+//       sequence, arrival time, service draw} by cp.async straight from where phase A and the
+//       prologue left them; owner list entry.  A flight that has not departed keeps the
+//       invalid key it was initialised with: the owner sees it sort last and stops there.
+//   ba_late_append       (tick j, phase A) entries served after their arrival time take slots
+//       from the top of the same buffer downwards (counter [8 + j % 3])
+//   ba_run_advance_async the airport's next calendar run, copied into its state record
+// ---------------------------------------------------------------------------
+BA_DEV void ba_stage_word(BaCtx &c, uint32_t i, uint32_t slice_lo, int parity)
+{
+    const uint32_t s = i - slice_lo;
+    if (s >= (uint32_t)BA_DUE_CAP_S) return;
+    ba_copy4<false>(c.wbuf + (uint32_t)parity * BA_DUE_CAP_S + s, c.cal + 3 * i);
+}
+
+BA_DEV void ba_complete_arrival(BaCtx &c, uint32_t s, uint32_t slice_lo, int parity)
+{
+    const uint32_t word = c.wbuf[(uint32_t)parity * BA_DUE_CAP_S + s];
+    const uint32_t f = word & BA_FID_MASK;
+    uint32_t *buf = c.due_base + (uint32_t)parity * c.due_stride;
+    uint32_t *de = buf + BA_DUE_WORDS * s;
+    const uint32_t *r = c.cal + 3 * (slice_lo + s);
+    de[0] = word;
+    ba_copy4<false>(de + 1, c.popkey + f);
+    ba_copy4<false>(de + 2, c.popseq + f);
+    ba_copy4<false>(de + 3, r + 1);
+    ba_copy4<false>(de + 4, r + 2);
+    ((uint16_t *)(buf + BA_DUE_WORDS * c.due_cap))[s] = (uint16_t)((word >> BA_Q_DST_SHIFT) & 0xFFFu);
+}
+
+BA_DEV void ba_late_append(BaCtx &c, BaAcc &acc, int tick, uint32_t n_slice, uint32_t word,
+                           uint32_t key, uint32_t owner, uint32_t seq, float qstart, float x)
+{
+    const uint32_t l = BA_ATOMIC_INC(&c.cta[8 + tick % 3]);
+    if (l + n_slice >= c.due_cap) { acc.status |= BA_S_OVERFLOW; return; }
+    const uint32_t slot = c.due_cap - 1u - l;
+    uint32_t *buf = c.due_base + (uint32_t)(tick & 1) * c.due_stride;
+    uint32_t *de = buf + BA_DUE_WORDS * slot;
+    BaPairU wk = {word, key};
+    BaPairUF os = {seq & 0xFFFFu, qstart};
+    BA_ST_PAIR(BaPairU, de, wk); BA_ST_PAIR(BaPairUF, de + 2, os);
+    de[4] = __float_as_uint_portable(x);
+    ((uint16_t *)(buf + BA_DUE_WORDS * c.due_cap))[slot] = (uint16_t)owner;
+}
+
+BA_DEV void ba_run_advance_async(BaCtx &c, int a)
+{
+    const uint32_t rp = c.run_ptr[a] + 1u;
+    c.run_ptr[a] = rp;
+    ba_copy4<false>(&c.run_tick[a], c.drun + 2 * rp);
+    ba_copy4<false>(&c.run_info[a], c.drun + 2 * rp + 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -1320,6 +1408,77 @@ BA_DEV void ba_phase_c_pull(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_
             const BaPairF xy = BA_LD_PAIR(BaPairF, d + 2);
             ba_push_one(c, acc, P, wq.a, wq.b, xy.a, xy.b);
         }
+    }
+    ba_push_end(c, a, P);
+}
+
+// Owner pull of the single-barrier scan: the slice's slots sit at [0, n_slice) of the buffer,
+// the late entries at [cap - n_late, cap).  Slots of flights that had not departed carry the
+// invalid (= largest) key: they sort last and end the selection.  After the arrivals the
+// airport appends its staged departures and asks for its next calendar run.
+BA_DEV void ba_phase_c_pull_fast(BaCtx &c, BaAcc &acc, int a, int parity, uint32_t n_slice,
+                                 uint32_t n_late, int tick)
+{
+    const bool has_run = c.run_tick[a] == (uint32_t)tick;
+    uint64_t m0 = 0, m1 = 0;
+    const uint32_t *due = c.due_base + (uint32_t)parity * c.due_stride;
+    const uint32_t *ow = due + BA_DUE_WORDS * c.due_cap;
+    const uint32_t aa = (uint32_t)a | ((uint32_t)a << 16);
+    const uint32_t cap = (uint32_t)BA_DUE_CAP_S;
+    const uint32_t g_lo_end = (n_slice + 7u) >> 3;                   // groups [0, g_lo_end)
+    const uint32_t first_late = cap - n_late;
+    const uint32_t g_hi_beg = n_late ? (first_late >> 3) : (cap >> 3);   // groups [g_hi_beg, 16)
+    for (uint32_t g = 0; g < (cap >> 3); ++g) {
+        if (g >= g_lo_end && g < g_hi_beg) { g = g_hi_beg - 1u; continue; }
+        uint32_t w0 = ow[4 * g], w1 = ow[4 * g + 1], w2 = ow[4 * g + 2], w3 = ow[4 * g + 3];
+        uint32_t bits = 0;
+        uint32_t x;
+        x = w0 ^ aa; bits |= ((x & 0xFFFFu) == 0u) | (((x >> 16) == 0u) << 1);
+        x = w1 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 2) | (((x >> 16) == 0u) << 3);
+        x = w2 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 4) | (((x >> 16) == 0u) << 5);
+        x = w3 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 6) | (((x >> 16) == 0u) << 7);
+        // slots outside [0, n_slice) and [first_late, cap) hold stale owners
+        const uint32_t base = 8u * g;
+        uint32_t valid = 0;
+        if (base < n_slice) valid |= (n_slice - base >= 8u) ? 0xFFu : ((1u << (n_slice - base)) - 1u);
+        if (base + 8u > first_late) valid |= (first_late <= base) ? 0xFFu : (0xFFu & ~((1u << (first_late - base)) - 1u));
+        bits &= valid;
+        if (g < 8u) m0 |= (uint64_t)bits << (8u * g); else m1 |= (uint64_t)bits << (8u * (g - 8u));
+    }
+    if (!(m0 | m1) && !has_run) return;
+    BaPush P;
+    ba_push_begin(c, a, P);
+    // ---- arrivals addressed to this airport, in in-transit list order ------------------
+    while (m0 | m1) {
+        uint64_t best = ~0ull; uint32_t bj = 0;
+        for (uint64_t m = m0; m; m &= m - 1) {
+            const uint32_t j = (uint32_t)ba_ctz64(m);
+            const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
+            if (o < best) { best = o; bj = j; }
+        }
+        for (uint64_t m = m1; m; m &= m - 1) {
+            const uint32_t j = 64u + (uint32_t)ba_ctz64(m);
+            const uint64_t o = ba_due_order(due + BA_DUE_WORDS * j);
+            if (o < best) { best = o; bj = j; }
+        }
+        if ((uint32_t)(best >> 16) == BA_KEY_INVALID) break;      // only not-yet-departed flights left
+        const uint32_t *de = due + BA_DUE_WORDS * bj;
+        ba_push_one(c, acc, P, de[0] & BA_FID_MASK, __uint_as_float_portable(de[3]),
+                    __uint_as_float_portable(de[4]), 0.0f);
+        if (bj < 64u) m0 &= ~(1ull << bj); else m1 &= ~(1ull << (bj - 64u));
+    }
+    // ---- this airport's newly ready departures: a static run of the staged slice ---------
+    if (has_run) {
+        const uint32_t ri = c.run_info[a];
+        const uint32_t cnt = ri & 0xFFFFu;
+        const uint32_t *d = c.dstage_base + (uint32_t)parity * c.dstage_stride +
+                            BA_DSTAGE_WORDS * (ri >> 16);
+        for (uint32_t i = 0; i < cnt; ++i, d += BA_DSTAGE_WORDS) {
+            const BaPairUF wq = BA_LD_PAIR(BaPairUF, d);
+            const BaPairF xy = BA_LD_PAIR(BaPairF, d + 2);
+            ba_push_one(c, acc, P, wq.a, wq.b, xy.a, xy.b);
+        }
+        ba_run_advance_async(c, a);
     }
     ba_push_end(c, a, P);
 }

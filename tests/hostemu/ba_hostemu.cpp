@@ -116,62 +116,136 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         for (uint32_t i : sl)
             ba_stage_departure<true>(c, acc[i % N], i, (uint32_t)day.dcal_off[k], (k - 1) & 1);
     };
-    auto stage_arrivals = [&](int k) {
-        uint32_t n = 0;
-        if (!PREDICT && (uint32_t)k < c.cal_cap) {
-            const uint32_t lo = c.cal_cnt[k - 1], hi = c.cal_cnt[k];
-            n = hi - lo;
-            if (n > c.due_cap) { n = c.due_cap; acc[0].status |= BA_S_OVERFLOW; }
-            std::vector<uint32_t> sl;
-            for (uint32_t i = lo; i < lo + n; ++i) sl.push_back(i);
-            if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
-            for (uint32_t i : sl) ba_stage_arrival<true>(c, i, lo, k & 1);
-        }
-        c.cta[k & 1] = n;
-    };
-    stage_departures(tick + 1);
-    stage_departures(tick + 2);
-    stage_arrivals(tick + 1);
     bool busy = day.F > 0;
     uint32_t st = 0;
-    while (busy) {
-        if (tick >= plan.max_ticks) { st |= BA_S_TICK_CAP; break; }
-        ++tick;
-        t = c.tick_time[tick];
-        const int prev = (tick - 1) & 1, cur = tick & 1;
-        uint32_t n_due = c.cta[prev];
-        if (n_due > c.due_cap) n_due = c.due_cap;
-        bool more = tick < day.last_ready_tick;
-        if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
-        for (int i = 0; i < N; ++i) {
-            const int a = day.lane_airport[order[i]];
-            ba_phase_c_pull<EXACT>(c, acc[order[i]], a, prev, n_due, tick);
-            ba_phase_a<EXACT, PREDICT, TRK>(c, acc[order[i]], a, t, tick);
-            more |= ba_airport_busy<TRK>(c, a);
-        }
-        if (!EXACT) {
+    if (!EXACT && !PREDICT) {
+        // single-barrier scan, exactly as in the kernel (ba_kernels.cu).  Asynchronous copies
+        // either land at once (odd shuffle seeds) or only when the tick's barrier is reached,
+        // in shuffled order (even seeds): the two extremes of cp.async.
+        const uint32_t cap = (uint32_t)BA_DUE_CAP_S;
+        std::vector<BaEmuCopy> pending;
+        ba_emu_defer = (shuffle_seed % 2 == 0) ? &pending : nullptr;
+        auto land = [&]() {
+            if (shuffle_seed) std::shuffle(pending.begin(), pending.end(), rng);
+            for (const BaEmuCopy &cp : pending) memcpy(cp.dst, cp.src, 4 * (size_t)cp.words);
+            pending.clear();
+        };
+        auto slice_lo = [&](int k) { return k >= 1 && (uint32_t)k < c.cal_cap ? c.cal_cnt[k - 1] : 0u; };
+        auto slice_n = [&](int k) {
+            if (k < 1 || (uint32_t)k >= c.cal_cap) return 0u;
+            const uint32_t n = c.cal_cnt[k] - c.cal_cnt[k - 1];
+            return n > cap ? cap : n;
+        };
+        auto stage_words = [&](int k) {
+            if (k < 1 || (uint32_t)k >= c.cal_cap) return;
+            const uint32_t lo = c.cal_cnt[k - 1], n = c.cal_cnt[k] - lo;
+            if (n > cap) acc[0].status |= BA_S_OVERFLOW;
+            std::vector<uint32_t> sl;
+            for (uint32_t i = lo; i < lo + (n > cap ? cap : n); ++i) sl.push_back(i);
+            if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
+            for (uint32_t i : sl) ba_stage_word(c, i, lo, k & 1);
+        };
+        auto stage_departures_async = [&](int k) {          // slice k -> buffer (k - 1) & 1
+            if (k > day.last_ready_tick) return;
+            std::vector<uint32_t> sl;
+            for (int i = day.dcal_off[k]; i < day.dcal_off[k + 1]; ++i) sl.push_back((uint32_t)i);
+            if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
+            for (uint32_t i : sl)
+                ba_stage_departure<false>(c, acc[i % N], i, (uint32_t)day.dcal_off[k], (k - 1) & 1);
+        };
+        stage_departures_async(tick + 1);
+        stage_words(tick + 1);
+        land();
+        while (busy) {
+            if (tick >= plan.max_ticks) { st |= BA_S_TICK_CAP; break; }
+            ++tick;
+            t = c.tick_time[tick];
+            const int prev = (tick - 1) & 1, cur = tick & 1;
+            const uint32_t n_cur = slice_n(tick), n_prev = slice_n(tick - 1);
+            uint32_t n_late = c.cta[8 + (tick - 1) % 3];
+            if (n_late > cap - n_prev) n_late = cap - n_prev;
+            c.cta[8 + (tick + 1) % 3] = 0;
+            {
+                const uint32_t lo = slice_lo(tick);
+                std::vector<uint32_t> sl;
+                for (uint32_t i = 0; i < n_cur; ++i) sl.push_back(i);
+                if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
+                for (uint32_t i : sl) ba_complete_arrival(c, i, lo, cur);
+            }
+            stage_words(tick + 1);
+            stage_departures_async(tick + 1);
+            bool more = tick < day.last_ready_tick;
+            if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
+            for (int i = 0; i < N; ++i) {
+                const int a = day.lane_airport[order[i]];
+                ba_phase_c_pull_fast(c, acc[order[i]], a, prev, n_prev, n_late, tick);
+                ba_phase_a<EXACT, PREDICT, TRK>(c, acc[order[i]], a, t, tick, n_cur);
+                more |= ba_airport_busy<TRK>(c, a);
+            }
+            land();                                          // cp.async.wait_all + barrier
             bool ovf = false;
             for (int i = 0; i < N; ++i) ovf |= (acc[i].status & BA_S_OVERFLOW) != 0;
-            if (ovf) break;                      // the kernel aborts: the item is re-run exactly
+            if (ovf) break;                                  // the kernel aborts: re-run exactly
+            busy = more;
         }
-        for (int i = 0; i < N; ++i) ba_run_advance(c, day.lane_airport[order[i]], tick);
-        if (PREDICT) {
-            std::vector<uint32_t> slice;
-            for (uint32_t i = c.cta[4]; i < c.cta[2]; ++i) slice.push_back(i);
-            if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
-            for (uint32_t i : slice) ba_phase_b_pool(c, acc[i % N], i, t, cur);
-            ba_pool_advance(c, 7u);
-        } else if ((uint32_t)tick < c.cal_cap) {
-            uint32_t n = c.cal_cnt[tick] - c.cal_cnt[tick - 1];
-            if (n > c.due_cap) n = c.due_cap;
-            std::vector<uint32_t> slice;
-            for (uint32_t i = 0; i < n; ++i) slice.push_back(i);
-            if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
-            for (uint32_t i : slice) ba_phase_b_arrival(c, i, cur);
-        }
-        stage_arrivals(tick + 1);
+        land();
+        ba_emu_defer = nullptr;
+    } else {
+        auto stage_arrivals = [&](int k) {
+            uint32_t n = 0;
+            if (!PREDICT && (uint32_t)k < c.cal_cap) {
+                const uint32_t lo = c.cal_cnt[k - 1], hi = c.cal_cnt[k];
+                n = hi - lo;
+                if (n > c.due_cap) { n = c.due_cap; acc[0].status |= BA_S_OVERFLOW; }
+                std::vector<uint32_t> sl;
+                for (uint32_t i = lo; i < lo + n; ++i) sl.push_back(i);
+                if (shuffle_seed) std::shuffle(sl.begin(), sl.end(), rng);
+                for (uint32_t i : sl) ba_stage_arrival<true>(c, i, lo, k & 1);
+            }
+            c.cta[k & 1] = n;
+        };
+        stage_departures(tick + 1);
         stage_departures(tick + 2);
-        busy = more;
+        stage_arrivals(tick + 1);
+        while (busy) {
+            if (tick >= plan.max_ticks) { st |= BA_S_TICK_CAP; break; }
+            ++tick;
+            t = c.tick_time[tick];
+            const int prev = (tick - 1) & 1, cur = tick & 1;
+            uint32_t n_due = c.cta[prev];
+            if (n_due > c.due_cap) n_due = c.due_cap;
+            bool more = tick < day.last_ready_tick;
+            if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
+            for (int i = 0; i < N; ++i) {
+                const int a = day.lane_airport[order[i]];
+                ba_phase_c_pull<EXACT>(c, acc[order[i]], a, prev, n_due, tick);
+                ba_phase_a<EXACT, PREDICT, TRK>(c, acc[order[i]], a, t, tick);
+                more |= ba_airport_busy<TRK>(c, a);
+            }
+            if (!EXACT) {
+                bool ovf = false;
+                for (int i = 0; i < N; ++i) ovf |= (acc[i].status & BA_S_OVERFLOW) != 0;
+                if (ovf) break;                      // the kernel aborts: the item is re-run exactly
+            }
+            for (int i = 0; i < N; ++i) ba_run_advance(c, day.lane_airport[order[i]], tick);
+            if (PREDICT) {
+                std::vector<uint32_t> slice;
+                for (uint32_t i = c.cta[4]; i < c.cta[2]; ++i) slice.push_back(i);
+                if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
+                for (uint32_t i : slice) ba_phase_b_pool(c, acc[i % N], i, t, cur);
+                ba_pool_advance(c, 7u);
+            } else if ((uint32_t)tick < c.cal_cap) {
+                uint32_t n = c.cal_cnt[tick] - c.cal_cnt[tick - 1];
+                if (n > c.due_cap) n = c.due_cap;
+                std::vector<uint32_t> slice;
+                for (uint32_t i = 0; i < n; ++i) slice.push_back(i);
+                if (shuffle_seed) std::shuffle(slice.begin(), slice.end(), rng);
+                for (uint32_t i : slice) ba_phase_b_arrival(c, i, cur);
+            }
+            stage_arrivals(tick + 1);
+            stage_departures(tick + 2);
+            busy = more;
+        }
     }
     if (!PREDICT) for (int f = 0; f < day.F; ++f) ba_epilogue_flight<TRK>(c, acc[f % N], f);
     if (c.grow && !PREDICT) {
