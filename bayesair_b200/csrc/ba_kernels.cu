@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
             //      will read, then runs its airport lane: phase C of tick j - 1, phase A of
             //      tick j.  Nothing a thread reads in tick j is written in tick j. ----------
             const uint32_t cap = (uint32_t)BA_DUE_CAP_S;
+            // the copy-issuing work goes to the threads in reverse order: the last warp holds
+            // the fewest (and lightest) airports, so it has the time
+            const uint32_t rtid = (uint32_t)(nthr - 1 - tid);
             auto slice_lo = [&](int k) { return k >= 1 && (uint32_t)k < c.cal_cap ? c.cal_cnt[k - 1] : 0u; };
             auto slice_n = [&](int k) {
                 if (k < 1 || (uint32_t)k >= c.cal_cap) return 0u;
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
                 if (k < 1 || (uint32_t)k >= c.cal_cap) return;
                 const uint32_t lo = c.cal_cnt[k - 1], n = c.cal_cnt[k] - lo;
                 if (n > cap) acc.status |= BA_S_OVERFLOW;       // more arrivals in one tick than slots
-                for (uint32_t i = lo + tid; i < lo + (n > cap ? cap : n); i += nthr) ba_stage_word(c, i, lo, k & 1);
+                for (uint32_t i = lo + rtid; i < lo + (n > cap ? cap : n); i += nthr) ba_stage_word(c, i, lo, k & 1);
             };
             uint32_t d_lo = dcal_at(tick + 1), d_hi = dcal_at(tick + 2), d_nx = dcal_at(tick + 3);
             stage_departures(tick + 1, d_lo, d_hi);             // slice tick + 1 -> buffer tick & 1
@@ -204,11 +207,12 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
                 // (1) this tick's arrival slice -> due buffer `cur` (read next tick)
                 {
                     const uint32_t lo = slice_lo(tick);
-                    for (uint32_t i = tid; i < n_cur; i += nthr) ba_complete_arrival(c, i, lo, cur);
+                    for (uint32_t i = rtid; i < n_cur; i += nthr) ba_complete_arrival(c, i, lo, cur);
                 }
                 // (2) what the next tick reads: its slice's queue words, its departures
                 stage_words(tick + 1);
-                stage_departures(tick + 1, d_lo, d_hi);         // slice tick + 1 -> buffer `cur`
+                for (uint32_t i = d_lo + rtid; i < d_hi; i += nthr)     // slice tick + 1 -> buffer `cur`
+                    ba_stage_departure<EXACT>(c, acc, i, d_lo, cur);
                 // (3) the airport lanes
                 int more = tick < day.last_ready_tick;
                 for (int s = tid; s < N; s += nthr) {
