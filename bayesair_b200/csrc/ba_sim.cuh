@@ -1425,26 +1425,36 @@ BA_DEV void ba_phase_c_pull_fast(BaCtx &c, BaAcc &acc, int a, int parity, uint32
     const uint32_t *ow = due + BA_DUE_WORDS * c.due_cap;
     const uint32_t aa = (uint32_t)a | ((uint32_t)a << 16);
     const uint32_t cap = (uint32_t)BA_DUE_CAP_S;
-    const uint32_t g_lo_end = (n_slice + 7u) >> 3;                   // groups [0, g_lo_end)
-    const uint32_t first_late = cap - n_late;
-    const uint32_t g_hi_beg = n_late ? (first_late >> 3) : (cap >> 3);   // groups [g_hi_beg, 16)
-    for (uint32_t g = 0; g < (cap >> 3); ++g) {
-        if (g >= g_lo_end && g < g_hi_beg) { g = g_hi_beg - 1u; continue; }
-        uint32_t w0 = ow[4 * g], w1 = ow[4 * g + 1], w2 = ow[4 * g + 2], w3 = ow[4 * g + 3];
-        uint32_t bits = 0;
-        uint32_t x;
-        x = w0 ^ aa; bits |= ((x & 0xFFFFu) == 0u) | (((x >> 16) == 0u) << 1);
-        x = w1 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 2) | (((x >> 16) == 0u) << 3);
-        x = w2 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 4) | (((x >> 16) == 0u) << 5);
-        x = w3 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 6) | (((x >> 16) == 0u) << 7);
-        // slots outside [0, n_slice) and [first_late, cap) hold stale owners
-        const uint32_t base = 8u * g;
-        uint32_t valid = 0;
-        if (base < n_slice) valid |= (n_slice - base >= 8u) ? 0xFFu : ((1u << (n_slice - base)) - 1u);
-        if (base + 8u > first_late) valid |= (first_late <= base) ? 0xFFu : (0xFFu & ~((1u << (first_late - base)) - 1u));
-        bits &= valid;
+#define BA_OWNER_BITS(g, bits)                                                                  \
+    do {                                                                                        \
+        const uint32_t w0 = ow[4 * (g)], w1 = ow[4 * (g) + 1], w2 = ow[4 * (g) + 2], w3 = ow[4 * (g) + 3]; \
+        uint32_t x;                                                                             \
+        bits = 0;                                                                               \
+        x = w0 ^ aa; bits |= ((x & 0xFFFFu) == 0u) | (((x >> 16) == 0u) << 1);                  \
+        x = w1 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 2) | (((x >> 16) == 0u) << 3);           \
+        x = w2 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 4) | (((x >> 16) == 0u) << 5);           \
+        x = w3 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 6) | (((x >> 16) == 0u) << 7);           \
+    } while (0)
+    // the slice: groups from the bottom; slots at and beyond n_slice hold stale owners
+    const uint32_t g_lo_end = (n_slice + 7u) >> 3;
+    for (uint32_t g = 0; g < g_lo_end; ++g) {
+        uint32_t bits;
+        BA_OWNER_BITS(g, bits);
+        const uint32_t left = n_slice - 8u * g;
+        if (left < 8u) bits &= (1u << left) - 1u;
         if (g < 8u) m0 |= (uint64_t)bits << (8u * g); else m1 |= (uint64_t)bits << (8u * (g - 8u));
     }
+    // the late entries (usually none): groups from the top; slots below cap - n_late are stale
+    if (n_late) {
+        const uint32_t first_late = cap - n_late;
+        for (uint32_t g = first_late >> 3; g < (cap >> 3); ++g) {
+            uint32_t bits;
+            BA_OWNER_BITS(g, bits);
+            if (first_late > 8u * g) bits &= ~((1u << (first_late - 8u * g)) - 1u);
+            if (g < 8u) m0 |= (uint64_t)bits << (8u * g); else m1 |= (uint64_t)bits << (8u * (g - 8u));
+        }
+    }
+#undef BA_OWNER_BITS
     if (!(m0 | m1) && !has_run) return;
     BaPush P;
     ba_push_begin(c, a, P);
