@@ -138,7 +138,7 @@ struct BaPlanView {
 static inline uint64_t ba_scratch_words(const BaDayView &d, bool exact, int max_ticks,
                                         int max_dslice_plan)
 {
-    uint64_t w = 19ull * (uint64_t)d.F + 2;   // incl. kept noise and the calendar-ordered {x_dep, arrival} pairs
+    uint64_t w = 20ull * (uint64_t)d.F + 2;   // incl. kept noise and the calendar-ordered {x_dep, arrival} pairs
     if (d.any_track_t) w += 2ull * (uint64_t)d.F;
     if (d.any_track_a) w += 3ull * (uint64_t)d.F;
     w += 7ull * d.q_total_x;          // draw history + exact rings (exact) / spill area (fast)

@@ -276,6 +276,7 @@ struct BaCtx {
     // per-flight global scratch
     float *xdk, *xak, *atk;       // prologue outputs, dep order (reused by the epilogue)
     float *xaf;                   // x_arr by flight (for departures served after arrival)
+    float *atf;                   // arrival time at the destination by flight (observed mode)
     float *ct;                    // epilogue: per-flight d/d mean_turnaround contributions
     float *wd, *wa;               // tape: total wait of the departure / arrival entry
     float *trl, *tre;             // turnaround release time and its noise (tracked days)
@@ -378,7 +379,7 @@ BA_DEV void ba_carve_lists(BaCtx &c, const BaDayView &day, int max_ticks, int ma
     c.nzs = (float *)g; g += 4 * F;           // first: 16-byte aligned
     c.dpair = g; g += 2 * F;                  // 8-byte aligned
     c.xdk = (float *)g; g += F; c.xak = (float *)g; g += F; c.atk = (float *)g; g += F;
-    c.ct = (float *)g; g += F; c.xaf = (float *)g; g += F;
+    c.ct = (float *)g; g += F; c.xaf = (float *)g; g += F; c.atf = (float *)g; g += F;
     c.wd = (float *)g; g += F; c.wa = (float *)g; g += F;
     c.karr = g; g += F;
     c.cal = g; g += 3 * F;
@@ -620,7 +621,7 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
         y_dep = fl.sched_dep; y_arr = fl.sched_dep;
     }
     const float at = BA_ADD(y_dep, tau);    // network.py:166-168 with the observed departure
-    c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at; c.xaf[f] = xa;
+    c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at; c.xaf[f] = xa; c.atf[f] = at;
     ba_store_dpair(c, k, xd, at);
     c.popkey[f] = BA_KEY_INVALID;
     // arrival tick: the first tick whose clock reaches `at` (exact: same fp32 clock table
@@ -1073,10 +1074,9 @@ BA_DEV void ba_calendar_scatter(BaCtx &c, int f)
     const uint32_t ka = c.karr[f];
     if (ka == 0xFFFFFFFFu) return;
     const uint32_t pos = BA_ATOMIC_INC(&c.cal_cnt[ka]);
-    const int k = c.pos_dep[f];
-    c.cal[3 * pos + 0] = c.dep_word[k] & BA_DW_ENTRY_MASK;      // dest << 18 | flight
-    c.cal[3 * pos + 1] = __float_as_uint_portable(c.atk[k]);
-    c.cal[3 * pos + 2] = __float_as_uint_portable(c.xak[k]);
+    // one word per record: dest << 18 | flight; the arrival time and the service draw are
+    // fetched by flight (atf, xaf) when the slice is assembled
+    c.cal[pos] = (uint32_t)f | (((ba_flight(c, f).od >> 12) & 0xFFFu) << BA_Q_DST_SHIFT);
 }
 
 // ---------------------------------------------------------------------------
@@ -1149,8 +1149,11 @@ BA_DEV void ba_stage_arrival(BaCtx &c, uint32_t i, uint32_t slice_lo, int parity
     const uint32_t slot = i - slice_lo;
     if (slot >= c.due_cap) return;                  // flagged by the caller
     uint32_t *de = c.due_base + (uint32_t)parity * c.due_stride + BA_DUE_WORDS * slot;
-    const uint32_t *r = c.cal + 3 * i;
-    ba_copy4<EXACT>(de, r); ba_copy4<EXACT>(de + 3, r + 1); ba_copy4<EXACT>(de + 4, r + 2);
+    const uint32_t word = c.cal[i];
+    const uint32_t f = word & BA_FID_MASK;
+    de[0] = word;
+    de[3] = __float_as_uint_portable(c.atf[f]);
+    de[4] = __float_as_uint_portable(c.xaf[f]);
 }
 
 BA_DEV void ba_phase_b_arrival(BaCtx &c, uint32_t slot, int parity)
@@ -1241,7 +1244,7 @@ BA_DEV void ba_stage_word(BaCtx &c, uint32_t i, uint32_t slice_lo, int parity)
 {
     const uint32_t s = i - slice_lo;
     if (s >= (uint32_t)BA_DUE_CAP_S) return;
-    ba_copy4<false>(c.wbuf + (uint32_t)parity * BA_DUE_CAP_S + s, c.cal + 3 * i);
+    ba_copy4<false>(c.wbuf + (uint32_t)parity * BA_DUE_CAP_S + s, c.cal + i);
 }
 
 BA_DEV void ba_complete_arrival(BaCtx &c, uint32_t s, uint32_t slice_lo, int parity)
@@ -1250,12 +1253,11 @@ BA_DEV void ba_complete_arrival(BaCtx &c, uint32_t s, uint32_t slice_lo, int par
     const uint32_t f = word & BA_FID_MASK;
     uint32_t *buf = c.due_base + (uint32_t)parity * c.due_stride;
     uint32_t *de = buf + BA_DUE_WORDS * s;
-    const uint32_t *r = c.cal + 3 * (slice_lo + s);
     de[0] = word;
     ba_copy4<false>(de + 1, c.popkey + f);
     ba_copy4<false>(de + 2, c.popseq + f);
-    ba_copy4<false>(de + 3, r + 1);
-    ba_copy4<false>(de + 4, r + 2);
+    ba_copy4<false>(de + 3, (const uint32_t *)c.atf + f);
+    ba_copy4<false>(de + 4, (const uint32_t *)c.xaf + f);
     ((uint16_t *)(buf + BA_DUE_WORDS * c.due_cap))[s] = (uint16_t)((word >> BA_Q_DST_SHIFT) & 0xFFFu);
 }
 
