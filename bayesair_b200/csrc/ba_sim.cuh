@@ -621,7 +621,10 @@ BA_DEV void ba_prologue_flight(BaCtx &c, BaAcc &acc, int f)
         y_dep = fl.sched_dep; y_arr = fl.sched_dep;
     }
     const float at = BA_ADD(y_dep, tau);    // network.py:166-168 with the observed departure
-    c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at; c.xaf[f] = xa; c.atf[f] = at;
+    // dep-order copies: only the aircraft-bookkeeping departures read them before the
+    // epilogue reuses the arrays
+    if (TRK) { c.xdk[k] = xd; c.xak[k] = xa; c.atk[k] = at; }
+    c.xaf[f] = xa; c.atf[f] = at;
     ba_store_dpair(c, k, xd, at);
     c.popkey[f] = BA_KEY_INVALID;
     // arrival tick: the first tick whose clock reaches `at` (exact: same fp32 clock table
