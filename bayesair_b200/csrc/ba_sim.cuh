@@ -1591,7 +1591,7 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
                     gvu += wgt * r_d * se * c.mt[o];
                 }
             }
-            c.ct[k] = turn;
+            if (TRK) c.ct[k] = turn;          // only summed for airports that track aircraft
             acc.g_vu += gvu;
         } else {
             c.xdk[k] = xd;
