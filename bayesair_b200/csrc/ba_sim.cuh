@@ -6,30 +6,30 @@
 //   PROLOGUE (flight-parallel, coalesced 16-byte loads of the flight table and the
 //       noise tensor): everything about a flight that does not depend on queue
 //       dynamics -- its two service-time draws, its travel time and hence (the
-//       departure time being observed) the time it reaches its destination -- is
-//       derived once and written to L2-resident per-CTA scratch in per-airport
-//       departure order.
+//       departure time being observed) the time it reaches its destination and the
+//       tick at which that time passes -- is derived once and written to L2-resident
+//       per-CTA scratch; the flights are counting-sorted by that tick (the ARRIVAL
+//       CALENDAR, exact: it uses the same fp32 clock table as the scan).
 //   SCAN (one lane per airport; the serial part): the tick loop of model.py:158-200.
-//       It touches shared memory only, apart from contiguous reads of the prologue's
-//       output when flights become ready and fire-and-forget stores of each entry's
-//       total wait W (the "tape").  Every tick has two phases separated by barriers:
+//       It touches shared memory only, apart from fire-and-forget stores of each
+//       entry's total wait W (the "tape") and of the in-transit ordering keys.
 //       phase A (per airport, no cross-airport reads): turnaround release -> reserve
 //           injection -> pop-ready / cancellation -> enqueue departures -> runway
 //           service loop (model.py:163-196).  A served departure records its
 //           in-transit ordering key (tick, origin, per-origin sequence).
 //       phase B (flight-parallel): the reference's in-transit list (network.py:178-198)
-//           is never materialised.  The prologue has counting-sorted all flights by the
-//           tick at which their arrival time passes (the ARRIVAL CALENDAR, exact: it
-//           uses the same fp32 clock table); at tick k the CTA reads that tick's slice
-//           and moves the flights whose departure has been served into a small "due"
-//           buffer.  A departure served at or after its own arrival tick goes to the
-//           due buffer directly from phase A.
-//       phase C (one thread per due entry): rank the due entries of each destination
-//           by their key -- this IS the reference's in-transit list order restricted to
-//           that destination (model.py:186-196) -- and append them to the destination
-//           runway queues.
-//   EPILOGUE (one lane per airport over its static departure / arrival lists; all
-//       loads independent): mu = queue_start + W for every entry, the seven per-flight
+//           is never materialised.  The flights of this tick's calendar slice whose
+//           departure has been served get a slot in a small "due" buffer; a departure
+//           served at or after its own arrival tick is put there by phase A itself.
+//       phase C (owner pull, at the start of the next tick): each airport lane takes
+//           the due entries addressed to it in key order -- this IS the reference's
+//           in-transit list order restricted to that destination (model.py:186-196) --
+//           appends them to its runway queue, then its newly ready departures.
+//       Shared-list kernel: one barrier per tick -- phase B is a set of asynchronous
+//       copies issued next to the lanes' work (see "SINGLE-BARRIER SCAN" below).
+//       Exact-list / predictive kernels: lanes, barrier, phase B, barrier.
+//   EPILOGUE (flight-parallel, then one owner per airport / route over static
+//       slices): mu = queue_start + W for every entry, the seven per-flight
 //       log-densities and the pathwise gradient sums.  Deterministic: every sum has a
 //       single owner and a fixed order; no floating-point atomics anywhere.
 //
