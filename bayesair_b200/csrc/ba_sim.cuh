@@ -229,8 +229,9 @@ struct BaCtx {
     BaCol<uint32_t> arr_left;             // arrivals this airport still waits for
     BaCol<uint32_t> run_ptr, run_tick;    // next run of the departure calendar, its tick,
     BaCol<uint32_t> run_info;             //   first staged record << 16 | records
-    BaCol<uint32_t> inmask;               // two words (even / odd due buffer): bit s = slot s < 32
-                                          //   of that buffer's slice is addressed to this airport
+    BaCol<uint32_t> inmask;               // two words per due buffer (even: [0], [1]; odd: [2], [3]):
+                                          //   bit s = slot s < 64 of that buffer's slice is
+                                          //   addressed to this airport
     BaCol<uint32_t> av_head, av_tail, zeros_left, dl_head, dl_tail;
     BaCol<uint32_t> s_flags, s_qw, s_goff, s_depoff, s_depcnt;
     // CTA-wide scalars (shared memory): [0], [1] entries in the even / odd due buffer,
@@ -305,8 +306,8 @@ struct BaAcc {
 // that consecutive lanes hit different banks): every field of an airport is then the
 // airport's record address plus a compile-time offset, which costs no address arithmetic
 // per access.  Only psum (8-byte) lives in its own array in front of the records.
-#define BA_REC_WORDS_SIMPLE 21    // 21 words, no aircraft bookkeeping
-#define BA_REC_WORDS_TRACK 35     // 35 words, some airport of the plan tracks aircraft
+#define BA_REC_WORDS_SIMPLE 23    // 23 words, no aircraft bookkeeping
+#define BA_REC_WORDS_TRACK 37     // 37 words, some airport of the plan tracks aircraft
 #define BA_NWORDS_STATE_SIMPLE (2 + BA_REC_WORDS_SIMPLE)
 #define BA_NWORDS_STATE_TRACK (2 + BA_REC_WORDS_TRACK)
 #define BA_Q_WORDS 6              // words per runway-queue entry
@@ -343,13 +344,13 @@ BA_DEV void ba_carve_state(BaCtx &c, uint32_t *w, int N, bool tracked)
     BA_COLU(arr_left, 10); BA_COLU(s_flags, 11); BA_COLU(s_qw, 12);
     BA_COLU(run_info, 13); BA_COLF(next_sched, 14);
     BA_COLU(q_fill, 15); BA_COLU(s_goff, 16); BA_COLU(run_ptr, 17); BA_COLU(run_tick, 18);
-    BA_COLU(inmask, 19);                       // words 19, 20
+    BA_COLU(inmask, 19);                       // words 19 .. 22
     if (tracked) {
-        BA_COLF(base, 21); BA_COLF(n_avail, 22); BA_COLF(n0, 23);
-        BA_COLF(acc_ln0, 24); BA_COLF(acc_bc, 25);
-        BA_COLU(next_dep, 26); BA_COLU(turn_n, 27); BA_COLU(av_head, 28);
-        BA_COLU(av_tail, 29); BA_COLU(zeros_left, 30); BA_COLU(dl_head, 31);
-        BA_COLU(dl_tail, 32); BA_COLU(s_depoff, 33); BA_COLU(s_depcnt, 34);
+        BA_COLF(base, 23); BA_COLF(n_avail, 24); BA_COLF(n0, 25);
+        BA_COLF(acc_ln0, 26); BA_COLF(acc_bc, 27);
+        BA_COLU(next_dep, 28); BA_COLU(turn_n, 29); BA_COLU(av_head, 30);
+        BA_COLU(av_tail, 31); BA_COLU(zeros_left, 32); BA_COLU(dl_head, 33);
+        BA_COLU(dl_tail, 34); BA_COLU(s_depoff, 35); BA_COLU(s_depcnt, 36);
     } else {
         c.base.p = c.n_avail.p = c.n0.p = c.acc_ln0.p = c.acc_bc.p = nullptr;
         c.next_dep.p = c.turn_n.p = c.av_head.p = c.av_tail.p = c.zeros_left.p = nullptr;
@@ -545,7 +546,7 @@ BA_DEV void ba_init_airport(BaCtx &c, int a, const float *lat_airport /* [C,N] *
     c.next_sched[a] = A.dep_cnt > 0 ? c.dep_sched[A.dep_off] : INFINITY;
     c.q_head[a] = 0; c.q_tail[a] = 0; c.q_fill[a] = 0; c.dep_pops[a] = 0;
     c.arr_left[a] = (uint32_t)A.arr_cnt;
-    (&c.inmask[a])[0] = 0; (&c.inmask[a])[1] = 0;
+    (&c.inmask[a])[0] = 0; (&c.inmask[a])[1] = 0; (&c.inmask[a])[2] = 0; (&c.inmask[a])[3] = 0;
     c.s_goff[a] = A.q_off_x;
     {
         const uint32_t rp = (uint32_t)c.drun_off[a];
@@ -1269,7 +1270,7 @@ BA_DEV void ba_complete_arrival(BaCtx &c, uint32_t s, uint32_t slice_lo, int par
     ba_copy4<false>(de + 4, (const uint32_t *)c.xaf + f);
     const uint32_t owner = (word >> BA_Q_DST_SHIFT) & 0xFFFu;
     ((uint16_t *)(buf + BA_DUE_WORDS * c.due_cap))[s] = (uint16_t)owner;
-    if (s < 32u) BA_ATOMIC_OR(&c.inmask[owner] + parity, 1u << s);
+    if (s < 64u) BA_ATOMIC_OR(&c.inmask[owner] + 2 * parity + (s >> 5), 1u << (s & 31u));
 }
 
 BA_DEV void ba_late_append(BaCtx &c, BaAcc &acc, int tick, uint32_t n_slice, uint32_t word,
@@ -1448,12 +1449,14 @@ BA_DEV void ba_phase_c_pull_fast(BaCtx &c, BaAcc &acc, int a, int parity, uint32
         x = w2 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 4) | (((x >> 16) == 0u) << 5);           \
         x = w3 ^ aa; bits |= (((x & 0xFFFFu) == 0u) << 6) | (((x >> 16) == 0u) << 7);           \
     } while (0)
-    // the slice: with at most 32 slots, the bit mask the copy-issuing threads filled says it
+    // the slice: with at most 64 slots, the bit mask the copy-issuing threads filled says it
     // all; else groups from the bottom (slots at and beyond n_slice hold stale owners)
-    const uint32_t im = (&c.inmask[a])[parity];
-    if (im) (&c.inmask[a])[parity] = 0;
-    m0 = n_slice <= 32u ? (uint64_t)im : 0ull;
-    const uint32_t g_lo_end = n_slice <= 32u ? 0u : (n_slice + 7u) >> 3;
+    uint32_t *imp = &c.inmask[a] + 2 * parity;
+    const uint32_t im0 = imp[0], im1 = imp[1];
+    if (im0) imp[0] = 0;
+    if (im1) imp[1] = 0;
+    m0 = n_slice <= 64u ? ((uint64_t)im1 << 32) | (uint64_t)im0 : 0ull;
+    const uint32_t g_lo_end = n_slice <= 64u ? 0u : (n_slice + 7u) >> 3;
     for (uint32_t g = 0; g < g_lo_end; ++g) {
         uint32_t bits;
         BA_OWNER_BITS(g, bits);
