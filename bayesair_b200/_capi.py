@@ -47,7 +47,7 @@ class BaPlanInfo(C.Structure):
 class BaForwardOpts(C.Structure):
     _fields_ = [("noise_is_value", C.c_int32), ("want_grad", C.c_int32),
                 ("force_exact_lists", C.c_int32), ("no_overflow_rerun", C.c_int32),
-                ("replay_waits", C.c_int32), ("reserved", C.c_int32),
+                ("replay_waits", C.c_int32), ("force_ring_lists", C.c_int32),
                 ("seed", C.c_uint64), ("d_pop_tick", C.c_void_p)]
 
 

@@ -39,6 +39,11 @@ struct BaPlan {
     size_t smem_fast = 0, smem_exact = 0;
     bool fast_ok = false;
     int grid_fast = 0, grid_exact = 0;
+    // ring-less scan (ba_scan2.cuh): bookkeeping-free, fully observed plans
+    bool scan2_ok = false;
+    size_t smem_scan2 = 0;
+    int grid_scan2 = 0;
+    uint64_t stride_scan2 = 0;
     uint32_t *d_scratch = nullptr;
     uint64_t stride_fast = 0, stride_exact = 0;
     unsigned int *d_counters = nullptr;  // [0] fast work, [1] exact work, [2] rerun count
@@ -200,8 +205,19 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     }
     pl->stride_fast = (pl->host.scratch_words_fast + 31) & ~31ull;
     pl->stride_exact = (pl->host.scratch_words_exact + 31) & ~31ull;
+    if (pl->host.view.scan2_ok && !(std::getenv("BA_SCAN2") && std::atoi(std::getenv("BA_SCAN2")) == 0)) {
+        int n_live_max = 0;
+        for (int d = 0; d < n_days; ++d) n_live_max = std::max(n_live_max, pl->host.days[d].view.n_live);
+        pl->smem_scan2 = ba_forward2_smem_bytes(N, n_live_max, pl->block);
+        if (pl->smem_scan2 <= (size_t)max_optin) {
+            pl->grid_scan2 = ba_forward2_configure(pl->block, pl->smem_scan2, device);
+            pl->stride_scan2 = (ba_forward2_scratch_words(pl->host.view.Fmax, N) + 31) & ~31ull;
+            pl->scan2_ok = pl->grid_scan2 > 0;
+        }
+    }
     uint64_t words = std::max<uint64_t>((uint64_t)pl->grid_fast * pl->stride_fast,
                                         (uint64_t)pl->grid_exact * pl->stride_exact);
+    if (pl->scan2_ok) words = std::max<uint64_t>(words, (uint64_t)pl->grid_scan2 * pl->stride_scan2);
     words = std::max<uint64_t>(words, 32);
     void *scr = nullptr;
     BA_PCUDA(cudaMalloc(&scr, words * 4));
@@ -226,8 +242,8 @@ extern "C" BaStatus ba_plan_info(const BaPlan *pl, BaPlanInfo *o)
     o->include_cancellations = v.include_cancellations; o->device = pl->device;
     o->delta_t = v.delta_t; o->max_t = v.max_t; o->max_ticks = v.max_ticks;
     o->block_threads = pl->block;
-    o->smem_bytes = (int32_t)(pl->fast_ok ? pl->smem_fast : pl->smem_exact);
-    o->resident_ctas = pl->fast_ok ? pl->grid_fast : pl->grid_exact;
+    o->smem_bytes = (int32_t)(pl->scan2_ok ? pl->smem_scan2 : (pl->fast_ok ? pl->smem_fast : pl->smem_exact));
+    o->resident_ctas = pl->scan2_ok ? pl->grid_scan2 : (pl->fast_ok ? pl->grid_fast : pl->grid_exact);
     return BA_OK;
 }
 
@@ -291,13 +307,20 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         BA_CUDA(cudaMemsetAsync(d_phase, 0, 8 * sizeof(unsigned long long), s));
         prm.phase_cycles = d_phase;
     }
+    const bool use_scan2 = pl->scan2_ok && !o.force_exact_lists && !o.force_ring_lists;
     const bool use_fast = pl->fast_ok && !o.force_exact_lists;
     const bool trk = pl->host.view.any_track != 0;
-    if (use_fast) {
-        prm.scratch_stride = pl->stride_fast;
+    if (use_scan2 || use_fast) {
         prm.work_counter = pl->d_counters + 0;
-        int grid = (int)std::min<long long>(n_work, pl->grid_fast);
-        BA_CUDA(ba_launch_forward(prm, false, trk, grid, pl->block, pl->smem_fast, s));
+        if (use_scan2) {
+            prm.scratch_stride = pl->stride_scan2;
+            int grid = (int)std::min<long long>(n_work, pl->grid_scan2);
+            BA_CUDA(ba_launch_forward2(prm, grid, pl->block, pl->smem_scan2, s));
+        } else {
+            prm.scratch_stride = pl->stride_fast;
+            int grid = (int)std::min<long long>(n_work, pl->grid_fast);
+            BA_CUDA(ba_launch_forward(prm, false, trk, grid, pl->block, pl->smem_fast, s));
+        }
         g_launches++;
         if (!o.no_overflow_rerun) {
             // particle-days whose shared-memory lists overflowed are re-run with

@@ -15,6 +15,7 @@
 // Nothing here is a dense contraction: no tensor cores, by design.
 #include "ba_kernels.cuh"
 #include "ba_sim.cuh"
+#include "ba_scan2.cuh"
 
 #define BA_RED_WORDS (32 * 6 + 4)
 
@@ -343,6 +344,224 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         __syncthreads();     // red[] and the state arrays are reused by the next item
         BA_MARK(6);
     }
+}
+
+
+// ---------------------------------------------------------------------------
+// ba_forward2_kernel: the ring-less scan (ba_scan2.cuh) for bookkeeping-free, fully
+// observed plans.  Persistent CTAs, one lane per airport, warps asynchronous in the scan.
+// ---------------------------------------------------------------------------
+#ifndef BA2_MIN_BLOCKS_128
+#define BA2_MIN_BLOCKS_128 8
+#endif
+#define BA2_MIN_BLOCKS(MAXT) ((MAXT) == 128 ? BA2_MIN_BLOCKS_128 : ((MAXT) == 256 ? 4 : ((MAXT) == 512 ? 2 : 1)))
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel(const BaFwdParams prm)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
+    const BaPlanView &plan = prm.plan;
+    const int N = plan.N, D = plan.D, R = plan.R;
+
+    Ba2Ctx c;
+    uint32_t *red = smem;                                    // [BA_RED_WORDS], 16 B aligned
+    c.s_m = (float *)(red + BA_RED_WORDS);
+    c.s_rate = c.s_m + N; c.s_mt = c.s_rate + N; c.s_tstd = c.s_mt + N;
+    c.kcnt = (uint32_t *)(c.s_tstd + N);
+    c.hist = c.kcnt + BA2_KC;
+    c.nwarp = nwarp;
+    c.n_ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
+    c.prog = (volatile int *)(c.hist + c.n_ranges * N);
+    uint32_t *ctaw = (uint32_t *)c.prog + 32;                // [16] CTA scalars
+    c.qsh = (volatile uint16_t *)(ctaw + 16);
+    uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
+
+    c.sigma = prm.scales[0]; c.v_t = prm.scales[1]; c.v_u = prm.scales[2];
+    c.inv_sigma = 1.0f / c.sigma;
+    c.inv_sigma2 = c.inv_sigma * c.inv_sigma;
+    c.inv_sigma3 = c.inv_sigma2 * c.inv_sigma;
+    c.log_sigma = logf(c.sigma);
+    c.inv_vt = 1.0f / c.v_t; c.inv_vu = 1.0f / c.v_u;
+    c.c0_lp = ba_relaxed_bernoulli_lp(0.0f, 0.0f, nullptr);
+    c.c1_lp = ba_relaxed_bernoulli_lp(0.0f, 1.0f, nullptr);
+    c.value_mode = prm.value_mode; c.want_grad = prm.want_grad && prm.tape != nullptr;
+    c.seed = prm.seed;
+    c.route_base = 2 * N;
+    c.tick_time = plan.tick_time;
+    c.max_ticks = plan.max_ticks;
+    c.N = N;
+
+    for (;;) {
+        // ---- next work item ------------------------------------------------
+        if (tid == 0) red[BA_RED_WORDS - 1] = atomicAdd(prm.work_counter, 1u);
+        __syncthreads();
+        const int wi = (int)red[BA_RED_WORDS - 1];
+        const int n_work = prm.n_work_dev ? (int)*prm.n_work_dev : prm.n_work;
+        if (wi >= n_work) break;
+        int p, d;
+        if (prm.work_list) { const int pd = prm.work_list[wi]; p = pd / D; d = pd - p * D; }
+        else { d = wi / prm.P; p = wi - d * prm.P; }     // same-day items adjacent in time
+        const size_t pd = (size_t)p * D + d;
+        const BaDayView day = plan.days[d];
+
+        c.F = day.F;
+        c.flights = day.flights; c.route = day.route; c.ap = day.airports;
+        c.pos_live = day.pos_live; c.pos_dep = day.pos_dep; c.pos_arr = day.pos_arr;
+        c.rt_gid = day.rt_gid; c.rt_off = day.rt_off; c.rt_flt = day.rt_flt; c.Rd = day.Rd;
+        c.lq = day.lq; c.drun = day.drun; c.drun_off = day.drun_off;
+        c.first_tick = day.first_tick;
+        c.lat_route = prm.lat_route + (size_t)p * R;
+        c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
+        c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
+        c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
+        c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
+        ba2_carve_scratch(c, gscr, day.F, N);
+        const uint32_t n_arr = (uint32_t)day.n_arr;
+        c.range_len = (n_arr + (uint32_t)c.n_ranges - 1u) / (uint32_t)c.n_ranges;
+        if (c.range_len == 0u) c.range_len = 1u;
+
+        // ---- setup -----------------------------------------------------------
+        const float *lat_airport = prm.lat_airport + (size_t)p * 2 * N;
+        for (int a = tid; a < N; a += nthr) ba2_init_airport(c, a, lat_airport, N);
+        for (int i = tid; i < BA2_KC + c.n_ranges * N; i += nthr) c.kcnt[i] = 0;   // buckets + cursors
+        {
+            uint32_t *q32 = (uint32_t *)c.qsh;
+            const int nq = (day.n_live + N + 1) / 2;
+            for (int i = tid; i < nq; i += nthr) q32[i] = 0xFFFFFFFFu;
+        }
+        if (tid < nwarp) c.prog[tid] = day.first_tick - 1;
+        if (tid < 16) ctaw[tid] = 0;
+        if (c.grow && day.Rd < R)
+            for (int i = tid; i < R; i += nthr) c.grow[c.route_base + i] = 0.0f;
+        if (c.pop_tick)
+            for (int i = 2 * day.F + tid; i < 2 * plan.Fmax; i += nthr) c.pop_tick[i] = -1;
+        BaAcc acc = {0.0, 0.0f, 0.0f, 0.0f, 0u};
+        __syncthreads();
+
+        // ---- prologue ----------------------------------------------------------
+        for (int f = tid; f < day.F; f += nthr) ba2_prologue_flight(c, acc, f);
+        __syncthreads();
+        if (tid < 32) ba2_bucket_scan(c, tid);
+        __syncthreads();
+        for (int f = tid; f < day.F; f += nthr) ba2_scatter_flight(c, f);
+        __syncthreads();
+        for (int a = tid; a < N; a += nthr) ba2_split_cursors(c, a);
+        __syncthreads();
+        if (warp < c.n_ranges) ba2_split_range(c, warp, lane, n_arr);
+        const bool aborted = __syncthreads_or((acc.status & BA_S_OVERFLOW) != 0u) != 0;
+
+        // ---- scan: one lane per airport, warps asynchronous ------------------------
+        uint32_t k = (uint32_t)(day.first_tick - 1);
+        if (!aborted) {
+            Ba2Lane L;
+            Ba2Cold Q;
+            if (tid < N) ba2_lane_init(c, L, Q, day.lane_airport[tid]);
+            else { L.left = 0; L.last = 0; Q.status = 0; }
+            for (;;) {
+                const bool active = L.left != 0u;
+                if (!__any_sync(0xffffffffu, active)) break;
+                if ((int)k >= plan.max_ticks) { Q.status |= BA_S_TICK_CAP; break; }
+                ++k;
+                const float t = c.tick_time[k];                 // model.py:161
+                if (active) ba2_lane_tick(c, L, Q, k, t);
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); c.prog[warp] = (int)k; }
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); c.prog[warp] = BA2_PROG_DONE; }
+            acc.status |= Q.status;
+            uint32_t last = L.last;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+            if (lane == 0) atomicMax(&ctaw[0], last);
+        }
+        __syncthreads();          // every wait of the tape is written
+        int tick = (int)ctaw[0];
+        if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
+
+        // ---- epilogue ----------------------------------------------------------
+        if (!aborted)
+            for (int f = tid; f < day.F; f += nthr) ba2_epilogue_flight(c, acc, f);
+        if (c.grow && !aborted) {
+            __syncthreads();
+            for (int s = tid; s < N; s += nthr) ba2_epilogue_airport(c, day.lane_airport[s], N);
+            for (int r = tid; r < day.Rd; r += nthr) ba2_epilogue_route(c, r);
+        }
+        // deterministic block reduction: lanes -> warp (shuffle tree) -> warps in order
+        double v0 = acc.lp;
+        float v1 = acc.g_sigma, v2 = acc.g_vt, v3 = acc.g_vu;
+        uint32_t st = acc.status;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_down_sync(0xffffffffu, v0, o);
+            v1 += __shfl_down_sync(0xffffffffu, v1, o);
+            v2 += __shfl_down_sync(0xffffffffu, v2, o);
+            v3 += __shfl_down_sync(0xffffffffu, v3, o);
+            st |= __shfl_down_sync(0xffffffffu, st, o);
+        }
+        float *redf = (float *)red;
+        double *redd = (double *)red;          // red is 16-byte aligned; 6 words per warp
+        if (lane == 0) {
+            redd[warp * 3 + 0] = v0;
+            redf[warp * 6 + 2] = v1; redf[warp * 6 + 3] = v2;
+            redf[warp * 6 + 4] = v3; red[warp * 6 + 5] = st;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            uint32_t ss = 0;
+            for (int w = 0; w < nwarp; ++w) {
+                s0 += redd[w * 3 + 0]; s1 += redf[w * 6 + 2]; s2 += redf[w * 6 + 3];
+                s3 += redf[w * 6 + 4]; ss |= red[w * 6 + 5];
+            }
+            prm.logp[pd] = (float)s0;
+            prm.status[pd] = ss;
+            if (prm.ticks) prm.ticks[pd] = tick;
+            if (c.grow) {
+                c.grow[c.route_base + R + 0] = (float)s1;
+                c.grow[c.route_base + R + 1] = (float)s2;
+                c.grow[c.route_base + R + 2] = (float)s3;
+            }
+        }
+        __syncthreads();     // red[] and the shared tables are reused by the next item
+    }
+}
+
+size_t ba_forward2_smem_bytes(int n_airports, int n_live_max, int block_threads)
+{
+    return (BA_RED_WORDS + ba2_smem_words(n_airports, n_live_max, (block_threads + 31) / 32)) * 4;
+}
+
+uint64_t ba_forward2_scratch_words(int Fmax, int n_airports) { return ba2_scratch_words(Fmax, n_airports); }
+
+#define BA2_DISPATCH(BLOCK, STMT)                                                    \
+    do {                                                                             \
+        if ((BLOCK) <= 128) { auto kfn = ba_forward2_kernel<128>; STMT; }             \
+        else if ((BLOCK) <= 256) { auto kfn = ba_forward2_kernel<256>; STMT; }        \
+        else if ((BLOCK) <= 512) { auto kfn = ba_forward2_kernel<512>; STMT; }        \
+        else { auto kfn = ba_forward2_kernel<1024>; STMT; }                           \
+    } while (0)
+
+// sets the dynamic shared-memory limit (on the current device) and returns the resident grid
+int ba_forward2_configure(int block, size_t smem, int device)
+{
+    cudaError_t e = cudaSuccess;
+    BA2_DISPATCH(block, e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (e != cudaSuccess) return -1;
+    int per_sm = 0, sms = 0;
+    BA2_DISPATCH(block, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, block, smem));
+    if (e != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+    if (const char *v = getenv("BA_MAX_CTAS_PER_SM")) { const int cap = atoi(v); if (cap > 0 && cap < per_sm) per_sm = cap; }
+    return per_sm * sms;
+}
+
+cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, int block, size_t smem, cudaStream_t s)
+{
+    BA2_DISPATCH(block, (kfn<<<grid, block, smem, s>>>(p)));
+    return cudaGetLastError();
 }
 
 // g[p, j] = sum_d dlogp[p, d] * tape[p, d, j]

@@ -48,6 +48,11 @@ int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, bo
 
 cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, bool tracked, int grid, int block,
                               size_t smem, cudaStream_t s);
+// ring-less scan (ba_scan2.cuh)
+size_t ba_forward2_smem_bytes(int n_airports, int n_live_max, int block_threads);
+uint64_t ba_forward2_scratch_words(int Fmax, int n_airports);
+int ba_forward2_configure(int block, size_t smem, int device);
+cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, int block, size_t smem, cudaStream_t s);
 cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
                               cudaStream_t s);
 cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s);

@@ -60,13 +60,21 @@ struct BaAirport {                    // 80 B static row per (day, airport)
     uint32_t flags;
     uint32_t q_off_s, q_mask_s;       // runway-queue ring, shared-memory variant
     uint32_t q_off_x, q_mask_x;       // exact-capacity variant (global scratch)
-    uint32_t pad2, pad3, pad4, pad5;
+    uint32_t lq_off;                  // ring-less scan (ba_scan2.cuh): first live departure of
+                                      //   this airport in BaDayView::lq (one sentinel per airport)
+    uint32_t as_off;                  // ... first slot of its arrival list (arr_cnt + 1 slots)
+    uint32_t pad4, pad5;
     uint32_t turn_off;                // turnaround list (cap = arr_cnt), global scratch
     uint32_t av_off, av_mask;         // aircraft FIFO ring, global scratch
     uint32_t dl_off, dl_mask;         // delayed-departure deque ring, global scratch
     int32_t arr_off;                  // slice of arrival order (arr_cnt entries)
     int32_t dep_live;                 // departures not observed as cancelled
 };
+
+// One live (= not observed as cancelled) departure of a bookkeeping-free airport, in
+// (origin, pending order) order: the tick at which it becomes ready (network.py:60-68) and
+// its queue start max(0, scheduled departure) (network.py:118-126 with 1000 reserves).
+struct BaLiveDep { uint32_t tick; float qstart; };
 
 struct BaDayView {
     int32_t N, F;
@@ -102,6 +110,10 @@ struct BaDayView {
     uint32_t any_track_t, any_track_a; // does any airport of the day track aircraft
     int32_t first_tick;               // ticks [1, first_tick) are provably idle
     float t_before_first;             // clock after first_tick-1 sequential fp32 adds
+    // ring-less scan (ba_scan2.cuh)
+    const BaLiveDep *lq;              // [n_live + N] live departures grouped by origin + sentinels
+    const int32_t *pos_live;          // [F] flight -> index into lq ("lpos"), -1: cancelled
+    int32_t n_live, n_arr;            // live departures / arrivals of the day (equal)
 };
 
 struct BaPlanView {
@@ -112,6 +124,7 @@ struct BaPlanView {
     int32_t max_ticks;
     float delta_t, max_t;
     int32_t grad_stride;              // C*N + R + 3
+    int32_t scan2_ok;                 // the ring-less scan (ba_scan2.cuh) can run this plan
     const float *tick_time;           // [max_ticks + 2] clock after k sequential fp32 adds
     const BaDayView *days;            // [D]
 };

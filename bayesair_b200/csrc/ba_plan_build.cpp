@@ -276,6 +276,35 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             H.view.max_dslice = max_slice;
             out->max_dslice = std::max(out->max_dslice, max_slice);
         }
+        // ring-less scan (ba_scan2.cuh): live departures grouped by origin (day order), pending
+        // order inside a group, one sentinel record per airport; arrival lists of arr_cnt + 1
+        // slots.  The list position of a flight ("lpos") is also the static part of the
+        // in-transit ordering key: at bookkeeping-free airports departures leave in this order.
+        {
+            H.lq.clear();
+            H.pos_live.assign((size_t)F, -1);
+            uint32_t as = 0;
+            for (int a = 0; a < N; ++a) {
+                BaAirport &A = H.airports[a];
+                A.lq_off = (uint32_t)H.lq.size();
+                A.as_off = as;
+                as += (uint32_t)arr_cnt[a] + 1u;
+                for (int i = 0; i < dep_cnt[a]; ++i) {
+                    const int f = H.dep_fid[(size_t)A.dep_off + i];
+                    if (((H.flights[f].od >> 24) & 3u) == 1u) continue;
+                    H.pos_live[f] = (int32_t)H.lq.size();
+                    BaLiveDep r;
+                    r.tick = (uint32_t)ready_tick[f];
+                    r.qstart = std::max(0.0f, T.h_sched_dep[f]);
+                    H.lq.push_back(r);
+                }
+                BaLiveDep sentinel;
+                sentinel.tick = 0xFFFFFFFFu; sentinel.qstart = 0.0f;
+                H.lq.push_back(sentinel);
+            }
+            H.view.n_live = (int32_t)H.lq.size() - N;
+            H.view.n_arr = (int32_t)as - N;
+        }
         // lane -> airport, heaviest first
         H.lane_airport.resize(N);
         std::iota(H.lane_airport.begin(), H.lane_airport.end(), 0);
@@ -329,6 +358,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         V.q_total_s = q_s; V.q_total_x = q_x;
         V.turn_total = turn; V.av_total = av; V.dl_total = dl;
         V.first_tick = first_tick; V.t_before_first = t_before;
+        V.lq = H.lq.data(); V.pos_live = H.pos_live.data();
         smem_words = std::max(smem_words, 6u * q_s);
     }
 
@@ -348,6 +378,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
     P.any_track = 0;
     for (int d = 0; d < n_days; ++d) P.any_track |= (int32_t)out->days[d].view.any_track_t;
     P.max_ticks = max_ticks; P.delta_t = delta_t; P.max_t = max_t;
+    // the ring-less scan handles fully bookkeeping-free plans with one lane per airport
+    P.scan2_ok = (!P.any_track && N <= 1024 && Fmax + N < (1 << 18)) ? 1 : 0;
     P.grad_stride = P.C * N + R + 3;
     P.days = out->day_views.data();
     P.tick_time = out->tick_time.data();

@@ -14,6 +14,8 @@ struct BaHostDay {
     std::vector<int32_t> dcal_off, drun_off, dep_cpos;
     std::vector<uint32_t> drun;
     std::vector<BaAirport> airports;
+    std::vector<BaLiveDep> lq;
+    std::vector<int32_t> pos_live;
     BaDayView view;   // pointers into the vectors above (host view)
 };
 

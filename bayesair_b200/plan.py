@@ -100,7 +100,8 @@ class SimulationPlan:
                 noise_is_value: bool = False, want_grad: bool = False,
                 force_exact_lists: bool = False, no_overflow_rerun: bool = False,
                 want_ticks: bool = False, want_pop_ticks: bool = False,
-                replay_waits: bool = False) -> Dict[str, torch.Tensor]:
+                replay_waits: bool = False,
+                force_ring_lists: bool = False) -> Dict[str, torch.Tensor]:
         """``lat_airport [P,C,N]``, ``lat_route [P,R]``, ``scales [3]``,
         ``noise [P,D,Fmax,4]`` or None (Philox from ``seed``).  Asynchronous."""
         P = int(lat_airport.shape[0])
@@ -119,8 +120,8 @@ class SimulationPlan:
             pop = (torch.empty((P, D, F, 2), dtype=torch.int32, device=self.device)
                    if want_pop_ticks else None)
             opts = _capi.BaForwardOpts(int(noise_is_value), int(want_grad), int(force_exact_lists),
-                                       int(no_overflow_rerun), int(replay_waits), 0,
-                                       int(seed) & (2**64 - 1),
+                                       int(no_overflow_rerun), int(replay_waits),
+                                       int(force_ring_lists), int(seed) & (2**64 - 1),
                                        None if pop is None else pop.data_ptr())
             self._h.forward(P, _ptr(la), _ptr(lr), _ptr(sc), _ptr(nz), opts, _ptr(logp),
                             _ptr(status), _ptr(ticks), _ptr(tape), self._stream())

@@ -102,7 +102,7 @@ typedef struct BaForwardOpts {
     int32_t replay_waits;       /* 1: always form queue waits with the reference's sequential
                                       fp32 adds instead of only when a decision is within
                                       rounding distance of the clock (testing; same results) */
-    int32_t reserved;
+    int32_t force_ring_lists;   /* 1: skip the ring-less scan, use the shared-ring kernel (testing) */
     uint64_t seed;              /* Philox seed, used when d_noise == NULL                  */
     int32_t *d_pop_tick;        /* nullable diagnostics [P, D, Fmax, 2]: tick at which each
                                    flight left its departure / arrival runway queue (-1 =

@@ -14,7 +14,7 @@ _OUT = os.path.join(_ROOT, "tests", "_build", "libba_hostemu.so")
 _SRCS = [os.path.join(_HERE, "ba_hostemu.cpp"),
          os.path.join(_ROOT, "bayesair_b200", "csrc", "ba_plan_build.cpp")]
 _DEPS = _SRCS + [os.path.join(_ROOT, "bayesair_b200", "csrc", f)
-                 for f in ("ba_sim.cuh", "ba_plan.h", "ba_plan_build.h")]
+                 for f in ("ba_sim.cuh", "ba_scan2.cuh", "ba_plan.h", "ba_plan_build.h")]
 _lib = None
 
 
@@ -31,7 +31,7 @@ def build():
     if (not os.path.exists(_OUT)
             or any(os.path.getmtime(s) > os.path.getmtime(_OUT) for s in _DEPS)):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC",
-                               "-shared", "-Wno-unknown-pragmas", "-o", _OUT] + _SRCS)
+                               "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", _OUT] + _SRCS)
     return _OUT
 
 
@@ -95,7 +95,7 @@ class EmuPlan:
 
     def forward(self, latents, scales, noise, *, seed=0, value_mode=False, want_grad=True,
                 exact=False, rerun_overflow=True, shuffle_seed=1, want_pop=False,
-                replay_waits=False):
+                replay_waits=False, scan2=False):
         lib = _load()
         la, lr = self.pack_latents(latents)
         P = la.shape[0]
@@ -109,9 +109,18 @@ class EmuPlan:
         tape = np.zeros((P, self.D, self.stride), np.float32) if want_grad else None
         pop = np.zeros((P, self.D, self.Fmax, 2), np.int32) if want_pop else None
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
-        lib.ba_emu_forward(self.h, P, vp(la), vp(lr), vp(sc), vp(nz), C.c_uint64(seed),
-                           int(value_mode), int(want_grad), int(exact), int(rerun_overflow),
-                           int(replay_waits), C.c_uint(shuffle_seed), vp(logp), vp(status), vp(ticks), vp(tape), vp(pop))
+        if scan2:
+            rc = lib.ba_emu_forward2(self.h, P, vp(la), vp(lr), vp(sc), vp(nz), C.c_uint64(seed),
+                                     int(value_mode), int(want_grad), int(rerun_overflow),
+                                     C.c_uint(shuffle_seed), vp(logp), vp(status), vp(ticks),
+                                     vp(tape), vp(pop))
+            if rc != 0:
+                raise RuntimeError("the ring-less scan cannot run this plan")
+        else:
+            lib.ba_emu_forward(self.h, P, vp(la), vp(lr), vp(sc), vp(nz), C.c_uint64(seed),
+                               int(value_mode), int(want_grad), int(exact), int(rerun_overflow),
+                               int(replay_waits), C.c_uint(shuffle_seed), vp(logp), vp(status),
+                               vp(ticks), vp(tape), vp(pop))
         out = dict(logp=logp, status=status, ticks=ticks, pop_tick=pop)
         if want_grad:
             dl = np.ones((P, self.D), np.float32)
@@ -127,6 +136,10 @@ class EmuPlan:
                 g["base_cancel_logprob"] = ga[:, 3]
             out["grads"] = g
         return out
+
+    @property
+    def scan2_ok(self):
+        return bool(_load().ba_emu_scan2_ok(self.h))
 
     def philox_noise(self, P, seed):
         nz = np.zeros((P, self.D, self.Fmax, 4), np.float32)

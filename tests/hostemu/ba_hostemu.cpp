@@ -16,6 +16,9 @@
 
 #include "../../bayesair_b200/csrc/ba_plan_build.h"
 #include "../../bayesair_b200/csrc/ba_sim.cuh"
+#include "../../bayesair_b200/csrc/ba_scan2.cuh"
+#include <chrono>
+#include <thread>
 
 struct EmuPlan { BaHostPlan host; };
 
@@ -264,6 +267,171 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
         c.grow[c.route_base + R + 1] = (float)s2;
         c.grow[c.route_base + R + 2] = (float)s3;
     }
+}
+
+
+// ---------------------------------------------------------------------------
+// Ring-less scan (ba_scan2.cuh): the prologue and epilogue run serially (optionally in
+// shuffled flight order); the scan runs ONE std::thread PER WARP with the kernel's own
+// progress protocol (volatile shared words + fences), optionally with random stalls so that
+// warps drift apart by many ticks.
+// ---------------------------------------------------------------------------
+static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d,
+                      const float *lat_airport, const float *lat_route, const float *scales,
+                      const float *noise, uint64_t seed, int value_mode, int want_grad,
+                      unsigned shuffle_seed, float *logp, uint32_t *status, int32_t *ticks,
+                      float *tape, int32_t *pop_tick)
+{
+    const int N = plan.N, R = plan.R, D = plan.D;
+    const int nthr = ((N + 31) / 32) * 32, nwarp = nthr / 32;
+    const size_t pd = (size_t)p * D + d;
+    std::vector<uint32_t> sh(ba2_smem_words(N, day.n_live, nwarp) + 64, 0);
+    std::vector<uint32_t> gs(ba2_scratch_words(day.F, N) + 16, 0xDEADBEEFu);
+    Ba2Ctx c;
+    memset(&c, 0, sizeof(c));
+    c.s_m = (float *)sh.data();
+    c.s_rate = c.s_m + N; c.s_mt = c.s_rate + N; c.s_tstd = c.s_mt + N;
+    c.kcnt = (uint32_t *)(c.s_tstd + N);
+    c.hist = c.kcnt + BA2_KC;
+    c.nwarp = nwarp;
+    c.n_ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
+    c.prog = (volatile int *)(c.hist + c.n_ranges * N);
+    c.qsh = (volatile uint16_t *)((uint32_t *)c.prog + 32 + 16);
+    c.sigma = scales[0]; c.v_t = scales[1]; c.v_u = scales[2];
+    c.inv_sigma = 1.0f / c.sigma; c.inv_sigma2 = c.inv_sigma * c.inv_sigma;
+    c.inv_sigma3 = c.inv_sigma2 * c.inv_sigma; c.log_sigma = logf(c.sigma);
+    c.inv_vt = 1.0f / c.v_t; c.inv_vu = 1.0f / c.v_u;
+    c.c0_lp = ba_relaxed_bernoulli_lp(0.0f, 0.0f, nullptr);
+    c.c1_lp = ba_relaxed_bernoulli_lp(0.0f, 1.0f, nullptr);
+    c.value_mode = value_mode; c.want_grad = want_grad && tape;
+    c.seed = seed; c.route_base = 2 * N; c.tick_time = plan.tick_time; c.max_ticks = plan.max_ticks;
+    c.N = N; c.F = day.F;
+    c.flights = day.flights; c.route = day.route; c.ap = day.airports;
+    c.pos_live = day.pos_live; c.pos_dep = day.pos_dep; c.pos_arr = day.pos_arr;
+    c.rt_gid = day.rt_gid; c.rt_off = day.rt_off; c.rt_flt = day.rt_flt; c.Rd = day.Rd;
+    c.lq = day.lq; c.drun = day.drun; c.drun_off = day.drun_off; c.first_tick = day.first_tick;
+    c.lat_route = lat_route + (size_t)p * R;
+    c.noise = noise ? noise + pd * (size_t)plan.Fmax * 4 : nullptr;
+    c.particle = p; c.dayidx = d;
+    c.grow = c.want_grad ? tape + pd * (size_t)plan.grad_stride : nullptr;
+    c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
+    ba2_carve_scratch(c, (uint32_t *)(((uintptr_t)gs.data() + 15) & ~(uintptr_t)15), day.F, N);
+    const uint32_t n_arr = (uint32_t)day.n_arr;
+    c.range_len = (n_arr + (uint32_t)c.n_ranges - 1u) / (uint32_t)c.n_ranges;
+    if (c.range_len == 0u) c.range_len = 1u;
+
+    const float *la = lat_airport + (size_t)p * 2 * N;
+    for (int a = 0; a < N; ++a) ba2_init_airport(c, a, la, N);
+    for (int i = 0; i < BA2_KC + c.n_ranges * N; ++i) c.kcnt[i] = 0;
+    for (int i = 0; i < day.n_live + N + 1; ++i) ((uint16_t *)c.qsh)[i] = 0xFFFFu;
+    for (int w = 0; w < nwarp; ++w) c.prog[w] = day.first_tick - 1;
+    if (c.grow) for (int i = 0; i < R; ++i) c.grow[c.route_base + i] = 0.0f;
+    if (c.pop_tick) for (int i = 2 * day.F; i < 2 * plan.Fmax; ++i) c.pop_tick[i] = -1;
+
+    std::vector<BaAcc> acc(N, BaAcc{0, 0, 0, 0, 0});
+    std::mt19937 rng(shuffle_seed + 977u * (unsigned)pd);
+    std::vector<int> forder(day.F);
+    for (int f = 0; f < day.F; ++f) forder[f] = f;
+    if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
+    for (int f : forder) ba2_prologue_flight(c, acc[f % N], f);
+    ba2_bucket_scan(c, -1);
+    if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
+    for (int f : forder) ba2_scatter_flight(c, f);
+    for (int a = 0; a < N; ++a) ba2_split_cursors(c, a);
+    for (int r = 0; r < c.n_ranges; ++r) ba2_split_range(c, r, -1, n_arr);
+    uint32_t st = 0;
+    for (int i = 0; i < N; ++i) st |= acc[i].status;
+    const bool aborted = (st & BA_S_OVERFLOW) != 0;
+
+    std::vector<uint32_t> last_w(nwarp, 0), st_w(nwarp, 0);
+    if (!aborted) {
+        auto warp_fn = [&](int w) {
+            std::mt19937 wr(shuffle_seed * 7919u + 13u * (unsigned)w + (unsigned)pd);
+            Ba2Lane L[32];
+            Ba2Cold Q[32];
+            bool valid[32];
+            for (int l = 0; l < 32; ++l) {
+                const int tid = 32 * w + l;
+                valid[l] = tid < N;
+                if (valid[l]) ba2_lane_init(c, L[l], Q[l], day.lane_airport[tid]);
+                else { L[l].left = 0; L[l].last = 0; Q[l].status = 0; }
+            }
+            uint32_t k = (uint32_t)(day.first_tick - 1);
+            for (;;) {
+                bool any = false;
+                for (int l = 0; l < 32; ++l) any = any || L[l].left != 0u;
+                if (!any) break;
+                if ((int)k >= plan.max_ticks) { st_w[w] |= BA_S_TICK_CAP; break; }
+                ++k;
+                const float t = c.tick_time[k];
+                // random stalls: let the warps drift apart
+                if (shuffle_seed > 1 && (wr() % 16u) == 0u)
+                    std::this_thread::sleep_for(std::chrono::microseconds(wr() % 200u));
+                int order[32];
+                for (int l = 0; l < 32; ++l) order[l] = l;
+                if (shuffle_seed) std::shuffle(order, order + 32, wr);
+                for (int i = 0; i < 32; ++i) {
+                    const int l = order[i];
+                    if (L[l].left != 0u) ba2_lane_tick(c, L[l], Q[l], k, t);
+                }
+                BA2_FENCE();
+                c.prog[w] = (int)k;
+            }
+            BA2_FENCE();
+            c.prog[w] = BA2_PROG_DONE;
+            for (int l = 0; l < 32; ++l) {
+                last_w[w] = std::max(last_w[w], L[l].last);
+                st_w[w] |= Q[l].status;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int w = 0; w < nwarp; ++w) th.emplace_back(warp_fn, w);
+        for (auto &t : th) t.join();
+    }
+    int tick = 0;
+    for (int w = 0; w < nwarp; ++w) { tick = std::max(tick, (int)last_w[w]); st |= st_w[w]; }
+    if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
+    if (!aborted) for (int f = 0; f < day.F; ++f) ba2_epilogue_flight(c, acc[f % N], f);
+    if (c.grow && !aborted) {
+        for (int i = 0; i < N; ++i) ba2_epilogue_airport(c, day.lane_airport[i], N);
+        for (int r = 0; r < day.Rd; ++r) ba2_epilogue_route(c, r);
+    }
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int i = 0; i < N; ++i) {
+        s0 += acc[i].lp; s1 += acc[i].g_sigma; s2 += acc[i].g_vt; s3 += acc[i].g_vu;
+        st |= acc[i].status;
+    }
+    logp[pd] = (float)s0; status[pd] = st;
+    if (ticks) ticks[pd] = tick;
+    if (c.grow) {
+        c.grow[c.route_base + R + 0] = (float)s1;
+        c.grow[c.route_base + R + 1] = (float)s2;
+        c.grow[c.route_base + R + 2] = (float)s3;
+    }
+}
+
+extern "C" int ba_emu_scan2_ok(const EmuPlan *pl) { return pl->host.view.scan2_ok; }
+
+// same selection as ba_forward: the ring-less scan, overflowed items re-run with exact lists
+extern "C" int ba_emu_forward2(const EmuPlan *pl, int P, const float *lat_airport,
+                               const float *lat_route, const float *scales, const float *noise,
+                               uint64_t seed, int value_mode, int want_grad, int rerun_overflow,
+                               unsigned shuffle_seed, float *logp, uint32_t *status,
+                               int32_t *ticks, float *tape, int32_t *pop_tick)
+{
+    const BaPlanView &plan = pl->host.view;
+    if (!plan.scan2_ok) return 1;
+    for (int d = 0; d < plan.D; ++d)
+        for (int p = 0; p < P; ++p) {
+            const BaDayView &day = plan.days[d];
+            run_item2(plan, day, p, d, lat_airport, lat_route, scales, noise, seed, value_mode,
+                      want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick);
+            if (rerun_overflow && (status[(size_t)p * plan.D + d] & BA_S_OVERFLOW))
+                run_item<true, false, false>(plan, day, p, d, P, lat_airport, lat_route, scales, noise,
+                                             seed, value_mode, want_grad, 0, shuffle_seed, logp, status,
+                                             ticks, tape, pop_tick);
+        }
+    return 0;
 }
 
 extern "C" int ba_emu_forward(const EmuPlan *pl, int P, const float *lat_airport,

@@ -48,7 +48,7 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
                 assert "ba_oracle" not in src, f
-                assert "hostemu" not in src or f == "ba_sim.cuh", f
+                assert "hostemu" not in src or f in ("ba_sim.cuh", "ba_scan2.cuh"), f
 
 
 # ------------------------------------------------------- schedule compiler --
