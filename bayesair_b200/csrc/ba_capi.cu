@@ -44,6 +44,7 @@ struct BaPlan {
     size_t smem_scan2 = 0;
     int grid_scan2 = 0;
     uint64_t stride_scan2 = 0;
+    int qsh_words = 0;
     uint32_t *d_scratch = nullptr;
     uint64_t stride_fast = 0, stride_exact = 0;
     unsigned int *d_counters = nullptr;  // [0] fast work, [1] exact work, [2] rerun count
@@ -169,6 +170,8 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         BA_PCUDA(upload(pl, H.drun, &v.drun));
         BA_PCUDA(upload(pl, H.airports, &v.airports));
         BA_PCUDA(upload(pl, H.lane_airport, &v.lane_airport));
+        BA_PCUDA(upload(pl, H.lq, &v.lq));
+        BA_PCUDA(upload(pl, H.pos_live, &v.pos_live));
         dviews[d] = v;
     }
     const BaDayView *dd = nullptr;
@@ -209,6 +212,7 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         int n_live_max = 0;
         for (int d = 0; d < n_days; ++d) n_live_max = std::max(n_live_max, pl->host.days[d].view.n_live);
         pl->smem_scan2 = ba_forward2_smem_bytes(N, n_live_max, pl->block);
+        pl->qsh_words = ba_forward2_qsh_words(N, n_live_max);
         if (pl->smem_scan2 <= (size_t)max_optin) {
             pl->grid_scan2 = ba_forward2_configure(pl->block, pl->smem_scan2, device);
             pl->stride_scan2 = (ba_forward2_scratch_words(pl->host.view.Fmax, N) + 31) & ~31ull;
@@ -314,6 +318,7 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         prm.work_counter = pl->d_counters + 0;
         if (use_scan2) {
             prm.scratch_stride = pl->stride_scan2;
+            prm.qsh_words = pl->qsh_words;
             int grid = (int)std::min<long long>(n_work, pl->grid_scan2);
             BA_CUDA(ba_launch_forward2(prm, grid, pl->block, pl->smem_scan2, s));
         } else {

@@ -365,17 +365,19 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
     const BaPlanView &plan = prm.plan;
     const int N = plan.N, D = plan.D, R = plan.R;
 
+    // shared memory: everything the scan touches sits at compile-time offsets (progress
+    // words, q table); the size-dependent prologue tables follow
     Ba2Ctx c;
     uint32_t *red = smem;                                    // [BA_RED_WORDS], 16 B aligned
-    c.s_m = (float *)(red + BA_RED_WORDS);
-    c.s_rate = c.s_m + N; c.s_mt = c.s_rate + N; c.s_tstd = c.s_mt + N;
-    c.kcnt = (uint32_t *)(c.s_tstd + N);
-    c.hist = c.kcnt + BA2_KC;
+    uint32_t *ctaw = red + BA_RED_WORDS;                     // [16] CTA scalars
+    c.kcnt = ctaw + 16;                                      // [BA2_KC]
+    c.qsh = (volatile uint16_t *)(c.kcnt + BA2_KC);          // [qsh_words * 2]
     c.nwarp = nwarp;
     c.n_ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
-    c.prog = (volatile int *)(c.hist + c.n_ranges * N);
-    uint32_t *ctaw = (uint32_t *)c.prog + 32;                // [16] CTA scalars
-    c.qsh = (volatile uint16_t *)(ctaw + 16);
+    c.prog = (volatile int *)(c.kcnt + BA2_KC + prm.qsh_words);   // [N]
+    c.s_m = (float *)c.prog + N;
+    c.s_rate = c.s_m + N; c.s_mt = c.s_rate + N; c.s_tstd = c.s_mt + N;
+    c.hist = (uint32_t *)(c.s_tstd + N);                     // [n_ranges * N]
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
 
     c.sigma = prm.scales[0]; c.v_t = prm.scales[1]; c.v_u = prm.scales[2];
@@ -425,13 +427,14 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
         // ---- setup -----------------------------------------------------------
         const float *lat_airport = prm.lat_airport + (size_t)p * 2 * N;
         for (int a = tid; a < N; a += nthr) ba2_init_airport(c, a, lat_airport, N);
-        for (int i = tid; i < BA2_KC + c.n_ranges * N; i += nthr) c.kcnt[i] = 0;   // buckets + cursors
+        for (int i = tid; i < BA2_KC; i += nthr) c.kcnt[i] = 0;
+        for (int i = tid; i < c.n_ranges * N; i += nthr) c.hist[i] = 0;
         {
             uint32_t *q32 = (uint32_t *)c.qsh;
             const int nq = (day.n_live + N + 1) / 2;
             for (int i = tid; i < nq; i += nthr) q32[i] = 0xFFFFFFFFu;
         }
-        if (tid < nwarp) c.prog[tid] = day.first_tick - 1;
+        for (int a = tid; a < N; a += nthr) c.prog[a] = day.first_tick - 1;
         if (tid < 16) ctaw[tid] = 0;
         if (c.grow && day.Rd < R)
             for (int i = tid; i < R; i += nthr) c.grow[c.route_base + i] = 0.0f;
@@ -453,24 +456,20 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
         const bool aborted = __syncthreads_or((acc.status & BA_S_OVERFLOW) != 0u) != 0;
 
         // ---- scan: one lane per airport, warps asynchronous ------------------------
-        uint32_t k = (uint32_t)(day.first_tick - 1);
         if (!aborted) {
             Ba2Lane L;
             Ba2Cold Q;
             if (tid < N) ba2_lane_init(c, L, Q, day.lane_airport[tid]);
             else { L.left = 0; L.last = 0; Q.status = 0; }
+            __syncwarp();
             for (;;) {
                 const bool active = L.left != 0u;
                 if (!__any_sync(0xffffffffu, active)) break;
-                if ((int)k >= plan.max_ticks) { Q.status |= BA_S_TICK_CAP; break; }
-                ++k;
-                const float t = c.tick_time[k];                 // model.py:161
-                if (active) ba2_lane_tick(c, L, Q, k, t);
-                __syncwarp();
-                if (lane == 0) { __threadfence_block(); c.prog[warp] = (int)k; }
+                bool adv = false;
+                if (active) adv = ba2_lane_step(c, L, Q);
+                // every lane is waiting for an airport of another warp
+                if (!__any_sync(0xffffffffu, adv)) __nanosleep(500);
             }
-            __syncwarp();
-            if (lane == 0) { __threadfence_block(); c.prog[warp] = BA2_PROG_DONE; }
             acc.status |= Q.status;
             uint32_t last = L.last;
 #pragma unroll
@@ -529,9 +528,17 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
     }
 }
 
+int ba_forward2_qsh_words(int n_airports, int n_live_max)
+{
+    return ((n_live_max + n_airports + 1) / 2 + 3) & ~3;
+}
+
 size_t ba_forward2_smem_bytes(int n_airports, int n_live_max, int block_threads)
 {
-    return (BA_RED_WORDS + ba2_smem_words(n_airports, n_live_max, (block_threads + 31) / 32)) * 4;
+    const int nwarp = (block_threads + 31) / 32;
+    const int ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
+    return ((size_t)BA_RED_WORDS + 16 + BA2_KC + ba_forward2_qsh_words(n_airports, n_live_max) +
+            5 * (size_t)n_airports + (size_t)ranges * n_airports + 4) * 4;
 }
 
 uint64_t ba_forward2_scratch_words(int Fmax, int n_airports) { return ba2_scratch_words(Fmax, n_airports); }

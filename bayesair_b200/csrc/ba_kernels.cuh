@@ -28,6 +28,7 @@ struct BaFwdParams {
     int32_t n_work;
     const unsigned int *n_work_dev; // if set, overrides n_work (device-side count)
     unsigned long long *phase_cycles; // optional [8] per-phase cycle totals (debug, BA_PHASE_PROFILE)
+    int32_t qsh_words;            // ring-less scan: words of the shared q table
 };
 
 struct BaBwdParams {
@@ -50,6 +51,7 @@ cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, bool tracked, in
                               size_t smem, cudaStream_t s);
 // ring-less scan (ba_scan2.cuh)
 size_t ba_forward2_smem_bytes(int n_airports, int n_live_max, int block_threads);
+int ba_forward2_qsh_words(int n_airports, int n_live_max);
 uint64_t ba_forward2_scratch_words(int Fmax, int n_airports);
 int ba_forward2_configure(int block, size_t smem, int device);
 cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, int block, size_t smem, cudaStream_t s);

@@ -63,7 +63,8 @@ struct BaAirport {                    // 80 B static row per (day, airport)
     uint32_t lq_off;                  // ring-less scan (ba_scan2.cuh): first live departure of
                                       //   this airport in BaDayView::lq (one sentinel per airport)
     uint32_t as_off;                  // ... first slot of its arrival list (arr_cnt + 1 slots)
-    uint32_t pad4, pad5;
+    uint32_t slot;                    // lane slot that runs this airport (BaDayView::lane_airport)
+    uint32_t pad5;
     uint32_t turn_off;                // turnaround list (cap = arr_cnt), global scratch
     uint32_t av_off, av_mask;         // aircraft FIFO ring, global scratch
     uint32_t dl_off, dl_mask;         // delayed-departure deque ring, global scratch

@@ -327,6 +327,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
                 H.lane_airport = lanes;
             }
         }
+        for (int sl = 0; sl < N; ++sl) H.airports[(size_t)H.lane_airport[sl]].slot = (uint32_t)sl;
         // idle prefix of the day: ticks before the first scheduled departure do nothing
         // (no pending flight is ready, nothing is queued or in transit) as long as the
         // reserve injection (t >= max_t, model.py:170-174) has not started.

@@ -24,10 +24,12 @@
 //     the whole head group; when an older accumulator cannot be continued (a new group
 //     reaches the head) the fold is replayed from a history of draws that is only written
 //     when a younger group is waiting (rare outside saturated queues).
-//   * Warps run ASYNCHRONOUSLY: a lane needs another airport's state only when a departure
-//     it is waiting for has not been served yet; only then does it wait until every warp has
-//     finished the previous tick (per-warp progress words in shared memory).  The normal
-//     case (the flight left its origin many ticks ago) touches no synchronisation at all.
+//   * Airports run ASYNCHRONOUSLY, each lane on its own clock: a lane needs another
+//     airport's state only when a departure it is waiting for has not been served yet; only
+//     then does it check how far the ORIGIN's lane has come (per-airport progress words in
+//     shared memory) and, if the origin is behind, gives up its turn and retries the tick in
+//     the warp's next round.  The normal case (the flight left its origin many ticks ago)
+//     touches no synchronisation at all; nobody ever spins.
 //
 // The same source is compiled by nvcc (sm_100a kernel) and by g++ (tests/hostemu: one
 // std::thread per warp, same protocol).
@@ -49,9 +51,10 @@
 #define BA2_PROG_DONE 0x7FFFFFFF
 
 // arrival record: list position of the flight's departure (static part of the ordering key;
-// bits [29:18] carry the destination until the split is done), arrival time at the
-// destination (= queue start), arrival service draw, arrival tick (late joiners: the tick at
-// whose end they joined)
+// bits [29:18] carry the destination until the split is done, afterwards the origin
+// airport), arrival time at the destination (= queue start), arrival service draw, arrival
+// tick (late joiners: the tick at whose end they joined; until the split is done bits
+// [27:16] carry the origin airport)
 struct alignas(16) Ba2Rec { uint32_t lpos; float at; float xa; uint32_t ka; };
 
 #if defined(__CUDA_ARCH__)
@@ -71,10 +74,10 @@ BA_DEV void ba2_st_rec(Ba2Rec *p, const Ba2Rec &r) { *p = r; }
 #endif
 #if defined(__CUDACC__)
 #define BA2_FENCE() __threadfence_block()
-#define BA2_PAUSE() __nanosleep(100)
+#define BA2_PAUSE(ns) __nanosleep(ns)
 #else
 #define BA2_FENCE() std::atomic_thread_fence(std::memory_order_seq_cst)
-#define BA2_PAUSE() std::this_thread::yield()
+#define BA2_PAUSE(ns) std::this_thread::yield()
 #endif
 
 struct Ba2Ctx {
@@ -103,7 +106,7 @@ struct Ba2Ctx {
     uint32_t *hist;                           // [n_ranges * N] split cursors
     volatile uint16_t *qsh;                   // [n_live + N] tick at which each live departure
                                               //   left its runway queue (BA2_Q_INVALID: not yet)
-    volatile int *prog;                       // [nwarp] last tick each warp has completed
+    volatile int *prog;                       // [N] last tick each airport has completed
     int nwarp, n_ranges;
     uint32_t range_len;
     // global scratch of this CTA
@@ -147,15 +150,6 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
     c.qarr = g; g += fn;
     c.hx = (float *)g; g += 2 * f;
     c.glog = g;
-}
-
-// shared-memory words: per-airport constants, buckets, split cursors, progress, q table
-static inline size_t ba2_smem_words(int N, int n_live_max, int nwarp)
-{
-    const int ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
-    size_t w = 4 * (size_t)N + BA2_KC + (size_t)ranges * N + 32 /* prog */ + 16;
-    w += ((size_t)n_live_max + N + 1) / 2 + 2;            // u16 table
-    return (w + 3) & ~(size_t)3;
 }
 
 BA_DEV BaFlight ba2_flight(const Ba2Ctx &c, int f)
@@ -241,7 +235,7 @@ BA_DEV void ba2_prologue_flight(Ba2Ctx &c, BaAcc &acc, int f)
         const int lpos = c.pos_live[f];
         c.xdep[lpos] = xd;
         rec.lpos = (uint32_t)lpos | ((uint32_t)d << 18);
-        rec.at = at; rec.xa = xa; rec.ka = (uint32_t)kk;
+        rec.at = at; rec.xa = xa; rec.ka = (uint32_t)kk | ((uint32_t)o << 16);
         BA_ATOMIC_INC(&c.kcnt[kk]);
     }
     ba2_st_rec(c.tmpf + f, rec);
@@ -276,7 +270,7 @@ BA_DEV void ba2_scatter_flight(Ba2Ctx &c, int f)
 {
     const uint32_t ka = c.tmpf[f].ka;
     if (ka == BA2_NONE) return;
-    const uint32_t pos = BA_ATOMIC_INC(&c.kcnt[ka]);
+    const uint32_t pos = BA_ATOMIC_INC(&c.kcnt[ka & 0xFFFFu]);
     c.idx1[pos] = (uint32_t)f;
     const uint32_t d = (c.tmpf[f].lpos >> 18) & 0xFFFu;
     BA_ATOMIC_INC(&c.hist[(pos / c.range_len) * (uint32_t)c.N + d]);
@@ -318,7 +312,8 @@ BA_DEV void ba2_split_range(Ba2Ctx &c, int r, int lane, uint32_t n_arr)
             const uint32_t pos = cur[d] + rank;
             __syncwarp(act);
             if (rank + 1u == (uint32_t)__popc(m)) cur[d] = pos + 1u;
-            rec.lpos &= BA2_LPOS_MASK;
+            rec.lpos = (rec.lpos & BA2_LPOS_MASK) | ((rec.ka >> 16) << 18);
+            rec.ka &= 0xFFFFu;
             ba2_st_rec(c.As + pos, rec);
             __syncwarp(act);
         }
@@ -328,7 +323,8 @@ BA_DEV void ba2_split_range(Ba2Ctx &c, int r, int lane, uint32_t n_arr)
     for (uint32_t i = lo; i < hi; ++i) {
         Ba2Rec rec = c.tmpf[c.idx1[i]];
         const uint32_t d = (rec.lpos >> 18) & 0xFFFu;
-        rec.lpos &= BA2_LPOS_MASK;
+        rec.lpos = (rec.lpos & BA2_LPOS_MASK) | ((rec.ka >> 16) << 18);
+        rec.ka &= 0xFFFFu;
         c.As[cur[d]++] = rec;
     }
 #endif
@@ -359,6 +355,11 @@ struct Ba2Lane {
     uint64_t pk;              // ordering key of As[w - 1] (current block)
     uint32_t left;            // entries still to serve
     uint32_t last;            // tick of the last pop
+    uint32_t k;               // this airport's clock: the tick it is working on / has finished
+    uint32_t wb;              // start of the block of this tick's joiners
+    uint32_t fl;              // bit 0: the tick's joins are under way (a retry resumes them),
+                              // bit 1: somebody joined in this tick
+    uint32_t a;               // the airport
 };
 
 // Rarely touched lane state.  Its address is taken by the out-of-line slow paths, so it
@@ -390,29 +391,11 @@ BA_DEV void ba2_lane_init(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q, int a)
     Q.lw = Q.lr = 0; Q.status = 0; L.pk = 0;
     L.left = (uint32_t)(A.dep_live + A.arr_cnt);
     L.last = 0;
+    L.k = (uint32_t)(c.first_tick - 1); L.wb = L.w; L.fl = 0; L.a = (uint32_t)a;
+    if (L.left == 0u) c.prog[a] = BA2_PROG_DONE;
 }
 
 BA_DEV uint64_t ba2_key(uint32_t q, uint32_t lpos) { return ((uint64_t)q << 32) | (uint64_t)lpos; }
-
-// The departure at `lpos` shows "not served": before the lane may conclude that it was not
-// served by the end of tick km1, every warp must have finished that tick.
-#if defined(__CUDACC__)
-__device__ __noinline__
-#else
-static
-#endif
-uint32_t ba2_resolve(volatile const int *prog, int nwarp, volatile const uint16_t *qsh,
-                     uint32_t lpos, uint32_t km1)
-{
-    for (;;) {
-        bool ok = true;
-        for (int w = 0; w < nwarp; ++w) ok = ok && prog[w] >= (int)km1;
-        if (ok) break;
-        BA2_PAUSE();
-    }
-    BA2_FENCE();
-    return (uint32_t)qsh[lpos];
-}
 
 // Inserts `rec` (its departure was served at tick q <= km1) into the block [wb, w) of this
 // tick's joiners, kept sorted by in-transit list order; the slot As[w] is free.
@@ -427,7 +410,8 @@ void ba2_insert(Ba2Rec *As, volatile const uint16_t *qsh, Ba2Blk &B, Ba2Rec rec,
     uint32_t j = B.w;
     while (j > wb) {
         const Ba2Rec e = ba2_ld_rec(As + j - 1);
-        if (ba2_key((uint32_t)qsh[e.lpos], e.lpos) <= key) break;
+        const uint32_t el = e.lpos & BA2_LPOS_MASK;
+        if (ba2_key((uint32_t)qsh[el], el) <= key) break;
         ba2_st_rec(As + j, e);
         --j;
     }
@@ -444,22 +428,27 @@ __device__ __noinline__
 #else
 static
 #endif
-bool ba2_recheck_deferred(Ba2Rec *As, volatile const uint16_t *qsh, volatile const int *prog,
-                          int nwarp, Ba2Blk &B, uint32_t r, uint32_t km1, uint32_t wb, uint32_t ha)
+uint32_t ba2_recheck_deferred(Ba2Rec *As, volatile const uint16_t *qsh, volatile const int *prog,
+                              Ba2Blk &B, uint32_t r, uint32_t km1, uint32_t wb, uint32_t ha)
 {
-    bool joined = false;
+    uint32_t rc = 0;                                // bit 0: somebody joined, bit 1: blocked
     for (uint32_t i = B.w; i < r; ++i) {
         Ba2Rec rec = ba2_ld_rec(As + i);
-        uint32_t q = (uint32_t)qsh[rec.lpos];
-        if (q == BA2_Q_INVALID) q = ba2_resolve(prog, nwarp, qsh, rec.lpos, km1);
+        const uint32_t lpos = rec.lpos & BA2_LPOS_MASK;
+        uint32_t q = (uint32_t)qsh[lpos];
+        if (q == BA2_Q_INVALID) {
+            if (prog[rec.lpos >> 18] < (int)km1) return rc | 2u;   // the origin is not there yet
+            BA2_FENCE();
+            q = (uint32_t)qsh[lpos];
+        }
         if (q > km1) continue;
         // the vacated slot i takes the (already examined) record at w
         if (i != B.w) ba2_st_rec(As + i, ba2_ld_rec(As + B.w));
         rec.ka = km1;                               // joined at the end of tick km1
-        ba2_insert(As, qsh, B, rec, ba2_key(q, rec.lpos), wb, ha);
-        joined = true;
+        ba2_insert(As, qsh, B, rec, ba2_key(q, lpos), wb, ha);
+        rc |= 1u;
     }
-    return joined;
+    return rc;
 }
 
 // A new group (joining tick p) reaches the head: its waits are the fold of the draws
@@ -487,22 +476,38 @@ float ba2_replay(const uint32_t *glog, const float *hxb, Ba2Cold &Q, uint32_t hx
 }
 
 // One tick of one airport: joins (model.py:181-183,186-196), then update_runway_queue
-// (types/airport.py:86-128).
-BA_DEV void ba2_lane_tick(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q, uint32_t k, float t)
+// (types/airport.py:86-128).  Returns false when the tick cannot be finished yet because a
+// departure this airport is waiting for may still be served by an origin that is behind;
+// the state is consistent and the next call resumes the same tick.
+BA_DEV bool ba2_lane_step(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q)
 {
-    const uint32_t km1 = k - 1u;
-    bool joined = false;
-    const uint32_t wb = L.w;
+    if (!(L.fl & 1u)) {                                      // a new tick starts (model.py:161)
+        if ((int)L.k >= c.max_ticks) {
+            Q.status |= BA_S_TICK_CAP; L.left = 0u;
+            c.prog[L.a] = BA2_PROG_DONE;
+            return true;
+        }
+        L.k += 1u; L.wb = L.w; L.fl = 1u;
+    }
+    const uint32_t k = L.k, km1 = k - 1u;
+    const uint32_t wb = L.wb;
     // ---- arrivals that joined at the end of tick k - 1 ------------------------------
     if (L.w != L.r) {
         Ba2Blk B; B.w = L.w; B.hvalid = L.hvalid; B.pk = L.pk;
-        joined = ba2_recheck_deferred(c.As, c.qsh, c.prog, c.nwarp, B, L.r, km1, wb, L.ha);
+        const uint32_t rc = ba2_recheck_deferred(c.As, c.qsh, c.prog, B, L.r, km1, wb, L.ha);
         L.w = B.w; L.hvalid = B.hvalid; L.pk = B.pk;
+        if (rc & 1u) L.fl |= 2u;
+        if (rc & 2u) return false;
     }
     while (L.n.ka <= km1) {
-        const uint32_t lpos = L.n.lpos;
+        const uint32_t lpos = L.n.lpos & BA2_LPOS_MASK;
         uint32_t q = (uint32_t)c.qsh[lpos];
-        if (q == BA2_Q_INVALID) q = ba2_resolve(c.prog, c.nwarp, c.qsh, lpos, km1);
+        if (q == BA2_Q_INVALID) {
+            // not served yet: final only once the origin has finished tick k - 1
+            if (c.prog[L.n.lpos >> 18] < (int)km1) return false;
+            BA2_FENCE();
+            q = (uint32_t)c.qsh[lpos];
+        }
         if (q <= km1) {
             const uint64_t key = ba2_key(q, lpos);
             if (L.w == L.r && (L.w == wb || key >= L.pk)) {
@@ -513,11 +518,13 @@ BA_DEV void ba2_lane_tick(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q, uint32_t k, f
                 ba2_insert(c.As, c.qsh, B, L.n, key, wb, L.ha);
                 L.w = B.w; L.hvalid = B.hvalid; L.pk = B.pk;
             }
-            joined = true;
+            L.fl |= 2u;
         }
         L.r += 1;
         L.n = ba2_ld_rec(c.As + L.r);
     }
+    bool joined = (L.fl & 2u) != 0u;
+    const float t = c.tick_time[k];
     // ---- departures that become ready at tick k (static calendar run) -----------------
     if (L.rt == k) {
         L.td += L.rcnt;
@@ -551,8 +558,8 @@ BA_DEV void ba2_lane_tick(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q, uint32_t k, f
         }
         if (!(L.A <= t)) break;                              // airport.py:111
         if (L.asg == 1u) {
-            c.wa[L.h.lpos] = L.wacc;
-            if (c.pop_tick) c.qarr[L.h.lpos] = k;
+            c.wa[L.h.lpos & BA2_LPOS_MASK] = L.wacc;
+            if (c.pop_tick) c.qarr[L.h.lpos & BA2_LPOS_MASK] = k;
             L.ha += 1; L.hvalid = 0u;
             if (L.ha < L.w) { L.h = ba2_ld_rec(c.As + L.ha); L.hvalid = 1u; }
         } else {
@@ -571,6 +578,11 @@ BA_DEV void ba2_lane_tick(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q, uint32_t k, f
         lg[0] = k; lg[1] = cnt0;
         Q.lw += 1;
     }
+    // publish: everything this airport serves in tick k is in the q table
+    L.fl = 0u;
+    BA2_FENCE();
+    c.prog[L.a] = L.left != 0u ? (int)k : BA2_PROG_DONE;
+    return true;
 }
 
 // ---------------------------------------------------------------------------
