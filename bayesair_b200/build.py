@@ -13,7 +13,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "_lib")
-LIB_PATH = os.path.join(LIB_DIR, "libbayesair_b200.so")
+# BA_LIB_PATH selects an alternative build of the same library (tuning experiments)
+LIB_PATH = os.environ.get("BA_LIB_PATH") or os.path.join(LIB_DIR, "libbayesair_b200.so")
 SOURCES = ["ba_kernels.cu", "ba_capi.cu", "ba_plan_build.cpp"]
 HEADERS = ["ba_sim.cuh", "ba_scan2.cuh", "ba_kernels.cuh", "ba_plan.h", "ba_plan_build.h",
            os.path.join("..", "..", "include", "bayesair_b200.h")]
@@ -33,6 +34,8 @@ def _nvcc() -> str:
 
 
 def needs_build() -> bool:
+    if os.environ.get("BA_LIB_PATH") and os.path.exists(LIB_PATH):
+        return False
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

@@ -307,8 +307,8 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
 
     static unsigned long long *d_phase = nullptr;
     if (std::getenv("BA_PHASE_PROFILE")) {
-        if (!d_phase) { BA_CUDA(cudaMalloc((void **)&d_phase, 8 * sizeof(unsigned long long))); }
-        BA_CUDA(cudaMemsetAsync(d_phase, 0, 8 * sizeof(unsigned long long), s));
+        if (!d_phase) { BA_CUDA(cudaMalloc((void **)&d_phase, 16 * sizeof(unsigned long long))); }
+        BA_CUDA(cudaMemsetAsync(d_phase, 0, 16 * sizeof(unsigned long long), s));
         prm.phase_cycles = d_phase;
     }
     const bool use_scan2 = pl->scan2_ok && !o.force_exact_lists && !o.force_ring_lists;
@@ -349,7 +349,17 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         BA_CUDA(ba_launch_forward(prm, true, trk, grid, pl->block, pl->smem_exact, s));
         g_launches++;
     }
-    if (prm.phase_cycles) {
+    if (prm.phase_cycles && use_scan2) {
+        unsigned long long h[16];
+        BA_CUDA(cudaStreamSynchronize(s));
+        BA_CUDA(cudaMemcpy(h, prm.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost));
+        const char *names[5] = {"setup", "prologue", "sort", "scan(wall)", "epilogue"};
+        fprintf(stderr, "[BA_PHASE_PROFILE] scan2 cycles per particle-day (warp 0 wall):");
+        for (int i = 0; i < 5; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / (double)n_work);
+        fprintf(stderr, " | own scan time of warps 0-3:");
+        for (int i = 8; i < 12; ++i) fprintf(stderr, " %.0f", (double)h[i] / (double)n_work);
+        fprintf(stderr, "\n");
+    } else if (prm.phase_cycles) {
         unsigned long long h[8];
         BA_CUDA(cudaStreamSynchronize(s));
         BA_CUDA(cudaMemcpy(h, prm.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost));

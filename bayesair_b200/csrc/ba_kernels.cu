@@ -370,12 +370,13 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
     Ba2Ctx c;
     uint32_t *red = smem;                                    // [BA_RED_WORDS], 16 B aligned
     uint32_t *ctaw = red + BA_RED_WORDS;                     // [16] CTA scalars
-    c.kcnt = ctaw + 16;                                      // [BA2_KC]
+    c.bars = (uint64_t *)(ctaw + 16);                        // [32] one mbarrier per warp
+    c.prog = (volatile int *)(ctaw + 16 + 64);               // [32]
+    c.kcnt = ctaw + 16 + 64 + 32;                            // [BA2_KC]
     c.qsh = (volatile uint16_t *)(c.kcnt + BA2_KC);          // [qsh_words * 2]
     c.nwarp = nwarp;
     c.n_ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
-    c.prog = (volatile int *)(c.kcnt + BA2_KC + prm.qsh_words);   // [N]
-    c.s_m = (float *)c.prog + N;
+    c.s_m = (float *)(c.kcnt + BA2_KC + prm.qsh_words);
     c.s_rate = c.s_m + N; c.s_mt = c.s_rate + N; c.s_tstd = c.s_mt + N;
     c.hist = (uint32_t *)(c.s_tstd + N);                     // [n_ranges * N]
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
@@ -394,8 +395,14 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
     c.tick_time = plan.tick_time;
     c.max_ticks = plan.max_ticks;
     c.N = N;
+    bool first_item = true;
+    // optional phase timing (BA_PHASE_PROFILE): lane 0 of every warp reads the SM clock
+    long long pc_last = 0;
+    const bool prof = prm.phase_cycles != nullptr && lane == 0;
+#define BA2_MARK(slot) do { if (prof) { long long now_ = clock64(); atomicAdd(prm.phase_cycles + (slot), (unsigned long long)(now_ - pc_last)); pc_last = now_; } } while (0)
 
     for (;;) {
+        if (prof) pc_last = clock64();
         // ---- next work item ------------------------------------------------
         if (tid == 0) red[BA_RED_WORDS - 1] = atomicAdd(prm.work_counter, 1u);
         __syncthreads();
@@ -434,7 +441,8 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
             const int nq = (day.n_live + N + 1) / 2;
             for (int i = tid; i < nq; i += nthr) q32[i] = 0xFFFFFFFFu;
         }
-        for (int a = tid; a < N; a += nthr) c.prog[a] = day.first_tick - 1;
+        if (tid < nwarp) { c.prog[tid] = day.first_tick - 1; ba2_bar_init(c.bars + tid, first_item); }
+        first_item = false;
         if (tid < 16) ctaw[tid] = 0;
         if (c.grow && day.Rd < R)
             for (int i = tid; i < R; i += nthr) c.grow[c.route_base + i] = 0.0f;
@@ -444,8 +452,10 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
         __syncthreads();
 
         // ---- prologue ----------------------------------------------------------
+        if (warp == 0) BA2_MARK(0);
         for (int f = tid; f < day.F; f += nthr) ba2_prologue_flight(c, acc, f);
         __syncthreads();
+        if (warp == 0) BA2_MARK(1);
         if (tid < 32) ba2_bucket_scan(c, tid);
         __syncthreads();
         for (int f = tid; f < day.F; f += nthr) ba2_scatter_flight(c, f);
@@ -454,29 +464,37 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
         __syncthreads();
         if (warp < c.n_ranges) ba2_split_range(c, warp, lane, n_arr);
         const bool aborted = __syncthreads_or((acc.status & BA_S_OVERFLOW) != 0u) != 0;
+        if (warp == 0) BA2_MARK(2);
+        if (prof) pc_last = clock64();
 
         // ---- scan: one lane per airport, warps asynchronous ------------------------
         if (!aborted) {
             Ba2Lane L;
             Ba2Cold Q;
             if (tid < N) ba2_lane_init(c, L, Q, day.lane_airport[tid]);
-            else { L.left = 0; L.last = 0; Q.status = 0; }
-            __syncwarp();
+            else { L.left = 0; Q.status = 0; }
+            uint32_t k = (uint32_t)(day.first_tick - 1);
             for (;;) {
                 const bool active = L.left != 0u;
                 if (!__any_sync(0xffffffffu, active)) break;
-                bool adv = false;
-                if (active) adv = ba2_lane_step(c, L, Q);
-                // every lane is waiting for an airport of another warp
-                if (!__any_sync(0xffffffffu, adv)) __nanosleep(500);
+                if ((int)k >= plan.max_ticks) { Q.status |= BA_S_TICK_CAP; break; }
+                ++k;
+                const float t = c.tick_time[k];                 // model.py:161
+                if (active) ba2_lane_tick(c, L, Q, k, t);
+                __syncwarp();
+                // publish: everything this warp's airports serve in tick k is in the q table
+                if (lane == 0) { __threadfence_block(); c.prog[warp] = (int)k; ba2_bar_arrive(c.bars + warp); }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block(); c.prog[warp] = BA2_PROG_DONE; ba2_bar_arrive(c.bars + warp);
+                atomicMax(&ctaw[0], k);
             }
             acc.status |= Q.status;
-            uint32_t last = L.last;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-            if (lane == 0) atomicMax(&ctaw[0], last);
         }
+        if (warp < 4) BA2_MARK(8 + warp);   // this warp's own scan time
         __syncthreads();          // every wait of the tape is written
+        if (warp == 0) BA2_MARK(3);
         int tick = (int)ctaw[0];
         if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
 
@@ -525,7 +543,9 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
             }
         }
         __syncthreads();     // red[] and the shared tables are reused by the next item
+        if (warp == 0) BA2_MARK(4);
     }
+#undef BA2_MARK
 }
 
 int ba_forward2_qsh_words(int n_airports, int n_live_max)
@@ -537,8 +557,8 @@ size_t ba_forward2_smem_bytes(int n_airports, int n_live_max, int block_threads)
 {
     const int nwarp = (block_threads + 31) / 32;
     const int ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
-    return ((size_t)BA_RED_WORDS + 16 + BA2_KC + ba_forward2_qsh_words(n_airports, n_live_max) +
-            5 * (size_t)n_airports + (size_t)ranges * n_airports + 4) * 4;
+    return ((size_t)BA_RED_WORDS + 16 + 64 + 32 + BA2_KC + ba_forward2_qsh_words(n_airports, n_live_max) +
+            4 * (size_t)n_airports + (size_t)ranges * n_airports + 4) * 4;
 }
 
 uint64_t ba_forward2_scratch_words(int Fmax, int n_airports) { return ba2_scratch_words(Fmax, n_airports); }

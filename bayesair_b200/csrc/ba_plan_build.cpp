@@ -380,7 +380,8 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
     for (int d = 0; d < n_days; ++d) P.any_track |= (int32_t)out->days[d].view.any_track_t;
     P.max_ticks = max_ticks; P.delta_t = delta_t; P.max_t = max_t;
     // the ring-less scan handles fully bookkeeping-free plans with one lane per airport
-    P.scan2_ok = (!P.any_track && N <= 1024 && Fmax + N < (1 << 18)) ? 1 : 0;
+    // (list positions are 16-bit: flights + airports of a day below 65536)
+    P.scan2_ok = (!P.any_track && N <= 1024 && Fmax + N < (1 << 16)) ? 1 : 0;
     P.grad_stride = P.C * N + R + 3;
     P.days = out->day_views.data();
     P.tick_time = out->tick_time.data();

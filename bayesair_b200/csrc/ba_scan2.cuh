@@ -24,12 +24,12 @@
 //     the whole head group; when an older accumulator cannot be continued (a new group
 //     reaches the head) the fold is replayed from a history of draws that is only written
 //     when a younger group is waiting (rare outside saturated queues).
-//   * Airports run ASYNCHRONOUSLY, each lane on its own clock: a lane needs another
+//   * Warps run ASYNCHRONOUSLY (the lanes of a warp share a clock): a lane needs another
 //     airport's state only when a departure it is waiting for has not been served yet; only
-//     then does it check how far the ORIGIN's lane has come (per-airport progress words in
-//     shared memory) and, if the origin is behind, gives up its turn and retries the tick in
-//     the warp's next round.  The normal case (the flight left its origin many ticks ago)
-//     touches no synchronisation at all; nobody ever spins.
+//     then does it look at how far the ORIGIN's warp has come (per-warp progress words in
+//     shared memory) and, if that warp is behind, suspends on the origin warp's mbarrier
+//     (one phase per tick) -- nobody spins.  The normal case (the flight left its origin
+//     many ticks ago) touches no synchronisation at all.
 //
 // The same source is compiled by nvcc (sm_100a kernel) and by g++ (tests/hostemu: one
 // std::thread per warp, same protocol).
@@ -45,16 +45,15 @@
 #define BA2_KC 768                    // arrival-tick buckets kept in shared memory
 #endif
 #define BA2_MAX_RANGES 8              // ranges (= warps) of the stable split by destination
-#define BA2_LPOS_MASK 0x3FFFFu
 #define BA2_Q_INVALID 0xFFFFu         // departure not served yet
 #define BA2_NONE 0xFFFFFFFFu
 #define BA2_PROG_DONE 0x7FFFFFFF
 
-// arrival record: list position of the flight's departure (static part of the ordering key;
-// bits [29:18] carry the destination until the split is done, afterwards the origin
-// airport), arrival time at the destination (= queue start), arrival service draw, arrival
-// tick (late joiners: the tick at whose end they joined; until the split is done bits
-// [27:16] carry the origin airport)
+// arrival record: list position of the flight's departure (16 bits: the static part of the
+// ordering key; the high half carries the destination until the split is done, afterwards the
+// warp that runs the origin airport), arrival time at the destination (= queue start),
+// arrival service draw, arrival tick (late joiners: the tick at whose end they joined; until
+// the split is done the high half carries the origin's warp)
 struct alignas(16) Ba2Rec { uint32_t lpos; float at; float xa; uint32_t ka; };
 
 #if defined(__CUDA_ARCH__)
@@ -71,6 +70,11 @@ BA_DEV void ba2_st_rec(Ba2Rec *p, const Ba2Rec &r)
 #else
 BA_DEV Ba2Rec ba2_ld_rec(const Ba2Rec *p) { return *p; }
 BA_DEV void ba2_st_rec(Ba2Rec *p, const Ba2Rec &r) { *p = r; }
+#endif
+#if defined(__CUDA_ARCH__) && !defined(BA2_NO_PREFETCH)
+#define BA2_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#else
+#define BA2_PREFETCH(p) ((void)0)
 #endif
 #if defined(__CUDACC__)
 #define BA2_FENCE() __threadfence_block()
@@ -106,7 +110,8 @@ struct Ba2Ctx {
     uint32_t *hist;                           // [n_ranges * N] split cursors
     volatile uint16_t *qsh;                   // [n_live + N] tick at which each live departure
                                               //   left its runway queue (BA2_Q_INVALID: not yet)
-    volatile int *prog;                       // [N] last tick each airport has completed
+    volatile int *prog;                       // [nwarp] last tick each warp has completed
+    uint64_t *bars;                           // [nwarp] mbarrier of each warp (one phase per tick)
     int nwarp, n_ranges;
     uint32_t range_len;
     // global scratch of this CTA
@@ -114,8 +119,8 @@ struct Ba2Ctx {
     Ba2Rec *tmpf;                             // [F] prologue: records by flight
     uint32_t *idx1;                           // [F] prologue: flights sorted by arrival tick
     float *xdep;                              // [n_live + N] departure service draw by lpos
-    float *wd, *wa;                           // [n_live + N] tape: total wait of the departure /
-                                              //   arrival entry of the flight at lpos
+    float *wt;                                // [2 (n_live + N)] tape: total wait of the departure
+                                              //   (even) / arrival (odd) entry of the flight at lpos
     uint32_t *qarr;                           // [n_live + N] tick at which the arrival entry left
     float *hx;                                // [2 F] history of draws by assignment index
     uint32_t *glog;                           // [4 F] (tick, assignments before it) of ticks that
@@ -145,8 +150,7 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
     g += 4 * f;
     c.idx1 = g; g += f;
     c.xdep = (float *)g; g += fn;
-    c.wd = (float *)g; g += fn;
-    c.wa = (float *)g; g += fn;
+    c.wt = (float *)g; g += 2 * fn;
     c.qarr = g; g += fn;
     c.hx = (float *)g; g += 2 * f;
     c.glog = g;
@@ -234,8 +238,8 @@ BA_DEV void ba2_prologue_flight(Ba2Ctx &c, BaAcc &acc, int f)
         if (kk < c.first_tick) kk = c.first_tick;
         const int lpos = c.pos_live[f];
         c.xdep[lpos] = xd;
-        rec.lpos = (uint32_t)lpos | ((uint32_t)d << 18);
-        rec.at = at; rec.xa = xa; rec.ka = (uint32_t)kk | ((uint32_t)o << 16);
+        rec.lpos = (uint32_t)lpos | ((uint32_t)d << 16);
+        rec.at = at; rec.xa = xa; rec.ka = (uint32_t)kk | ((c.ap[o].slot >> 5) << 16);
         BA_ATOMIC_INC(&c.kcnt[kk]);
     }
     ba2_st_rec(c.tmpf + f, rec);
@@ -272,7 +276,7 @@ BA_DEV void ba2_scatter_flight(Ba2Ctx &c, int f)
     if (ka == BA2_NONE) return;
     const uint32_t pos = BA_ATOMIC_INC(&c.kcnt[ka & 0xFFFFu]);
     c.idx1[pos] = (uint32_t)f;
-    const uint32_t d = (c.tmpf[f].lpos >> 18) & 0xFFFu;
+    const uint32_t d = c.tmpf[f].lpos >> 16;
     BA_ATOMIC_INC(&c.hist[(pos / c.range_len) * (uint32_t)c.N + d]);
 }
 
@@ -306,13 +310,13 @@ BA_DEV void ba2_split_range(Ba2Ctx &c, int r, int lane, uint32_t n_arr)
         if (ok) {
             const uint32_t f = c.idx1[i];
             Ba2Rec rec = ba2_ld_rec(c.tmpf + f);
-            const uint32_t d = (rec.lpos >> 18) & 0xFFFu;
+            const uint32_t d = rec.lpos >> 16;
             const uint32_t m = __match_any_sync(act, d);
             const uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
             const uint32_t pos = cur[d] + rank;
             __syncwarp(act);
             if (rank + 1u == (uint32_t)__popc(m)) cur[d] = pos + 1u;
-            rec.lpos = (rec.lpos & BA2_LPOS_MASK) | ((rec.ka >> 16) << 18);
+            rec.lpos = (rec.lpos & 0xFFFFu) | (rec.ka & 0xFFFF0000u);
             rec.ka &= 0xFFFFu;
             ba2_st_rec(c.As + pos, rec);
             __syncwarp(act);
@@ -322,8 +326,8 @@ BA_DEV void ba2_split_range(Ba2Ctx &c, int r, int lane, uint32_t n_arr)
     (void)lane;
     for (uint32_t i = lo; i < hi; ++i) {
         Ba2Rec rec = c.tmpf[c.idx1[i]];
-        const uint32_t d = (rec.lpos >> 18) & 0xFFFu;
-        rec.lpos = (rec.lpos & BA2_LPOS_MASK) | ((rec.ka >> 16) << 18);
+        const uint32_t d = rec.lpos >> 16;
+        rec.lpos = (rec.lpos & 0xFFFFu) | (rec.ka & 0xFFFF0000u);
         rec.ka &= 0xFFFFu;
         c.As[cur[d]++] = rec;
     }
@@ -331,17 +335,16 @@ BA_DEV void ba2_split_range(Ba2Ctx &c, int r, int lane, uint32_t n_arr)
 }
 
 // ---------------------------------------------------------------------------
-// SCAN: one lane per airport
+// SCAN: one lane per airport, the lanes of a warp on a common clock, warps asynchronous
 // ---------------------------------------------------------------------------
 struct Ba2Lane {
     // arrival list of this airport: [as0, ha) served, [ha, w) queued (FIFO order),
     // [w, r) deferred (arrival tick passed, departure not served), [r, ...) unexamined
     uint32_t r, w, ha;
-    Ba2Rec n;                 // As[r], fetched ahead
-    Ba2Rec h;                 // As[ha] when hvalid
-    uint32_t hvalid;
-    // departures: [.., hd) served, [hd, td) queued, next calendar run (tick rt, rcnt records)
-    uint32_t hd, td, rp, rt, rcnt;
+    uint32_t n_w0, n_ka;      // first and last word of As[r], fetched ahead
+    Ba2Rec h;                 // As[ha] (h.ka == BA2_NONE: not loaded)
+    // departures: [.., hd) served, [hd, td) queued; next calendar run (tick << 16 | records)
+    uint32_t hd, td, rp, rtc;
     uint32_t dk;              // ready tick of lq[hd]
     float dqs, dx;            // its queue start and service draw
     // service state
@@ -351,51 +354,100 @@ struct Ba2Lane {
     uint32_t g;               // joining tick of the group the accumulator belongs to
     uint32_t gnew;            // joining tick of the youngest group in the queue
     uint32_t cnt;             // assignments made so far
-    uint32_t hxo;             // this airport's slice of hx / glog
-    uint64_t pk;              // ordering key of As[w - 1] (current block)
+    uint32_t pk;              // ordering key of As[w - 1] (current block)
     uint32_t left;            // entries still to serve
-    uint32_t last;            // tick of the last pop
-    uint32_t k;               // this airport's clock: the tick it is working on / has finished
-    uint32_t wb;              // start of the block of this tick's joiners
-    uint32_t fl;              // bit 0: the tick's joins are under way (a retry resumes them),
-                              // bit 1: somebody joined in this tick
-    uint32_t a;               // the airport
 };
 
 // Rarely touched lane state.  Its address is taken by the out-of-line slow paths, so it
 // lives in local memory; everything in Ba2Lane stays in registers.
 struct Ba2Cold {
+    uint32_t hxo;             // this airport's slice of hx / glog
     uint32_t lw, lr;          // log of (tick, cnt) pairs: written / consumed
     uint32_t status;
 };
 
 // Block of this tick's joiners while an out-of-line path works on it.
 struct Ba2Blk {
-    uint32_t w, hvalid;
-    uint64_t pk;
+    uint32_t w, hka, pk;
 };
 
 BA_DEV void ba2_lane_init(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q, int a)
 {
     const BaAirport A = c.ap[a];
     L.r = L.w = L.ha = A.as_off;
-    L.n = ba2_ld_rec(c.As + L.r);
-    L.hvalid = 0; L.h = L.n;
+    { const Ba2Rec n = ba2_ld_rec(c.As + L.r); L.n_w0 = n.lpos; L.n_ka = n.ka; }
+    L.h.lpos = 0; L.h.at = 0.0f; L.h.xa = 0.0f; L.h.ka = BA2_NONE;
     L.hd = L.td = A.lq_off;
     L.rp = (uint32_t)c.drun_off[a];
-    L.rt = c.drun[2 * L.rp]; L.rcnt = c.drun[2 * L.rp + 1] & 0xFFFFu;
+    L.rtc = (c.drun[2 * L.rp] << 16) | (c.drun[2 * L.rp + 1] & 0xFFFFu);
     { const BaLiveDep q = c.lq[L.hd]; L.dk = q.tick; L.dqs = q.qstart; }
     L.dx = c.xdep[L.hd];
     L.asg = 0; L.A = 0.0f; L.wacc = 0.0f; L.g = BA2_NONE; L.gnew = BA2_NONE; L.cnt = 0;
-    L.hxo = A.lq_off + A.as_off - 2u * (uint32_t)a;
+    Q.hxo = A.lq_off + A.as_off - 2u * (uint32_t)a;
     Q.lw = Q.lr = 0; Q.status = 0; L.pk = 0;
     L.left = (uint32_t)(A.dep_live + A.arr_cnt);
-    L.last = 0;
-    L.k = (uint32_t)(c.first_tick - 1); L.wb = L.w; L.fl = 0; L.a = (uint32_t)a;
-    if (L.left == 0u) c.prog[a] = BA2_PROG_DONE;
 }
 
-BA_DEV uint64_t ba2_key(uint32_t q, uint32_t lpos) { return ((uint64_t)q << 32) | (uint64_t)lpos; }
+// in-transit list order of an arrival: (tick at which its departure was served, origin,
+// position in the origin's queue) = (q, list position of the departure)
+BA_DEV uint32_t ba2_key(uint32_t q, uint32_t lpos) { return (q << 16) | lpos; }
+
+// ---- waiting for another warp ----------------------------------------------------------
+// Every warp owns an mbarrier it arrives on once per tick (after publishing the tick in
+// prog[]); a warp that needs another one to get further suspends on that barrier's current
+// phase instead of spinning.  The host emulation yields.
+#if defined(__CUDACC__)
+BA_DEV void ba2_bar_init(uint64_t *bar, int first)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    if (!first) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+}
+BA_DEV void ba2_bar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+// suspends until the phase of that parity has completed (the hardware wakes the thread on
+// any barrier traffic of the SM or after the time limit: stay in the short loop; bounded,
+// the caller re-reads the progress word and comes back)
+BA_DEV void ba2_bar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    for (int i = 0; i < 64; ++i) {
+        uint32_t ok;
+        asm volatile(
+            "{\n .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            " selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity), "r"(100000u) : "memory");
+        if (ok) break;
+    }
+}
+#else
+BA_DEV void ba2_bar_init(uint64_t *, int) {}
+BA_DEV void ba2_bar_arrive(uint64_t *) {}
+BA_DEV void ba2_bar_wait(uint64_t *, uint32_t) { std::this_thread::yield(); }
+#endif
+
+// The departure behind `word` (list position | origin's warp << 16) shows "not served".
+// That is final for tick km1 only once the origin's warp has finished that tick.
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+static
+#endif
+uint32_t ba2_resolve(volatile const int *prog, uint64_t *bars, volatile const uint16_t *qsh,
+                     uint32_t word, uint32_t km1, uint32_t t0)
+{
+    const uint32_t lpos = word & 0xFFFFu, ow = word >> 16;
+    for (;;) {
+        const int p = prog[ow];
+        BA2_FENCE();
+        const uint32_t q = (uint32_t)qsh[lpos];
+        if (q != BA2_Q_INVALID || p >= (int)km1) return q;
+        // the origin's warp is working on tick p + 1: suspend until that phase completes
+        ba2_bar_wait(bars + ow, ((uint32_t)p - t0) & 1u);
+    }
+}
 
 // Inserts `rec` (its departure was served at tick q <= km1) into the block [wb, w) of this
 // tick's joiners, kept sorted by in-transit list order; the slot As[w] is free.
@@ -404,20 +456,20 @@ __device__ __noinline__
 #else
 static
 #endif
-void ba2_insert(Ba2Rec *As, volatile const uint16_t *qsh, Ba2Blk &B, Ba2Rec rec, uint64_t key,
+void ba2_insert(Ba2Rec *As, volatile const uint16_t *qsh, Ba2Blk &B, Ba2Rec rec, uint32_t key,
                 uint32_t wb, uint32_t ha)
 {
     uint32_t j = B.w;
     while (j > wb) {
         const Ba2Rec e = ba2_ld_rec(As + j - 1);
-        const uint32_t el = e.lpos & BA2_LPOS_MASK;
+        const uint32_t el = e.lpos & 0xFFFFu;
         if (ba2_key((uint32_t)qsh[el], el) <= key) break;
         ba2_st_rec(As + j, e);
         --j;
     }
     ba2_st_rec(As + j, rec);
     if (key > B.pk || B.w == wb) B.pk = key;
-    if (ha >= wb) B.hvalid = 0;
+    if (ha >= wb) B.hka = BA2_NONE;                 // the cached head may have moved
     B.w += 1;
 }
 
@@ -428,27 +480,24 @@ __device__ __noinline__
 #else
 static
 #endif
-uint32_t ba2_recheck_deferred(Ba2Rec *As, volatile const uint16_t *qsh, volatile const int *prog,
-                              Ba2Blk &B, uint32_t r, uint32_t km1, uint32_t wb, uint32_t ha)
+bool ba2_recheck_deferred(Ba2Rec *As, volatile const uint16_t *qsh, volatile const int *prog,
+                          uint64_t *bars, Ba2Blk &B, uint32_t r, uint32_t km1, uint32_t wb,
+                          uint32_t ha, uint32_t t0)
 {
-    uint32_t rc = 0;                                // bit 0: somebody joined, bit 1: blocked
+    bool joined = false;
     for (uint32_t i = B.w; i < r; ++i) {
         Ba2Rec rec = ba2_ld_rec(As + i);
-        const uint32_t lpos = rec.lpos & BA2_LPOS_MASK;
+        const uint32_t lpos = rec.lpos & 0xFFFFu;
         uint32_t q = (uint32_t)qsh[lpos];
-        if (q == BA2_Q_INVALID) {
-            if (prog[rec.lpos >> 18] < (int)km1) return rc | 2u;   // the origin is not there yet
-            BA2_FENCE();
-            q = (uint32_t)qsh[lpos];
-        }
+        if (q == BA2_Q_INVALID) q = ba2_resolve(prog, bars, qsh, rec.lpos, km1, t0);
         if (q > km1) continue;
         // the vacated slot i takes the (already examined) record at w
         if (i != B.w) ba2_st_rec(As + i, ba2_ld_rec(As + B.w));
         rec.ka = km1;                               // joined at the end of tick km1
         ba2_insert(As, qsh, B, rec, ba2_key(q, lpos), wb, ha);
-        rc |= 1u;
+        joined = true;
     }
-    return rc;
+    return joined;
 }
 
 // A new group (joining tick p) reaches the head: its waits are the fold of the draws
@@ -458,78 +507,64 @@ __device__ __noinline__
 #else
 static
 #endif
-float ba2_replay(const uint32_t *glog, const float *hxb, Ba2Cold &Q, uint32_t hxo, uint32_t cnt,
-                 uint32_t p, uint32_t k, uint32_t cnt0)
+float ba2_replay(const uint32_t *glog, const float *hxb, Ba2Cold &Q, uint32_t cnt, uint32_t p,
+                 uint32_t k, uint32_t cnt0)
 {
     uint32_t lo = cnt0;
     if (p != k) {
-        const uint32_t *lg = glog + 2u * hxo;
+        const uint32_t *lg = glog + 2u * Q.hxo;
         while (Q.lr < Q.lw && lg[2u * Q.lr] != p) Q.lr += 1;
         if (Q.lr == Q.lw) { Q.status |= BA_S_INTERNAL; return 0.0f; }
         lo = lg[2u * Q.lr + 1u];
         Q.lr += 1;
     }
     float w = 0.0f;
-    const float *hx = hxb + hxo;
+    const float *hx = hxb + Q.hxo;
     for (uint32_t j = lo; j < cnt; ++j) w = BA_ADD(w, hx[j]);
     return w;
 }
 
 // One tick of one airport: joins (model.py:181-183,186-196), then update_runway_queue
-// (types/airport.py:86-128).  Returns false when the tick cannot be finished yet because a
-// departure this airport is waiting for may still be served by an origin that is behind;
-// the state is consistent and the next call resumes the same tick.
-BA_DEV bool ba2_lane_step(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q)
+// (types/airport.py:86-128).
+BA_DEV void ba2_lane_tick(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q, uint32_t k, float t)
 {
-    if (!(L.fl & 1u)) {                                      // a new tick starts (model.py:161)
-        if ((int)L.k >= c.max_ticks) {
-            Q.status |= BA_S_TICK_CAP; L.left = 0u;
-            c.prog[L.a] = BA2_PROG_DONE;
-            return true;
-        }
-        L.k += 1u; L.wb = L.w; L.fl = 1u;
-    }
-    const uint32_t k = L.k, km1 = k - 1u;
-    const uint32_t wb = L.wb;
+    const uint32_t km1 = k - 1u;
+    bool joined = false;
+    const uint32_t wb = L.w;
     // ---- arrivals that joined at the end of tick k - 1 ------------------------------
     if (L.w != L.r) {
-        Ba2Blk B; B.w = L.w; B.hvalid = L.hvalid; B.pk = L.pk;
-        const uint32_t rc = ba2_recheck_deferred(c.As, c.qsh, c.prog, B, L.r, km1, wb, L.ha);
-        L.w = B.w; L.hvalid = B.hvalid; L.pk = B.pk;
-        if (rc & 1u) L.fl |= 2u;
-        if (rc & 2u) return false;
+        Ba2Blk B; B.w = L.w; B.hka = L.h.ka; B.pk = L.pk;
+        joined = ba2_recheck_deferred(c.As, c.qsh, c.prog, c.bars, B, L.r, km1, wb, L.ha,
+                                      (uint32_t)(c.first_tick - 1));
+        L.w = B.w; L.h.ka = B.hka; L.pk = B.pk;
     }
-    while (L.n.ka <= km1) {
-        const uint32_t lpos = L.n.lpos & BA2_LPOS_MASK;
+    while (L.n_ka <= km1) {
+        const uint32_t lpos = L.n_w0 & 0xFFFFu;
         uint32_t q = (uint32_t)c.qsh[lpos];
-        if (q == BA2_Q_INVALID) {
-            // not served yet: final only once the origin has finished tick k - 1
-            if (c.prog[L.n.lpos >> 18] < (int)km1) return false;
-            BA2_FENCE();
-            q = (uint32_t)c.qsh[lpos];
-        }
+        if (q == BA2_Q_INVALID)
+            q = ba2_resolve(c.prog, c.bars, c.qsh, L.n_w0, km1, (uint32_t)(c.first_tick - 1));
         if (q <= km1) {
-            const uint64_t key = ba2_key(q, lpos);
+            const uint32_t key = ba2_key(q, lpos);
             if (L.w == L.r && (L.w == wb || key >= L.pk)) {
                 L.pk = key; L.w += 1;                        // already in place
             } else {
+                const Ba2Rec rec = ba2_ld_rec(c.As + L.r);
                 if (L.w != L.r) ba2_st_rec(c.As + L.r, ba2_ld_rec(c.As + L.w));
-                Ba2Blk B; B.w = L.w; B.hvalid = L.hvalid; B.pk = L.pk;
-                ba2_insert(c.As, c.qsh, B, L.n, key, wb, L.ha);
-                L.w = B.w; L.hvalid = B.hvalid; L.pk = B.pk;
+                Ba2Blk B; B.w = L.w; B.hka = L.h.ka; B.pk = L.pk;
+                ba2_insert(c.As, c.qsh, B, rec, key, wb, L.ha);
+                L.w = B.w; L.h.ka = B.hka; L.pk = B.pk;
             }
-            L.fl |= 2u;
+            joined = true;
         }
         L.r += 1;
-        L.n = ba2_ld_rec(c.As + L.r);
+        { const Ba2Rec n = ba2_ld_rec(c.As + L.r); L.n_w0 = n.lpos; L.n_ka = n.ka; }
+        BA2_PREFETCH(c.As + L.r + 2);
     }
-    bool joined = (L.fl & 2u) != 0u;
-    const float t = c.tick_time[k];
     // ---- departures that become ready at tick k (static calendar run) -----------------
-    if (L.rt == k) {
-        L.td += L.rcnt;
+    if ((L.rtc >> 16) == k) {
+        L.td += L.rtc & 0xFFFFu;
         L.rp += 1;
-        L.rt = c.drun[2 * L.rp]; L.rcnt = c.drun[2 * L.rp + 1] & 0xFFFFu;
+        L.rtc = (c.drun[2 * L.rp] << 16) | (c.drun[2 * L.rp + 1] & 0xFFFFu);
         joined = true;
     }
     if (joined) L.gnew = k;
@@ -539,7 +574,7 @@ BA_DEV bool ba2_lane_step(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q)
         if (L.asg == 0u) {
             const bool ha_ok = L.ha < L.w, hd_ok = L.hd < L.td;
             if (!ha_ok && !hd_ok) break;
-            if (ha_ok && !L.hvalid) { L.h = ba2_ld_rec(c.As + L.ha); L.hvalid = 1u; }
+            if (ha_ok && L.h.ka == BA2_NONE) L.h = ba2_ld_rec(c.As + L.ha);
             const uint32_t pa = ha_ok ? L.h.ka + 1u : BA2_NONE;
             const uint32_t pd = hd_ok ? L.dk : BA2_NONE;
             const bool arr = pa <= pd;                       // arrivals first on ties
@@ -547,10 +582,10 @@ BA_DEV bool ba2_lane_step(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q)
             const float x = arr ? L.h.xa : L.dx;
             const float qs = arr ? L.h.at : L.dqs;
             if (p != L.g) {
-                L.wacc = (p == k && L.cnt == cnt0) ? 0.0f : ba2_replay(c.glog, c.hx, Q, L.hxo, L.cnt, p, k, cnt0);
+                L.wacc = (p == k && L.cnt == cnt0) ? 0.0f : ba2_replay(c.glog, c.hx, Q, L.cnt, p, k, cnt0);
                 L.g = p;
             }
-            if (L.gnew != p) c.hx[L.hxo + L.cnt] = x;        // a younger group is waiting
+            if (L.gnew != p) c.hx[Q.hxo + L.cnt] = x;        // a younger group is waiting
             L.cnt += 1;
             L.wacc = BA_ADD(L.wacc, x);                      // airport.py:150-153
             L.A = BA_ADD(qs, L.wacc);                        // airport.py:156
@@ -558,31 +593,30 @@ BA_DEV bool ba2_lane_step(const Ba2Ctx &c, Ba2Lane &L, Ba2Cold &Q)
         }
         if (!(L.A <= t)) break;                              // airport.py:111
         if (L.asg == 1u) {
-            c.wa[L.h.lpos & BA2_LPOS_MASK] = L.wacc;
-            if (c.pop_tick) c.qarr[L.h.lpos & BA2_LPOS_MASK] = k;
-            L.ha += 1; L.hvalid = 0u;
-            if (L.ha < L.w) { L.h = ba2_ld_rec(c.As + L.ha); L.hvalid = 1u; }
+            const uint32_t lpos = L.h.lpos & 0xFFFFu;
+            c.wt[2u * lpos + 1u] = L.wacc;
+            if (c.pop_tick) c.qarr[lpos] = k;
+            L.ha += 1;
+            if (L.ha < L.w) L.h = ba2_ld_rec(c.As + L.ha); else L.h.ka = BA2_NONE;
+            BA2_PREFETCH(c.As + L.ha + 2);
         } else {
-            c.wd[L.hd] = L.wacc;
+            c.wt[2u * L.hd] = L.wacc;
             c.qsh[L.hd] = (uint16_t)k;
             L.hd += 1;
             { const BaLiveDep q = c.lq[L.hd]; L.dk = q.tick; L.dqs = q.qstart; }
             L.dx = c.xdep[L.hd];
+            BA2_PREFETCH(c.lq + L.hd + 4);
+            BA2_PREFETCH(c.xdep + L.hd + 8);
         }
-        L.left -= 1; L.last = k; L.asg = 0u;
+        L.left -= 1; L.asg = 0u;
     }
     // a tick that ends with entries still waiting behind an assigned head: the entries that
     // joined in it will need the number of assignments made before it (ba2_replay)
     if (joined && L.asg != 0u) {
-        uint32_t *lg = c.glog + 2u * (L.hxo + Q.lw);
+        uint32_t *lg = c.glog + 2u * (Q.hxo + Q.lw);
         lg[0] = k; lg[1] = cnt0;
         Q.lw += 1;
     }
-    // publish: everything this airport serves in tick k is in the q table
-    L.fl = 0u;
-    BA2_FENCE();
-    c.prog[L.a] = L.left != 0u ? (int)k : BA2_PROG_DONE;
-    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -630,7 +664,7 @@ BA_DEV void ba2_epilogue_flight(Ba2Ctx &c, BaAcc &acc, int f)
     // (airport.py:144-147,175-182)
     const float rate_o = c.s_rate[o];
     const float xd = c.value_mode ? nz.e_dep : BA_DIV(nz.e_dep, rate_o);
-    const float wdep = c.wd[lpos];
+    const float wdep = c.wt[2 * lpos];
     const float qstart_d = fmaxf(0.0f, fl.sched_dep);
     const float mu_d = BA_ADD(qstart_d, wdep);              // queue_start + total_wait
     const float dy_d = y_dep - mu_d;
@@ -642,7 +676,7 @@ BA_DEV void ba2_epilogue_flight(Ba2Ctx &c, BaAcc &acc, int f)
     const float sc = BA_MUL(T, c.v_t);
     const float tau = c.value_mode ? nz.eps_travel : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
     const float qstart_a = BA_ADD(y_dep, tau);
-    const float warr = c.wa[lpos];
+    const float warr = c.wt[2 * lpos + 1];
     const float mu_a = BA_ADD(qstart_a, warr);
     const float dy_a = y_arr - mu_a;
     const float xa = c.value_mode ? nz.e_arr : BA_DIV(nz.e_arr, rate_d);

@@ -286,16 +286,17 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     const int nthr = ((N + 31) / 32) * 32, nwarp = nthr / 32;
     const size_t pd = (size_t)p * D + d;
     const int qsh_words = ((day.n_live + N + 1) / 2 + 3) & ~3;
-    std::vector<uint32_t> sh(16 + BA2_KC + qsh_words + 5 * N + BA2_MAX_RANGES * N + 64, 0);
+    std::vector<uint32_t> sh(16 + 64 + 32 + BA2_KC + qsh_words + 4 * N + BA2_MAX_RANGES * N + 64, 0);
     std::vector<uint32_t> gs(ba2_scratch_words(day.F, N) + 16, 0xDEADBEEFu);
     Ba2Ctx c;
     memset(&c, 0, sizeof(c));
-    c.kcnt = sh.data() + 16;
+    c.bars = (uint64_t *)(sh.data() + 16);
+    c.prog = (volatile int *)(sh.data() + 16 + 64);
+    c.kcnt = sh.data() + 16 + 64 + 32;
     c.qsh = (volatile uint16_t *)(c.kcnt + BA2_KC);
     c.nwarp = nwarp;
     c.n_ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
-    c.prog = (volatile int *)(c.kcnt + BA2_KC + qsh_words);
-    c.s_m = (float *)c.prog + N;
+    c.s_m = (float *)(c.kcnt + BA2_KC + qsh_words);
     c.s_rate = c.s_m + N; c.s_mt = c.s_rate + N; c.s_tstd = c.s_mt + N;
     c.hist = (uint32_t *)(c.s_tstd + N);
     c.sigma = scales[0]; c.v_t = scales[1]; c.v_u = scales[2];
@@ -326,7 +327,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     for (int i = 0; i < BA2_KC; ++i) c.kcnt[i] = 0;
     for (int i = 0; i < c.n_ranges * N; ++i) c.hist[i] = 0;
     for (int i = 0; i < day.n_live + N; ++i) ((uint16_t *)c.qsh)[i] = 0xFFFFu;
-    for (int a = 0; a < N; ++a) c.prog[a] = day.first_tick - 1;
+    for (int w = 0; w < nwarp; ++w) c.prog[w] = day.first_tick - 1;
     if (c.grow) for (int i = 0; i < R; ++i) c.grow[c.route_base + i] = 0.0f;
     if (c.pop_tick) for (int i = 2 * day.F; i < 2 * plan.Fmax; ++i) c.pop_tick[i] = -1;
 
@@ -356,31 +357,33 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
                 const int tid = 32 * w + l;
                 valid[l] = tid < N;
                 if (valid[l]) ba2_lane_init(c, L[l], Q[l], day.lane_airport[tid]);
-                else { L[l].left = 0; L[l].last = 0; Q[l].status = 0; }
+                else { L[l].left = 0; Q[l].status = 0; }
             }
+            uint32_t k = (uint32_t)(day.first_tick - 1);
             for (;;) {
                 bool any = false;
                 for (int l = 0; l < 32; ++l) any = any || L[l].left != 0u;
                 if (!any) break;
+                if ((int)k >= plan.max_ticks) { st_w[w] |= BA_S_TICK_CAP; break; }
+                ++k;
+                const float t = c.tick_time[k];
                 // random stalls: let the warps drift apart
                 if (shuffle_seed > 1 && (wr() % 16u) == 0u)
                     std::this_thread::sleep_for(std::chrono::microseconds(wr() % 200u));
                 int order[32];
                 for (int l = 0; l < 32; ++l) order[l] = l;
                 if (shuffle_seed) std::shuffle(order, order + 32, wr);
-                bool adv = false;
                 for (int i = 0; i < 32; ++i) {
                     const int l = order[i];
-                    // odd seeds: a lane may run several ticks ahead of its warp
-                    int rounds = (shuffle_seed & 1u) ? 1 + (int)(wr() % 4u) : 1;
-                    while (rounds-- > 0 && L[l].left != 0u && ba2_lane_step(c, L[l], Q[l])) adv = true;
+                    if (L[l].left != 0u) ba2_lane_tick(c, L[l], Q[l], k, t);
                 }
-                if (!adv) std::this_thread::yield();
+                BA2_FENCE();
+                c.prog[w] = (int)k;
             }
-            for (int l = 0; l < 32; ++l) {
-                last_w[w] = std::max(last_w[w], L[l].last);
-                st_w[w] |= Q[l].status;
-            }
+            BA2_FENCE();
+            c.prog[w] = BA2_PROG_DONE;
+            last_w[w] = k;
+            for (int l = 0; l < 32; ++l) st_w[w] |= Q[l].status;
         };
         std::vector<std::thread> th;
         for (int w = 0; w < nwarp; ++w) th.emplace_back(warp_fn, w);
