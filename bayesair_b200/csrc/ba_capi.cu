@@ -44,7 +44,6 @@ struct BaPlan {
     size_t smem_scan2 = 0;
     int grid_scan2 = 0;
     uint64_t stride_scan2 = 0;
-    int qsh_words = 0;
     uint32_t *d_scratch = nullptr;
     uint64_t stride_fast = 0, stride_exact = 0;
     unsigned int *d_counters = nullptr;  // [0] fast work, [1] exact work, [2] rerun count
@@ -170,6 +169,7 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
         BA_PCUDA(upload(pl, H.drun, &v.drun));
         BA_PCUDA(upload(pl, H.airports, &v.airports));
         BA_PCUDA(upload(pl, H.lane_airport, &v.lane_airport));
+        BA_PCUDA(upload(pl, H.lane_sorted, &v.lane_sorted));
         BA_PCUDA(upload(pl, H.lq, &v.lq));
         BA_PCUDA(upload(pl, H.pos_live, &v.pos_live));
         dviews[d] = v;
@@ -209,12 +209,9 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     pl->stride_fast = (pl->host.scratch_words_fast + 31) & ~31ull;
     pl->stride_exact = (pl->host.scratch_words_exact + 31) & ~31ull;
     if (pl->host.view.scan2_ok && !(std::getenv("BA_SCAN2") && std::atoi(std::getenv("BA_SCAN2")) == 0)) {
-        int n_live_max = 0;
-        for (int d = 0; d < n_days; ++d) n_live_max = std::max(n_live_max, pl->host.days[d].view.n_live);
-        pl->smem_scan2 = ba_forward2_smem_bytes(N, n_live_max, pl->block);
-        pl->qsh_words = ba_forward2_qsh_words(N, n_live_max);
+        pl->smem_scan2 = ba_forward2_smem_bytes(N);
         if (pl->smem_scan2 <= (size_t)max_optin) {
-            pl->grid_scan2 = ba_forward2_configure(pl->block, pl->smem_scan2, device);
+            pl->grid_scan2 = ba_forward2_configure(pl->smem_scan2, device);
             pl->stride_scan2 = (ba_forward2_scratch_words(pl->host.view.Fmax, N) + 31) & ~31ull;
             pl->scan2_ok = pl->grid_scan2 > 0;
         }
@@ -318,9 +315,8 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         prm.work_counter = pl->d_counters + 0;
         if (use_scan2) {
             prm.scratch_stride = pl->stride_scan2;
-            prm.qsh_words = pl->qsh_words;
             int grid = (int)std::min<long long>(n_work, pl->grid_scan2);
-            BA_CUDA(ba_launch_forward2(prm, grid, pl->block, pl->smem_scan2, s));
+            BA_CUDA(ba_launch_forward2(prm, grid, pl->smem_scan2, s));
         } else {
             prm.scratch_stride = pl->stride_fast;
             int grid = (int)std::min<long long>(n_work, pl->grid_fast);
@@ -353,11 +349,9 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         unsigned long long h[16];
         BA_CUDA(cudaStreamSynchronize(s));
         BA_CUDA(cudaMemcpy(h, prm.phase_cycles, sizeof(h), cudaMemcpyDeviceToHost));
-        const char *names[5] = {"setup", "prologue", "sort", "scan(wall)", "epilogue"};
-        fprintf(stderr, "[BA_PHASE_PROFILE] scan2 cycles per particle-day (warp 0 wall):");
+        const char *names[5] = {"setup", "prologue", "sort", "scan", "epilogue"};
+        fprintf(stderr, "[BA_PHASE_PROFILE] scan2 cycles per particle-day:");
         for (int i = 0; i < 5; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / (double)n_work);
-        fprintf(stderr, " | own scan time of warps 0-3:");
-        for (int i = 8; i < 12; ++i) fprintf(stderr, " %.0f", (double)h[i] / (double)n_work);
         fprintf(stderr, "\n");
     } else if (prm.phase_cycles) {
         unsigned long long h[8];

@@ -349,36 +349,30 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
 
 // ---------------------------------------------------------------------------
 // ba_forward2_kernel: the ring-less scan (ba_scan2.cuh) for bookkeeping-free, fully
-// observed plans.  Persistent CTAs, one lane per airport, warps asynchronous in the scan.
+// observed plans.  Persistent one-warp CTAs: a warp owns a (particle, day) from the prologue
+// to the epilogue, so an SM runs ~30 independent particle-days and nothing ever waits for
+// another warp.
 // ---------------------------------------------------------------------------
-#ifndef BA2_MIN_BLOCKS_128
-#define BA2_MIN_BLOCKS_128 8
+#ifndef BA2_MIN_BLOCKS
+#define BA2_MIN_BLOCKS 32
 #endif
-#define BA2_MIN_BLOCKS(MAXT) ((MAXT) == 128 ? BA2_MIN_BLOCKS_128 : ((MAXT) == 256 ? 4 : ((MAXT) == 512 ? 2 : 1)))
 
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel(const BaFwdParams prm)
+__global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const BaFwdParams prm)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
+    const int lane = threadIdx.x;
     const BaPlanView &plan = prm.plan;
     const int N = plan.N, D = plan.D, R = plan.R;
 
-    // shared memory: everything the scan touches sits at compile-time offsets (progress
-    // words, q table); the size-dependent prologue tables follow
     Ba2Ctx c;
-    uint32_t *red = smem;                                    // [BA_RED_WORDS], 16 B aligned
-    uint32_t *ctaw = red + BA_RED_WORDS;                     // [16] CTA scalars
-    c.bars = (uint64_t *)(ctaw + 16);                        // [32] one mbarrier per warp
-    c.prog = (volatile int *)(ctaw + 16 + 64);               // [32]
-    c.kcnt = ctaw + 16 + 64 + 32;                            // [BA2_KC]
-    c.qsh = (volatile uint16_t *)(c.kcnt + BA2_KC);          // [qsh_words * 2]
-    c.nwarp = nwarp;
-    c.n_ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
-    c.s_m = (float *)(c.kcnt + BA2_KC + prm.qsh_words);
-    c.s_rate = c.s_m + N; c.s_mt = c.s_rate + N; c.s_tstd = c.s_mt + N;
-    c.hist = (uint32_t *)(c.s_tstd + N);                     // [n_ranges * N]
+    c.nslot = ((uint32_t)N + 31u) & ~31u;
+    c.un = smem;
+    {
+        const uint32_t un_words = BA2_STATE_WORDS * c.nslot > (uint32_t)(BA2_KC + N) ? BA2_STATE_WORDS * c.nslot
+                                                                                    : (uint32_t)(BA2_KC + N);
+        c.s_rate = (float *)(smem + un_words);
+        c.s_mt = c.s_rate + N;
+    }
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
 
     c.sigma = prm.scales[0]; c.v_t = prm.scales[1]; c.v_u = prm.scales[2];
@@ -395,8 +389,7 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
     c.tick_time = plan.tick_time;
     c.max_ticks = plan.max_ticks;
     c.N = N;
-    bool first_item = true;
-    // optional phase timing (BA_PHASE_PROFILE): lane 0 of every warp reads the SM clock
+    // optional phase timing (BA_PHASE_PROFILE)
     long long pc_last = 0;
     const bool prof = prm.phase_cycles != nullptr && lane == 0;
 #define BA2_MARK(slot) do { if (prof) { long long now_ = clock64(); atomicAdd(prm.phase_cycles + (slot), (unsigned long long)(now_ - pc_last)); pc_last = now_; } } while (0)
@@ -404,9 +397,9 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
     for (;;) {
         if (prof) pc_last = clock64();
         // ---- next work item ------------------------------------------------
-        if (tid == 0) red[BA_RED_WORDS - 1] = atomicAdd(prm.work_counter, 1u);
-        __syncthreads();
-        const int wi = (int)red[BA_RED_WORDS - 1];
+        int wi = 0;
+        if (lane == 0) wi = (int)atomicAdd(prm.work_counter, 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
         const int n_work = prm.n_work_dev ? (int)*prm.n_work_dev : prm.n_work;
         if (wi >= n_work) break;
         int p, d;
@@ -419,8 +412,9 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
         c.flights = day.flights; c.route = day.route; c.ap = day.airports;
         c.pos_live = day.pos_live; c.pos_dep = day.pos_dep; c.pos_arr = day.pos_arr;
         c.rt_gid = day.rt_gid; c.rt_off = day.rt_off; c.rt_flt = day.rt_flt; c.Rd = day.Rd;
-        c.lq = day.lq; c.drun = day.drun; c.drun_off = day.drun_off;
+        c.lq = day.lq; c.drun = day.drun; c.drun_off = day.drun_off; c.order = day.lane_sorted;
         c.first_tick = day.first_tick;
+        c.lat_airport = prm.lat_airport + (size_t)p * 2 * N;
         c.lat_route = prm.lat_route + (size_t)p * R;
         c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
         c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
@@ -428,85 +422,64 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
         ba2_carve_scratch(c, gscr, day.F, N);
         const uint32_t n_arr = (uint32_t)day.n_arr;
-        c.range_len = (n_arr + (uint32_t)c.n_ranges - 1u) / (uint32_t)c.n_ranges;
-        if (c.range_len == 0u) c.range_len = 1u;
 
         // ---- setup -----------------------------------------------------------
-        const float *lat_airport = prm.lat_airport + (size_t)p * 2 * N;
-        for (int a = tid; a < N; a += nthr) ba2_init_airport(c, a, lat_airport, N);
-        for (int i = tid; i < BA2_KC; i += nthr) c.kcnt[i] = 0;
-        for (int i = tid; i < c.n_ranges * N; i += nthr) c.hist[i] = 0;
-        {
-            uint32_t *q32 = (uint32_t *)c.qsh;
-            const int nq = (day.n_live + N + 1) / 2;
-            for (int i = tid; i < nq; i += nthr) q32[i] = 0xFFFFFFFFu;
-        }
-        if (tid < nwarp) { c.prog[tid] = day.first_tick - 1; ba2_bar_init(c.bars + tid, first_item); }
-        first_item = false;
-        if (tid < 16) ctaw[tid] = 0;
+        for (int a = lane; a < N; a += 32) ba2_init_airport(c, a, N);
+        for (int i = lane; i < BA2_KC; i += 32) c.un[i] = 0;
         if (c.grow && day.Rd < R)
-            for (int i = tid; i < R; i += nthr) c.grow[c.route_base + i] = 0.0f;
+            for (int i = lane; i < R; i += 32) c.grow[c.route_base + i] = 0.0f;
         if (c.pop_tick)
-            for (int i = 2 * day.F + tid; i < 2 * plan.Fmax; i += nthr) c.pop_tick[i] = -1;
+            for (int i = 2 * day.F + lane; i < 2 * plan.Fmax; i += 32) c.pop_tick[i] = -1;
         BaAcc acc = {0.0, 0.0f, 0.0f, 0.0f, 0u};
-        __syncthreads();
+        __syncwarp();
+        BA2_MARK(0);
 
         // ---- prologue ----------------------------------------------------------
-        if (warp == 0) BA2_MARK(0);
-        for (int f = tid; f < day.F; f += nthr) ba2_prologue_flight(c, acc, f);
-        __syncthreads();
-        if (warp == 0) BA2_MARK(1);
-        if (tid < 32) ba2_bucket_scan(c, tid);
-        __syncthreads();
-        for (int f = tid; f < day.F; f += nthr) ba2_scatter_flight(c, f);
-        __syncthreads();
-        for (int a = tid; a < N; a += nthr) ba2_split_cursors(c, a);
-        __syncthreads();
-        if (warp < c.n_ranges) ba2_split_range(c, warp, lane, n_arr);
-        const bool aborted = __syncthreads_or((acc.status & BA_S_OVERFLOW) != 0u) != 0;
-        if (warp == 0) BA2_MARK(2);
-        if (prof) pc_last = clock64();
+        for (int f = lane; f < day.F; f += 32) ba2_prologue_flight(c, acc, f);
+        __syncwarp();
+        BA2_MARK(1);
+        ba2_bucket_scan(c, lane);
+        __syncwarp();
+        for (int f = lane; f < day.F; f += 32) ba2_scatter_flight(c, f);
+        for (int a = lane; a < N; a += 32) ba2_split_cursor(c, a);
+        __syncwarp();
+        ba2_split(c, lane, n_arr);
+        __syncwarp();
+        const bool aborted = __any_sync(0xffffffffu, (acc.status & BA_S_OVERFLOW) != 0u) != 0;
+        BA2_MARK(2);
 
-        // ---- scan: one lane per airport, warps asynchronous ------------------------
+        // ---- scan: the lanes walk the airports in rounds, one clock ------------------
+        uint32_t k = (uint32_t)(day.first_tick - 1);
         if (!aborted) {
-            Ba2Lane L;
-            Ba2Cold Q;
-            if (tid < N) ba2_lane_init(c, L, Q, day.lane_airport[tid]);
-            else { L.left = 0; Q.status = 0; }
-            uint32_t k = (uint32_t)(day.first_tick - 1);
-            for (;;) {
-                const bool active = L.left != 0u;
-                if (!__any_sync(0xffffffffu, active)) break;
-                if ((int)k >= plan.max_ticks) { Q.status |= BA_S_TICK_CAP; break; }
-                ++k;
-                const float t = c.tick_time[k];                 // model.py:161
-                if (active) ba2_lane_tick(c, L, Q, k, t);
-                __syncwarp();
-                // publish: everything this warp's airports serve in tick k is in the q table
-                if (lane == 0) { __threadfence_block(); c.prog[warp] = (int)k; ba2_bar_arrive(c.bars + warp); }
+            uint32_t nleft = 0;
+            for (uint32_t slot = lane; slot < (uint32_t)N; slot += 32u) {
+                const int a = c.order[slot];
+                ba2_state_init(c, slot, a);
+                nleft += (c.ap[a].dep_live + c.ap[a].arr_cnt) != 0 ? 1u : 0u;
             }
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block(); c.prog[warp] = BA2_PROG_DONE; ba2_bar_arrive(c.bars + warp);
-                atomicMax(&ctaw[0], k);
+            while (__any_sync(0xffffffffu, nleft != 0u)) {
+                if ((int)k >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
+                ++k;
+                const float t = c.tick_time[k];                 // model.py:161
+                for (uint32_t slot = lane; slot < (uint32_t)N; slot += 32u)
+                    if (ba2_airport_tick(c, slot, k, t, acc.status)) nleft -= 1u;
+                __syncwarp();        // every airport's tick k is in memory before tick k + 1
             }
-            acc.status |= Q.status;
         }
-        if (warp < 4) BA2_MARK(8 + warp);   // this warp's own scan time
-        __syncthreads();          // every wait of the tape is written
-        if (warp == 0) BA2_MARK(3);
-        int tick = (int)ctaw[0];
+        BA2_MARK(3);
+        int tick = (int)k;
         if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
 
         // ---- epilogue ----------------------------------------------------------
         if (!aborted)
-            for (int f = tid; f < day.F; f += nthr) ba2_epilogue_flight(c, acc, f);
+            for (int f = lane; f < day.F; f += 32) ba2_epilogue_flight(c, acc, f);
         if (c.grow && !aborted) {
-            __syncthreads();
-            for (int s = tid; s < N; s += nthr) ba2_epilogue_airport(c, day.lane_airport[s], N);
-            for (int r = tid; r < day.Rd; r += nthr) ba2_epilogue_route(c, r);
+            __syncwarp();
+            for (int s = lane; s < N; s += 32) ba2_epilogue_airport(c, s, N);
+            for (int r = lane; r < day.Rd; r += 32) ba2_epilogue_route(c, r);
         }
-        // deterministic block reduction: lanes -> warp (shuffle tree) -> warps in order
+        // deterministic reduction: shuffle tree over the lanes
         double v0 = acc.lp;
         float v1 = acc.g_sigma, v2 = acc.g_vt, v3 = acc.g_vu;
         uint32_t st = acc.status;
@@ -518,76 +491,42 @@ __global__ void __launch_bounds__(MAXT, BA2_MIN_BLOCKS(MAXT)) ba_forward2_kernel
             v3 += __shfl_down_sync(0xffffffffu, v3, o);
             st |= __shfl_down_sync(0xffffffffu, st, o);
         }
-        float *redf = (float *)red;
-        double *redd = (double *)red;          // red is 16-byte aligned; 6 words per warp
         if (lane == 0) {
-            redd[warp * 3 + 0] = v0;
-            redf[warp * 6 + 2] = v1; redf[warp * 6 + 3] = v2;
-            redf[warp * 6 + 4] = v3; red[warp * 6 + 5] = st;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            uint32_t ss = 0;
-            for (int w = 0; w < nwarp; ++w) {
-                s0 += redd[w * 3 + 0]; s1 += redf[w * 6 + 2]; s2 += redf[w * 6 + 3];
-                s3 += redf[w * 6 + 4]; ss |= red[w * 6 + 5];
-            }
-            prm.logp[pd] = (float)s0;
-            prm.status[pd] = ss;
+            prm.logp[pd] = (float)v0;
+            prm.status[pd] = st;
             if (prm.ticks) prm.ticks[pd] = tick;
             if (c.grow) {
-                c.grow[c.route_base + R + 0] = (float)s1;
-                c.grow[c.route_base + R + 1] = (float)s2;
-                c.grow[c.route_base + R + 2] = (float)s3;
+                c.grow[c.route_base + R + 0] = v1;
+                c.grow[c.route_base + R + 1] = v2;
+                c.grow[c.route_base + R + 2] = v3;
             }
         }
-        __syncthreads();     // red[] and the shared tables are reused by the next item
-        if (warp == 0) BA2_MARK(4);
+        __syncwarp();        // the shared tables are reused by the next item
+        BA2_MARK(4);
     }
 #undef BA2_MARK
 }
 
-int ba_forward2_qsh_words(int n_airports, int n_live_max)
-{
-    return ((n_live_max + n_airports + 1) / 2 + 3) & ~3;
-}
-
-size_t ba_forward2_smem_bytes(int n_airports, int n_live_max, int block_threads)
-{
-    const int nwarp = (block_threads + 31) / 32;
-    const int ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
-    return ((size_t)BA_RED_WORDS + 16 + 64 + 32 + BA2_KC + ba_forward2_qsh_words(n_airports, n_live_max) +
-            4 * (size_t)n_airports + (size_t)ranges * n_airports + 4) * 4;
-}
+size_t ba_forward2_smem_bytes(int n_airports) { return ba2_smem_words(n_airports) * 4; }
 
 uint64_t ba_forward2_scratch_words(int Fmax, int n_airports) { return ba2_scratch_words(Fmax, n_airports); }
 
-#define BA2_DISPATCH(BLOCK, STMT)                                                    \
-    do {                                                                             \
-        if ((BLOCK) <= 128) { auto kfn = ba_forward2_kernel<128>; STMT; }             \
-        else if ((BLOCK) <= 256) { auto kfn = ba_forward2_kernel<256>; STMT; }        \
-        else if ((BLOCK) <= 512) { auto kfn = ba_forward2_kernel<512>; STMT; }        \
-        else { auto kfn = ba_forward2_kernel<1024>; STMT; }                           \
-    } while (0)
-
 // sets the dynamic shared-memory limit (on the current device) and returns the resident grid
-int ba_forward2_configure(int block, size_t smem, int device)
+int ba_forward2_configure(size_t smem, int device)
 {
-    cudaError_t e = cudaSuccess;
-    BA2_DISPATCH(block, e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaError_t e = cudaFuncSetAttribute(ba_forward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -1;
     int per_sm = 0, sms = 0;
-    BA2_DISPATCH(block, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, block, smem));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_forward2_kernel, 32, smem);
     if (e != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
     if (const char *v = getenv("BA_MAX_CTAS_PER_SM")) { const int cap = atoi(v); if (cap > 0 && cap < per_sm) per_sm = cap; }
     return per_sm * sms;
 }
 
-cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, int block, size_t smem, cudaStream_t s)
+cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, size_t smem, cudaStream_t s)
 {
-    BA2_DISPATCH(block, (kfn<<<grid, block, smem, s>>>(p)));
+    ba_forward2_kernel<<<grid, 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 

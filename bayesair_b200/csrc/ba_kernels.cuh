@@ -28,7 +28,6 @@ struct BaFwdParams {
     int32_t n_work;
     const unsigned int *n_work_dev; // if set, overrides n_work (device-side count)
     unsigned long long *phase_cycles; // optional [8] per-phase cycle totals (debug, BA_PHASE_PROFILE)
-    int32_t qsh_words;            // ring-less scan: words of the shared q table
 };
 
 struct BaBwdParams {
@@ -49,12 +48,11 @@ int ba_forward_max_resident(int block_threads, size_t smem_bytes, bool exact, bo
 
 cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, bool tracked, int grid, int block,
                               size_t smem, cudaStream_t s);
-// ring-less scan (ba_scan2.cuh)
-size_t ba_forward2_smem_bytes(int n_airports, int n_live_max, int block_threads);
-int ba_forward2_qsh_words(int n_airports, int n_live_max);
+// ring-less scan (ba_scan2.cuh): one-warp CTAs
+size_t ba_forward2_smem_bytes(int n_airports);
 uint64_t ba_forward2_scratch_words(int Fmax, int n_airports);
-int ba_forward2_configure(int block, size_t smem, int device);
-cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, int block, size_t smem, cudaStream_t s);
+int ba_forward2_configure(size_t smem, int device);
+cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, size_t smem, cudaStream_t s);
 cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
                               cudaStream_t s);
 cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s);

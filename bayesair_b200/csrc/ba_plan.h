@@ -105,6 +105,7 @@ struct BaDayView {
     int32_t max_dslice;               // largest calendar slice of any tick of the day
     const BaAirport *airports;        // [N] day order
     const int32_t *lane_airport;      // [N] airport handled by lane slot i (load-sorted)
+    const int32_t *lane_sorted;       // [N] airports by decreasing traffic (ring-less scan)
     uint32_t q_total_s;               // queue pool size (entries) of the shared variant
     uint32_t q_total_x;               // queue pool size of the exact variant
     uint32_t turn_total, av_total, dl_total;

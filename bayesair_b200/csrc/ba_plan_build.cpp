@@ -311,6 +311,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         std::stable_sort(H.lane_airport.begin(), H.lane_airport.end(), [&](int x, int y) {
             return dep_cnt[x] + arr_cnt[x] > dep_cnt[y] + arr_cnt[y];
         });
+        H.lane_sorted = H.lane_airport;
         {
             // ... and dealt round-robin over the full warps: a warp's time per tick is the sum
             // over its loops of the longest trip count among its lanes, and the maxima over
@@ -356,6 +357,7 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
         V.drun_off = H.drun_off.data(); V.drun = H.drun.data();
         V.any_track_t = any_t; V.any_track_a = any_a;
         V.airports = H.airports.data(); V.lane_airport = H.lane_airport.data();
+        V.lane_sorted = H.lane_sorted.data();
         V.q_total_s = q_s; V.q_total_x = q_x;
         V.turn_total = turn; V.av_total = av; V.dl_total = dl;
         V.first_tick = first_tick; V.t_before_first = t_before;

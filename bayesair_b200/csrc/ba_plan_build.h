@@ -8,7 +8,7 @@
 
 struct BaHostDay {
     std::vector<BaFlight> flights;
-    std::vector<int32_t> route, dep_fid, lane_airport, pos_dep, pos_arr, rt_gid, rt_off, rt_flt;
+    std::vector<int32_t> route, dep_fid, lane_airport, lane_sorted, pos_dep, pos_arr, rt_gid, rt_off, rt_flt;
     std::vector<float> dep_sched;
     std::vector<uint32_t> dep_word, dcal_rec;
     std::vector<int32_t> dcal_off, drun_off, dep_cpos;

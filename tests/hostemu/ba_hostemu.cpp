@@ -271,10 +271,9 @@ static void run_item(const BaPlanView &plan, const BaDayView &day, int p, int d,
 
 
 // ---------------------------------------------------------------------------
-// Ring-less scan (ba_scan2.cuh): the prologue and epilogue run serially (optionally in
-// shuffled flight order); the scan runs ONE std::thread PER WARP with the kernel's own
-// progress protocol (volatile shared words + fences), optionally with random stalls so that
-// warps drift apart by many ticks.
+// Ring-less scan (ba_scan2.cuh): one warp per particle-day.  The emulation runs the lanes of
+// every step in a SHUFFLED order (flights in the prologue, airports inside a round of a
+// tick), the two extremes of what lockstep lanes may observe of each other's writes.
 // ---------------------------------------------------------------------------
 static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d,
                       const float *lat_airport, const float *lat_route, const float *scales,
@@ -283,22 +282,19 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
                       float *tape, int32_t *pop_tick)
 {
     const int N = plan.N, R = plan.R, D = plan.D;
-    const int nthr = ((N + 31) / 32) * 32, nwarp = nthr / 32;
     const size_t pd = (size_t)p * D + d;
-    const int qsh_words = ((day.n_live + N + 1) / 2 + 3) & ~3;
-    std::vector<uint32_t> sh(16 + 64 + 32 + BA2_KC + qsh_words + 4 * N + BA2_MAX_RANGES * N + 64, 0);
+    std::vector<uint32_t> sh(ba2_smem_words(N) + 64, 0);
     std::vector<uint32_t> gs(ba2_scratch_words(day.F, N) + 16, 0xDEADBEEFu);
     Ba2Ctx c;
     memset(&c, 0, sizeof(c));
-    c.bars = (uint64_t *)(sh.data() + 16);
-    c.prog = (volatile int *)(sh.data() + 16 + 64);
-    c.kcnt = sh.data() + 16 + 64 + 32;
-    c.qsh = (volatile uint16_t *)(c.kcnt + BA2_KC);
-    c.nwarp = nwarp;
-    c.n_ranges = nwarp < BA2_MAX_RANGES ? nwarp : BA2_MAX_RANGES;
-    c.s_m = (float *)(c.kcnt + BA2_KC + qsh_words);
-    c.s_rate = c.s_m + N; c.s_mt = c.s_rate + N; c.s_tstd = c.s_mt + N;
-    c.hist = (uint32_t *)(c.s_tstd + N);
+    c.nslot = ((uint32_t)N + 31u) & ~31u;
+    c.un = sh.data();
+    {
+        const uint32_t un_words = BA2_STATE_WORDS * c.nslot > (uint32_t)(BA2_KC + N) ? BA2_STATE_WORDS * c.nslot
+                                                                                    : (uint32_t)(BA2_KC + N);
+        c.s_rate = (float *)(sh.data() + un_words);
+        c.s_mt = c.s_rate + N;
+    }
     c.sigma = scales[0]; c.v_t = scales[1]; c.v_u = scales[2];
     c.inv_sigma = 1.0f / c.sigma; c.inv_sigma2 = c.inv_sigma * c.inv_sigma;
     c.inv_sigma3 = c.inv_sigma2 * c.inv_sigma; c.log_sigma = logf(c.sigma);
@@ -311,7 +307,9 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     c.flights = day.flights; c.route = day.route; c.ap = day.airports;
     c.pos_live = day.pos_live; c.pos_dep = day.pos_dep; c.pos_arr = day.pos_arr;
     c.rt_gid = day.rt_gid; c.rt_off = day.rt_off; c.rt_flt = day.rt_flt; c.Rd = day.Rd;
-    c.lq = day.lq; c.drun = day.drun; c.drun_off = day.drun_off; c.first_tick = day.first_tick;
+    c.lq = day.lq; c.drun = day.drun; c.drun_off = day.drun_off; c.order = day.lane_sorted;
+    c.first_tick = day.first_tick;
+    c.lat_airport = lat_airport + (size_t)p * 2 * N;
     c.lat_route = lat_route + (size_t)p * R;
     c.noise = noise ? noise + pd * (size_t)plan.Fmax * 4 : nullptr;
     c.particle = p; c.dayidx = d;
@@ -319,86 +317,59 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
     ba2_carve_scratch(c, (uint32_t *)(((uintptr_t)gs.data() + 15) & ~(uintptr_t)15), day.F, N);
     const uint32_t n_arr = (uint32_t)day.n_arr;
-    c.range_len = (n_arr + (uint32_t)c.n_ranges - 1u) / (uint32_t)c.n_ranges;
-    if (c.range_len == 0u) c.range_len = 1u;
 
-    const float *la = lat_airport + (size_t)p * 2 * N;
-    for (int a = 0; a < N; ++a) ba2_init_airport(c, a, la, N);
-    for (int i = 0; i < BA2_KC; ++i) c.kcnt[i] = 0;
-    for (int i = 0; i < c.n_ranges * N; ++i) c.hist[i] = 0;
-    for (int i = 0; i < day.n_live + N; ++i) ((uint16_t *)c.qsh)[i] = 0xFFFFu;
-    for (int w = 0; w < nwarp; ++w) c.prog[w] = day.first_tick - 1;
+    for (int a = 0; a < N; ++a) ba2_init_airport(c, a, N);
+    for (int i = 0; i < BA2_KC; ++i) c.un[i] = 0;
     if (c.grow) for (int i = 0; i < R; ++i) c.grow[c.route_base + i] = 0.0f;
     if (c.pop_tick) for (int i = 2 * day.F; i < 2 * plan.Fmax; ++i) c.pop_tick[i] = -1;
 
-    std::vector<BaAcc> acc(N, BaAcc{0, 0, 0, 0, 0});
+    std::vector<BaAcc> acc(32, BaAcc{0, 0, 0, 0, 0});
     std::mt19937 rng(shuffle_seed + 977u * (unsigned)pd);
     std::vector<int> forder(day.F);
     for (int f = 0; f < day.F; ++f) forder[f] = f;
     if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
-    for (int f : forder) ba2_prologue_flight(c, acc[f % N], f);
+    for (int f : forder) ba2_prologue_flight(c, acc[f % 32], f);
     ba2_bucket_scan(c, -1);
     if (shuffle_seed) std::shuffle(forder.begin(), forder.end(), rng);
     for (int f : forder) ba2_scatter_flight(c, f);
-    for (int a = 0; a < N; ++a) ba2_split_cursors(c, a);
-    for (int r = 0; r < c.n_ranges; ++r) ba2_split_range(c, r, -1, n_arr);
+    for (int a = 0; a < N; ++a) ba2_split_cursor(c, a);
+    ba2_split(c, -1, n_arr);
     uint32_t st = 0;
-    for (int i = 0; i < N; ++i) st |= acc[i].status;
+    for (int i = 0; i < 32; ++i) st |= acc[i].status;
     const bool aborted = (st & BA_S_OVERFLOW) != 0;
 
-    std::vector<uint32_t> last_w(nwarp, 0), st_w(nwarp, 0);
+    uint32_t k = (uint32_t)(day.first_tick - 1);
     if (!aborted) {
-        auto warp_fn = [&](int w) {
-            std::mt19937 wr(shuffle_seed * 7919u + 13u * (unsigned)w + (unsigned)pd);
-            Ba2Lane L[32];
-            Ba2Cold Q[32];
-            bool valid[32];
-            for (int l = 0; l < 32; ++l) {
-                const int tid = 32 * w + l;
-                valid[l] = tid < N;
-                if (valid[l]) ba2_lane_init(c, L[l], Q[l], day.lane_airport[tid]);
-                else { L[l].left = 0; Q[l].status = 0; }
-            }
-            uint32_t k = (uint32_t)(day.first_tick - 1);
-            for (;;) {
-                bool any = false;
-                for (int l = 0; l < 32; ++l) any = any || L[l].left != 0u;
-                if (!any) break;
-                if ((int)k >= plan.max_ticks) { st_w[w] |= BA_S_TICK_CAP; break; }
-                ++k;
-                const float t = c.tick_time[k];
-                // random stalls: let the warps drift apart
-                if (shuffle_seed > 1 && (wr() % 16u) == 0u)
-                    std::this_thread::sleep_for(std::chrono::microseconds(wr() % 200u));
-                int order[32];
+        int nleft = 0;
+        for (int slot = 0; slot < N; ++slot) {
+            const int a = c.order[slot];
+            ba2_state_init(c, (uint32_t)slot, a);
+            nleft += (c.ap[a].dep_live + c.ap[a].arr_cnt) != 0 ? 1 : 0;
+        }
+        std::vector<int> order(32);
+        while (nleft > 0) {
+            if ((int)k >= plan.max_ticks) { st |= BA_S_TICK_CAP; break; }
+            ++k;
+            const float t = c.tick_time[k];
+            for (int base = 0; base < N; base += 32) {          // rounds
                 for (int l = 0; l < 32; ++l) order[l] = l;
-                if (shuffle_seed) std::shuffle(order, order + 32, wr);
-                for (int i = 0; i < 32; ++i) {
-                    const int l = order[i];
-                    if (L[l].left != 0u) ba2_lane_tick(c, L[l], Q[l], k, t);
+                if (shuffle_seed) std::shuffle(order.begin(), order.end(), rng);
+                for (int l : order) {
+                    const int slot = base + l;
+                    if (slot < N && ba2_airport_tick(c, (uint32_t)slot, k, t, acc[l].status)) nleft -= 1;
                 }
-                BA2_FENCE();
-                c.prog[w] = (int)k;
             }
-            BA2_FENCE();
-            c.prog[w] = BA2_PROG_DONE;
-            last_w[w] = k;
-            for (int l = 0; l < 32; ++l) st_w[w] |= Q[l].status;
-        };
-        std::vector<std::thread> th;
-        for (int w = 0; w < nwarp; ++w) th.emplace_back(warp_fn, w);
-        for (auto &t : th) t.join();
+        }
     }
-    int tick = 0;
-    for (int w = 0; w < nwarp; ++w) { tick = std::max(tick, (int)last_w[w]); st |= st_w[w]; }
+    int tick = (int)k;
     if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
-    if (!aborted) for (int f = 0; f < day.F; ++f) ba2_epilogue_flight(c, acc[f % N], f);
+    if (!aborted) for (int f = 0; f < day.F; ++f) ba2_epilogue_flight(c, acc[f % 32], f);
     if (c.grow && !aborted) {
-        for (int i = 0; i < N; ++i) ba2_epilogue_airport(c, day.lane_airport[i], N);
+        for (int a = 0; a < N; ++a) ba2_epilogue_airport(c, a, N);
         for (int r = 0; r < day.Rd; ++r) ba2_epilogue_route(c, r);
     }
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (int i = 0; i < N; ++i) {
+    for (int i = 0; i < 32; ++i) {
         s0 += acc[i].lp; s1 += acc[i].g_sigma; s2 += acc[i].g_vt; s3 += acc[i].g_vu;
         st |= acc[i].status;
     }
