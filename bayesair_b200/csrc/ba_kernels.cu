@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
     const int N = plan.N, D = plan.D, R = plan.R;
 
     Ba2Ctx c;
-    c.nslot = ((uint32_t)N + 31u) & ~31u;
+    c.nslot = (uint32_t)N;
     c.un = smem;
     {
         const uint32_t un_words = BA2_STATE_WORDS * c.nslot > (uint32_t)(BA2_KC + N) ? BA2_STATE_WORDS * c.nslot

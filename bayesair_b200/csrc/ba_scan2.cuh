@@ -46,27 +46,27 @@
 #endif
 #define BA2_NONE 0xFFFFFFFFu
 #define BA2_TICK_NONE 0xFFFFu
-#define BA2_STATE_WORDS 10            // packed words per airport
+#define BA2_STATE_WORDS 11            // packed words per airport
 
 // per-flight payload, indexed by the list position of the flight's departure
 struct alignas(16) Ba2Pay {
     float xw;        // departure service draw; once the departure is served: its total wait
+    uint32_t q;      // tick at which the departure left its runway queue (BA2_NONE: not yet)
     float at;        // arrival time at the destination = queue start of the arrival entry
                      //   (diagnostics: overwritten by the arrival's pop tick when it is served)
     float xa;        // arrival service draw; once the arrival is served: its total wait
-    uint32_t q;      // tick at which the departure left its runway queue (BA2_NONE: not yet)
 };
 
 #if defined(__CUDA_ARCH__)
 BA_DEV Ba2Pay ba2_ld_pay(const Ba2Pay *p)
 {
     const uint4 v = *reinterpret_cast<const uint4 *>(p);
-    Ba2Pay r; r.xw = __uint_as_float(v.x); r.at = __uint_as_float(v.y); r.xa = __uint_as_float(v.z); r.q = v.w;
+    Ba2Pay r; r.xw = __uint_as_float(v.x); r.q = v.y; r.at = __uint_as_float(v.z); r.xa = __uint_as_float(v.w);
     return r;
 }
 BA_DEV void ba2_st_pay(Ba2Pay *p, const Ba2Pay &r)
 {
-    *reinterpret_cast<uint4 *>(p) = make_uint4(__float_as_uint(r.xw), __float_as_uint(r.at), __float_as_uint(r.xa), r.q);
+    *reinterpret_cast<uint4 *>(p) = make_uint4(__float_as_uint(r.xw), r.q, __float_as_uint(r.at), __float_as_uint(r.xa));
 }
 struct Ba2U2 { uint32_t x, y; };
 BA_DEV Ba2U2 ba2_ld2(const uint32_t *p) { const uint2 v = *reinterpret_cast<const uint2 *>(p); Ba2U2 r = {v.x, v.y}; return r; }
@@ -77,6 +77,12 @@ BA_DEV Ba2Pay ba2_ld_pay(const Ba2Pay *p) { return *p; }
 BA_DEV void ba2_st_pay(Ba2Pay *p, const Ba2Pay &r) { *p = r; }
 BA_DEV Ba2U2 ba2_ld2(const uint32_t *p) { Ba2U2 v; v.x = p[0]; v.y = p[1]; return v; }
 BA_DEV void ba2_st2(uint32_t *p, uint32_t a, uint32_t b) { p[0] = a; p[1] = b; }
+#endif
+
+#if defined(__CUDA_ARCH__) && !defined(BA2_NO_PREFETCH)
+#define BA2_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#else
+#define BA2_PREFETCH_L2(p) ((void)0)
 #endif
 
 struct Ba2Ctx {
@@ -105,7 +111,7 @@ struct Ba2Ctx {
     float *s_rate, *s_mt;                     // [N] per airport (day-local index)
     uint32_t *un;                             // union: prologue {kcnt [BA2_KC], cursors [N]} /
                                               //        scan {state [BA2_STATE_WORDS][nslot]}
-    uint32_t nslot;                           // N rounded up to a multiple of 32
+    uint32_t nslot;                           // stride of the state arrays (= N)
     // global scratch of this warp
     Ba2Pay *P;                                // [n_live + N] payload / tape / q by lpos
     uint32_t *Ak;                             // [n_arr + N] arrival keys per destination (+ sentinels)
@@ -145,7 +151,7 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
 // shared-memory words per warp
 static inline size_t ba2_smem_words(int N)
 {
-    const size_t nslot = ((size_t)N + 31) & ~(size_t)31;
+    const size_t nslot = (size_t)N;
     const size_t un = BA2_STATE_WORDS * nslot > BA2_KC + (size_t)N ? BA2_STATE_WORDS * nslot : BA2_KC + (size_t)N;
     return (un + 2 * (size_t)N + 3) & ~(size_t)3;
 }
@@ -318,6 +324,7 @@ BA_DEV void ba2_split(Ba2Ctx &c, int lane, uint32_t n_arr)
 //   [7] g | gnew << 16     joining tick of the accumulator's group / of the youngest group
 //   [8] cnt | asg << 16    assignments made so far; 0: head not assigned, 1: arrival, 2: departure
 //   [9] lw | lr << 16      log of (tick, cnt) pairs: written / consumed
+//  [10] hxo                this airport's slice of hx / glog
 BA_DEV void ba2_state_init(const Ba2Ctx &c, uint32_t slot, int a)
 {
     const BaAirport A = c.ap[a];
@@ -332,6 +339,7 @@ BA_DEV void ba2_state_init(const Ba2Ctx &c, uint32_t slot, int a)
     s[5 * ns] = 0; s[6 * ns] = 0;
     s[7 * ns] = BA2_TICK_NONE | (BA2_TICK_NONE << 16);
     s[8 * ns] = 0; s[9 * ns] = 0;
+    s[10 * ns] = A.lq_off + A.as_off - 2u * (uint32_t)a;
 }
 
 // in-transit list order of an arrival: (tick at which its departure was served, origin,
@@ -497,8 +505,7 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
             if (p != g) {
                 if (p == k && cnt == cnt0) wacc = 0.0f;
                 else {
-                    const int a = c.order[slot];
-                    const uint32_t hxo = c.ap[a].lq_off + c.ap[a].as_off - 2u * (uint32_t)a;
+                    const uint32_t hxo = s[10 * ns];
                     if (lwr == BA2_NONE) lwr = s[9 * ns];
                     uint32_t lr = lwr >> 16;
                     wacc = ba2_replay(c.glog + 2u * hxo, c.hx + hxo, lwr & 0xFFFFu, &lr, cnt, p, k, cnt0, &status);
@@ -506,10 +513,7 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
                 }
                 g = p;
             }
-            if (gnew != p) {                                 // a younger group is waiting
-                const int a = c.order[slot];
-                c.hx[c.ap[a].lq_off + c.ap[a].as_off - 2u * (uint32_t)a + cnt] = x;
-            }
+            if (gnew != p) c.hx[s[10 * ns] + cnt] = x;       // a younger group is waiting
             cnt += 1;
             wacc = BA_ADD(wacc, x);                          // airport.py:150-153
             A = BA_ADD(qs, wacc);                            // airport.py:156
@@ -523,9 +527,8 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
             if (c.pop_tick) pp->at = __uint_as_float_portable(k);
             ha += 1; hkey = BA2_NONE;
         } else {
-            Ba2Pay *pp = c.P + hd;
-            pp->xw = wacc;                                   // tape: total wait of the departure
-            pp->q = k;
+            // tape: total wait of the departure, and the message to the destination
+            ba2_st2((uint32_t *)(c.P + hd), __float_as_uint_portable(wacc), k);
             hd += 1; dk = BA2_NONE;
         }
         left -= 1; asg = 0u;
@@ -533,13 +536,14 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
     // a tick that ends with entries still waiting behind an assigned head: the entries that
     // joined in it will need the number of assignments made before it (ba2_replay)
     if (joined && asg != 0u) {
-        const int a = c.order[slot];
-        const uint32_t hxo = c.ap[a].lq_off + c.ap[a].as_off - 2u * (uint32_t)a;
         if (lwr == BA2_NONE) lwr = s[9 * ns];
-        uint32_t *lg = c.glog + 2u * (hxo + (lwr & 0xFFFFu));
+        uint32_t *lg = c.glog + 2u * (s[10 * ns] + (lwr & 0xFFFFu));
         lg[0] = k; lg[1] = cnt0;
         lwr += 1u;
     }
+    // what the next tick touches first: on its way to L2 while the other airports run
+    if ((nkey >> 16) <= k) BA2_PREFETCH_L2(c.P + (nkey & 0xFFFFu));
+    if (hd < td || rt == k + 1u) BA2_PREFETCH_L2(c.P + hd);
     s[0] = r | (w << 16);
     s[1 * ns] = ha | (left << 16);
     s[2 * ns] = hd | (td << 16);

@@ -287,7 +287,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     std::vector<uint32_t> gs(ba2_scratch_words(day.F, N) + 16, 0xDEADBEEFu);
     Ba2Ctx c;
     memset(&c, 0, sizeof(c));
-    c.nslot = ((uint32_t)N + 31u) & ~31u;
+    c.nslot = (uint32_t)N;
     c.un = sh.data();
     {
         const uint32_t un_words = BA2_STATE_WORDS * c.nslot > (uint32_t)(BA2_KC + N) ? BA2_STATE_WORDS * c.nslot
