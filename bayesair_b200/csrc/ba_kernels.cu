@@ -367,12 +367,7 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
     Ba2Ctx c;
     c.nslot = (uint32_t)N;
     c.un = smem;
-    {
-        const uint32_t un_words = BA2_STATE_WORDS * c.nslot > (uint32_t)(BA2_KC + N) ? BA2_STATE_WORDS * c.nslot
-                                                                                    : (uint32_t)(BA2_KC + N);
-        c.s_rate = (float *)(smem + un_words);
-        c.s_mt = c.s_rate + N;
-    }
+    c.s_rate = (float *)(smem + BA2_KC + N);                 // prologue: behind buckets and cursors
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
 
     c.sigma = prm.scales[0]; c.v_t = prm.scales[1]; c.v_u = prm.scales[2];
@@ -424,7 +419,8 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
         const uint32_t n_arr = (uint32_t)day.n_arr;
 
         // ---- setup -----------------------------------------------------------
-        for (int a = lane; a < N; a += 32) ba2_init_airport(c, a, N);
+        c.s_rate = (float *)(smem + BA2_KC + N); c.s_mt = nullptr;
+        for (int a = lane; a < N; a += 32) ba2_init_airport(c, a, N, false);
         for (int i = lane; i < BA2_KC; i += 32) c.un[i] = 0;
         if (c.grow && day.Rd < R)
             for (int i = lane; i < R; i += 32) c.grow[c.route_base + i] = 0.0f;
@@ -472,6 +468,10 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
         if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
 
         // ---- epilogue ----------------------------------------------------------
+        __syncwarp();
+        c.s_rate = (float *)smem; c.s_mt = c.s_rate + N;         // the scan state is dead
+        for (int a = lane; a < N; a += 32) ba2_init_airport(c, a, N, true);
+        __syncwarp();
         if (!aborted)
             for (int f = lane; f < day.F; f += 32) ba2_epilogue_flight(c, acc, f);
         if (c.grow && !aborted) {

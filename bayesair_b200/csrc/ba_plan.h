@@ -75,7 +75,11 @@ struct BaAirport {                    // 80 B static row per (day, airport)
 // One live (= not observed as cancelled) departure of a bookkeeping-free airport, in
 // (origin, pending order) order: the tick at which it becomes ready (network.py:60-68) and
 // its queue start max(0, scheduled departure) (network.py:118-126 with 1000 reserves).
-struct BaLiveDep { uint32_t tick; float qstart; };
+struct BaLiveDep {
+    uint32_t tick; float qstart;
+    uint32_t dslot;                   // slot (BaDayView::lane_sorted) that runs the destination
+    uint32_t das_off;                 // BaAirport::as_off of the destination
+};
 
 struct BaDayView {
     int32_t N, F;

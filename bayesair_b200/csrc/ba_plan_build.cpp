@@ -296,10 +296,12 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
                     BaLiveDep r;
                     r.tick = (uint32_t)ready_tick[f];
                     r.qstart = std::max(0.0f, T.h_sched_dep[f]);
+                    r.dslot = (uint32_t)T.h_dest[f];        // airport for now, slot below
+                    r.das_off = 0;
                     H.lq.push_back(r);
                 }
                 BaLiveDep sentinel;
-                sentinel.tick = 0xFFFFFFFFu; sentinel.qstart = 0.0f;
+                sentinel.tick = 0xFFFFFFFFu; sentinel.qstart = 0.0f; sentinel.dslot = 0; sentinel.das_off = 0;
                 H.lq.push_back(sentinel);
             }
             H.view.n_live = (int32_t)H.lq.size() - N;
@@ -329,6 +331,16 @@ int ba_build_host_plan(const BaDayTable *days, int n_days, int n_airports, float
             }
         }
         for (int sl = 0; sl < N; ++sl) H.airports[(size_t)H.lane_airport[sl]].slot = (uint32_t)sl;
+        {
+            std::vector<uint32_t> sorted_slot((size_t)N, 0);
+            for (int sl = 0; sl < N; ++sl) sorted_slot[(size_t)H.lane_sorted[sl]] = (uint32_t)sl;
+            for (BaLiveDep &r : H.lq) {
+                if (r.tick == 0xFFFFFFFFu) continue;
+                const uint32_t dest = r.dslot;
+                r.das_off = H.airports[dest].as_off;
+                r.dslot = sorted_slot[dest];
+            }
+        }
         // idle prefix of the day: ticks before the first scheduled departure do nothing
         // (no pending flight is ready, nothing is queued or in transit) as long as the
         // reserve injection (t >= max_t, model.py:170-174) has not started.

@@ -27,9 +27,10 @@
 //     come and whose departure has been served (q <= k-1), orders that small block by
 //     (q, lpos) = the reference's in-transit list order (network.py:136-198; at
 //     bookkeeping-free airports departures leave in list order), and the block simply becomes
-//     part of the FIFO prefix of the same array.  Flights whose departure is still queued
-//     stay behind in a "deferred" zone between the FIFO prefix and the unexamined suffix and
-//     are polled each tick (late path, network.py:186).
+//     part of the FIFO prefix of the same array.  A flight whose departure is served only at
+//     or after its arrival tick (late path, network.py:186) is dropped from the list when its
+//     tick comes; the ORIGIN hands it over when it serves the departure (an entry in the
+//     destination's late box), and it joins at the end of that tick.  Nobody polls.
 //   * Waits are EXACT by construction: the total wait of an entry is the left fold of the
 //     service draws assigned while it was queued (types/airport.py:150-153).  Entries that
 //     joined in the same tick share the fold's start, so one running fp32 accumulator serves
@@ -46,7 +47,7 @@
 #endif
 #define BA2_NONE 0xFFFFFFFFu
 #define BA2_TICK_NONE 0xFFFFu
-#define BA2_STATE_WORDS 11            // packed words per airport
+#define BA2_STATE_WORDS 12            // packed words per airport
 
 // per-flight payload, indexed by the list position of the flight's departure
 struct alignas(16) Ba2Pay {
@@ -108,13 +109,18 @@ struct Ba2Ctx {
     float c0_lp, c1_lp;
     int value_mode, want_grad;
     // shared memory of this warp
-    float *s_rate, *s_mt;                     // [N] per airport (day-local index)
-    uint32_t *un;                             // union: prologue {kcnt [BA2_KC], cursors [N]} /
-                                              //        scan {state [BA2_STATE_WORDS][nslot]}
+    uint32_t *un;                             // union: prologue {kcnt [BA2_KC], cursors [N], rate [N]} /
+                                              //   scan {state [BA2_STATE_WORDS][nslot]} /
+                                              //   epilogue {rate [N], mean turnaround [N]}
+    float *s_rate, *s_mt;                     // [N] per airport (day-local index), inside `un`
     uint32_t nslot;                           // stride of the state arrays (= N)
     // global scratch of this warp
     Ba2Pay *P;                                // [n_live + N] payload / tape / q by lpos
     uint32_t *Ak;                             // [n_arr + N] arrival keys per destination (+ sentinels)
+    uint32_t *Lb;                             // [2][n_arr + N] late boxes per destination (even /
+                                              //   odd ticks): lpos of the flights served at or
+                                              //   after their arrival tick
+    uint32_t lb_stride;
     uint32_t *S0, *S1;                        // [2 F] each, prologue: {key, destination} by flight /
                                               //   sorted by arrival tick
     float *hx;                                // [2 F] history of draws by assignment index
@@ -132,7 +138,7 @@ struct Ba2Ctx {
 static inline uint64_t ba2_scratch_words(int F, int N)
 {
     const uint64_t f = (uint64_t)F, n = (uint64_t)N;
-    return 4 * f + 4 * (f + n + 4) + (f + n + 4) + 4 * f + 2 * f + 4 * f + 64;
+    return 4 * f + 4 * (f + n + 4) + 3 * (f + n + 4) + 4 * f + 2 * f + 4 * f + 64;
 }
 
 BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
@@ -144,6 +150,7 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
     c.xdk = (float *)g; c.xak = (float *)g + f; c.atk = (float *)g + 2 * f; c.ct = (float *)g + 3 * f;
     g += 4 * f;
     c.Ak = g; g += fn;
+    c.Lb = g; g += 2 * fn; c.lb_stride = fn;
     c.hx = (float *)g; g += 2 * f;
     c.glog = g;
 }
@@ -152,8 +159,9 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
 static inline size_t ba2_smem_words(int N)
 {
     const size_t nslot = (size_t)N;
-    const size_t un = BA2_STATE_WORDS * nslot > BA2_KC + (size_t)N ? BA2_STATE_WORDS * nslot : BA2_KC + (size_t)N;
-    return (un + 2 * (size_t)N + 3) & ~(size_t)3;
+    const size_t pro = BA2_KC + 2 * (size_t)N;
+    const size_t un = BA2_STATE_WORDS * nslot > pro ? BA2_STATE_WORDS * nslot : pro;
+    return (un + 3) & ~(size_t)3;
 }
 
 BA_DEV BaFlight ba2_flight(const Ba2Ctx &c, int f)
@@ -186,10 +194,10 @@ BA_DEV BaNoise4 ba2_noise(const Ba2Ctx &c, int f)
 // ---------------------------------------------------------------------------
 // per-airport constants (model.py:139-146)
 // ---------------------------------------------------------------------------
-BA_DEV void ba2_init_airport(Ba2Ctx &c, int a, int Ng)
+BA_DEV void ba2_init_airport(Ba2Ctx &c, int a, int Ng, bool epilogue)
 {
     const int g = c.ap[a].global;
-    c.s_mt[a] = c.lat_airport[0 * Ng + g];
+    if (epilogue) c.s_mt[a] = c.lat_airport[0 * Ng + g];
     c.s_rate[a] = BA_DIV(1.0f, c.lat_airport[1 * Ng + g]);     // airport.py:146
 }
 
@@ -324,7 +332,9 @@ BA_DEV void ba2_split(Ba2Ctx &c, int lane, uint32_t n_arr)
 //   [7] g | gnew << 16     joining tick of the accumulator's group / of the youngest group
 //   [8] cnt | asg << 16    assignments made so far; 0: head not assigned, 1: arrival, 2: departure
 //   [9] lw | lr << 16      log of (tick, cnt) pairs: written / consumed
-//  [10] hxo                this airport's slice of hx / glog
+//  [10] entries of this airport's two late boxes (even | odd << 16 ticks), incremented by
+//       the origins
+//  [11] hxo                this airport's slice of hx / glog
 BA_DEV void ba2_state_init(const Ba2Ctx &c, uint32_t slot, int a)
 {
     const BaAirport A = c.ap[a];
@@ -339,7 +349,8 @@ BA_DEV void ba2_state_init(const Ba2Ctx &c, uint32_t slot, int a)
     s[5 * ns] = 0; s[6 * ns] = 0;
     s[7 * ns] = BA2_TICK_NONE | (BA2_TICK_NONE << 16);
     s[8 * ns] = 0; s[9 * ns] = 0;
-    s[10 * ns] = A.lq_off + A.as_off - 2u * (uint32_t)a;
+    s[10 * ns] = 0;
+    s[11 * ns] = A.lq_off + A.as_off - 2u * (uint32_t)a;
 }
 
 // in-transit list order of an arrival: (tick at which its departure was served, origin,
@@ -351,7 +362,7 @@ struct Ba2Blk { uint32_t w, pk; };
 
 // Inserts the arrival `key` (its departure was served at tick q <= km1; `okey` = its place
 // in in-transit list order) into the block [wb, w) of this tick's joiners, kept sorted; the
-// slot Ak[w] is free.
+// slot Ak[w] is free (w <= r: the flights that went to the late box left holes).
 #if defined(__CUDACC__)
 __device__ __noinline__
 #else
@@ -370,30 +381,6 @@ void ba2_insert(uint32_t *Ak, const Ba2Pay *P, Ba2Blk &B, uint32_t key, uint32_t
     Ak[j] = key;
     if (okey > B.pk || B.w == wb) B.pk = okey;
     B.w += 1;
-}
-
-// Deferred zone [w, r): flights whose arrival tick has passed but whose departure had not
-// been served.  Those served by the end of tick km1 join now (late path, network.py:186).
-#if defined(__CUDACC__)
-__device__ __noinline__
-#else
-static
-#endif
-bool ba2_recheck_deferred(uint32_t *Ak, const Ba2Pay *P, Ba2Blk &B, uint32_t r, uint32_t km1,
-                          uint32_t wb)
-{
-    bool joined = false;
-    for (uint32_t i = B.w; i < r; ++i) {
-        const uint32_t key = Ak[i];
-        const uint32_t lpos = key & 0xFFFFu;
-        const uint32_t q = P[lpos].q;
-        if (q > km1) continue;                      // not served yet (BA2_NONE) or in this tick
-        // the vacated slot i takes the (already examined) key at w
-        if (i != B.w) Ak[i] = Ak[B.w];
-        ba2_insert(Ak, P, B, (km1 << 16) | lpos, ba2_key(q, lpos), wb);   // joined at the end of km1
-        joined = true;
-    }
-    return joined;
 }
 
 // A new group (joining tick p) reaches the head: its waits are the fold of the draws
@@ -435,8 +422,11 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
     uint32_t hd = s2 & 0xFFFFu, td = s2 >> 16, rp = s3 & 0xFFFFu, rt = s3 >> 16;
     uint32_t cnt = s8 & 0xFFFFu, asg = s8 >> 16;
     const uint32_t km1 = k - 1u;
+    // late entries handed over during tick k - 1 (the box of that tick's parity)
+    const uint32_t lsh = (km1 & 1u) * 16u;
+    const uint32_t nlate = (*(volatile uint32_t *)(s + 10 * ns) >> lsh) & 0xFFFFu;
     // nothing queued, nothing joins: most airport-ticks of the light airports
-    if ((nkey >> 16) > km1 && r == w && rt != k && ha == w && hd == td && asg == 0u) return false;
+    if ((nkey >> 16) > km1 && nlate == 0u && rt != k && ha == w && hd == td && asg == 0u) return false;
     float A = __uint_as_float_portable(s[5 * ns]), wacc = __uint_as_float_portable(s[6 * ns]);
     const uint32_t s7 = s[7 * ns];
     uint32_t g = s7 & 0xFFFFu, gnew = s7 >> 16;
@@ -445,20 +435,16 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
     const uint32_t wb = w;
     uint32_t pk = 0;
     // ---- arrivals that joined at the end of tick k - 1 ------------------------------
-    if (w != r) {
-        Ba2Blk B; B.w = w; B.pk = 0;
-        joined = ba2_recheck_deferred(c.Ak, c.P, B, r, km1, wb);
-        w = B.w; pk = B.pk;
-    }
+    // (1) from the list: arrival tick k - 1, departure served before that tick.  A flight
+    //     whose departure had not been served by then comes through the late box instead.
     while ((nkey >> 16) <= km1) {
         const uint32_t lpos = nkey & 0xFFFFu;
         const uint32_t q = c.P[lpos].q;
-        if (q <= km1) {                                      // served by the end of tick k - 1
+        if (q < (nkey >> 16)) {
             const uint32_t okey = ba2_key(q, lpos);
             if (w == r && (w == wb || okey >= pk)) {
                 pk = okey; w += 1;                           // already in place
             } else {
-                if (w != r) c.Ak[r] = c.Ak[w];
                 Ba2Blk B; B.w = w; B.pk = pk;
                 ba2_insert(c.Ak, c.P, B, nkey, okey, wb);
                 w = B.w; pk = B.pk;
@@ -467,6 +453,19 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
         }
         r += 1;
         nkey = c.Ak[r];
+    }
+    // (2) from the late box: departures served in tick k - 1 at or after the arrival tick
+    //     (network.py:186); they sort behind (1): their q is larger
+    if (nlate != 0u) {
+        const uint32_t *lb = c.Lb + (km1 & 1u) * c.lb_stride + c.ap[c.order[slot]].as_off;
+        Ba2Blk B; B.w = w; B.pk = pk;
+        for (uint32_t i = 0; i < nlate; ++i) {
+            const uint32_t lpos = lb[i];
+            ba2_insert(c.Ak, c.P, B, (km1 << 16) | lpos, ba2_key(km1, lpos), wb);
+        }
+        w = B.w; pk = B.pk;
+        BA_ATOMIC_AND(s + 10 * ns, ~(0xFFFFu << lsh));       // the box is empty again
+        joined = true;
     }
     // ---- departures that become ready at tick k (static calendar run) -----------------
     if (rt == k) {
@@ -480,8 +479,8 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
     const uint32_t cnt0 = cnt;
     uint32_t hkey = BA2_NONE;                 // Ak[ha] and its payload, valid within this tick
     float hat = 0.0f, hxa = 0.0f;
-    uint32_t dk = BA2_NONE;                   // lq[hd] and its draw, valid within this tick
-    float dqs = 0.0f, dx = 0.0f;
+    uint32_t dk = BA2_NONE;                   // lq[hd], its draw and its arrival time, valid
+    float dqs = 0.0f, dx = 0.0f, dat = 0.0f;  //   within this tick
     uint32_t lwr = BA2_NONE;                  // log indices, loaded on demand
     for (;;) {
         if (asg == 0u) {
@@ -493,8 +492,8 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
                 hat = pay.at; hxa = pay.xa;
             }
             if (hd_ok && dk == BA2_NONE) {
-                const BaLiveDep q = c.lq[hd];
-                dk = q.tick; dqs = q.qstart; dx = c.P[hd].xw;
+                const Ba2Pay pay = ba2_ld_pay(c.P + hd);
+                dk = c.lq[hd].tick; dqs = c.lq[hd].qstart; dx = pay.xw; dat = pay.at;
             }
             const uint32_t pa = ha_ok ? (hkey >> 16) + 1u : BA2_NONE;
             const uint32_t pd = hd_ok ? dk : BA2_NONE;
@@ -505,7 +504,7 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
             if (p != g) {
                 if (p == k && cnt == cnt0) wacc = 0.0f;
                 else {
-                    const uint32_t hxo = s[10 * ns];
+                    const uint32_t hxo = s[11 * ns];
                     if (lwr == BA2_NONE) lwr = s[9 * ns];
                     uint32_t lr = lwr >> 16;
                     wacc = ba2_replay(c.glog + 2u * hxo, c.hx + hxo, lwr & 0xFFFFu, &lr, cnt, p, k, cnt0, &status);
@@ -513,7 +512,7 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
                 }
                 g = p;
             }
-            if (gnew != p) c.hx[s[10 * ns] + cnt] = x;       // a younger group is waiting
+            if (gnew != p) c.hx[s[11 * ns] + cnt] = x; // a younger group is waiting
             cnt += 1;
             wacc = BA_ADD(wacc, x);                          // airport.py:150-153
             A = BA_ADD(qs, wacc);                            // airport.py:156
@@ -528,7 +527,16 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
             ha += 1; hkey = BA2_NONE;
         } else {
             // tape: total wait of the departure, and the message to the destination
+            if (dk == BA2_NONE) dat = c.P[hd].at;           // assigned in an earlier tick
             ba2_st2((uint32_t *)(c.P + hd), __float_as_uint_portable(wacc), k);
+            if (dat <= t) {
+                // served at or after its arrival time: joins the destination's queue at the
+                // end of this very tick (update_in_transit_flights, network.py:186)
+                const BaLiveDep ld = c.lq[hd];
+                const uint32_t sh = (k & 1u) * 16u;
+                const uint32_t n = (BA_ATOMIC_ADD(&c.un[10u * ns + ld.dslot], 1u << sh) >> sh) & 0xFFFFu;
+                c.Lb[(k & 1u) * c.lb_stride + ld.das_off + n] = hd;
+            }
             hd += 1; dk = BA2_NONE;
         }
         left -= 1; asg = 0u;
@@ -537,7 +545,7 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
     // joined in it will need the number of assignments made before it (ba2_replay)
     if (joined && asg != 0u) {
         if (lwr == BA2_NONE) lwr = s[9 * ns];
-        uint32_t *lg = c.glog + 2u * (s[10 * ns] + (lwr & 0xFFFFu));
+        uint32_t *lg = c.glog + 2u * (s[11 * ns] + (lwr & 0xFFFFu));
         lg[0] = k; lg[1] = cnt0;
         lwr += 1u;
     }

@@ -66,6 +66,8 @@
 #define BA_DIV(a, b) __fdiv_rn((a), (b))
 #define BA_ATOMIC_INC(p) atomicAdd((p), 1u)
 #define BA_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define BA_ATOMIC_AND(p, v) atomicAnd((p), (v))
+#define BA_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define BA_ATOMIC_DEC(p) atomicSub((p), 1u)
 #define ba_ctz64(x) (__ffsll((long long)(x)) - 1)
 #define __float_as_uint_portable(x) __float_as_uint(x)
@@ -85,6 +87,9 @@ static inline uint32_t __float_as_uint_portable(float x) { uint32_t u; memcpy(&u
 static inline float __uint_as_float_portable(uint32_t u) { float x; memcpy(&x, &u, 4); return x; }
 #define BA_ATOMIC_INC(p) ba_host_inc(p)
 #define BA_ATOMIC_OR(p, v) (*(p) |= (v))
+#define BA_ATOMIC_AND(p, v) (*(p) &= (v))
+static inline uint32_t ba_host_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+#define BA_ATOMIC_ADD(p, v) ba_host_add((p), (v))
 #define BA_ATOMIC_DEC(p) ba_host_dec(p)
 #define ba_ctz64(x) __builtin_ctzll((unsigned long long)(x))
 #define BA_LOG(x) logf(x)
@@ -1546,7 +1551,9 @@ BA_DEV void ba_epilogue_flight(BaCtx &c, BaAcc &acc, int f)
     // exactly 0 (ba_plan.h: BA_SIMPLE_RATIO); other airports score it in the scan
     if (!(ba_ap_flags<TRK>(c, o) & BA_AP_TRACK_T)) acc.lp += (double)(cobs == 1u ? c.c1_lp : c.c0_lp);
     if (cobs == 1u) {                 // observed as cancelled: never queued anywhere
-        if (c.want_grad) { c.xdk[k] = 0.0f; c.ct[k] = 0.0f; c.atk[f] = 0.0f; }
+        // (value mode keeps the turnaround terms in ARRIVAL order in ct: position k of that
+        //  array belongs to another, live flight there -- leave it alone)
+        if (c.want_grad) { c.xdk[k] = 0.0f; if (!c.value_mode) c.ct[k] = 0.0f; c.atk[f] = 0.0f; }
         return;
     }
     const int j = c.pos_arr[f];

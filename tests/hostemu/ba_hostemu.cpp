@@ -289,12 +289,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     memset(&c, 0, sizeof(c));
     c.nslot = (uint32_t)N;
     c.un = sh.data();
-    {
-        const uint32_t un_words = BA2_STATE_WORDS * c.nslot > (uint32_t)(BA2_KC + N) ? BA2_STATE_WORDS * c.nslot
-                                                                                    : (uint32_t)(BA2_KC + N);
-        c.s_rate = (float *)(sh.data() + un_words);
-        c.s_mt = c.s_rate + N;
-    }
+    c.s_rate = (float *)(sh.data() + BA2_KC + N); c.s_mt = nullptr;
     c.sigma = scales[0]; c.v_t = scales[1]; c.v_u = scales[2];
     c.inv_sigma = 1.0f / c.sigma; c.inv_sigma2 = c.inv_sigma * c.inv_sigma;
     c.inv_sigma3 = c.inv_sigma2 * c.inv_sigma; c.log_sigma = logf(c.sigma);
@@ -318,7 +313,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     ba2_carve_scratch(c, (uint32_t *)(((uintptr_t)gs.data() + 15) & ~(uintptr_t)15), day.F, N);
     const uint32_t n_arr = (uint32_t)day.n_arr;
 
-    for (int a = 0; a < N; ++a) ba2_init_airport(c, a, N);
+    for (int a = 0; a < N; ++a) ba2_init_airport(c, a, N, false);
     for (int i = 0; i < BA2_KC; ++i) c.un[i] = 0;
     if (c.grow) for (int i = 0; i < R; ++i) c.grow[c.route_base + i] = 0.0f;
     if (c.pop_tick) for (int i = 2 * day.F; i < 2 * plan.Fmax; ++i) c.pop_tick[i] = -1;
@@ -363,6 +358,8 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     }
     int tick = (int)k;
     if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
+    c.s_rate = (float *)sh.data(); c.s_mt = c.s_rate + N;
+    for (int a = 0; a < N; ++a) ba2_init_airport(c, a, N, true);
     if (!aborted) for (int f = 0; f < day.F; ++f) ba2_epilogue_flight(c, acc[f % 32], f);
     if (c.grow && !aborted) {
         for (int a = 0; a < N; ++a) ba2_epilogue_airport(c, a, N);

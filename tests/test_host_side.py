@@ -217,6 +217,107 @@ def test_emulated_overflow_rerun():
     np.testing.assert_allclose(fixed["logp"], ref["logp"], rtol=5e-6)
 
 
+# ------------------------------ emulated ring-less scan (ba_scan2.cuh, g++) --
+@pytest.mark.parametrize("name", [n for n in golden_names()
+                                  if n not in ("cancel4", "cancel5", "cancel2day")])
+def test_emulated_scan2_vs_golden(name):
+    """The one-warp ring-less scan (the kernel the training configurations run) against the
+    reference-generated fixtures: log-prob, every gradient element, and the same queue
+    decisions as the exact-list kernel."""
+    from tests.hostemu import EmuPlan
+    g = Golden(name)
+    plan = EmuPlan(g.specs, len(g.global_codes), g.delta_t, g.max_t, False)
+    assert plan.scan2_ok
+    lat = {k: v[None] for k, v in g.latents.items()}
+    ex = plan.forward(lat, g.scales, g.noise[None], exact=True, want_pop=True)
+    for shuffle in (0, 3):
+        o = plan.forward(lat, g.scales, g.noise[None], scan2=True, shuffle_seed=shuffle, want_pop=True)
+        assert (o["status"] == 0).all()
+        ref = sum(g.ref_class.values())
+        assert abs(float(o["logp"].astype(np.float64).sum()) - ref) <= 5e-6 * abs(ref)
+        for k, v in g.ref_grads.items():
+            assert rel_err(o["grads"][k][0], v) <= 1e-4, k
+        assert rel_err(o["grads"]["scales"][0], g.ref_grad_scales) <= 1e-4
+        assert np.array_equal(o["pop_tick"], ex["pop_tick"])
+        assert np.array_equal(o["ticks"], ex["ticks"])
+
+
+SCAN2_CASES = [  # N, [F/day], P, mean service, spread
+    (8, [320, 300], 4, 0.06, 0.6),       # one round, two days of different length
+    (40, [900], 3, 0.15, 0.5),           # two rounds, saturated hubs: late boxes, replays
+    (70, [1500, 1400], 2, 0.05, 0.5),    # three rounds
+    (100, [3876], 2, 0.012, 0.3),        # the benchmark's day, nominal
+    (100, [3876], 1, 0.12, 0.3),         # ... and with every hub saturated (671 ticks)
+    (130, [2600], 2, 0.03, 0.5),         # five rounds
+]
+
+
+@pytest.mark.parametrize("case", SCAN2_CASES, ids=lambda c: f"N{c[0]}F{c[1][0]}s{c[3]}")
+def test_emulated_scan2_vs_oracle(case):
+    """Queue decisions (pop tick of every flight), tick counts, log-probs and gradients of the
+    ring-less scan equal to the C oracle, for shuffled lane orders inside the rounds."""
+    from bayesair_b200.compiler import day_spec_from_frame
+    from bayesair_b200.synth import synth_day_frame, synth_latents
+    from oracle import ba_oracle
+    from tests.hostemu import EmuPlan
+    N, Fs, P, svc, spread = case
+    frames = [synth_day_frame(N, F, d, seed=50 + N) for d, F in enumerate(Fs)]
+    specs = [day_spec_from_frame(frames[0])]
+    specs += [day_spec_from_frame(f, specs[0].codes) for f in frames[1:]]
+    lat = synth_latents(N, P, seed=N + 1, service_scale=svc, spread=spread)
+    noise = std_noise(P, len(Fs), max(Fs), seed=N)
+    sc = (0.09, 0.11, 0.1)
+    ref = ba_oracle.run_batch(specs, lat, sc, noise, delta_t=0.2, n_threads=4)
+    plan = EmuPlan(specs, N, 0.2, 30.0, False)
+    for shuffle in (1, 2):
+        o = plan.forward(lat, sc, noise, scan2=True, shuffle_seed=shuffle, want_pop=True)
+        assert (o["status"] == 0).all()
+        assert np.array_equal(o["ticks"], ref["n_ticks"])
+        np.testing.assert_allclose(o["logp"], ref["logp"], rtol=5e-6, atol=5e-6 * np.abs(ref["logp"]).max())
+        for k, v in ref["grads"].items():
+            if k in o["grads"]:
+                assert rel_err(o["grads"][k], v) <= 1e-4, k
+        for d, spec in enumerate(specs):
+            r = ba_oracle.run_day(spec, {k: v[0] for k, v in lat.items()}, sc, noise[0, d],
+                                  delta_t=0.2, want_grad=False)
+            assert np.array_equal(o["pop_tick"][0, d, :spec.n_flights], r["pop_tick"])
+
+
+def test_emulated_scan2_value_mode_and_philox():
+    """noise_is_value (site values fixed by a guide) and in-kernel Philox noise on the
+    ring-less scan agree with the exact-list kernel."""
+    from tests.hostemu import EmuPlan
+    g = Golden("twoday5")
+    plan = EmuPlan(g.specs, len(g.global_codes), g.delta_t, g.max_t, False)
+    lat = {k: v[None] for k, v in g.latents.items()}
+    vals = np.nan_to_num(g.ref_values, nan=1.0)[None]
+    a = plan.forward(lat, g.scales, vals, value_mode=True, scan2=True)
+    b = plan.forward(lat, g.scales, vals, value_mode=True, exact=True)
+    ref_sum = sum(g.ref_class.values())
+    assert abs(float(a["logp"].sum()) - ref_sum) <= 5e-6 * abs(ref_sum)
+    for k in b["grads"]:
+        assert rel_err(a["grads"][k], b["grads"][k]) <= 1e-5, k
+    p1 = plan.forward(lat, g.scales, None, seed=11, scan2=True)
+    p2 = plan.forward(lat, g.scales, plan.philox_noise(1, 11), scan2=True)
+    assert np.array_equal(p1["logp"], p2["logp"])
+
+
+def test_emulated_scan2_bucket_overflow_reruns_exact():
+    """An arrival beyond the shared tick buckets flags BA_PD_OVERFLOW and the particle-day is
+    re-run with the exact lists (same answer as the oracle)."""
+    from oracle import ba_oracle
+    from tests.hostemu import EmuPlan
+    g = Golden("tiny4")
+    plan = EmuPlan(g.specs, len(g.global_codes), 0.02, g.max_t, False)   # 50 ticks per hour
+    lat = {k: v[None] for k, v in g.latents.items()}
+    flagged = plan.forward(lat, g.scales, g.noise[None], scan2=True, rerun_overflow=False)
+    assert (flagged["status"] & 2).all()
+    fixed = plan.forward(lat, g.scales, g.noise[None], scan2=True)
+    ref = ba_oracle.run_batch(g.specs, lat, g.scales, g.noise[None], delta_t=0.02)
+    assert (fixed["status"] == 0).all()
+    np.testing.assert_allclose(fixed["logp"], ref["logp"], rtol=5e-6)
+
+
 def test_clock_matches_torch_inplace_add():
     """The kernel's clock (sequential fp32 adds, model.py:158-161) equals torch's
     in-place `t += delta_t` on an fp32 tensor, tick for tick."""

@@ -100,7 +100,26 @@ class Golden:
         self.ref_grad_scales = z["ref_grad_scales"]
 
 
-def rel_err(a, b):
+def rel_err(a, b, floor=0.0):
+    """Largest PER-ELEMENT relative error |a - b| / |b|.  Elements whose reference is
+    exactly zero (unused routes, diagonal travel times) must be exactly zero too: there the
+    absolute error is reported against the smallest normal number, i.e. any non-zero value
+    fails every tolerance.  `floor` > 0 bounds the denominator of the NON-zero elements from
+    below by floor * max|b|: an element many orders of magnitude below the largest of its
+    family is a sum of cancelling fp32 terms, and the reference's own fp32 autograd carries
+    the same absolute uncertainty there."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0
+    den = np.maximum(np.abs(b), 1e-30)
+    if floor > 0.0:
+        den = np.where(b != 0.0, np.maximum(den, floor * np.abs(b).max()), den)
+    return float((np.abs(a - b) / den).max())
+
+
+def max_norm_err(a, b):
+    """|a - b|_inf / |b|_inf (for quantities that are sums with cancellation, e.g. log-probs)."""
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
