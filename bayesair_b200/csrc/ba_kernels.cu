@@ -18,6 +18,7 @@
 #include "ba_scan2.cuh"
 
 #define BA_RED_WORDS (32 * 6 + 4)
+#define BA_MAX_DEVICES 64
 
 int ba_forward_block_threads(int n_airports)
 {
@@ -514,8 +515,15 @@ uint64_t ba_forward2_scratch_words(int Fmax, int n_airports) { return ba2_scratc
 // sets the dynamic shared-memory limit (on the current device) and returns the resident grid
 int ba_forward2_configure(size_t smem, int device)
 {
-    cudaError_t e = cudaFuncSetAttribute(ba_forward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -1;
+    // the limit is a property of the kernel function on one device, shared by every plan of
+    // the process there: only ever raise it
+    static size_t cur[BA_MAX_DEVICES] = {0};
+    cudaError_t e = cudaSuccess;
+    if (device >= 0 && device < BA_MAX_DEVICES && smem > cur[device] && smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(ba_forward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -1;
+        cur[device] = smem;
+    }
     int per_sm = 0, sms = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_forward2_kernel, 32, smem);
     if (e != cudaSuccess) return -1;
@@ -535,15 +543,16 @@ __global__ void __launch_bounds__(256) ba_backward_kernel(const BaBwdParams prm)
 {
     const int CN = prm.C * prm.N;
     const int stride = prm.stride;
-    const int p = blockIdx.y;
-    const float *tp = prm.tape + (size_t)p * prm.D * stride;
-    const float *dl = prm.dlogp + (size_t)p * prm.D;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < stride; j += gridDim.x * blockDim.x) {
-        float s = 0.0f;
-        for (int d = 0; d < prm.D; ++d) s = fmaf(__ldg(dl + d), __ldg(tp + (size_t)d * stride + j), s);
-        if (j < CN) prm.g_airport[(size_t)p * CN + j] = s;
-        else if (j < CN + prm.R) prm.g_route[(size_t)p * prm.R + (j - CN)] = s;
-        else prm.g_scales[(size_t)p * 3 + (j - CN - prm.R)] = s;
+    for (int p = blockIdx.y; p < prm.P; p += gridDim.y) {
+        const float *tp = prm.tape + (size_t)p * prm.D * stride;
+        const float *dl = prm.dlogp + (size_t)p * prm.D;
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < stride; j += gridDim.x * blockDim.x) {
+            float s = 0.0f;
+            for (int d = 0; d < prm.D; ++d) s = fmaf(__ldg(dl + d), __ldg(tp + (size_t)d * stride + j), s);
+            if (j < CN) prm.g_airport[(size_t)p * CN + j] = s;
+            else if (j < CN + prm.R) prm.g_route[(size_t)p * prm.R + (j - CN)] = s;
+            else prm.g_scales[(size_t)p * 3 + (j - CN - prm.R)] = s;
+        }
     }
 }
 
@@ -591,8 +600,11 @@ __global__ void __launch_bounds__(256) ba_collect_kernel(const uint32_t *status,
 // earlier one).
 cudaError_t ba_forward_configure(int block, size_t smem_fast, size_t smem_exact, bool tracked)
 {
-    static size_t cur_all[2][2][4] = {{{0, 0, 0, 0}, {0, 0, 0, 0}}, {{0, 0, 0, 0}, {0, 0, 0, 0}}};
-    size_t (*cur)[4] = cur_all[tracked ? 1 : 0];
+    // (cudaFuncSetAttribute applies to the current device: one cache per device)
+    static size_t cur_dev[BA_MAX_DEVICES][2][2][4] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= BA_MAX_DEVICES) dev = 0;
+    size_t (*cur)[4] = cur_dev[dev][tracked ? 1 : 0];
     const int cls = block <= 128 ? 0 : (block <= 256 ? 1 : (block <= 512 ? 2 : 3));
     cudaError_t e = cudaSuccess;
     // tuning knob: share of the SM's L1/shared array given to shared memory (percent); the
@@ -656,7 +668,10 @@ cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, bool tracked, in
 cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
                               cudaStream_t s)
 {
-    static size_t cur[4] = {0, 0, 0, 0};
+    static size_t cur_dev[BA_MAX_DEVICES][4] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= BA_MAX_DEVICES) dev = 0;
+    size_t *cur = cur_dev[dev];
     const int cls = block <= 128 ? 0 : (block <= 256 ? 1 : (block <= 512 ? 2 : 3));
     if (smem > cur[cls]) {
         cudaError_t e = cudaSuccess;
@@ -671,7 +686,7 @@ cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t 
 
 cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s)
 {
-    dim3 grid((unsigned)((p.stride + 255) / 256), (unsigned)p.P);
+    dim3 grid((unsigned)((p.stride + 255) / 256), (unsigned)(p.P < 65535 ? p.P : 65535));
     if (grid.x > 64) grid.x = 64;
     ba_backward_kernel<<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();

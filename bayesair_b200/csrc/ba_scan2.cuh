@@ -427,6 +427,18 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
     const uint32_t nlate = (*(volatile uint32_t *)(s + 10 * ns) >> lsh) & 0xFFFFu;
     // nothing queued, nothing joins: most airport-ticks of the light airports
     if ((nkey >> 16) > km1 && nlate == 0u && rt != k && ha == w && hd == td && asg == 0u) return false;
+    // What this tick will certainly touch first is requested up front, as independent loads
+    // (one memory round trip instead of a chain): the q of the first due arrival and the key
+    // behind it, the record of the departure at the head of its list.
+    uint32_t q_first = BA2_NONE, nkey2 = BA2_NONE;
+    if ((nkey >> 16) <= km1) { q_first = c.P[nkey & 0xFFFFu].q; nkey2 = c.Ak[r + 1u]; }
+    uint32_t dk = BA2_NONE;                   // lq[hd] and its draw, valid within this tick; bit 31:
+    float dqs = 0.0f, dx = 0.0f;              //   its arrival time has passed already
+    if (hd < td || rt == k) {
+        const Ba2Pay pay = ba2_ld_pay(c.P + hd);
+        const Ba2U2 lq2 = ba2_ld2((const uint32_t *)(c.lq + hd));
+        dk = lq2.x | (pay.at <= t ? 0x80000000u : 0u); dqs = __uint_as_float_portable(lq2.y); dx = pay.xw;
+    }
     float A = __uint_as_float_portable(s[5 * ns]), wacc = __uint_as_float_portable(s[6 * ns]);
     const uint32_t s7 = s[7 * ns];
     uint32_t g = s7 & 0xFFFFu, gnew = s7 >> 16;
@@ -439,7 +451,8 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
     //     whose departure had not been served by then comes through the late box instead.
     while ((nkey >> 16) <= km1) {
         const uint32_t lpos = nkey & 0xFFFFu;
-        const uint32_t q = c.P[lpos].q;
+        const uint32_t q = q_first != BA2_NONE ? q_first : c.P[lpos].q;
+        q_first = BA2_NONE;
         if (q < (nkey >> 16)) {
             const uint32_t okey = ba2_key(q, lpos);
             if (w == r && (w == wb || okey >= pk)) {
@@ -452,7 +465,8 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
             joined = true;
         }
         r += 1;
-        nkey = c.Ak[r];
+        nkey = nkey2 != BA2_NONE ? nkey2 : c.Ak[r];
+        nkey2 = BA2_NONE;
     }
     // (2) from the late box: departures served in tick k - 1 at or after the arrival tick
     //     (network.py:186); they sort behind (1): their q is larger
@@ -479,8 +493,6 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
     const uint32_t cnt0 = cnt;
     uint32_t hkey = BA2_NONE;                 // Ak[ha] and its payload, valid within this tick
     float hat = 0.0f, hxa = 0.0f;
-    uint32_t dk = BA2_NONE;                   // lq[hd], its draw and its arrival time, valid
-    float dqs = 0.0f, dx = 0.0f, dat = 0.0f;  //   within this tick
     uint32_t lwr = BA2_NONE;                  // log indices, loaded on demand
     for (;;) {
         if (asg == 0u) {
@@ -493,10 +505,11 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
             }
             if (hd_ok && dk == BA2_NONE) {
                 const Ba2Pay pay = ba2_ld_pay(c.P + hd);
-                dk = c.lq[hd].tick; dqs = c.lq[hd].qstart; dx = pay.xw; dat = pay.at;
+                const Ba2U2 lq2 = ba2_ld2((const uint32_t *)(c.lq + hd));
+                dk = lq2.x | (pay.at <= t ? 0x80000000u : 0u); dqs = __uint_as_float_portable(lq2.y); dx = pay.xw;
             }
             const uint32_t pa = ha_ok ? (hkey >> 16) + 1u : BA2_NONE;
-            const uint32_t pd = hd_ok ? dk : BA2_NONE;
+            const uint32_t pd = hd_ok ? (dk & 0xFFFFu) : BA2_NONE;
             const bool arr = pa <= pd;                       // arrivals first on ties
             const uint32_t p = arr ? pa : pd;
             const float x = arr ? hxa : dx;
@@ -527,9 +540,10 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
             ha += 1; hkey = BA2_NONE;
         } else {
             // tape: total wait of the departure, and the message to the destination
-            if (dk == BA2_NONE) dat = c.P[hd].at;           // assigned in an earlier tick
+            // (an entry assigned in an earlier tick: look its arrival time up again)
+            const bool late = dk == BA2_NONE ? c.P[hd].at <= t : (dk >> 31) != 0u;
             ba2_st2((uint32_t *)(c.P + hd), __float_as_uint_portable(wacc), k);
-            if (dat <= t) {
+            if (late) {
                 // served at or after its arrival time: joins the destination's queue at the
                 // end of this very tick (update_in_transit_flights, network.py:186)
                 const BaLiveDep ld = c.lq[hd];
