@@ -42,8 +42,11 @@ struct BaPlan {
     // ring-less scan (ba_scan2.cuh): bookkeeping-free, fully observed plans
     bool scan2_ok = false;
     size_t smem_scan2 = 0;
-    int grid_scan2 = 0;
+    int grid_scan2 = 0;                  // resident grid at the plan's default warp count
+    int grids_scan2[4] = {0, 0, 0, 0};   // ... at 1, 2, 4, 8 warps per particle-day
+    int sm_count = 0;
     uint64_t stride_scan2 = 0;
+    int warps_scan2 = 1;
     uint32_t *d_scratch = nullptr;
     uint64_t stride_fast = 0, stride_exact = 0;
     unsigned int *d_counters = nullptr;  // [0] fast work, [1] exact work, [2] rerun count
@@ -211,9 +214,19 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     if (pl->host.view.scan2_ok && !(std::getenv("BA_SCAN2") && std::atoi(std::getenv("BA_SCAN2")) == 0)) {
         pl->smem_scan2 = ba_forward2_smem_bytes(N);
         if (pl->smem_scan2 <= (size_t)max_optin) {
-            pl->grid_scan2 = ba_forward2_configure(pl->smem_scan2, device);
+            pl->warps_scan2 = ba_forward2_warps(N);
+            int gmax = 0;
+            bool ok = true;
+            for (int i = 0; i < 4; ++i) {
+                pl->grids_scan2[i] = ba_forward2_configure(1 << i, pl->smem_scan2, device);
+                ok = ok && pl->grids_scan2[i] > 0;
+                gmax = std::max(gmax, pl->grids_scan2[i]);
+                if ((1 << i) == pl->warps_scan2) pl->grid_scan2 = pl->grids_scan2[i];
+            }
+            cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
             pl->stride_scan2 = (ba_forward2_scratch_words(pl->host.view.Fmax, N) + 31) & ~31ull;
-            pl->scan2_ok = pl->grid_scan2 > 0;
+            pl->scan2_ok = ok && pl->grid_scan2 > 0 && pl->sm_count > 0;
+            if (pl->scan2_ok) pl->grid_scan2 = gmax;     // sizes the scratch
         }
     }
     uint64_t words = std::max<uint64_t>((uint64_t)pl->grid_fast * pl->stride_fast,
@@ -242,7 +255,7 @@ extern "C" BaStatus ba_plan_info(const BaPlan *pl, BaPlanInfo *o)
     o->n_airport_latents = v.C; o->grad_stride = v.grad_stride;
     o->include_cancellations = v.include_cancellations; o->device = pl->device;
     o->delta_t = v.delta_t; o->max_t = v.max_t; o->max_ticks = v.max_ticks;
-    o->block_threads = pl->block;
+    o->block_threads = pl->scan2_ok ? 32 * pl->warps_scan2 : pl->block;
     o->smem_bytes = (int32_t)(pl->scan2_ok ? pl->smem_scan2 : (pl->fast_ok ? pl->smem_fast : pl->smem_exact));
     o->resident_ctas = pl->scan2_ok ? pl->grid_scan2 : (pl->fast_ok ? pl->grid_fast : pl->grid_exact);
     return BA_OK;
@@ -315,8 +328,14 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
         prm.work_counter = pl->d_counters + 0;
         if (use_scan2) {
             prm.scratch_stride = pl->stride_scan2;
-            int grid = (int)std::min<long long>(n_work, pl->grid_scan2);
-            BA_CUDA(ba_launch_forward2(prm, grid, pl->smem_scan2, s));
+            // warps per particle-day: the plan's default for its network size, more when the
+            // batch is too small to fill the SMs with one-warp particle-days (SVI steps,
+            // strong-scaling shards)
+            int nw = pl->warps_scan2, li = nw == 1 ? 0 : (nw == 2 ? 1 : (nw == 4 ? 2 : 3));
+            const bool pinned_w = std::getenv("BA_WARPS") != nullptr;
+            while (!pinned_w && li < 3 && n_work * (long long)(2 * nw) <= 32LL * pl->sm_count) { nw *= 2; ++li; }
+            int grid = (int)std::min<long long>(n_work, pl->grids_scan2[li]);
+            BA_CUDA(ba_launch_forward2(prm, nw, grid, pl->smem_scan2, s));
         } else {
             prm.scratch_stride = pl->stride_fast;
             int grid = (int)std::min<long long>(n_work, pl->grid_fast);

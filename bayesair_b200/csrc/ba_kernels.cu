@@ -349,26 +349,46 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
 
 
 // ---------------------------------------------------------------------------
-// ba_forward2_kernel: the ring-less scan (ba_scan2.cuh) for bookkeeping-free, fully
-// observed plans.  Persistent one-warp CTAs: a warp owns a (particle, day) from the prologue
-// to the epilogue, so an SM runs ~30 independent particle-days and nothing ever waits for
-// another warp.
+// ba_forward2_kernel<NW>: the ring-less scan (ba_scan2.cuh) for bookkeeping-free, fully
+// observed plans.  Persistent small CTAs: NW warps (1 for networks up to ~128 airports) own a
+// (particle, day) from the prologue to the epilogue, so an SM runs ~30 independent
+// particle-days.  With NW = 1 nothing ever waits for another warp; larger networks spread the
+// rounds of a tick over NW warps (one CTA barrier per tick) so that an SM still holds ~30
+// warps although a particle-day's state takes more shared memory.
 // ---------------------------------------------------------------------------
-#ifndef BA2_MIN_BLOCKS
-#define BA2_MIN_BLOCKS 32
-#endif
+#define BA2_RED_WORDS (8 * 6 + 8)
 
-__global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const BaFwdParams prm)
+template <int NW> __device__ __forceinline__ void ba2_sync()
+{
+    if (NW == 1) __syncwarp(); else __syncthreads();
+}
+template <int NW> __device__ __forceinline__ bool ba2_any(bool v)
+{
+    if (NW == 1) return __any_sync(0xffffffffu, v) != 0;
+    return __syncthreads_or(v ? 1 : 0) != 0;
+}
+// rounds of 32 airports are dealt to the warps in snake order (0 1 2 3 3 2 1 0 ...): the
+// airports are sorted by traffic, so every warp gets heavy and light rounds
+template <int NW> __device__ __forceinline__ bool ba2_my_round(int j, int warp)
+{
+    if (NW == 1) return true;
+    const int pos = j % (2 * NW);
+    return (pos < NW ? pos : 2 * NW - 1 - pos) == warp;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaFwdParams prm)
 {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NT = 32 * NW;
     const BaPlanView &plan = prm.plan;
     const int N = plan.N, D = plan.D, R = plan.R;
 
     Ba2Ctx c;
     c.nslot = (uint32_t)N;
-    c.un = smem;
-    c.s_rate = (float *)(smem + BA2_KC + N);                 // prologue: behind buckets and cursors
+    c.un = smem + BA2_RED_WORDS;
+    uint32_t *red = smem;
     uint32_t *gscr = prm.scratch + (size_t)blockIdx.x * prm.scratch_stride;
 
     c.sigma = prm.scales[0]; c.v_t = prm.scales[1]; c.v_u = prm.scales[2];
@@ -387,15 +407,21 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
     c.N = N;
     // optional phase timing (BA_PHASE_PROFILE)
     long long pc_last = 0;
-    const bool prof = prm.phase_cycles != nullptr && lane == 0;
+    const bool prof = prm.phase_cycles != nullptr && tid == 0;
 #define BA2_MARK(slot) do { if (prof) { long long now_ = clock64(); atomicAdd(prm.phase_cycles + (slot), (unsigned long long)(now_ - pc_last)); pc_last = now_; } } while (0)
 
     for (;;) {
         if (prof) pc_last = clock64();
         // ---- next work item ------------------------------------------------
         int wi = 0;
-        if (lane == 0) wi = (int)atomicAdd(prm.work_counter, 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (NW == 1) {
+            if (lane == 0) wi = (int)atomicAdd(prm.work_counter, 1u);
+            wi = __shfl_sync(0xffffffffu, wi, 0);
+        } else {
+            if (tid == 0) red[BA2_RED_WORDS - 1] = atomicAdd(prm.work_counter, 1u);
+            __syncthreads();
+            wi = (int)red[BA2_RED_WORDS - 1];
+        }
         const int n_work = prm.n_work_dev ? (int)*prm.n_work_dev : prm.n_work;
         if (wi >= n_work) break;
         int p, d;
@@ -420,48 +446,56 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
         const uint32_t n_arr = (uint32_t)day.n_arr;
 
         // ---- setup -----------------------------------------------------------
-        c.s_rate = (float *)(smem + BA2_KC + N); c.s_mt = nullptr;
-        for (int a = lane; a < N; a += 32) ba2_init_airport(c, a, N, false);
-        for (int i = lane; i < BA2_KC; i += 32) c.un[i] = 0;
+        c.s_rate = (float *)(c.un + BA2_KC + N); c.s_mt = nullptr;   // behind buckets and cursors
+        for (int a = tid; a < N; a += NT) ba2_init_airport(c, a, N, false);
+        for (int i = tid; i < BA2_KC; i += NT) c.un[i] = 0;
         if (c.grow && day.Rd < R)
-            for (int i = lane; i < R; i += 32) c.grow[c.route_base + i] = 0.0f;
+            for (int i = tid; i < R; i += NT) c.grow[c.route_base + i] = 0.0f;
         if (c.pop_tick)
-            for (int i = 2 * day.F + lane; i < 2 * plan.Fmax; i += 32) c.pop_tick[i] = -1;
+            for (int i = 2 * day.F + tid; i < 2 * plan.Fmax; i += NT) c.pop_tick[i] = -1;
         BaAcc acc = {0.0, 0.0f, 0.0f, 0.0f, 0u};
-        __syncwarp();
+        ba2_sync<NW>();
         BA2_MARK(0);
 
         // ---- prologue ----------------------------------------------------------
-        for (int f = lane; f < day.F; f += 32) ba2_prologue_flight(c, acc, f);
-        __syncwarp();
+        for (int f = tid; f < day.F; f += NT) ba2_prologue_flight(c, acc, f);
+        ba2_sync<NW>();
         BA2_MARK(1);
-        ba2_bucket_scan(c, lane);
-        __syncwarp();
-        for (int f = lane; f < day.F; f += 32) ba2_scatter_flight(c, f);
-        for (int a = lane; a < N; a += 32) ba2_split_cursor(c, a);
-        __syncwarp();
-        ba2_split(c, lane, n_arr);
-        __syncwarp();
-        const bool aborted = __any_sync(0xffffffffu, (acc.status & BA_S_OVERFLOW) != 0u) != 0;
+        if (warp == 0) ba2_bucket_scan(c, lane);
+        ba2_sync<NW>();
+        for (int f = tid; f < day.F; f += NT) ba2_scatter_flight(c, f);
+        for (int a = tid; a < N; a += NT) ba2_split_cursor(c, a);
+        ba2_sync<NW>();
+        if (warp == 0) ba2_split(c, lane, n_arr);              // stable: one warp walks the order
+        const bool aborted = ba2_any<NW>((acc.status & BA_S_OVERFLOW) != 0u);
         BA2_MARK(2);
 
         // ---- scan: the lanes walk the airports in rounds, one clock ------------------
         uint32_t k = (uint32_t)(day.first_tick - 1);
         if (!aborted) {
             uint32_t nleft = 0;
-            for (uint32_t slot = lane; slot < (uint32_t)N; slot += 32u) {
+            for (uint32_t slot = tid; slot < (uint32_t)N; slot += NT) {
                 const int a = c.order[slot];
                 ba2_state_init(c, slot, a);
+            }
+            for (int j = 0; 32 * j < N; ++j) {
+                const uint32_t slot = 32u * (uint32_t)j + (uint32_t)lane;
+                if (!ba2_my_round<NW>(j, warp) || slot >= (uint32_t)N) continue;
+                const int a = c.order[slot];
                 nleft += (c.ap[a].dep_live + c.ap[a].arr_cnt) != 0 ? 1u : 0u;
             }
-            __syncwarp();
-            while (__any_sync(0xffffffffu, nleft != 0u)) {
+            bool go = ba2_any<NW>(nleft != 0u);
+            while (go) {
                 if ((int)k >= plan.max_ticks) { acc.status |= BA_S_TICK_CAP; break; }
                 ++k;
                 const float t = c.tick_time[k];                 // model.py:161
-                for (uint32_t slot = lane; slot < (uint32_t)N; slot += 32u)
+                for (int j = 0; 32 * j < N; ++j) {
+                    const uint32_t slot = 32u * (uint32_t)j + (uint32_t)lane;
+                    if (!ba2_my_round<NW>(j, warp) || slot >= (uint32_t)N) continue;
                     if (ba2_airport_tick(c, slot, k, t, acc.status)) nleft -= 1u;
-                __syncwarp();        // every airport's tick k is in memory before tick k + 1
+                }
+                // every airport's tick k is in memory before tick k + 1
+                go = ba2_any<NW>(nleft != 0u);
             }
         }
         BA2_MARK(3);
@@ -469,18 +503,18 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
         if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
 
         // ---- epilogue ----------------------------------------------------------
-        __syncwarp();
-        c.s_rate = (float *)smem; c.s_mt = c.s_rate + N;         // the scan state is dead
-        for (int a = lane; a < N; a += 32) ba2_init_airport(c, a, N, true);
-        __syncwarp();
+        ba2_sync<NW>();
+        c.s_rate = (float *)c.un; c.s_mt = c.s_rate + N;          // the scan state is dead
+        for (int a = tid; a < N; a += NT) ba2_init_airport(c, a, N, true);
+        ba2_sync<NW>();
         if (!aborted)
-            for (int f = lane; f < day.F; f += 32) ba2_epilogue_flight(c, acc, f);
+            for (int f = tid; f < day.F; f += NT) ba2_epilogue_flight(c, acc, f);
         if (c.grow && !aborted) {
-            __syncwarp();
-            for (int s = lane; s < N; s += 32) ba2_epilogue_airport(c, s, N);
-            for (int r = lane; r < day.Rd; r += 32) ba2_epilogue_route(c, r);
+            ba2_sync<NW>();
+            for (int s = tid; s < N; s += NT) ba2_epilogue_airport(c, s, N);
+            for (int r = tid; r < day.Rd; r += NT) ba2_epilogue_route(c, r);
         }
-        // deterministic reduction: shuffle tree over the lanes
+        // deterministic reduction: shuffle tree over the lanes, warps in order
         double v0 = acc.lp;
         float v1 = acc.g_sigma, v2 = acc.g_vt, v3 = acc.g_vu;
         uint32_t st = acc.status;
@@ -492,7 +526,24 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
             v3 += __shfl_down_sync(0xffffffffu, v3, o);
             st |= __shfl_down_sync(0xffffffffu, st, o);
         }
-        if (lane == 0) {
+        if (NW > 1) {
+            float *redf = (float *)red;
+            double *redd = (double *)red;          // 16-byte aligned; 6 words per warp
+            if (lane == 0) {
+                redd[warp * 3 + 0] = v0;
+                redf[warp * 6 + 2] = v1; redf[warp * 6 + 3] = v2;
+                redf[warp * 6 + 4] = v3; red[warp * 6 + 5] = st;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                v0 = 0; v1 = v2 = v3 = 0; st = 0;
+                for (int w = 0; w < NW; ++w) {
+                    v0 += redd[w * 3 + 0]; v1 += redf[w * 6 + 2]; v2 += redf[w * 6 + 3];
+                    v3 += redf[w * 6 + 4]; st |= red[w * 6 + 5];
+                }
+            }
+        }
+        if (tid == 0) {
             prm.logp[pd] = (float)v0;
             prm.status[pd] = st;
             if (prm.ticks) prm.ticks[pd] = tick;
@@ -502,39 +553,58 @@ __global__ void __launch_bounds__(32, BA2_MIN_BLOCKS) ba_forward2_kernel(const B
                 c.grow[c.route_base + R + 2] = v3;
             }
         }
-        __syncwarp();        // the shared tables are reused by the next item
+        ba2_sync<NW>();        // the shared tables are reused by the next item
         BA2_MARK(4);
     }
 #undef BA2_MARK
 }
 
-size_t ba_forward2_smem_bytes(int n_airports) { return ba2_smem_words(n_airports) * 4; }
+size_t ba_forward2_smem_bytes(int n_airports) { return (BA2_RED_WORDS + ba2_smem_words(n_airports)) * 4; }
 
 uint64_t ba_forward2_scratch_words(int Fmax, int n_airports) { return ba2_scratch_words(Fmax, n_airports); }
 
+// warps per particle-day: one up to 128 airports; beyond that the state takes more shared
+// memory per particle-day, and more warps keep the SM's warp count up
+int ba_forward2_warps(int n_airports)
+{
+    if (const char *v = getenv("BA_WARPS")) { const int w = atoi(v); if (w == 1 || w == 2 || w == 4 || w == 8) return w; }
+    // (measured on B200: N = 100 nominal 1.32e6 / 1.34e6 pd/s at 1 / 2 warps, congested
+    //  7.9e5 / 7.0e5; N = 500: 0.88 / 1.23 / 1.47 / 1.38 e5 at 1 / 2 / 4 / 8 warps)
+    return n_airports <= 128 ? 1 : (n_airports <= 256 ? 2 : 4);
+}
+
+#define BA2_DISPATCH(NWV, STMT)                                              \
+    do {                                                                     \
+        if ((NWV) == 1) { auto kfn = ba_forward2_kernel<1>; STMT; }           \
+        else if ((NWV) == 2) { auto kfn = ba_forward2_kernel<2>; STMT; }      \
+        else if ((NWV) == 4) { auto kfn = ba_forward2_kernel<4>; STMT; }      \
+        else { auto kfn = ba_forward2_kernel<8>; STMT; }                      \
+    } while (0)
+
 // sets the dynamic shared-memory limit (on the current device) and returns the resident grid
-int ba_forward2_configure(size_t smem, int device)
+int ba_forward2_configure(int nw, size_t smem, int device)
 {
     // the limit is a property of the kernel function on one device, shared by every plan of
     // the process there: only ever raise it
-    static size_t cur[BA_MAX_DEVICES] = {0};
+    static size_t cur[BA_MAX_DEVICES][4] = {};
+    const int cls = nw == 1 ? 0 : (nw == 2 ? 1 : (nw == 4 ? 2 : 3));
     cudaError_t e = cudaSuccess;
-    if (device >= 0 && device < BA_MAX_DEVICES && smem > cur[device] && smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(ba_forward2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (device >= 0 && device < BA_MAX_DEVICES && smem > cur[device][cls] && smem > 48 * 1024) {
+        BA2_DISPATCH(nw, e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (e != cudaSuccess) return -1;
-        cur[device] = smem;
+        cur[device][cls] = smem;
     }
     int per_sm = 0, sms = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_forward2_kernel, 32, smem);
+    BA2_DISPATCH(nw, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 32 * nw, smem));
     if (e != cudaSuccess) return -1;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
     if (const char *v = getenv("BA_MAX_CTAS_PER_SM")) { const int cap = atoi(v); if (cap > 0 && cap < per_sm) per_sm = cap; }
     return per_sm * sms;
 }
 
-cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, size_t smem, cudaStream_t s)
+cudaError_t ba_launch_forward2(const BaFwdParams &p, int nw, int grid, size_t smem, cudaStream_t s)
 {
-    ba_forward2_kernel<<<grid, 32, smem, s>>>(p);
+    BA2_DISPATCH(nw, (kfn<<<grid, 32 * nw, smem, s>>>(p)));
     return cudaGetLastError();
 }
 

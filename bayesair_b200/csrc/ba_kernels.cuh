@@ -51,8 +51,9 @@ cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, bool tracked, in
 // ring-less scan (ba_scan2.cuh): one-warp CTAs
 size_t ba_forward2_smem_bytes(int n_airports);
 uint64_t ba_forward2_scratch_words(int Fmax, int n_airports);
-int ba_forward2_configure(size_t smem, int device);
-cudaError_t ba_launch_forward2(const BaFwdParams &p, int grid, size_t smem, cudaStream_t s);
+int ba_forward2_warps(int n_airports);
+int ba_forward2_configure(int nw, size_t smem, int device);
+cudaError_t ba_launch_forward2(const BaFwdParams &p, int nw, int grid, size_t smem, cudaStream_t s);
 cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
                               cudaStream_t s);
 cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s);
