@@ -24,6 +24,8 @@ EXPORTS = (
     "ba_plan_routes", "ba_tape_bytes", "ba_forward", "ba_backward", "ba_predict",
     "ba_generate_noise",
     "ba_logjoint_host", "ba_launch_count",
+    "ba_mf_work_bytes", "ba_mf_sample", "ba_mf_backward",
+    "ba_rqs_forward", "ba_rqs_backward",
 )
 
 
@@ -48,7 +50,9 @@ class BaForwardOpts(C.Structure):
     _fields_ = [("noise_is_value", C.c_int32), ("want_grad", C.c_int32),
                 ("force_exact_lists", C.c_int32), ("no_overflow_rerun", C.c_int32),
                 ("replay_waits", C.c_int32), ("force_ring_lists", C.c_int32),
-                ("seed", C.c_uint64), ("d_pop_tick", C.c_void_p)]
+                ("seed", C.c_uint64), ("d_pop_tick", C.c_void_p),
+                ("d_seed", C.c_void_p), ("particle_offset", C.c_uint32),
+                ("reserved1", C.c_uint32)]
 
 
 class BayesAirLibraryError(RuntimeError):
@@ -100,6 +104,19 @@ def load_library(build_if_missing: bool = True):
     lib.ba_generate_noise.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.ba_logjoint_host.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + \
         [C.POINTER(BaForwardOpts)] + [C.c_void_p] * 5
+    lib.ba_mf_work_bytes.restype = C.c_size_t
+    lib.ba_mf_work_bytes.argtypes = [C.c_void_p, C.c_int32]
+    lib.ba_mf_sample.restype = C.c_int
+    lib.ba_mf_sample.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                 C.c_uint32] + [C.c_void_p] * 5
+    lib.ba_mf_backward.restype = C.c_int
+    lib.ba_mf_backward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
+                                   C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ba_rqs_forward.restype = C.c_int
+    lib.ba_rqs_forward.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]
+    lib.ba_rqs_backward.restype = C.c_int
+    lib.ba_rqs_backward.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]
     _lib = lib
     return lib
 
@@ -184,6 +201,22 @@ class PlanHandle:
         _check(load_library().ba_generate_noise(self.handle, int(P), C.c_uint64(int(seed)),
                                                 noise, stream), "ba_generate_noise")
 
+    def mf_work_bytes(self, P: int) -> int:
+        return int(load_library().ba_mf_work_bytes(self.handle, int(P)))
+
+    def mf_sample(self, P, params, seed, d_seed, particle_offset, lat_airport, lat_route, lp0, z,
+                  stream):
+        _check(load_library().ba_mf_sample(self.handle, int(P), params, C.c_uint64(int(seed)),
+                                           d_seed, int(particle_offset), lat_airport, lat_route,
+                                           lp0, z, stream), "ba_mf_sample")
+
+    def mf_backward(self, P, params, seed, d_seed, particle_offset, tape, logp, lp0,
+                    inv_count_flights, work, flat, stream):
+        _check(load_library().ba_mf_backward(self.handle, int(P), params, C.c_uint64(int(seed)),
+                                             d_seed, int(particle_offset), tape, logp, lp0,
+                                             C.c_float(float(inv_count_flights)), work, flat,
+                                             stream), "ba_mf_backward")
+
     def logjoint_host(self, P, lat_airport, lat_route, scales, noise, opts, logp, status,
                       g_airport, g_route, g_scales):
         _check(load_library().ba_logjoint_host(self.handle, int(P), lat_airport, lat_route,
@@ -201,3 +234,27 @@ class PlanHandle:
             self.close()
         except Exception:
             pass
+
+
+def _tensor_stream(t):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def rqs_forward(x, params, y, logdet, bins: int, bound: float):
+    """``ba_rqs_forward`` on contiguous fp32 CUDA tensors (torch's current stream)."""
+    import torch
+    with torch.cuda.device(x.device):
+        _check(load_library().ba_rqs_forward(x.data_ptr(), params.data_ptr(), y.data_ptr(),
+                                             logdet.data_ptr(), x.numel(), int(bins), float(bound),
+                                             _tensor_stream(x)), "ba_rqs_forward")
+
+
+def rqs_backward(x, params, gy, gld, gx, gparams, bins: int, bound: float):
+    """``ba_rqs_backward`` on contiguous fp32 CUDA tensors (torch's current stream)."""
+    import torch
+    with torch.cuda.device(x.device):
+        _check(load_library().ba_rqs_backward(x.data_ptr(), params.data_ptr(), gy.data_ptr(),
+                                              gld.data_ptr(), gx.data_ptr(), gparams.data_ptr(),
+                                              x.numel(), int(bins), float(bound), _tensor_stream(x)),
+               "ba_rqs_backward")

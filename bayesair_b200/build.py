@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "_lib")
 # BA_LIB_PATH selects an alternative build of the same library (tuning experiments)
 LIB_PATH = os.environ.get("BA_LIB_PATH") or os.path.join(LIB_DIR, "libbayesair_b200.so")
-SOURCES = ["ba_kernels.cu", "ba_capi.cu", "ba_plan_build.cpp"]
+SOURCES = ["ba_kernels.cu", "ba_guide.cu", "ba_capi.cu", "ba_plan_build.cpp"]
 HEADERS = ["ba_sim.cuh", "ba_scan2.cuh", "ba_kernels.cuh", "ba_plan.h", "ba_plan_build.h",
            os.path.join("..", "..", "include", "bayesair_b200.h")]
 

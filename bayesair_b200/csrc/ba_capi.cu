@@ -56,6 +56,7 @@ struct BaPlan {
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    int32_t *d_route_of = nullptr;       // [N*N] (origin, dest) -> route index or -1
     // scratch log-prob output of ba_predict (the kernel writes one float per item)
     float *d_plogp = nullptr;
     size_t plogp_cap = 0;
@@ -183,6 +184,14 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     pl->dev_view = pl->host.view;
     pl->dev_view.days = pl->d_days;
     BA_PCUDA(upload(pl, pl->host.tick_time, &pl->dev_view.tick_time));
+    {
+        std::vector<int32_t> route_of((size_t)n_airports * n_airports, -1);
+        for (size_t r = 0; r < pl->host.route_origin.size(); ++r)
+            route_of[(size_t)pl->host.route_origin[r] * n_airports + pl->host.route_dest[r]] = (int32_t)r;
+        const int32_t *d = nullptr;
+        BA_PCUDA(upload(pl, route_of, &d));
+        pl->d_route_of = const_cast<int32_t *>(d);
+    }
 
     // launch geometry
     const int N = n_airports;
@@ -308,6 +317,7 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
     prm.P = P;
     prm.lat_airport = d_lat_airport; prm.lat_route = d_lat_route; prm.scales = d_scales;
     prm.noise = d_noise; prm.seed = o.seed;
+    prm.seed_dev = o.d_seed; prm.particle_offset = o.particle_offset;
     prm.value_mode = o.noise_is_value; prm.want_grad = o.want_grad;
     prm.replay_waits = o.replay_waits;
     prm.logp = d_logp; prm.status = d_status; prm.ticks = d_ticks;
@@ -411,6 +421,7 @@ extern "C" BaStatus ba_predict(BaPlan *pl, int32_t P, const float *d_lat_airport
     prm.P = P;
     prm.lat_airport = d_lat_airport; prm.lat_route = d_lat_route; prm.scales = d_scales;
     prm.noise = d_noise; prm.noise2 = d_noise2; prm.sim = d_sim; prm.seed = o.seed;
+    prm.seed_dev = o.d_seed; prm.particle_offset = o.particle_offset;
     prm.value_mode = o.noise_is_value;
     prm.logp = pl->d_predict_logp(P * pl->host.view.D);
     if (!prm.logp) return set_err(BA_ERR_CUDA, "ba_predict: out of device memory");
@@ -437,6 +448,89 @@ extern "C" BaStatus ba_backward(BaPlan *pl, int32_t P, const float *d_dlogp, con
     b.dlogp = d_dlogp; b.tape = (const float *)d_tape;
     b.g_airport = d_g_airport; b.g_route = d_g_route; b.g_scales = d_g_scales;
     BA_CUDA(ba_launch_backward(b, (cudaStream_t)stream));
+    g_launches++;
+    return BA_OK;
+}
+
+// ---- mean-field guide fused with the simulation's gradient (ba_guide.cu) -----------------
+static BaStatus mf_params(BaPlan *pl, int32_t P, BaMfParams *m, const char *who)
+{
+    if (!pl || P <= 0) return set_err(BA_ERR_BAD_ARG, std::string(who) + ": null / empty argument");
+    const BaPlanView &v = pl->host.view;
+    if (v.C != 2) return set_err(BA_ERR_BAD_ARG, std::string(who) + ": plans with cancellations are not supported");
+    std::memset(m, 0, sizeof(*m));
+    m->P = P; m->D = v.D; m->N = v.N; m->R = v.R; m->n = 2 * v.N + v.N * v.N; m->stride = v.grad_stride;
+    m->route_of = pl->d_route_of;
+    m->chunks = ba_mf_chunks(P);
+    return BA_OK;
+}
+
+extern "C" size_t ba_mf_work_bytes(const BaPlan *pl, int32_t P)
+{
+    if (!pl || P <= 0) return 0;
+    const size_t n = 2 * (size_t)pl->host.view.N + (size_t)pl->host.view.N * pl->host.view.N;
+    return (size_t)ba_mf_chunks(P) * (2 * n + 4) * sizeof(float);
+}
+
+extern "C" BaStatus ba_mf_sample(BaPlan *pl, int32_t P, const float *d_params, uint64_t seed,
+                                 const uint64_t *d_seed, uint32_t particle_offset,
+                                 float *d_lat_airport, float *d_lat_route, float *d_lp0, float *d_z,
+                                 void *stream)
+{
+    BaMfParams m;
+    BaStatus rc = mf_params(pl, P, &m, "ba_mf_sample");
+    if (rc != BA_OK) return rc;
+    if (!d_params || !d_lat_airport || !d_lat_route || !d_lp0)
+        return set_err(BA_ERR_BAD_ARG, "ba_mf_sample: null argument");
+    BA_CUDA(cudaSetDevice(pl->device));
+    m.params = d_params; m.seed = seed; m.seed_dev = d_seed; m.particle_offset = particle_offset;
+    m.lat_airport = d_lat_airport; m.lat_route = d_lat_route; m.lp0 = d_lp0; m.z = d_z;
+    BA_CUDA(ba_launch_mf_sample(m, (cudaStream_t)stream));
+    g_launches++;
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_mf_backward(BaPlan *pl, int32_t P, const float *d_params, uint64_t seed,
+                                   const uint64_t *d_seed, uint32_t particle_offset,
+                                   const void *d_tape, const float *d_logp, const float *d_lp0,
+                                   float inv_count_flights, void *d_work, float *d_flat, void *stream)
+{
+    BaMfParams m;
+    BaStatus rc = mf_params(pl, P, &m, "ba_mf_backward");
+    if (rc != BA_OK) return rc;
+    if (!d_params || !d_tape || !d_logp || !d_lp0 || !d_work || !d_flat)
+        return set_err(BA_ERR_BAD_ARG, "ba_mf_backward: null argument");
+    BA_CUDA(cudaSetDevice(pl->device));
+    m.params = d_params; m.seed = seed; m.seed_dev = d_seed; m.particle_offset = particle_offset;
+    m.tape = (const float *)d_tape; m.logp = d_logp; m.lp0 = const_cast<float *>(d_lp0);
+    m.inv_count_flights = inv_count_flights; m.work = (float *)d_work; m.flat = d_flat;
+    BA_CUDA(ba_launch_mf_backward(m, (cudaStream_t)stream));
+    g_launches += 2;
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_rqs_forward(const float *d_x, const float *d_params, float *d_y, float *d_logdet,
+                                   int64_t M, int32_t bins, float bound, void *stream)
+{
+    if (!d_x || !d_params || !d_y || !d_logdet || M <= 0 || !(bound > 0.0f))
+        return set_err(BA_ERR_BAD_ARG, "ba_rqs_forward: null / empty argument");
+    if (bins != 4 && bins != 8 && bins != 12)
+        return set_err(BA_ERR_BAD_ARG, "ba_rqs_forward: bins must be 4, 8 or 12");
+    BA_CUDA(ba_launch_rqs_forward(d_x, d_params, d_y, d_logdet, (long long)M, bins, bound, (cudaStream_t)stream));
+    g_launches++;
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_rqs_backward(const float *d_x, const float *d_params, const float *d_gy,
+                                    const float *d_glogdet, float *d_gx, float *d_gparams,
+                                    int64_t M, int32_t bins, float bound, void *stream)
+{
+    if (!d_x || !d_params || !d_gy || !d_glogdet || !d_gx || !d_gparams || M <= 0 || !(bound > 0.0f))
+        return set_err(BA_ERR_BAD_ARG, "ba_rqs_backward: null / empty argument");
+    if (bins != 4 && bins != 8 && bins != 12)
+        return set_err(BA_ERR_BAD_ARG, "ba_rqs_backward: bins must be 4, 8 or 12");
+    BA_CUDA(ba_launch_rqs_backward(d_x, d_params, d_gy, d_glogdet, d_gx, d_gparams, (long long)M, bins, bound,
+                                   (cudaStream_t)stream));
     g_launches++;
     return BA_OK;
 }

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
     c.cancel_mode = plan.include_cancellations;
     c.replay_always = prm.replay_waits;
     c.max_t = plan.max_t;
-    c.seed = prm.seed;
+    c.seed = prm.seed_dev ? *prm.seed_dev : prm.seed;
     c.route_base = C * N;
     c.tick_time = plan.tick_time;
     c.cta = ctaw;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
         c.noise2 = (PREDICT && prm.noise2) ? prm.noise2 + pd * (size_t)plan.Fmax * 4 : nullptr;
         c.sim = PREDICT ? prm.sim + pd * (size_t)plan.Fmax * 3 : nullptr;
-        c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
+        c.particle = (uint32_t)p + prm.particle_offset; c.dayidx = (uint32_t)d;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
         ba_carve_lists<EXACT>(c, day, plan.max_ticks, plan.max_dslice, fixed, pool, gscr);
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
     c.c0_lp = ba_relaxed_bernoulli_lp(0.0f, 0.0f, nullptr);
     c.c1_lp = ba_relaxed_bernoulli_lp(0.0f, 1.0f, nullptr);
     c.value_mode = prm.value_mode; c.want_grad = prm.want_grad && prm.tape != nullptr;
-    c.seed = prm.seed;
+    c.seed = prm.seed_dev ? *prm.seed_dev : prm.seed;
     c.route_base = 2 * N;
     c.tick_time = plan.tick_time;
     c.max_ticks = plan.max_ticks;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         c.lat_airport = prm.lat_airport + (size_t)p * 2 * N;
         c.lat_route = prm.lat_route + (size_t)p * R;
         c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
-        c.particle = (uint32_t)p; c.dayidx = (uint32_t)d;
+        c.particle = (uint32_t)p + prm.particle_offset; c.dayidx = (uint32_t)d;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
         ba2_carve_scratch(c, gscr, day.F, N);

@@ -15,6 +15,8 @@ struct BaFwdParams {
     const float *noise2;          // predictive: [P, D, Fmax, 4] or nullptr (Philox)
     float *sim;                   // predictive: [P, D, Fmax, 3] out
     uint64_t seed;
+    const uint64_t *seed_dev;     // if set, the seed is read from device memory
+    uint32_t particle_offset;     // added to the particle index in the Philox counters
     int32_t value_mode, want_grad, replay_waits;
     float *logp;                  // [P, D]
     uint32_t *status;             // [P, D]
@@ -54,6 +56,30 @@ uint64_t ba_forward2_scratch_words(int Fmax, int n_airports);
 int ba_forward2_warps(int n_airports);
 int ba_forward2_configure(int nw, size_t smem, int device);
 cudaError_t ba_launch_forward2(const BaFwdParams &p, int nw, int grid, size_t smem, cudaStream_t s);
+// mean-field guide kernels (ba_guide.cu)
+struct BaMfParams {
+    int32_t P, D, N, R, n, stride;
+    uint32_t particle_offset;
+    uint64_t seed;
+    const uint64_t *seed_dev;
+    const float *params;          // [2n] loc | log_scale
+    const int32_t *route_of;      // [N*N] route index of (origin, dest) or -1
+    float *lat_airport, *lat_route, *lp0, *z;
+    const float *tape, *logp;
+    float inv_count_flights;
+    float *work;                  // [chunks, 2n + 4]
+    int32_t chunks;
+    float *flat;
+};
+cudaError_t ba_launch_mf_sample(const BaMfParams &p, cudaStream_t s);
+cudaError_t ba_launch_mf_backward(const BaMfParams &p, cudaStream_t s);
+int ba_mf_chunks(int P);
+// rational-quadratic spline of the flow guide (ba_guide.cu)
+cudaError_t ba_launch_rqs_forward(const float *x, const float *params, float *y, float *ld,
+                                  long long M, int bins, float bound, cudaStream_t s);
+cudaError_t ba_launch_rqs_backward(const float *x, const float *params, const float *gy,
+                                   const float *gld, float *gx, float *gparams, long long M,
+                                   int bins, float bound, cudaStream_t s);
 cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
                               cudaStream_t s);
 cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s);

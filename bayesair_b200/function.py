@@ -42,12 +42,17 @@ class _SimulateLogJoint(torch.autograd.Function):
 
 def simulate_log_joint(plan: SimulationPlan, lat_airport: torch.Tensor, lat_route: torch.Tensor,
                        scales: torch.Tensor, noise: Optional[torch.Tensor] = None, *,
-                       seed: int = 0, noise_is_value: bool = False, check_status: bool = True):
+                       seed: int = 0, noise_is_value: bool = False, check_status: bool = True,
+                       status_out: Optional[torch.Tensor] = None):
     """``logp [P, D]``: per-day sum of the 7F per-flight site log-probs.
 
     ``lat_airport [P,C,N]``, ``lat_route [P,R]``, ``scales [3]`` (all differentiable),
     ``noise [P,D,Fmax,4]`` or None (in-kernel Philox from ``seed``).
-    ``check_status=True`` synchronises once to raise on failed particle-days."""
-    logp, _ = _SimulateLogJoint.apply(plan, lat_airport, lat_route, scales, noise, int(seed),
+    ``check_status=True`` synchronises once to raise on failed particle-days;
+    ``status_out`` (a 0-d int32 device tensor) instead accumulates a failure flag on the
+    device, to be read when the caller chooses (no host sync per call)."""
+    logp, status = _SimulateLogJoint.apply(plan, lat_airport, lat_route, scales, noise, int(seed),
                                       bool(noise_is_value), bool(check_status))
+    if status_out is not None:
+        status_out.bitwise_or_(status.amax().to(status_out.dtype))
     return logp

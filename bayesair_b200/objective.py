@@ -95,15 +95,22 @@ class MeanFieldGuide(torch.nn.Module):
 
 def model_log_joint(plan: SimulationPlan, sample: torch.Tensor, scales: torch.Tensor,
                     noise: Optional[torch.Tensor] = None, seed: int = 0,
-                    check_status: bool = True) -> torch.Tensor:
+                    check_status: bool = True,
+                    day_weights: Optional[torch.Tensor] = None,
+                    status_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``[P]``: what ``trace(condition(model, data)).get_trace(...).log_prob_sum()`` gives
-    the reference per particle (``train.py:306-314``), for all P at once."""
+    the reference per particle (``train.py:306-314``), for all P at once.  ``day_weights
+    [D]``: multiplicity of each day of the plan in the list of states the reference would be
+    given (a bootstrap subsample with repeats, ``training.py:134-136,200-214``, is a weighting
+    of the per-day log-probs: days are independent given the latents, ``model.py:126-155``)."""
     lat = map_to_latents(sample, plan.n_airports, plan.include_cancellations)
     lat_airport, lat_route = plan.pack_latents(
         lat["mean_turnaround"], lat["mean_service"], lat["travel"],
         lat.get("log_initial_aircraft"), lat.get("base_cancel_logprob"))
     logp = simulate_log_joint(plan, lat_airport, lat_route, scales, noise, seed=seed,
-                              check_status=check_status)
+                              check_status=check_status, status_out=status_out)
+    if day_weights is not None:
+        logp = logp * day_weights.to(logp)
     return prior_log_prob(lat, plan.include_cancellations) + logp.sum(1)
 
 

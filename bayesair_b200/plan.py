@@ -101,9 +101,13 @@ class SimulationPlan:
                 force_exact_lists: bool = False, no_overflow_rerun: bool = False,
                 want_ticks: bool = False, want_pop_ticks: bool = False,
                 replay_waits: bool = False,
-                force_ring_lists: bool = False) -> Dict[str, torch.Tensor]:
+                force_ring_lists: bool = False, seed_tensor: Optional[torch.Tensor] = None,
+                particle_offset: int = 0) -> Dict[str, torch.Tensor]:
         """``lat_airport [P,C,N]``, ``lat_route [P,R]``, ``scales [3]``,
-        ``noise [P,D,Fmax,4]`` or None (Philox from ``seed``).  Asynchronous."""
+        ``noise [P,D,Fmax,4]`` or None (Philox from ``seed``).  Asynchronous.
+        ``seed_tensor``: one int64 on the device, read by the kernel when it starts (CUDA
+        graphs replay with a fresh seed); ``particle_offset``: index of the first particle in
+        the global batch (ranks sharing a seed then draw different per-flight noise)."""
         P = int(lat_airport.shape[0])
         D, N, Cn, R, F = (self.n_days, self.n_airports, self.n_airport_latents, self.n_routes,
                           self.max_flights)
@@ -122,11 +126,13 @@ class SimulationPlan:
             opts = _capi.BaForwardOpts(int(noise_is_value), int(want_grad), int(force_exact_lists),
                                        int(no_overflow_rerun), int(replay_waits),
                                        int(force_ring_lists), int(seed) & (2**64 - 1),
-                                       None if pop is None else pop.data_ptr())
+                                       None if pop is None else pop.data_ptr(),
+                                       None if seed_tensor is None else seed_tensor.data_ptr(),
+                                       int(particle_offset) & 0xFFFFFFFF, 0)
             self._h.forward(P, _ptr(la), _ptr(lr), _ptr(sc), _ptr(nz), opts, _ptr(logp),
                             _ptr(status), _ptr(ticks), _ptr(tape), self._stream())
         return {"logp": logp, "status": status, "ticks": ticks, "tape": tape, "pop_tick": pop,
-                "_keep": (la, lr, sc, nz)}
+                "_keep": (la, lr, sc, nz, seed_tensor)}
 
     def predict(self, lat_airport: torch.Tensor, lat_route: torch.Tensor, scales: torch.Tensor,
                 noise: Optional[torch.Tensor] = None, obs_noise: Optional[torch.Tensor] = None,

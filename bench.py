@@ -55,6 +55,18 @@ def build_workload(name, seed=21):
     return N, Fs, P, svc, specs
 
 
+def workload_config(name, particles=0):
+    """The `config` both arms print (identical dicts: the driver compares them)."""
+    N, Fs, P, svc = WORKLOADS[name]
+    P = particles or P
+    return {"workload": f"{name}: WN-like synthetic network N={N} airports, D={len(Fs)} days, "
+                        f"F/day={Fs}, P={P} particles per GPU, delta_t=0.2, no cancellations, "
+                        f"mean service {svc} h x LogNormal(0, 0.3), network seed 21",
+            "particles_per_gpu": P, "days": len(Fs), "delta_t": 0.2,
+            "l2_policy": "inputs larger than L2 (the per-flight noise tensor alone is "
+                         f"{P * sum(Fs) * 16 / 1e9:.2f} GB per GPU)"}
+
+
 def algorithmic_bytes_per_particle_day(N, Fs, R, with_noise=True):
     """16 F (noise in) + 4 (2N+R) (latents in) + 4 (2N+R) (grads out)
     + 4 (logp) + 12 (scale grads), static flight tables amortised over particles."""
@@ -187,7 +199,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: N={N} airports, F/day={Fs}", "delta_t": 0.2},
+        "config": workload_config(name, args.particles),
+        "reference_kind": f"C port of the reference algorithm (oracle/ba_oracle.c), {cores} host threads",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -271,6 +284,36 @@ def run_native(args):
     ms_per_step = ms / args.steps
     value = world * P * D / (ms_per_step * 1e-3)
 
+    # ---- strong scaling: the SAME total batch (P particles x D days) split over the ranks --
+    strong = {"value": value, "particles_total": P, "ms_per_step": ms_per_step,
+              "note": "fixed total work split over n_gpus ranks (contiguous particle shards)"}
+    if world > 1:
+        from bayesair_b200.parallel import shard_particles
+        s0, cnt = shard_particles(P, rank, world)
+        la_s, lr_s = la[s0:s0 + cnt].contiguous(), lr[s0:s0 + cnt].contiguous()
+        nz_s, ones_s = noise[s0:s0 + cnt], ones[:cnt]
+
+        def strong_step():
+            o = plan.forward(la_s, lr_s, scales, nz_s, want_grad=True)
+            g3 = plan.backward(ones_s, o["tape"])
+            guide_grad[:N * 2] = g3[0].sum(0).reshape(-1)[:N * 2]
+            dist.all_reduce(guide_grad)
+
+        for _ in range(3):
+            strong_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            strong_step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong["ms_per_step"] = float(t.item())
+        strong["value"] = P * D / (strong["ms_per_step"] * 1e-3)
+        del la_s, lr_s
+
     # ---- forward kernel alone (roofline): one launch per call, no re-run kernels --
     fwd_ms = []
     for _ in range(max(3, min(args.steps, 10))):
@@ -334,14 +377,46 @@ def run_native(args):
     # ---- "SVI step ms" (BASELINE metric, cfg2 shape): mean-field guide over the 2N+N^2
     #      log-latents, 1024 particles, one day: guide sample -> model log-joint (kernel) ->
     #      backward -> gradient all-reduce -> Adam step (scripts/wn/train.py:301-326 batched)
-    svi_ms = None
+    svi = None
     if not args.no_svi:
         from bayesair_b200.objective import MeanFieldGuide, n_latent, objective_fn
         from bayesair_b200.parallel import allreduce_gradients
+        from bayesair_b200.svi import FusedMeanFieldSVI
         plan1 = SimulationPlan(specs[:1], specs[0].codes, delta_t=0.2, device=dev)
         init = torch.zeros(n_latent(N), device=dev)
         init[:N] = float(np.log(0.5)); init[N:2 * N] = float(np.log(svc))
         init[2 * N:] = torch.log(torch.tensor(np.maximum(lat["travel"][0], 0.5), device=dev)).reshape(-1)
+
+        def time_steps(fn, n=20, warm=6):
+            for _ in range(warm):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        # fused: ba_mf_sample -> ba_forward -> ba_mf_backward -> all-reduce(flat) -> fused Adam,
+        # replayed as one CUDA graph; the status flag is read once after the timed steps
+        fused = FusedMeanFieldSVI(plan1, scales, 1024, init_loc=init, init_scale=0.05, lr=1e-3, seed=11)
+        fused_ms = time_steps(fused.step)
+        fused.check()
+        graph = fused._graph is not None
+        # strong: the same 1024 particles split over the ranks
+        strong_ms = fused_ms
+        if world > 1:
+            fs = FusedMeanFieldSVI(plan1, scales, max(1, 1024 // world), init_loc=init,
+                                   init_scale=0.05, lr=1e-3, seed=11)
+            strong_ms = time_steps(fs.step)
+            fs.check()
+            del fs
+        # framework-autograd variant of the same step (round-1 path, for comparison)
         guide = MeanFieldGuide(n_latent(N), init_loc=init, init_scale=0.05).to(dev)
         opt = torch.optim.Adam(guide.parameters(), lr=1e-3)
 
@@ -353,17 +428,16 @@ def run_native(args):
             opt.step()
             return loss
 
-        for _ in range(3):
-            svi_step()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        n_svi = 10
-        for _ in range(n_svi):
-            svi_step()
-        e1.record()
-        torch.cuda.synchronize()
-        svi_ms = e0.elapsed_time(e1) / n_svi
+        auto_ms = time_steps(svi_step, n=10, warm=3)
+        svi = {"value": fused_ms, "strong_value": strong_ms, "autograd_value": auto_ms,
+               "cuda_graph": graph,
+               "config": "cfg2: N=100, one day F=3876, mean-field guide over 10200 log-latents, Adam. "
+                         "value: 1024 particles per GPU, fused library step (sample, simulate, guide "
+                         "backward into the flat all-reduce buffer, fused Adam) as one CUDA graph, "
+                         "status flag checked after the timed steps; strong_value: 1024 particles "
+                         "in total split over the GPUs; autograd_value: the same step through "
+                         "torch autograd with a host status check per step (round-1 path)"}
+        del fused
         plan1.close()
 
     # ---- end to end through the host-buffer C ABI --------------------------------
@@ -399,17 +473,22 @@ def run_native(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": f"{name}: WN-like network N={N} airports, D={D} days, F/day={Fs}, "
-                            f"P={P} particles per GPU, delta_t=0.2, no cancellations",
-                "particles_per_gpu": P, "days": D, "routes": R,
+            "config": workload_config(name, args.particles),
+            "launch": {
+                "routes": R, "kernel": "ba_forward2_kernel (one warp per particle-day up to 128 "
+                                       "airports, NW warps beyond)",
                 "noise": "explicit [P,D,F,4] fp32 tensor resident in HBM "
-                         f"({noise.numel() * 4 / 1e9:.2f} GB per GPU > 126 MB L2: inputs larger than L2)",
-                "parallelism": f"particles sharded over {world} GPU(s); allreduce of guide-gradient "
-                               "buffer only" if world > 1 else "single GPU",
+                         f"({noise.numel() * 4 / 1e9:.2f} GB per GPU)",
+                "parallelism": f"particles sharded over {world} GPU(s); one all-reduce of the "
+                               f"{guide_grad.numel()}-float mean-field guide-gradient buffer per step"
+                               if world > 1 else "single GPU",
                 "block_threads": plan.block_threads, "smem_bytes": plan.smem_bytes,
                 "resident_ctas": plan.resident_ctas,
             },
+            "reference_kind": "the --impl reference arm and cpu_baseline are a C port of the "
+                              "reference algorithm (oracle/ba_oracle.c) on all host threads; the "
+                              "Pyro reference itself cannot run on the GPU box",
+            "strong": strong,
             "clocks": clocks.summary(),
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -418,15 +497,13 @@ def run_native(args):
                             "log-probs + gradients out, synchronised"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "ba_forward_kernel", "kernel_ms": fwd,
+                         "kernel": "ba_forward2_kernel", "kernel_ms": fwd,
                          "algorithmic_bytes_per_particle_day": B,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
                          if peaks else "fallback 6650 GB/s (of fallback)",
                          "note": "serial tick loop per particle-day: latency/issue bound by "
                                  "construction (SURVEY.md §8d); see profiles/ for issue-slot use"},
-            "svi_step_ms": {"value": svi_ms, "config": "cfg2: N=100, one day F=3876, 1024 particles per "
-                            "GPU, mean-field guide over 10200 log-latents, Adam; includes the status "
-                            "check (one host sync) per step"},
+            "svi_step_ms": svi,
             "philox_value": philox_value,
             "congested_value": congested_value,
             "regimes": {"value": f"posterior-like latents: mean service {svc} h x LogNormal(0, 0.3); "

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BA_VERSION 100
+#define BA_VERSION 200
 
 typedef enum BaStatus {
     BA_OK = 0,
@@ -107,6 +107,13 @@ typedef struct BaForwardOpts {
     int32_t *d_pop_tick;        /* nullable diagnostics [P, D, Fmax, 2]: tick at which each
                                    flight left its departure / arrival runway queue (-1 =
                                    never); the "queue decisions" parity tests compare      */
+    const uint64_t *d_seed;     /* nullable: the Philox seed is read from DEVICE memory when the
+                                   kernel starts (a captured CUDA graph replays with a new seed
+                                   each step); overrides `seed`                             */
+    uint32_t particle_offset;   /* index of this call's first particle in the global batch:
+                                   Philox counters use particle_offset + p, so ranks that share
+                                   a seed draw different per-flight noise                   */
+    uint32_t reserved1;
 } BaForwardOpts;
 
 int ba_version(void);
@@ -191,6 +198,50 @@ BaStatus ba_logjoint_host(BaPlan *plan, int32_t n_particles,
                           const BaForwardOpts *opts,
                           float *h_logp, uint32_t *h_status,
                           float *h_g_airport, float *h_g_route, float *h_g_scales);
+
+/* ---- mean-field guide, fused with the simulation's gradient ------------
+ * The guide of scripts/wn/train.py's objective when it is a diagonal Normal over the
+ * n = 2N + N^2 log-latents [turnaround N | service N | travel N x N] (train.py:228-235,
+ * 254-267): z = loc + exp(log_scale) * eps, latents = exp(z).  Two kernels bracket
+ * ba_forward so that nothing of the ELBO's backward pass runs in the host framework:
+ *
+ * ba_mf_sample    draws eps (Philox: seed, particle_offset + p, latent index), writes the
+ *                 kernel-layout latents d_lat_airport [P,2,N] / d_lat_route [P,R], and per
+ *                 particle d_lp0 [P] = log prior(latents) - log q(z)  (model.py:58-87 priors;
+ *                 train.py:301-316 single_particle_elbo).  d_z [P,n] nullable (diagnostics).
+ * ba_mf_backward  contracts the tape of ba_forward with the guide's Jacobian and writes ONE
+ *                 flat buffer d_flat [2n + 4] ready for a sum all-reduce:
+ *                   [0,n)    d loss / d loc         [n,2n)  d loss / d log_scale
+ *                   [2n,2n+3) d loss / d scales     [2n+3]  loss
+ *                 with loss = -(1 / (count * flights)) sum_p ELBO_p  (train.py:318-326);
+ *                 `inv_count_flights` = 1 / (global particle count * total flights).
+ *                 d_work: ba_mf_work_bytes() bytes of scratch.
+ * d_params [2n] = loc | log_scale.  Only plans without cancellations (C = 2). */
+size_t ba_mf_work_bytes(const BaPlan *plan, int32_t n_particles);
+BaStatus ba_mf_sample(BaPlan *plan, int32_t n_particles, const float *d_params,
+                      uint64_t seed, const uint64_t *d_seed, uint32_t particle_offset,
+                      float *d_lat_airport, float *d_lat_route, float *d_lp0, float *d_z,
+                      void *stream);
+BaStatus ba_mf_backward(BaPlan *plan, int32_t n_particles, const float *d_params,
+                        uint64_t seed, const uint64_t *d_seed, uint32_t particle_offset,
+                        const void *d_tape, const float *d_logp, const float *d_lp0,
+                        float inv_count_flights, void *d_work, float *d_flat, void *stream);
+
+/* ---- conditional flow guide: monotonic rational-quadratic spline -------------------------
+ * The elementwise transform of the CalNF guide (the reference's guide is zuko.flows.NSF,
+ * scripts/wn/train.py:622-626; its surface is used by scripts/training.py:184-294).  Each
+ * of the M = samples x transformed-features elements has 3*bins-1 unconstrained parameters
+ * (d_params [M, 3*bins-1], the conditioner GEMM's output): bin-width logits, bin-height
+ * logits, interior knot-slope logits; knots span [-bound, bound], identity outside.
+ * ba_rqs_forward  -> d_y [M], d_logdet [M] = log dy/dx.
+ * ba_rqs_backward -> d_gx [M], d_gparams [M, 3*bins-1]: the gradient of
+ *                    sum(d_gy * y + d_glogdet * logdet) w.r.t. x and the parameters.
+ * bins in {4, 8, 12}.  Device pointers, fp32. */
+BaStatus ba_rqs_forward(const float *d_x, const float *d_params, float *d_y, float *d_logdet,
+                        int64_t n_elements, int32_t bins, float bound, void *stream);
+BaStatus ba_rqs_backward(const float *d_x, const float *d_params, const float *d_gy,
+                         const float *d_glogdet, float *d_gx, float *d_gparams,
+                         int64_t n_elements, int32_t bins, float bound, void *stream);
 
 /* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
 uint64_t ba_launch_count(void);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ba_version() == 100
+    assert lib.ba_version() == 200
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
