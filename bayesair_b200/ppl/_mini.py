@@ -84,11 +84,12 @@ class _Unit:
 class _Delta:
     has_rsample = True
 
-    def __init__(self, v, log_density=0.0):
-        self.v, self.log_density = v, log_density
+    def __init__(self, v, log_density=0.0, event_dim=0):
+        self.v, self.log_density, self.event_dim = v, log_density, event_dim
 
     def log_prob(self, value):
-        return torch.zeros_like(self.v) + self.log_density
+        shape = self.v.shape[:self.v.dim() - self.event_dim]
+        return torch.zeros(shape, device=self.v.device, dtype=self.v.dtype) + self.log_density
 
     def __call__(self, sample_shape=torch.Size()):
         return self.v
@@ -289,9 +290,25 @@ class Trace:
         self.nodes[site_name] = site
 
     def compute_log_prob(self, site_filter=lambda name, site: True):
+        # Sites that share ONE distribution object (the drop-in model declares its 2N + N^2
+        # global latents from three prior objects) are evaluated with one stacked log_prob
+        # call per (object, value shape) instead of one tiny call per site.
+        groups: Dict[tuple, list] = {}
         for name, site in self.nodes.items():
             if site["type"] == "sample" and site_filter(name, site) and "log_prob" not in site:
-                lp = site["fn"].log_prob(site["value"])
+                fn, v = site["fn"], site["value"]
+                if isinstance(fn, _td.Distribution) and fn.batch_shape == () and fn.event_shape == () \
+                        and torch.is_tensor(v):
+                    groups.setdefault((id(fn), tuple(v.shape), v.device, v.dtype), []).append(site)
+        for sites in groups.values():
+            if len(sites) < 8:
+                continue
+            lp_all = sites[0]["fn"].log_prob(torch.stack([s["value"] for s in sites]))
+            for i, s in enumerate(sites):
+                s["_lp"] = lp_all[i]
+        for name, site in self.nodes.items():
+            if site["type"] == "sample" and site_filter(name, site) and "log_prob" not in site:
+                lp = site.pop("_lp") if "_lp" in site else site["fn"].log_prob(site["value"])
                 sc = site["scale"]
                 if not (isinstance(sc, (int, float)) and sc == 1.0):
                     lp = lp * sc
@@ -393,7 +410,12 @@ class _BlockMessenger(Messenger):
             msg["stop"] = True
 
 
+_PARTICLE_SHAPE = ()        # set by Trace_ELBO(vectorize_particles=True) around a step
+
 poutine = types.SimpleNamespace(
     trace=_TraceMessenger, condition=_ConditionMessenger, scale=_ScaleMessenger,
     replay=_ReplayMessenger, block=_BlockMessenger, Trace=Trace, Messenger=Messenger,
 )
+
+
+from ._infer import infer, optim  # noqa: E402,F401  (pyro.infer / pyro.optim)

@@ -406,3 +406,51 @@ def test_emulated_predictive_vs_oracle_batch():
     assert np.array_equal(o["ticks"], ref["n_ticks"])
     assert np.array_equal(o["sim"][..., 0], ref["sim"][..., 0])
     np.testing.assert_array_equal(np.nan_to_num(o["sim"], nan=-1.0), np.nan_to_num(ref["sim"], nan=-1.0))
+
+
+def test_mini_infer_surface_trains_a_toy_model():
+    """pyro.infer / pyro.optim of the mini runtime (the surface of wn_network.py:285-302) on a
+    conjugate-ish toy: every autoguide, looped and vectorised particles, scale handler."""
+    from bayesair_b200.ppl import USING_REAL_PYRO, dist, poutine, pyro
+    if USING_REAL_PYRO:
+        pytest.skip("real pyro installed: its own infer module is used")
+    y = torch.tensor([2.1, 1.9, 2.3, 2.0])
+
+    def m(y):
+        mu = pyro.sample("mu", dist.Normal(torch.tensor(0.0), torch.tensor(10.0)))
+        s = pyro.sample("s", dist.Gamma(torch.tensor(2.0), torch.tensor(2.0)))
+        pyro.factor("lik", dist.Normal(mu, s).log_prob(y.reshape((-1,) + (1,) * mu.dim())).sum(0))
+
+    for name in ("AutoNormal", "AutoMultivariateNormal", "AutoDelta"):
+        for vec in (True, False):
+            pyro.clear_param_store()
+            torch.manual_seed(0)
+            model = poutine.scale(m, scale=0.5)
+            guide = getattr(pyro.infer.autoguide, name)(model)
+            svi = pyro.infer.SVI(model, guide, pyro.optim.ClippedAdam({"lr": 0.05, "lrd": 0.999}),
+                                 pyro.infer.Trace_ELBO(num_particles=8, vectorize_particles=vec))
+            losses = [svi.step(y) for _ in range(250)]
+            assert np.mean(losses[-20:]) < np.mean(losses[:20]), (name, vec)
+            med = guide.median(y)
+            assert abs(float(med["mu"]) - 2.075) < 1.0, (name, vec, med)
+            assert float(med["s"]) > 0
+
+
+def test_trace_batches_sites_that_share_a_distribution():
+    from bayesair_b200.ppl import USING_REAL_PYRO, dist, poutine, pyro
+    if USING_REAL_PYRO:
+        pytest.skip("mini runtime only")
+    prior = dist.Gamma(torch.tensor(1.5), torch.tensor(10.0))
+
+    def model():
+        for i in range(40):
+            pyro.sample(f"s{i}", prior)
+        pyro.sample("odd", dist.Normal(torch.tensor(0.0), torch.tensor(1.0)))
+
+    data = {f"s{i}": torch.rand(5) + 0.01 for i in range(40)}
+    data["odd"] = torch.randn(5)
+    tr = poutine.trace(poutine.scale(poutine.condition(model, data=data), scale=0.25)).get_trace()
+    expect = 0.25 * (sum(prior.log_prob(data[f"s{i}"]).sum() for i in range(40))
+                     + dist.Normal(torch.tensor(0.0), torch.tensor(1.0)).log_prob(data["odd"]).sum())
+    assert abs(float(tr.log_prob_sum()) - float(expect)) < 1e-4
+    assert tr.nodes["s3"]["log_prob"].shape == (5,)

@@ -94,3 +94,89 @@ def test_graph_replay_equals_eager_and_trains():
     assert torch.equal(l0, l1)
     assert torch.equal(t0, t1)
     assert float(l0[-5:].mean()) < float(l0[:5].mean())
+
+
+# ---------------------------------------------------------------- call site (ii) ----------
+def _golden_states(g):
+    from tests.test_cuda_parity import _states_from_golden
+    return _states_from_golden(g)
+
+
+def test_scaled_model_trace_matches_reference_total():
+    """poutine.scale(model, 1/days) -- scripts/wn/wn_network.py:285-287 -- scales every site,
+    the fused factor included: the trace's log_prob_sum is the reference-generated total of
+    the golden divided by the number of days."""
+    import bayesair_b200 as ba
+    from bayesair_b200.ppl import poutine, pyro
+    g = Golden("twoday5")
+    states = _golden_states(g)
+    dev = torch.device("cuda:0")
+    codes = g.global_codes
+    data = {}
+    for i, c in enumerate(codes):
+        data[f"{c}_mean_turnaround_time"] = torch.tensor(g.latents["mean_turnaround"][i], device=dev)
+        data[f"{c}_mean_service_time"] = torch.tensor(g.latents["mean_service"][i], device=dev)
+        for j, c2 in enumerate(codes):
+            if i != j:
+                data[f"travel_time_{c}_{c2}"] = torch.tensor(g.latents["travel"][i, j], device=dev)
+    pyro.clear_param_store()
+    for nme, v in zip(("runway_use_time_std_dev", "travel_time_variation",
+                       "turnaround_time_variation"), g.scales):
+        pyro.param(nme, torch.tensor(v, device=dev), constraint=torch.distributions.constraints.positive)
+    days = len(states)
+    model = poutine.scale(ba.air_traffic_network_model, scale=1.0 / days)
+    with ba.flight_noise(torch.tensor(g.noise[None], device=dev)):
+        tr = poutine.trace(poutine.condition(model, data=data)).get_trace(states, g.delta_t, device=dev)
+    assert abs(float(tr.log_prob_sum()) - g.ref_total / days) <= 1e-4 * abs(g.ref_total / days)
+
+
+@pytest.mark.parametrize("guide_name", ["AutoNormal", "AutoMultivariateNormal"])
+def test_svi_with_autoguide_over_the_scaled_model(guide_name):
+    """The whole of wn_network.py:285-302 against the drop-in model: scale handler, autoguide
+    over the global latent sites, ClippedAdam, Trace_ELBO, ``svi.step(states, dt)`` with a
+    positional delta_t.  The loss of a step equals the ELBO assembled by hand from the same
+    draws, and it falls over a short run."""
+    import bayesair_b200 as ba
+    from bayesair_b200.ppl import USING_REAL_PYRO, poutine, pyro
+    g = Golden("twoday5")
+    states = _golden_states(g)
+    dev = torch.device("cuda:0")
+    days = len(states)
+    pyro.clear_param_store()
+    torch.manual_seed(0)
+    model = poutine.scale(ba.air_traffic_network_model, scale=1.0 / days)
+
+    def model_on_device(states, dt):
+        return model(states, dt, device=dev)
+
+    guide = getattr(pyro.infer.autoguide, guide_name)(model_on_device)
+    elbo = pyro.infer.Trace_ELBO(num_particles=8, vectorize_particles=not USING_REAL_PYRO)
+    svi = pyro.infer.SVI(model_on_device, guide, pyro.optim.ClippedAdam({"lr": 0.02, "lrd": 0.999}), elbo)
+    with ba.flight_noise(seed=5):
+        first = svi.step(states, g.delta_t)
+    assert np.isfinite(first)
+    # one step's loss, by hand: guide trace -> replayed model trace -> scaled sums
+    if not USING_REAL_PYRO:
+        torch.manual_seed(123)
+        with ba.flight_noise(seed=9):
+            loss = float(elbo.differentiable_loss(model_on_device, guide, states, g.delta_t))
+        torch.manual_seed(123)
+        pyro._PARTICLE_SHAPE = (8,)
+        try:
+            gtr = poutine.trace(guide).get_trace(states, g.delta_t)
+            with ba.flight_noise(seed=9):
+                mtr = poutine.trace(poutine.replay(model_on_device, trace=gtr)).get_trace(states, g.delta_t)
+        finally:
+            pyro._PARTICLE_SHAPE = ()
+        lp_model = sum((s["fn"].log_prob(s["value"]) / days).sum() for s in mtr.nodes.values()
+                       if s["type"] == "sample")
+        lp_guide = sum(s["fn"].log_prob(s["value"]).sum() for s in gtr.nodes.values()
+                       if s["type"] == "sample")
+        assert abs(loss - float(-(lp_model - lp_guide) / 8)) <= 1e-4 * abs(loss)
+    losses = []
+    for i in range(60):
+        with ba.flight_noise(seed=100 + i):
+            losses.append(svi.step(states, g.delta_t))
+    assert np.mean(losses[-10:]) < np.mean(losses[:10])
+    med = guide.median(states, g.delta_t)
+    assert set(med) >= {f"{c}_mean_service_time" for c in g.global_codes}
