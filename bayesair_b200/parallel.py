@@ -30,23 +30,40 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], extra: Optional[to
                         group=None, average: bool = False) -> Optional[torch.Tensor]:
     """Sums ``p.grad`` of every parameter (and ``extra``, e.g. the scalar loss or the three
     noise-scale gradients) over all ranks with ONE collective on one flat fp32 buffer."""
-    plist: List[torch.nn.Parameter] = [p for p in params if p.grad is not None]
+    # EVERY parameter takes part, in the caller's order (a missing gradient counts as zero):
+    # the flat layout is then identical on all ranks whatever each rank's graph touched
+    plist: List[torch.nn.Parameter] = list(params)
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return extra
-    chunks = [p.grad.reshape(-1) for p in plist]
+    if not plist and extra is None:
+        return None
+    ref = plist[0] if plist else extra
+    chunks = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32)
+              for p in plist]
     if extra is not None:
-        chunks.append(extra.reshape(-1).to(chunks[0].dtype if chunks else extra.dtype))
-    flat = torch.cat(chunks) if chunks else None
-    if flat is None:
-        return extra
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        chunks.append(extra.reshape(-1).to(torch.float32))
+    flat = torch.cat(chunks)
+    with torch.cuda.nvtx.range("ba.allreduce") if ref.is_cuda else _no_range():
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
     off = 0
     for p in plist:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        n = p.numel()
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
         off += n
     if extra is not None:
-        return flat[off:].view_as(extra).clone()
+        return flat[off:].view_as(extra).to(extra.dtype).clone()
     return None
+
+
+class _no_range:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

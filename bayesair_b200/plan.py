@@ -129,8 +129,9 @@ class SimulationPlan:
                                        None if pop is None else pop.data_ptr(),
                                        None if seed_tensor is None else seed_tensor.data_ptr(),
                                        int(particle_offset) & 0xFFFFFFFF, 0)
-            self._h.forward(P, _ptr(la), _ptr(lr), _ptr(sc), _ptr(nz), opts, _ptr(logp),
-                            _ptr(status), _ptr(ticks), _ptr(tape), self._stream())
+            with torch.cuda.nvtx.range("ba.forward"):
+                self._h.forward(P, _ptr(la), _ptr(lr), _ptr(sc), _ptr(nz), opts, _ptr(logp),
+                                _ptr(status), _ptr(ticks), _ptr(tape), self._stream())
         return {"logp": logp, "status": status, "ticks": ticks, "tape": tape, "pop_tick": pop,
                 "_keep": (la, lr, sc, nz, seed_tensor)}
 
@@ -170,7 +171,8 @@ class SimulationPlan:
                              device=self.device)
             gr = torch.empty((P, self.n_routes), dtype=torch.float32, device=self.device)
             gs = torch.empty((P, 3), dtype=torch.float32, device=self.device)
-            self._h.backward(P, _ptr(dl), _ptr(tape), _ptr(ga), _ptr(gr), _ptr(gs), self._stream())
+            with torch.cuda.nvtx.range("ba.backward"):
+                self._h.backward(P, _ptr(dl), _ptr(tape), _ptr(ga), _ptr(gr), _ptr(gs), self._stream())
         return ga, gr, gs
 
     def generate_noise(self, n_particles: int, seed: int) -> torch.Tensor:
@@ -185,8 +187,34 @@ class SimulationPlan:
                       noise_is_value: bool = False, out: Optional[dict] = None) -> dict:
         """Host-buffer end-to-end call (``ba_logjoint_host``): numpy / pinned arrays in,
         numpy arrays out; copies, both kernels and the final synchronise included."""
+        lat_airport = np.asarray(lat_airport)
         P = int(lat_airport.shape[0])
         D, N, Cn, R = self.n_days, self.n_airports, self.n_airport_latents, self.n_routes
+
+        def host(a, shape, name, dtype=np.float32):
+            # the C side reads / writes raw pointers: dtype, shape and contiguity are checked here
+            if a is None:
+                return None
+            b = np.ascontiguousarray(a, dtype=dtype)
+            if tuple(b.shape) != tuple(shape):
+                raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(b.shape)}")
+            return b
+
+        def host_out(a, shape, name, dtype=np.float32):
+            if a is None:
+                return None
+            if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags.c_contiguous
+                    and a.flags.writeable and tuple(a.shape) == tuple(shape)):
+                raise ValueError(f"out[{name!r}]: needs a writable C-contiguous {np.dtype(dtype).name} "
+                                 f"array of shape {tuple(shape)}")
+            return a
+
+        lat_airport = host(lat_airport, (P, Cn, N), "lat_airport")
+        lat_route = host(lat_route, (P, R), "lat_route")
+        scales = host(scales, (3,), "scales")
+        noise = host(noise, (P, D, self.max_flights, 4), "noise")
+        if noise_is_value and noise is None:
+            raise ValueError("noise_is_value needs a noise array")
         if out is None:
             out = {
                 "logp": np.empty((P, D), np.float32), "status": np.empty((P, D), np.uint32),
@@ -194,9 +222,18 @@ class SimulationPlan:
                 "g_route": np.empty((P, R), np.float32) if want_grad else None,
                 "g_scales": np.empty((P, 3), np.float32) if want_grad else None,
             }
+        host_out(out["logp"], (P, D), "logp")
+        host_out(out["status"], (P, D), "status", np.uint32)
+        if want_grad:
+            host_out(out["g_airport"], (P, Cn, N), "g_airport")
+            host_out(out["g_route"], (P, R), "g_route")
+            host_out(out["g_scales"], (P, 3), "g_scales")
         vp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)  # noqa: E731
         opts = _capi.BaForwardOpts(int(noise_is_value), int(want_grad), 0, 0, 0, 0,
                                    int(seed) & (2**64 - 1), None)
+        # the call shares the plan's scratch with forward(): order it after whatever the
+        # caller's torch stream still has in flight on this plan
+        torch.cuda.current_stream(self.device).synchronize()
         self._h.logjoint_host(P, vp(lat_airport), vp(lat_route), vp(scales), vp(noise), opts,
                               vp(out["logp"]), vp(out["status"]), vp(out["g_airport"]),
                               vp(out["g_route"]), vp(out["g_scales"]))
@@ -235,24 +272,60 @@ _PLAN_CACHE: "OrderedDict[tuple, Tuple[SimulationPlan, list]]" = OrderedDict()
 _PLAN_CACHE_SIZE = 16
 
 
+def _tensor_tag(t):
+    # identity + in-place version counter: a replaced attribute (``f.actual_arrival_time =
+    # None`` to make a flight unobserved) and an in-place edit (``t.fill_(..)``) both change it
+    return None if t is None else (id(t), getattr(t, "_version", 0))
+
+
+def states_fingerprint(states) -> int:
+    """Cheap content fingerprint of what the schedule compiler reads from ``states``: per
+    flight its identity, endpoints and the identity / version of its observation tensors.
+    O(flights) Python, no device or tensor reads."""
+    acc = []
+    for s in states:
+        acc.append(tuple(s.airports.keys()))
+        acc.append(tuple(
+            (id(f), f.origin, f.destination, _tensor_tag(f.scheduled_departure_time),
+             _tensor_tag(f.actual_departure_time), _tensor_tag(f.actual_arrival_time),
+             _tensor_tag(f.actually_cancelled))
+            for f in s.pending_flights))
+    return hash(tuple(acc))
+
+
 def plan_for_states(states, delta_t, max_t, include_cancellations, device) -> SimulationPlan:
+    """Compiled plan of ``states``, cached.  The key holds a content fingerprint
+    (``states_fingerprint``), so editing a flight's observations -- in place or by
+    assignment -- or swapping flights yields a fresh plan instead of the stale one."""
     device = _resolve_device(device)
-    key = (tuple(id(s) for s in states),
-           tuple(len(s.pending_flights) for s in states),
+    key = (tuple(id(s) for s in states), states_fingerprint(states),
            float(delta_t), float(max_t), bool(include_cancellations), device.index)
     hit = _PLAN_CACHE.get(key)
     if hit is not None:
         _PLAN_CACHE.move_to_end(key)
         return hit[0]
-    plan = SimulationPlan.from_states(states, delta_t, max_t, include_cancellations, device)
-    _PLAN_CACHE[key] = (plan, list(states))   # strong refs keep the ids valid
+    with torch.cuda.nvtx.range("ba.plan_build") if torch.cuda.is_available() else _no_range():
+        plan = SimulationPlan.from_states(states, delta_t, max_t, include_cancellations, device)
+    # strong refs to the states and their tensors keep the ids in the key valid
+    keep = [list(states), [(f.scheduled_departure_time, f.actual_departure_time,
+                            f.actual_arrival_time, f.actually_cancelled)
+                           for s in states for f in s.pending_flights]]
+    _PLAN_CACHE[key] = (plan, keep)
     while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
-        _, (old, _) = _PLAN_CACHE.popitem(last=False)
-        old.close()
+        # drop the reference only: a live autograd graph may still hold the plan; its
+        # device memory is released when the last reference goes (PlanHandle.__del__)
+        _PLAN_CACHE.popitem(last=False)
     return plan
 
 
+class _no_range:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def clear_plan_cache():
-    while _PLAN_CACHE:
-        _, (old, _) = _PLAN_CACHE.popitem()
-        old.close()
+    """Forgets every cached plan (their memory is freed once nothing else refers to them)."""
+    _PLAN_CACHE.clear()

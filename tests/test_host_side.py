@@ -454,3 +454,27 @@ def test_trace_batches_sites_that_share_a_distribution():
                      + dist.Normal(torch.tensor(0.0), torch.tensor(1.0)).log_prob(data["odd"]).sum())
     assert abs(float(tr.log_prob_sum()) - float(expect)) < 1e-4
     assert tr.nodes["s3"]["log_prob"].shape == (5,)
+
+
+def test_plan_cache_fingerprint_sees_edited_observations():
+    """plan.states_fingerprint: the plan cache key changes when a flight's observations are
+    replaced (obs stripped for a predictive run), edited in place, or flights are swapped at
+    equal count -- and does not change otherwise."""
+    import bayesair_b200 as ba
+    from bayesair_b200.plan import states_fingerprint
+    from bayesair_b200.synth import synth_day_frame
+    fl, ap = ba.parse_schedule(synth_day_frame(4, 40))
+    st = [ba.NetworkState({a.code: a for a in ap}, fl)]
+    f0 = states_fingerprint(st)
+    assert states_fingerprint(st) == f0
+    keep = fl[3].actual_arrival_time
+    fl[3].actual_arrival_time = None                       # stripped observation
+    f1 = states_fingerprint(st)
+    assert f1 != f0
+    fl[3].actual_arrival_time = keep
+    assert states_fingerprint(st) == f0
+    fl[5].actual_departure_time.add_(0.25)                 # in-place edit
+    f2 = states_fingerprint(st)
+    assert f2 != f0
+    st[0].pending_flights[7], st[0].pending_flights[8] = st[0].pending_flights[8], st[0].pending_flights[7]
+    assert states_fingerprint(st) != f2
