@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         const uint32_t n_arr = (uint32_t)day.n_arr;
 
         // ---- setup -----------------------------------------------------------
-        c.s_rate = (float *)(c.un + BA2_KC + N); c.s_mt = nullptr;   // behind buckets and cursors
+        c.s_rate = (float *)(c.un + BA2_KC + N); c.s_mt = c.s_rate + N;   // behind buckets and cursors
         for (int a = tid; a < N; a += NT) ba2_init_airport(c, a, N, false);
         for (int i = tid; i < BA2_KC; i += NT) c.un[i] = 0;
         if (c.grow && day.Rd < R)
@@ -458,7 +458,16 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         BA2_MARK(0);
 
         // ---- prologue ----------------------------------------------------------
-        for (int f = tid; f < day.F; f += NT) ba2_prologue_flight(c, acc, f);
+        // two flights per lane and step: both flights' loads are in flight together
+        for (int f = tid; f < day.F; f += 2 * NT) {
+            const int f1 = f + NT;
+            const bool two = f1 < day.F;
+            const Ba2FlightIn in0 = ba2_prologue_load(c, f);
+            const Ba2FlightIn in1 = ba2_prologue_load(c, two ? f1 : f);
+            const float T0 = c.lat_route[in0.rt], T1 = c.lat_route[in1.rt];
+            ba2_prologue_compute(c, acc, f, in0, T0);
+            if (two) ba2_prologue_compute(c, acc, f1, in1, T1);
+        }
         ba2_sync<NW>();
         BA2_MARK(1);
         if (warp == 0) ba2_bucket_scan(c, lane);
@@ -508,7 +517,16 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         for (int a = tid; a < N; a += NT) ba2_init_airport(c, a, N, true);
         ba2_sync<NW>();
         if (!aborted)
-            for (int f = tid; f < day.F; f += NT) ba2_epilogue_flight(c, acc, f);
+            for (int f = tid; f < day.F; f += 2 * NT) {
+                const int f1 = f + NT;
+                const bool two = f1 < day.F;
+                const Ba2EpiIn in0 = ba2_epilogue_load(c, f);
+                const Ba2EpiIn in1 = ba2_epilogue_load(c, two ? f1 : f);
+                const Ba2Pay pay0 = ba2_epilogue_pay(c, in0), pay1 = ba2_epilogue_pay(c, in1);
+                const float T0 = c.lat_route[in0.rt], T1 = c.lat_route[in1.rt];
+                ba2_epilogue_compute(c, acc, f, in0, pay0, T0);
+                if (two) ba2_epilogue_compute(c, acc, f1, in1, pay1, T1);
+            }
         if (c.grow && !aborted) {
             ba2_sync<NW>();
             for (int s = tid; s < N; s += NT) ba2_epilogue_airport(c, s, N);

@@ -109,7 +109,7 @@ struct Ba2Ctx {
     float c0_lp, c1_lp;
     int value_mode, want_grad;
     // shared memory of this warp
-    uint32_t *un;                             // union: prologue {kcnt [BA2_KC], cursors [N], rate [N]} /
+    uint32_t *un;                             // union: prologue {kcnt [BA2_KC], cursors [N], rate [N], mean turnaround [N]} /
                                               //   scan {state [BA2_STATE_WORDS][nslot]} /
                                               //   epilogue {rate [N], mean turnaround [N]}
     float *s_rate, *s_mt;                     // [N] per airport (day-local index), inside `un`
@@ -126,7 +126,7 @@ struct Ba2Ctx {
     float *hx;                                // [2 F] history of draws by assignment index
     uint32_t *glog;                           // [4 F] (tick, assignments before it) of ticks that
                                               //   ended with younger entries still waiting
-    float *nzs;                               // [4 F] generated noise kept for the epilogue
+    float *eps;                               // [F] travel-time draw of every flight, kept for the epilogue
     float *xdk, *xak, *atk, *ct;              // epilogue contributions (alias S0 / S1)
     // outputs
     float *grow;
@@ -138,13 +138,13 @@ struct Ba2Ctx {
 static inline uint64_t ba2_scratch_words(int F, int N)
 {
     const uint64_t f = (uint64_t)F, n = (uint64_t)N;
-    return 4 * f + 4 * (f + n + 4) + 3 * (f + n + 4) + 4 * f + 2 * f + 4 * f + 64;
+    return (f + 4) + 4 * (f + n + 4) + 3 * (f + n + 4) + 4 * f + 2 * f + 4 * f + 64;
 }
 
 BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
 {
     const uint32_t f = (uint32_t)F, fn = ((uint32_t)(F + N) + 3u) & ~3u;
-    c.nzs = (float *)g; g += 4 * f;                       // 16-byte aligned blocks first
+    c.eps = (float *)g; g += (f + 3u) & ~3u;              // 16-byte aligned blocks first
     c.P = (Ba2Pay *)g; g += 4 * fn;
     c.S0 = g; c.S1 = g + 2 * f;
     c.xdk = (float *)g; c.xak = (float *)g + f; c.atk = (float *)g + 2 * f; c.ct = (float *)g + 3 * f;
@@ -159,7 +159,7 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
 static inline size_t ba2_smem_words(int N)
 {
     const size_t nslot = (size_t)N;
-    const size_t pro = BA2_KC + 2 * (size_t)N;
+    const size_t pro = BA2_KC + 3 * (size_t)N;
     const size_t un = BA2_STATE_WORDS * nslot > pro ? BA2_STATE_WORDS * nslot : pro;
     return (un + 3) & ~(size_t)3;
 }
@@ -197,35 +197,59 @@ BA_DEV BaNoise4 ba2_noise(const Ba2Ctx &c, int f)
 BA_DEV void ba2_init_airport(Ba2Ctx &c, int a, int Ng, bool epilogue)
 {
     const int g = c.ap[a].global;
-    if (epilogue) c.s_mt[a] = c.lat_airport[0 * Ng + g];
+    (void)epilogue;
+    c.s_mt[a] = c.lat_airport[0 * Ng + g];
     c.s_rate[a] = BA_DIV(1.0f, c.lat_airport[1 * Ng + g]);     // airport.py:146
 }
 
 // ---------------------------------------------------------------------------
 // PROLOGUE sweep 1: one flight -> its draws, arrival time and arrival tick
 // ---------------------------------------------------------------------------
-BA_DEV void ba2_prologue_flight(Ba2Ctx &c, BaAcc &acc, int f)
+// What a flight's prologue / epilogue step reads, gathered up front so that the loads of two
+// flights are in flight together (the loops are latency-bound: one warp per particle-day).
+struct Ba2FlightIn {
+    BaFlight fl;
+    BaNoise4 nz;
+    int rt, lpos;
+};
+
+BA_DEV Ba2FlightIn ba2_prologue_load(const Ba2Ctx &c, int f)
 {
-    const BaFlight fl = ba2_flight(c, f);
+    Ba2FlightIn in;
+    in.fl = ba2_flight(c, f);
+    in.nz = ba2_noise(c, f);
+    in.rt = c.route[f];
+    in.lpos = c.pos_live[f];
+    return in;
+}
+
+// The flight's draws, arrival time and arrival tick; and the part of its log-probability that
+// does not depend on any wait: the four latent per-flight sites (airport.py:144-147,
+// network.py:158-163, airport.py:217-220).  The wait-dependent observed sites are the
+// epilogue's.
+BA_DEV void ba2_prologue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2FlightIn &in, float T)
+{
+    const BaFlight &fl = in.fl;
+    const BaNoise4 &nz = in.nz;
     const uint32_t cobs = (fl.od >> 24) & 3u;
     const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
-    const BaNoise4 nz = ba2_noise(c, f);
-    if (!c.noise) {
-#if defined(__CUDA_ARCH__)
-        reinterpret_cast<float4 *>(c.nzs)[f] = make_float4(nz.e_dep, nz.eps_travel, nz.e_arr, nz.eps_turn);
-#else
-        c.nzs[4 * f] = nz.e_dep; c.nzs[4 * f + 1] = nz.eps_travel; c.nzs[4 * f + 2] = nz.e_arr; c.nzs[4 * f + 3] = nz.eps_turn;
-#endif
-    }
+    c.eps[f] = nz.eps_travel;
     uint32_t key = BA2_NONE;
     if (cobs != 1u) {
-        const float T = c.lat_route[c.route[f]];
+        const float rate_o = c.s_rate[o], rate_d = c.s_rate[d], mt = c.s_mt[d];
         // Exponential(1/m).rsample = e / rate  (airport.py:144-147)
-        const float xd = c.value_mode ? nz.e_dep : BA_DIV(nz.e_dep, c.s_rate[o]);
-        const float xa = c.value_mode ? nz.e_arr : BA_DIV(nz.e_arr, c.s_rate[d]);
+        const float xd = c.value_mode ? nz.e_dep : BA_DIV(nz.e_dep, rate_o);
+        const float xa = c.value_mode ? nz.e_arr : BA_DIV(nz.e_arr, rate_d);
         // Normal(T, T v_t).rsample = T + eps * (T v_t)  (network.py:158-163)
         const float sc = BA_MUL(T, c.v_t);
         const float tau = c.value_mode ? nz.eps_travel : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
+        const float tstd = BA_MUL(c.v_u, mt);
+        const float u = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, tstd));
+        const float dz = (tau - T) / sc, du = (u - mt) / tstd;
+        const float lp1 = (BA_LOG(rate_o) - rate_o * xd) + (BA_LOG(rate_d) - rate_d * xa);
+        const float lp2 = (-0.5f * dz * dz - BA_LOG(sc) - BA_LOG_SQRT_2PI)
+                        + (-0.5f * du * du - BA_LOG(tstd) - BA_LOG_SQRT_2PI);
+        acc.lp += (double)lp1 + (double)lp2;
         float y_dep = fl.act_dep;
         if (cobs == 3u || isnan(y_dep) || isnan(fl.act_arr)) {
             acc.status |= BA_S_UNOBSERVED;      // this entry point is the fully observed path
@@ -240,13 +264,19 @@ BA_DEV void ba2_prologue_flight(Ba2Ctx &c, BaAcc &acc, int f)
         while (kk < kmax && c.tick_time[kk] < at) ++kk;
         if (c.tick_time[kk] < at) acc.status |= BA_S_OVERFLOW;      // beyond the buckets: exact lists
         if (kk < c.first_tick) kk = c.first_tick;
-        const int lpos = c.pos_live[f];
         Ba2Pay pay; pay.xw = xd; pay.at = at; pay.xa = xa; pay.q = BA2_NONE;
-        ba2_st_pay(c.P + lpos, pay);
-        key = ((uint32_t)kk << 16) | (uint32_t)lpos;
+        ba2_st_pay(c.P + in.lpos, pay);
+        key = ((uint32_t)kk << 16) | (uint32_t)in.lpos;
         BA_ATOMIC_INC(&c.un[kk]);
     }
     ba2_st2(c.S0 + 2 * f, key, (uint32_t)d);
+}
+
+// PROLOGUE sweep 1, one flight (host emulation; the kernel runs the two halves itself)
+BA_DEV void ba2_prologue_flight(Ba2Ctx &c, BaAcc &acc, int f)
+{
+    const Ba2FlightIn in = ba2_prologue_load(c, f);
+    ba2_prologue_compute(c, acc, f, in, c.lat_route[in.rt]);
 }
 
 // exclusive prefix over the tick buckets (the warp; host: lane = -1, serial)
@@ -581,11 +611,35 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
 // ---------------------------------------------------------------------------
 // EPILOGUE (flight-parallel, then owner sums); SURVEY.md App. A.3 / A.5
 // ---------------------------------------------------------------------------
-BA_DEV void ba2_epilogue_flight(Ba2Ctx &c, BaAcc &acc, int f)
+struct Ba2EpiIn {
+    BaFlight fl;
+    int lpos, k, j, rt;
+    float eps;
+};
+
+BA_DEV Ba2EpiIn ba2_epilogue_load(const Ba2Ctx &c, int f)
 {
-    const BaFlight fl = ba2_flight(c, f);
+    Ba2EpiIn in;
+    in.fl = ba2_flight(c, f);
+    in.lpos = c.pos_live[f]; in.k = c.pos_dep[f]; in.j = c.pos_arr[f]; in.rt = c.route[f];
+    in.eps = c.eps[f];
+    return in;
+}
+
+// second round of loads: the flight's payload record (waits, arrival time) and travel time
+BA_DEV Ba2Pay ba2_epilogue_pay(const Ba2Ctx &c, const Ba2EpiIn &in)
+{
+    if (((in.fl.od >> 24) & 3u) == 1u) { Ba2Pay z; z.xw = 0.0f; z.q = BA2_NONE; z.at = 0.0f; z.xa = 0.0f; return z; }
+    return ba2_ld_pay(c.P + in.lpos);
+}
+
+// The wait-dependent sites of a flight (*_simulated_departure_time, *_simulated_arrival_time,
+// airport.py:175-182,197-204), its cancellation site, and its gradient contributions.
+BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &in, const Ba2Pay &pay, float T)
+{
+    const BaFlight &fl = in.fl;
     const uint32_t cobs = (fl.od >> 24) & 3u;
-    const int k = c.pos_dep[f];
+    const int k = in.k;
     const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
     // *_cancelled (network.py:100-109): the cancellation probability is exactly 0 at every
     // airport of such a plan (ba_plan.h: BA_SIMPLE_RATIO)
@@ -595,56 +649,31 @@ BA_DEV void ba2_epilogue_flight(Ba2Ctx &c, BaAcc &acc, int f)
         if (c.pop_tick) { c.pop_tick[2 * f] = -1; c.pop_tick[2 * f + 1] = -1; }
         return;
     }
-    const int j = c.pos_arr[f];
-    const Ba2Pay pay = ba2_ld_pay(c.P + c.pos_live[f]);
-    BaNoise4 nz;
-    if (c.noise) nz = ba2_noise(c, f);
-    else {
-#if defined(__CUDA_ARCH__)
-        const float4 v = reinterpret_cast<const float4 *>(c.nzs)[f];
-        nz.e_dep = v.x; nz.eps_travel = v.y; nz.e_arr = v.z; nz.eps_turn = v.w;
-#else
-        nz.e_dep = c.nzs[4 * f]; nz.eps_travel = c.nzs[4 * f + 1]; nz.e_arr = c.nzs[4 * f + 2]; nz.eps_turn = c.nzs[4 * f + 3];
-#endif
-    }
+    const int j = in.j;
     if (c.pop_tick) {
         c.pop_tick[2 * f] = pay.q == BA2_NONE ? -1 : (int32_t)pay.q;
         c.pop_tick[2 * f + 1] = (int32_t)__float_as_uint_portable(pay.at);
     }
-    const float T = c.lat_route[c.route[f]];
     const bool grad = c.want_grad != 0;
     const float half_inv_var = 0.5f * c.inv_sigma2;
     const float lp_const = -c.log_sigma - BA_LOG_SQRT_2PI;
     float y_dep = fl.act_dep, y_arr = fl.act_arr;
     if (cobs == 3u || isnan(y_dep) || isnan(y_arr)) { y_dep = fl.sched_dep; y_arr = fl.sched_dep; }
 
-    // departure side: *_departure_service_time, *_simulated_departure_time
-    // (airport.py:144-147,175-182)
-    const float rate_o = c.s_rate[o];
-    const float xd = c.value_mode ? nz.e_dep : BA_DIV(nz.e_dep, rate_o);
+    // departure side (airport.py:175-182): Normal(queue_start + total_wait, sigma)
     const float wdep = pay.xw;
     const float qstart_d = fmaxf(0.0f, fl.sched_dep);
-    const float mu_d = BA_ADD(qstart_d, wdep);              // queue_start + total_wait
+    const float mu_d = BA_ADD(qstart_d, wdep);
     const float dy_d = y_dep - mu_d;
-    float lp = (BA_LOG(rate_o) - rate_o * xd) + (lp_const - dy_d * dy_d * half_inv_var);
-
-    // arrival side: *_travel_time, *_arrival_service_time, *_simulated_arrival_time,
-    // *_turnaround_time (network.py:158-163; airport.py:144-147,197-204,217-220)
-    const float rate_d = c.s_rate[d], mt = c.s_mt[d], tstd = BA_MUL(c.v_u, mt);
+    // arrival side (airport.py:197-204): queue_start = departure + travel time
     const float sc = BA_MUL(T, c.v_t);
-    const float tau = c.value_mode ? nz.eps_travel : BA_ADD(T, BA_MUL(nz.eps_travel, sc));
+    const float tau = c.value_mode ? in.eps : BA_ADD(T, BA_MUL(in.eps, sc));
     const float qstart_a = BA_ADD(y_dep, tau);
     const float warr = pay.xa;
     const float mu_a = BA_ADD(qstart_a, warr);
     const float dy_a = y_arr - mu_a;
-    const float xa = c.value_mode ? nz.e_arr : BA_DIV(nz.e_arr, rate_d);
-    const float u = c.value_mode ? nz.eps_turn : BA_ADD(mt, BA_MUL(nz.eps_turn, tstd));
-    const float dz = (tau - T) / sc;
-    const float du = (u - mt) / tstd;
-    lp += (BA_LOG(rate_d) - rate_d * xa) + (lp_const - dy_a * dy_a * half_inv_var);
-    const float lp2 = (-0.5f * dz * dz - BA_LOG(sc) - BA_LOG_SQRT_2PI)
-                    + (-0.5f * du * du - BA_LOG(tstd) - BA_LOG_SQRT_2PI);
-    acc.lp += (double)lp + (double)lp2;
+    const float lp = (lp_const - dy_d * dy_d * half_inv_var) + (lp_const - dy_a * dy_a * half_inv_var);
+    acc.lp += (double)lp;
 
     if (grad) {
         const float r_d = dy_d * c.inv_sigma2, r_a = dy_a * c.inv_sigma2;
@@ -653,18 +682,33 @@ BA_DEV void ba2_epilogue_flight(Ba2Ctx &c, BaAcc &acc, int f)
             c.xdk[k] = r_d * wdep;
             c.xak[j] = r_a * warr;
             // arrival queue_start = act_dep + tau, tau = T (1 + v_t eps)
-            c.atk[f] = r_a * (1.0f + c.v_t * nz.eps_travel) - 1.0f / T;
-            acc.g_vt += r_a * nz.eps_travel * T - c.inv_vt;
+            c.atk[f] = r_a * (1.0f + c.v_t * in.eps) - 1.0f / T;
+            acc.g_vt += r_a * in.eps * T - c.inv_vt;
             acc.g_vu += -c.inv_vu;
         } else {
-            c.xdk[k] = xd;
-            c.xak[j] = xa;
+            // value mode (tests, callers that pin the per-flight site values): the values
+            // are read again; the draws are not functions of the latents here
+            const BaNoise4 nz = ba2_noise(c, f);
+            const float mt = c.s_mt[d], tstd = BA_MUL(c.v_u, mt);
+            const float dz = (tau - T) / sc;
+            const float du = (nz.eps_turn - mt) / tstd;
+            c.xdk[k] = nz.e_dep;
+            c.xak[j] = nz.e_arr;
             c.atk[f] = dz / sc + (dz * dz - 1.0f) / T;
             acc.g_vt += (dz * dz - 1.0f) * c.inv_vt;
             c.ct[j] = du / tstd + (du * du - 1.0f) / mt;     // arrival order: no other writer
             acc.g_vu += (du * du - 1.0f) * c.inv_vu;
         }
     }
+    (void)o;
+}
+
+// EPILOGUE of one flight (host emulation; the kernel runs the stages itself)
+BA_DEV void ba2_epilogue_flight(Ba2Ctx &c, BaAcc &acc, int f)
+{
+    const Ba2EpiIn in = ba2_epilogue_load(c, f);
+    const Ba2Pay pay = ba2_epilogue_pay(c, in);
+    ba2_epilogue_compute(c, acc, f, in, pay, c.lat_route[in.rt]);
 }
 
 BA_DEV void ba2_epilogue_airport(Ba2Ctx &c, int a, int Ng)

@@ -289,7 +289,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     memset(&c, 0, sizeof(c));
     c.nslot = (uint32_t)N;
     c.un = sh.data();
-    c.s_rate = (float *)(sh.data() + BA2_KC + N); c.s_mt = nullptr;
+    c.s_rate = (float *)(sh.data() + BA2_KC + N); c.s_mt = c.s_rate + N;
     c.sigma = scales[0]; c.v_t = scales[1]; c.v_u = scales[2];
     c.inv_sigma = 1.0f / c.sigma; c.inv_sigma2 = c.inv_sigma * c.inv_sigma;
     c.inv_sigma3 = c.inv_sigma2 * c.inv_sigma; c.log_sigma = logf(c.sigma);
