@@ -345,6 +345,8 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
             const bool pinned_w = std::getenv("BA_WARPS") != nullptr;
             while (!pinned_w && li < 3 && n_work * (long long)(2 * nw) <= 32LL * pl->sm_count) { nw *= 2; ++li; }
             int grid = (int)std::min<long long>(n_work, pl->grids_scan2[li]);
+            // BA_GRID_CAP: fewer resident particle-days than the SMs hold (occupancy experiments)
+            if (const char *e = std::getenv("BA_GRID_CAP")) { int g = std::atoi(e); if (g > 0 && g < grid) grid = g; }
             BA_CUDA(ba_launch_forward2(prm, nw, grid, pl->smem_scan2, s));
         } else {
             prm.scratch_stride = pl->stride_fast;
