@@ -52,7 +52,7 @@ class BaForwardOpts(C.Structure):
                 ("replay_waits", C.c_int32), ("force_ring_lists", C.c_int32),
                 ("seed", C.c_uint64), ("d_pop_tick", C.c_void_p),
                 ("d_seed", C.c_void_p), ("particle_offset", C.c_uint32),
-                ("reserved1", C.c_uint32)]
+                ("day_offset", C.c_uint32)]
 
 
 class BayesAirLibraryError(RuntimeError):
@@ -111,7 +111,7 @@ def load_library(build_if_missing: bool = True):
                                  C.c_uint32] + [C.c_void_p] * 5
     lib.ba_mf_backward.restype = C.c_int
     lib.ba_mf_backward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
-                                   C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ba_rqs_forward.restype = C.c_int
     lib.ba_rqs_forward.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]
@@ -211,10 +211,11 @@ class PlanHandle:
                                            lp0, z, stream), "ba_mf_sample")
 
     def mf_backward(self, P, params, seed, d_seed, particle_offset, tape, logp, lp0,
-                    inv_count_flights, work, flat, stream):
+                    inv_count_flights, prior_weight, work, flat, stream):
         _check(load_library().ba_mf_backward(self.handle, int(P), params, C.c_uint64(int(seed)),
                                              d_seed, int(particle_offset), tape, logp, lp0,
-                                             C.c_float(float(inv_count_flights)), work, flat,
+                                             C.c_float(float(inv_count_flights)),
+                                             C.c_float(float(prior_weight)), work, flat,
                                              stream), "ba_mf_backward")
 
     def logjoint_host(self, P, lat_airport, lat_route, scales, noise, opts, logp, status,

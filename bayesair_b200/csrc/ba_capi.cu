@@ -317,7 +317,7 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
     prm.P = P;
     prm.lat_airport = d_lat_airport; prm.lat_route = d_lat_route; prm.scales = d_scales;
     prm.noise = d_noise; prm.seed = o.seed;
-    prm.seed_dev = o.d_seed; prm.particle_offset = o.particle_offset;
+    prm.seed_dev = o.d_seed; prm.particle_offset = o.particle_offset; prm.day_offset = o.day_offset;
     prm.value_mode = o.noise_is_value; prm.want_grad = o.want_grad;
     prm.replay_waits = o.replay_waits;
     prm.logp = d_logp; prm.status = d_status; prm.ticks = d_ticks;
@@ -343,8 +343,12 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
             // strong-scaling shards)
             int nw = pl->warps_scan2, li = nw == 1 ? 0 : (nw == 2 ? 1 : (nw == 4 ? 2 : 3));
             const bool pinned_w = std::getenv("BA_WARPS") != nullptr;
+            // (a makespan model that also trades waves against warps was measured and lost:
+            //  at N = 100 four warps per particle-day cost more than the idle tail they remove)
             while (!pinned_w && li < 3 && n_work * (long long)(2 * nw) <= 32LL * pl->sm_count) { nw *= 2; ++li; }
             int grid = (int)std::min<long long>(n_work, pl->grids_scan2[li]);
+            // (equalising the waves of a two-to-four-wave batch was measured too: 5 % slower
+            //  than letting the persistent CTAs drain the work counter)
             // BA_GRID_CAP: fewer resident particle-days than the SMs hold (occupancy experiments)
             if (const char *e = std::getenv("BA_GRID_CAP")) { int g = std::atoi(e); if (g > 0 && g < grid) grid = g; }
             BA_CUDA(ba_launch_forward2(prm, nw, grid, pl->smem_scan2, s));
@@ -423,7 +427,7 @@ extern "C" BaStatus ba_predict(BaPlan *pl, int32_t P, const float *d_lat_airport
     prm.P = P;
     prm.lat_airport = d_lat_airport; prm.lat_route = d_lat_route; prm.scales = d_scales;
     prm.noise = d_noise; prm.noise2 = d_noise2; prm.sim = d_sim; prm.seed = o.seed;
-    prm.seed_dev = o.d_seed; prm.particle_offset = o.particle_offset;
+    prm.seed_dev = o.d_seed; prm.particle_offset = o.particle_offset; prm.day_offset = o.day_offset;
     prm.value_mode = o.noise_is_value;
     prm.logp = pl->d_predict_logp(P * pl->host.view.D);
     if (!prm.logp) return set_err(BA_ERR_CUDA, "ba_predict: out of device memory");
@@ -495,7 +499,8 @@ extern "C" BaStatus ba_mf_sample(BaPlan *pl, int32_t P, const float *d_params, u
 extern "C" BaStatus ba_mf_backward(BaPlan *pl, int32_t P, const float *d_params, uint64_t seed,
                                    const uint64_t *d_seed, uint32_t particle_offset,
                                    const void *d_tape, const float *d_logp, const float *d_lp0,
-                                   float inv_count_flights, void *d_work, float *d_flat, void *stream)
+                                   float inv_count_flights, float prior_weight, void *d_work,
+                                   float *d_flat, void *stream)
 {
     BaMfParams m;
     BaStatus rc = mf_params(pl, P, &m, "ba_mf_backward");
@@ -505,7 +510,7 @@ extern "C" BaStatus ba_mf_backward(BaPlan *pl, int32_t P, const float *d_params,
     BA_CUDA(cudaSetDevice(pl->device));
     m.params = d_params; m.seed = seed; m.seed_dev = d_seed; m.particle_offset = particle_offset;
     m.tape = (const float *)d_tape; m.logp = d_logp; m.lp0 = const_cast<float *>(d_lp0);
-    m.inv_count_flights = inv_count_flights; m.work = (float *)d_work; m.flat = d_flat;
+    m.inv_count_flights = inv_count_flights; m.prior_weight = prior_weight; m.work = (float *)d_work; m.flat = d_flat;
     BA_CUDA(ba_launch_mf_backward(m, (cudaStream_t)stream));
     g_launches += 2;
     return BA_OK;

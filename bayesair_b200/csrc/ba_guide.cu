@@ -136,9 +136,9 @@ __global__ void __launch_bounds__(256) ba_mf_backward_kernel(const BaMfParams pr
                     for (int d = 0; d < D; ++d) g += __ldg(tp + (size_t)d * stride + col[i]);
                 float lp, dl;
                 ba_mf_prior(j, N, z, x, &lp, &dl);
-                const float gz = x * g + dl;              // chain rule of exp + the prior
+                const float gz = x * g + prm.prior_weight * dl;   // chain rule of exp + the prior
                 a1[i] += gz;
-                a2[i] += gz * e[i] * sg[i] + 1.0f;        // + 1: d(-log q)/d log_scale
+                a2[i] += gz * e[i] * sg[i] + prm.prior_weight;    // + 1: d(-log q)/d log_scale
             }
         }
 #pragma unroll
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) ba_mf_backward_kernel(const BaMfParams pr
             acc[0] += row[0]; acc[1] += row[1]; acc[2] += row[2];
             acc[3] += prm.logp[i];
         }
-        for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) acc[3] += prm.lp0[p];
+        for (int p = p0 + threadIdx.x; p < p1; p += blockDim.x) acc[3] += (double)prm.prior_weight * prm.lp0[p];
         __shared__ double red[4][8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(MAXT, BA_MIN_BLOCKS(MAXT)) ba_forward_kernel(c
         c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
         c.noise2 = (PREDICT && prm.noise2) ? prm.noise2 + pd * (size_t)plan.Fmax * 4 : nullptr;
         c.sim = PREDICT ? prm.sim + pd * (size_t)plan.Fmax * 3 : nullptr;
-        c.particle = (uint32_t)p + prm.particle_offset; c.dayidx = (uint32_t)d;
+        c.particle = (uint32_t)p + prm.particle_offset; c.dayidx = (uint32_t)d + prm.day_offset;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
         ba_carve_lists<EXACT>(c, day, plan.max_ticks, plan.max_dslice, fixed, pool, gscr);
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         c.lat_airport = prm.lat_airport + (size_t)p * 2 * N;
         c.lat_route = prm.lat_route + (size_t)p * R;
         c.noise = prm.noise ? prm.noise + pd * (size_t)plan.Fmax * 4 : nullptr;
-        c.particle = (uint32_t)p + prm.particle_offset; c.dayidx = (uint32_t)d;
+        c.particle = (uint32_t)p + prm.particle_offset; c.dayidx = (uint32_t)d + prm.day_offset;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
         ba2_carve_scratch(c, gscr, day.F, N);

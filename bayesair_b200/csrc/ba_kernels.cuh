@@ -17,6 +17,7 @@ struct BaFwdParams {
     uint64_t seed;
     const uint64_t *seed_dev;     // if set, the seed is read from device memory
     uint32_t particle_offset;     // added to the particle index in the Philox counters
+    uint32_t day_offset;          // added to the day index in the Philox counters
     int32_t value_mode, want_grad, replay_waits;
     float *logp;                  // [P, D]
     uint32_t *status;             // [P, D]
@@ -67,6 +68,7 @@ struct BaMfParams {
     float *lat_airport, *lat_route, *lp0, *z;
     const float *tape, *logp;
     float inv_count_flights;
+    float prior_weight;           // share of the per-particle terms (prior, -log q) counted here
     float *work;                  // [chunks, 2n + 4]
     int32_t chunks;
     float *flat;

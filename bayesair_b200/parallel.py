@@ -26,6 +26,28 @@ def shard_particles(n_particles: int, rank: int, world_size: int) -> Tuple[int, 
     return start, count
 
 
+def shard_particle_days(n_particles: int, n_days: int, rank: int, world_size: int
+                        ) -> Tuple[int, int, int, int]:
+    """2-D decomposition ``(particle_start, particle_count, day_start, day_count)`` of the
+    (particle, day) grid for ``rank``.  Particles are split first; only when there are more
+    ranks than particles can usefully fill (fewer than one particle per rank, or a particle
+    count that does not divide over the ranks while the day count does) are the DAYS split as
+    well: ``world_size = Gp x Gd`` with the largest ``Gp`` that divides ``world_size`` and is
+    at most ``n_particles``.  Ranks of one particle shard share the guide draws (same seed,
+    same ``particle_offset``) and each accounts for ``day_count / n_days`` of the per-particle
+    terms (``prior_weight`` of ``ba_mf_backward``)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    gp = max(g for g in range(1, world_size + 1) if world_size % g == 0 and g <= max(1, n_particles))
+    gd = world_size // gp
+    if gd > n_days:
+        raise ValueError(f"{world_size} ranks cannot be filled by {n_particles} particles x {n_days} days")
+    rp, rd = divmod(rank, gd)
+    p0, pc = shard_particles(n_particles, rp, gp)
+    d0, dc = shard_particles(n_days, rd, gd)
+    return p0, pc, d0, dc
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], extra: Optional[torch.Tensor] = None,
                         group=None, average: bool = False) -> Optional[torch.Tensor]:
     """Sums ``p.grad`` of every parameter (and ``extra``, e.g. the scalar loss or the three

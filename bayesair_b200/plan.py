@@ -102,12 +102,14 @@ class SimulationPlan:
                 want_ticks: bool = False, want_pop_ticks: bool = False,
                 replay_waits: bool = False,
                 force_ring_lists: bool = False, seed_tensor: Optional[torch.Tensor] = None,
-                particle_offset: int = 0) -> Dict[str, torch.Tensor]:
+                particle_offset: int = 0, day_offset: int = 0) -> Dict[str, torch.Tensor]:
         """``lat_airport [P,C,N]``, ``lat_route [P,R]``, ``scales [3]``,
         ``noise [P,D,Fmax,4]`` or None (Philox from ``seed``).  Asynchronous.
         ``seed_tensor``: one int64 on the device, read by the kernel when it starts (CUDA
         graphs replay with a fresh seed); ``particle_offset``: index of the first particle in
-        the global batch (ranks sharing a seed then draw different per-flight noise)."""
+        the global batch (ranks sharing a seed then draw different per-flight noise);
+        ``day_offset``: index of this plan's first day in the whole data set (a rank whose plan
+        holds a subset of the days then draws what the full plan would)."""
         P = int(lat_airport.shape[0])
         D, N, Cn, R, F = (self.n_days, self.n_airports, self.n_airport_latents, self.n_routes,
                           self.max_flights)
@@ -128,7 +130,7 @@ class SimulationPlan:
                                        int(force_ring_lists), int(seed) & (2**64 - 1),
                                        None if pop is None else pop.data_ptr(),
                                        None if seed_tensor is None else seed_tensor.data_ptr(),
-                                       int(particle_offset) & 0xFFFFFFFF, 0)
+                                       int(particle_offset) & 0xFFFFFFFF, int(day_offset) & 0xFFFFFFFF)
             with torch.cuda.nvtx.range("ba.forward"):
                 self._h.forward(P, _ptr(la), _ptr(lr), _ptr(sc), _ptr(nz), opts, _ptr(logp),
                                 _ptr(status), _ptr(ticks), _ptr(tape), self._stream())

@@ -41,7 +41,17 @@ class FusedMeanFieldSVI:
 
     def __init__(self, plan: SimulationPlan, scales: torch.Tensor, n_particles: int, *,
                  init_loc: Optional[torch.Tensor] = None, init_scale: float = 0.05,
-                 lr: float = 1e-3, seed: int = 0, group=None, use_graph: bool = True):
+                 lr: float = 1e-3, seed: int = 0, group=None, use_graph: bool = True,
+                 particle_offset: Optional[int] = None, n_particles_total: Optional[int] = None,
+                 n_flights_total: Optional[int] = None, prior_weight: float = 1.0,
+                 day_offset: int = 0):
+        """``plan``: this rank's days.  By default the ranks shard the PARTICLES (rank r owns
+        particles ``[r P, (r + 1) P)`` of ``world x P``, the plan holds every day).  With the
+        days sharded as well (``parallel.shard_particle_days``), pass the shard explicitly:
+        ``particle_offset`` (first particle of this rank's shard), ``n_particles_total``,
+        ``n_flights_total`` (flights of ALL days), ``day_offset`` (first day of this rank's
+        plan) and ``prior_weight`` = this rank's share of the days (the ranks of one particle
+        shard draw identical latents)."""
         if plan.include_cancellations:
             raise ValueError("the fused mean-field step supports plans without cancellations")
         self.plan, self.P, self.group = plan, int(n_particles), group
@@ -50,8 +60,12 @@ class FusedMeanFieldSVI:
         self.n = n_latent(N)
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
-        self.offset = self.rank * self.P
-        self.inv = 1.0 / (self.world * self.P * plan.n_flights_total)
+        self.offset = self.rank * self.P if particle_offset is None else int(particle_offset)
+        total_p = self.world * self.P if n_particles_total is None else int(n_particles_total)
+        total_f = plan.n_flights_total if n_flights_total is None else int(n_flights_total)
+        self.inv = 1.0 / (total_p * total_f)
+        self.prior_weight = float(prior_weight)
+        self.day_offset = int(day_offset)
         theta = torch.zeros(2 * self.n, device=dev)
         if init_loc is not None:
             theta[:self.n] = init_loc.to(dev)
@@ -96,9 +110,11 @@ class FusedMeanFieldSVI:
         h.mf_sample(self.P, _p(self.theta), 0, _p(self.seed), self.offset, _p(self.la),
                     _p(self.lr_), _p(self.lp0), _p(z_out), stream)
         out = plan.forward(self.la, self.lr_, self.scales, None, want_grad=True,
-                           seed_tensor=self.seed, particle_offset=self.offset)
+                           seed_tensor=self.seed, particle_offset=self.offset,
+                           day_offset=self.day_offset)
         h.mf_backward(self.P, _p(self.theta), 0, _p(self.seed), self.offset, _p(out["tape"]),
-                      _p(out["logp"]), _p(self.lp0), self.inv, _p(self.work), _p(self.flat), stream)
+                      _p(out["logp"]), _p(self.lp0), self.inv, self.prior_weight, _p(self.work),
+                      _p(self.flat), stream)
         return out
 
     def _enqueue(self):

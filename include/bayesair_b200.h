@@ -113,7 +113,9 @@ typedef struct BaForwardOpts {
     uint32_t particle_offset;   /* index of this call's first particle in the global batch:
                                    Philox counters use particle_offset + p, so ranks that share
                                    a seed draw different per-flight noise                   */
-    uint32_t reserved1;
+    uint32_t day_offset;        /* index of the plan's first day in the whole data set: Philox
+                                   counters use day_offset + d, so a rank whose plan holds a
+                                   subset of the days draws what the full plan would       */
 } BaForwardOpts;
 
 int ba_version(void);
@@ -215,6 +217,11 @@ BaStatus ba_logjoint_host(BaPlan *plan, int32_t n_particles,
  *                   [2n,2n+3) d loss / d scales     [2n+3]  loss
  *                 with loss = -(1 / (count * flights)) sum_p ELBO_p  (train.py:318-326);
  *                 `inv_count_flights` = 1 / (global particle count * total flights).
+ *                 `prior_weight`: share of the per-particle terms (prior, -log q) this call
+ *                 accounts for -- 1 when the plan holds every day of the data set; when the
+ *                 DAYS are sharded over ranks too (each rank's plan holds a subset of the
+ *                 days and the ranks of one particle shard share seed and particle_offset),
+ *                 the shares of those ranks must sum to 1.
  *                 d_work: ba_mf_work_bytes() bytes of scratch.
  * d_params [2n] = loc | log_scale.  Only plans without cancellations (C = 2). */
 size_t ba_mf_work_bytes(const BaPlan *plan, int32_t n_particles);
@@ -225,7 +232,8 @@ BaStatus ba_mf_sample(BaPlan *plan, int32_t n_particles, const float *d_params,
 BaStatus ba_mf_backward(BaPlan *plan, int32_t n_particles, const float *d_params,
                         uint64_t seed, const uint64_t *d_seed, uint32_t particle_offset,
                         const void *d_tape, const float *d_logp, const float *d_lp0,
-                        float inv_count_flights, void *d_work, float *d_flat, void *stream);
+                        float inv_count_flights, float prior_weight, void *d_work, float *d_flat,
+                        void *stream);
 
 /* ---- conditional flow guide: monotonic rational-quadratic spline -------------------------
  * The elementwise transform of the CalNF guide (the reference's guide is zuko.flows.NSF,

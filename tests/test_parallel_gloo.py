@@ -67,3 +67,21 @@ def test_allreduce_matches_single_process():
         assert torch.allclose(gl, guide.loc.grad, atol=1e-6)
         assert torch.allclose(gs, guide.log_scale.grad, atol=1e-6)
         assert torch.allclose(extra, loss.detach().reshape(1), atol=1e-6)
+
+
+def test_particle_day_grid_is_covered_once():
+    from bayesair_b200.parallel import shard_particle_days
+    for P, D, W in ((4096, 10, 8), (4, 30, 8), (1, 8, 8), (3, 10, 6), (7, 5, 1), (2, 2, 4)):
+        seen = {}
+        weight = {}
+        for r in range(W):
+            p0, pc, d0, dc = shard_particle_days(P, D, r, W)
+            for p in range(p0, p0 + pc):
+                weight[p] = weight.get(p, 0.0) + dc / D
+                for d in range(d0, d0 + dc):
+                    seen[(p, d)] = seen.get((p, d), 0) + 1
+        assert len(seen) == P * D and set(seen.values()) == {1}, (P, D, W)
+        # the ranks of one particle shard account for the whole prior between them
+        assert all(abs(w - 1.0) < 1e-12 for w in weight.values())
+    # plenty of particles: the days stay whole
+    assert shard_particle_days(4096, 10, 3, 8) == (1536, 512, 0, 10)

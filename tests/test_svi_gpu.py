@@ -180,3 +180,32 @@ def test_svi_with_autoguide_over_the_scaled_model(guide_name):
     assert np.mean(losses[-10:]) < np.mean(losses[:10])
     med = guide.median(states, g.delta_t)
     assert set(med) >= {f"{c}_mean_service_time" for c in g.global_codes}
+
+
+def test_day_sharded_ranks_sum_to_the_unsharded_gradient():
+    """Days sharded over ranks (parallel.shard_particle_days): two virtual ranks that own one
+    day each of the same particles -- same seed, same particle offset, prior_weight 1/2 --
+    produce flat buffers whose sum (what the all-reduce computes) is the unsharded buffer."""
+    from bayesair_b200.plan import SimulationPlan
+    from bayesair_b200.svi import FusedMeanFieldSVI
+    g = Golden("twoday5")
+    full = _plan(g)
+    N, P = full.n_airports, 32
+    scales = torch.tensor([0.1, 0.1, 0.1], device=full.device)
+    init = _init_loc(g, N)
+    ref = FusedMeanFieldSVI(full, scales, P, init_loc=init, init_scale=0.06, seed=77, use_graph=False)
+    ref.local_gradient()
+    torch.cuda.synchronize()
+    total = torch.zeros_like(ref.flat)
+    for d in range(2):
+        plan_d = SimulationPlan([g.specs[d]], g.global_codes, delta_t=g.delta_t, device="cuda:0")
+        part = FusedMeanFieldSVI(plan_d, scales, P, init_loc=init, init_scale=0.06, seed=77,
+                                 use_graph=False, particle_offset=0, n_particles_total=P,
+                                 n_flights_total=full.n_flights_total, prior_weight=0.5,
+                                 day_offset=d)
+        part.local_gradient()
+        torch.cuda.synchronize()
+        total += part.flat
+    a, b = total.cpu().double().numpy(), ref.flat.cpu().double().numpy()
+    scale = np.maximum(np.abs(b), 1e-6 * np.abs(b).max())
+    assert (np.abs(a - b) / scale).max() < 1e-4, (np.abs(a - b) / scale).max()
