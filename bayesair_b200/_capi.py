@@ -25,7 +25,7 @@ EXPORTS = (
     "ba_generate_noise",
     "ba_logjoint_host", "ba_launch_count",
     "ba_mf_work_bytes", "ba_mf_sample", "ba_mf_backward",
-    "ba_rqs_forward", "ba_rqs_backward",
+    "ba_rqs_forward", "ba_rqs_backward", "ba_backward_values",
 )
 
 
@@ -52,7 +52,7 @@ class BaForwardOpts(C.Structure):
                 ("replay_waits", C.c_int32), ("force_ring_lists", C.c_int32),
                 ("seed", C.c_uint64), ("d_pop_tick", C.c_void_p),
                 ("d_seed", C.c_void_p), ("particle_offset", C.c_uint32),
-                ("day_offset", C.c_uint32)]
+                ("day_offset", C.c_uint32), ("d_value_tape", C.c_void_p)]
 
 
 class BayesAirLibraryError(RuntimeError):
@@ -113,6 +113,8 @@ def load_library(build_if_missing: bool = True):
     lib.ba_mf_backward.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p,
                                    C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ba_backward_values.restype = C.c_int
+    lib.ba_backward_values.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4
     lib.ba_rqs_forward.restype = C.c_int
     lib.ba_rqs_forward.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p]
     lib.ba_rqs_backward.restype = C.c_int
@@ -200,6 +202,10 @@ class PlanHandle:
     def generate_noise(self, P, seed, noise, stream):
         _check(load_library().ba_generate_noise(self.handle, int(P), C.c_uint64(int(seed)),
                                                 noise, stream), "ba_generate_noise")
+
+    def backward_values(self, P, dlogp, vtape, g_noise, stream):
+        _check(load_library().ba_backward_values(self.handle, int(P), dlogp, vtape, g_noise, stream),
+               "ba_backward_values")
 
     def mf_work_bytes(self, P: int) -> int:
         return int(load_library().ba_mf_work_bytes(self.handle, int(P)))

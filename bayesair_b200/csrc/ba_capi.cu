@@ -298,6 +298,10 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
     if (o.want_grad && !d_tape) return set_err(BA_ERR_BAD_ARG, "ba_forward: want_grad needs d_tape");
     if (o.noise_is_value && !d_noise)
         return set_err(BA_ERR_BAD_ARG, "ba_forward: noise_is_value needs d_noise");
+    if (o.d_value_tape && (!o.noise_is_value || !pl->scan2_ok || o.force_exact_lists || o.force_ring_lists))
+        return set_err(BA_ERR_BAD_ARG, "ba_forward: d_value_tape needs noise_is_value and a plan the "
+                                       "ring-less scan runs (no cancellations, every flight observed)");
+    if (o.d_value_tape) o.no_overflow_rerun = 1;
     cudaStream_t s = (cudaStream_t)stream;
     BA_CUDA(cudaSetDevice(pl->device));
     const int D = pl->host.view.D;
@@ -322,6 +326,7 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
     prm.replay_waits = o.replay_waits;
     prm.logp = d_logp; prm.status = d_status; prm.ticks = d_ticks;
     prm.tape = (float *)d_tape; prm.pop_tick = o.d_pop_tick;
+    prm.vtape = o.d_value_tape;
     prm.scratch = pl->d_scratch;
     prm.n_work = (int)n_work;
 
@@ -454,6 +459,19 @@ extern "C" BaStatus ba_backward(BaPlan *pl, int32_t P, const float *d_dlogp, con
     b.dlogp = d_dlogp; b.tape = (const float *)d_tape;
     b.g_airport = d_g_airport; b.g_route = d_g_route; b.g_scales = d_g_scales;
     BA_CUDA(ba_launch_backward(b, (cudaStream_t)stream));
+    g_launches++;
+    return BA_OK;
+}
+
+extern "C" BaStatus ba_backward_values(BaPlan *pl, int32_t P, const float *d_dlogp,
+                                       const float *d_value_tape, float *d_g_noise, void *stream)
+{
+    if (!pl || P <= 0 || !d_dlogp || !d_value_tape || !d_g_noise)
+        return set_err(BA_ERR_BAD_ARG, "ba_backward_values: null / empty argument");
+    BA_CUDA(cudaSetDevice(pl->device));
+    const BaPlanView &v = pl->host.view;
+    BA_CUDA(ba_launch_backward_values(d_dlogp, d_value_tape, d_g_noise, (long long)P * v.D, v.Fmax,
+                                      (cudaStream_t)stream));
     g_launches++;
     return BA_OK;
 }

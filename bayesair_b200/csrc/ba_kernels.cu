@@ -13,6 +13,7 @@
 //   ba_collect_kernel          compacts the particle-days that must be re-run.
 //
 // Nothing here is a dense contraction: no tensor cores, by design.
+#include <algorithm>
 #include "ba_kernels.cuh"
 #include "ba_sim.cuh"
 #include "ba_scan2.cuh"
@@ -442,6 +443,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         c.particle = (uint32_t)p + prm.particle_offset; c.dayidx = (uint32_t)d + prm.day_offset;
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
+        c.vrow = prm.vtape ? prm.vtape + pd * (size_t)plan.Fmax * 4 : nullptr;
         ba2_carve_scratch(c, gscr, day.F, N);
         const uint32_t n_arr = (uint32_t)day.n_arr;
 
@@ -453,6 +455,8 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
             for (int i = tid; i < R; i += NT) c.grow[c.route_base + i] = 0.0f;
         if (c.pop_tick)
             for (int i = 2 * day.F + tid; i < 2 * plan.Fmax; i += NT) c.pop_tick[i] = -1;
+        if (c.vrow)
+            for (int i = 4 * day.F + tid; i < 4 * plan.Fmax; i += NT) c.vrow[i] = 0.0f;
         BaAcc acc = {0.0, 0.0f, 0.0f, 0.0f, 0u};
         ba2_sync<NW>();
         BA2_MARK(0);
@@ -531,6 +535,13 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
             ba2_sync<NW>();
             for (int s = tid; s < N; s += NT) ba2_epilogue_airport(c, s, N);
             for (int r = tid; r < day.Rd; r += NT) ba2_epilogue_route(c, r);
+        }
+        if (c.vrow && !aborted) {
+            // value mode: wait-mediated part of the gradient w.r.t. the service-time values
+            ba2_sync<NW>();
+            for (int s = tid; s < N; s += NT) ba2_value_grad_airport(c, s);
+            ba2_sync<NW>();
+            for (int f = tid; f < day.F; f += NT) ba2_value_grad_finish(c, f);
         }
         // deterministic reduction: shuffle tree over the lanes, warps in order
         double v0 = acc.lp;
@@ -777,6 +788,31 @@ cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s)
     dim3 grid((unsigned)((p.stride + 255) / 256), (unsigned)(p.P < 65535 ? p.P : 65535));
     if (grid.x > 64) grid.x = 64;
     ba_backward_kernel<<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// g_noise[pd, f, :] = dlogp[pd] * vtape[pd, f, :]
+__global__ void __launch_bounds__(256) ba_backward_values_kernel(const float *__restrict__ dlogp,
+                                                                 const float4 *__restrict__ vtape,
+                                                                 float4 *__restrict__ g_noise,
+                                                                 long long n_pd, int row)
+{
+    const long long total = n_pd * row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float w = __ldg(dlogp + i / row);
+        const float4 v = vtape[i];
+        g_noise[i] = make_float4(w * v.x, w * v.y, w * v.z, w * v.w);
+    }
+}
+
+cudaError_t ba_launch_backward_values(const float *dlogp, const float *vtape, float *g_noise,
+                                      long long n_pd, int row, cudaStream_t s)
+{
+    const long long total = n_pd * row;
+    int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    if (grid < 1) grid = 1;
+    ba_backward_values_kernel<<<grid, 256, 0, s>>>(dlogp, (const float4 *)vtape, (float4 *)g_noise, n_pd, row);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,7 @@ struct BaFwdParams {
     int32_t *ticks;               // [P, D] or nullptr
     float *tape;                  // [P, D, grad_stride] or nullptr
     int32_t *pop_tick;            // [P, D, Fmax, 2] or nullptr
+    float *vtape;                 // value mode: [P, D, Fmax, 4] d logp / d site values, or nullptr
     uint32_t *scratch;            // per-CTA global scratch
     uint64_t scratch_stride;      // words per CTA
     unsigned int *work_counter;   // dynamic work distribution
@@ -85,6 +86,8 @@ cudaError_t ba_launch_rqs_backward(const float *x, const float *params, const fl
 cudaError_t ba_launch_predict(const BaFwdParams &p, int grid, int block, size_t smem,
                               cudaStream_t s);
 cudaError_t ba_launch_backward(const BaBwdParams &p, cudaStream_t s);
+cudaError_t ba_launch_backward_values(const float *dlogp, const float *vtape, float *g_noise,
+                                      long long n_pd, int row, cudaStream_t s);
 cudaError_t ba_launch_noise(const BaPlanView &plan, int P, uint64_t seed, float *noise,
                             cudaStream_t s);
 // gathers the particle-days whose status has `bit` set into list (device), count in *n

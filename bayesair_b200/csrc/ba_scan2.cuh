@@ -132,13 +132,17 @@ struct Ba2Ctx {
     float *grow;
     int32_t *pop_tick;
     int route_base;
+    // value mode: gradient w.r.t. the four per-flight site values (nullable)
+    float *vrow;                              // [Fmax, 4] of this particle-day
+    float *rD, *rA;                           // [n_live + N] residual / gradient of the departure
+                                              //   and arrival entry of every live position
 };
 
 // words of per-warp global scratch
 static inline uint64_t ba2_scratch_words(int F, int N)
 {
     const uint64_t f = (uint64_t)F, n = (uint64_t)N;
-    return (f + 4) + 4 * (f + n + 4) + 3 * (f + n + 4) + 4 * f + 2 * f + 4 * f + 64;
+    return (f + 4) + 4 * (f + n + 4) + 3 * (f + n + 4) + 4 * f + 2 * f + 4 * f + 2 * (f + n + 4) + 64;
 }
 
 BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
@@ -152,7 +156,8 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
     c.Ak = g; g += fn;
     c.Lb = g; g += 2 * fn; c.lb_stride = fn;
     c.hx = (float *)g; g += 2 * f;
-    c.glog = g;
+    c.glog = g; g += 4 * f;
+    c.rD = (float *)g; c.rA = (float *)g + fn;
 }
 
 // shared-memory words per warp
@@ -566,7 +571,7 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
             if (hkey == BA2_NONE) hkey = c.Ak[ha];
             Ba2Pay *pp = c.P + (hkey & 0xFFFFu);
             pp->xa = wacc;                                   // tape: total wait of the arrival
-            if (c.pop_tick) pp->at = __uint_as_float_portable(k);
+            if (c.pop_tick || c.vrow) pp->at = __uint_as_float_portable(k);
             ha += 1; hkey = BA2_NONE;
         } else {
             // tape: total wait of the departure, and the message to the destination
@@ -611,6 +616,90 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
 // ---------------------------------------------------------------------------
 // EPILOGUE (flight-parallel, then owner sums); SURVEY.md App. A.3 / A.5
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// VALUE MODE: gradient of the log-probability w.r.t. the four per-flight site values (the
+// sites a guide over them proposes, wn_network.py:285-302).  Direct terms per flight here;
+// the wait-mediated terms per airport below.
+// ---------------------------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+static
+#endif
+void ba2_value_grad_flight(Ba2Ctx &c, int f, int lpos, int o, int d, float T, float tau, float r_d, float r_a)
+{
+    const BaNoise4 nz = ba2_noise(c, f);                  // the values themselves
+    const float mt = c.s_mt[d], tstd = BA_MUL(c.v_u, mt), sc = BA_MUL(T, c.v_t);
+    const float dz = (tau - T) / sc, du = (nz.eps_turn - mt) / tstd;
+    // Exponential(x; rate): -rate; Normal travel time: -dz / sc, and it moves the arrival's
+    // queue start (airport.py:197-204): + r_a; Normal turnaround time: -du / tstd
+    c.vrow[4 * f + 0] = -c.s_rate[o];
+    c.vrow[4 * f + 1] = -dz / sc + r_a;
+    c.vrow[4 * f + 2] = -c.s_rate[d];
+    c.vrow[4 * f + 3] = -du / tstd;
+    c.rD[lpos] = r_d;
+    c.rA[lpos] = r_a;
+}
+
+// The total wait of a queue entry is the sum of the service draws assigned while it was
+// queued (types/airport.py:150-153): the draws of the entries served from the tick it joined
+// up to and including its own.  So d logp / d (draw of the m-th served entry) is the sum of
+// the residuals r_e of the entries e whose waiting interval [lo_e, e] contains m.  The service
+// order is the FIFO merge of the airport's arrivals and departures by joining tick (arrivals
+// first on ties), an entry is assigned its draw when its predecessor is served or when it
+// joins an empty queue, and lo_e counts the assignments made before the tick e joined -- all
+// recoverable from what the scan left: joining and serving ticks of every entry.
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+static
+#endif
+void ba2_value_grad_airport(Ba2Ctx &c, int a)
+{
+    const BaAirport A = c.ap[a];
+    const uint32_t n_dep = (uint32_t)A.dep_live, n_arr = (uint32_t)A.arr_cnt, n = n_dep + n_arr;
+    if (n == 0u) return;
+    const uint32_t off = A.lq_off + A.as_off - 2u * (uint32_t)a;      // this airport's slices
+    float *D = c.hx + off;                     // [n] difference array, then the gradient
+    uint32_t *ident = c.glog + 2u * off;       // [n] {live position | departure << 31, assignment tick}
+    for (uint32_t m = 0; m < n; ++m) D[m] = 0.0f;
+    uint32_t ia = 0, id = 0, prev_pop = 0, lo = 0;
+    for (uint32_t m = 0; m < n; ++m) {
+        const bool a_ok = ia < n_arr, d_ok = id < n_dep;
+        uint32_t ja = BA2_NONE, jd = BA2_NONE, akey = 0;
+        if (a_ok) { akey = c.Ak[A.as_off + ia]; ja = (akey >> 16) + 1u; }
+        if (d_ok) jd = c.lq[A.lq_off + id].tick;
+        const bool arr = ja <= jd;                         // arrivals first on ties
+        const uint32_t join = arr ? ja : jd;
+        const uint32_t lpos = arr ? (akey & 0xFFFFu) : A.lq_off + id;
+        const uint32_t pop = arr ? __float_as_uint_portable(c.P[lpos].at) : c.P[lpos].q;
+        const float r = arr ? c.rA[lpos] : c.rD[lpos];
+        const uint32_t asg = m == 0u ? join : (prev_pop > join ? prev_pop : join);
+        ident[2u * m] = lpos | (arr ? 0u : 0x80000000u);
+        ident[2u * m + 1u] = asg;
+        while (lo < m && ident[2u * lo + 1u] < join) ++lo;   // assignments before the joining tick
+        D[lo] += r;
+        if (m + 1u < n) D[m + 1u] -= r;
+        prev_pop = pop;
+        if (arr) ++ia; else ++id;
+    }
+    float run = 0.0f;
+    for (uint32_t m = 0; m < n; ++m) {
+        run += D[m];
+        const uint32_t w = ident[2u * m];
+        if (w & 0x80000000u) c.rD[w & 0x7FFFFFFFu] = run; else c.rA[w] = run;
+    }
+}
+
+// adds the wait-mediated terms to the two service-time values of a flight
+BA_DEV void ba2_value_grad_finish(Ba2Ctx &c, int f)
+{
+    const int lpos = c.pos_live[f];
+    if (lpos < 0) return;
+    c.vrow[4 * f + 0] += c.rD[lpos];
+    c.vrow[4 * f + 2] += c.rA[lpos];
+}
+
 struct Ba2EpiIn {
     BaFlight fl;
     int lpos, k, j, rt;
@@ -647,6 +736,7 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
     if (cobs == 1u) {                 // observed as cancelled: never queued anywhere
         if (c.want_grad) { c.xdk[k] = 0.0f; c.atk[f] = 0.0f; }
         if (c.pop_tick) { c.pop_tick[2 * f] = -1; c.pop_tick[2 * f + 1] = -1; }
+        if (c.vrow) { c.vrow[4 * f] = 0.0f; c.vrow[4 * f + 1] = 0.0f; c.vrow[4 * f + 2] = 0.0f; c.vrow[4 * f + 3] = 0.0f; }
         return;
     }
     const int j = in.j;
@@ -674,6 +764,7 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
     const float dy_a = y_arr - mu_a;
     const float lp = (lp_const - dy_d * dy_d * half_inv_var) + (lp_const - dy_a * dy_a * half_inv_var);
     acc.lp += (double)lp;
+    if (c.vrow) ba2_value_grad_flight(c, f, in.lpos, o, d, T, tau, dy_d * c.inv_sigma2, dy_a * c.inv_sigma2);
 
     if (grad) {
         const float r_d = dy_d * c.inv_sigma2, r_a = dy_a * c.inv_sigma2;
@@ -700,7 +791,6 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
             acc.g_vu += (du * du - 1.0f) * c.inv_vu;
         }
     }
-    (void)o;
 }
 
 // EPILOGUE of one flight (host emulation; the kernel runs the stages itself)

@@ -20,24 +20,32 @@ class _SimulateLogJoint(torch.autograd.Function):
     def forward(ctx, plan: SimulationPlan, lat_airport, lat_route, scales, noise, seed,
                 noise_is_value, check_status):
         need = any(ctx.needs_input_grad[1:4])
+        # per-flight site values given by the caller (value mode) and differentiable: the
+        # route of a guide over the per-flight sites (wn_network.py:285-302)
+        need_values = bool(noise_is_value and noise is not None and ctx.needs_input_grad[4])
         out = plan.forward(lat_airport.detach(), lat_route.detach(), scales.detach(),
                            None if noise is None else noise.detach(), seed=seed,
-                           noise_is_value=noise_is_value, want_grad=need)
+                           noise_is_value=noise_is_value, want_grad=need,
+                           want_value_grad=need_values)
         if check_status:
             plan.check_status(out["status"])
         ctx.plan = plan
         ctx.tape = out["tape"]
+        ctx.value_tape = out["value_tape"]
         ctx.mark_non_differentiable(out["status"])
         return out["logp"], out["status"]
 
     @staticmethod
     def backward(ctx, dlogp, _dstatus):
+        gn = None
+        if ctx.value_tape is not None:
+            gn = ctx.plan.backward_values(dlogp.contiguous(), ctx.value_tape)
         if ctx.tape is None:
-            return (None,) * 8
+            return (None, None, None, None, gn, None, None, None)
         ga, gr, gs = ctx.plan.backward(dlogp.contiguous(), ctx.tape)
         need = ctx.needs_input_grad
         return (None, ga if need[1] else None, gr if need[2] else None,
-                gs.sum(0) if need[3] else None, None, None, None, None)
+                gs.sum(0) if need[3] else None, gn, None, None, None)
 
 
 def simulate_log_joint(plan: SimulationPlan, lat_airport: torch.Tensor, lat_route: torch.Tensor,

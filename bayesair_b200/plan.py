@@ -102,14 +102,17 @@ class SimulationPlan:
                 want_ticks: bool = False, want_pop_ticks: bool = False,
                 replay_waits: bool = False,
                 force_ring_lists: bool = False, seed_tensor: Optional[torch.Tensor] = None,
-                particle_offset: int = 0, day_offset: int = 0) -> Dict[str, torch.Tensor]:
+                particle_offset: int = 0, day_offset: int = 0,
+                want_value_grad: bool = False) -> Dict[str, torch.Tensor]:
         """``lat_airport [P,C,N]``, ``lat_route [P,R]``, ``scales [3]``,
         ``noise [P,D,Fmax,4]`` or None (Philox from ``seed``).  Asynchronous.
         ``seed_tensor``: one int64 on the device, read by the kernel when it starts (CUDA
         graphs replay with a fresh seed); ``particle_offset``: index of the first particle in
         the global batch (ranks sharing a seed then draw different per-flight noise);
         ``day_offset``: index of this plan's first day in the whole data set (a rank whose plan
-        holds a subset of the days then draws what the full plan would)."""
+        holds a subset of the days then draws what the full plan would);
+        ``want_value_grad`` (with ``noise_is_value``): also returns ``value_tape [P,D,Fmax,4]``,
+        the gradient of ``logp[p, d]`` w.r.t. the per-flight site values in ``noise``."""
         P = int(lat_airport.shape[0])
         D, N, Cn, R, F = (self.n_days, self.n_airports, self.n_airport_latents, self.n_routes,
                           self.max_flights)
@@ -125,17 +128,20 @@ class SimulationPlan:
                     if want_grad else None)
             pop = (torch.empty((P, D, F, 2), dtype=torch.int32, device=self.device)
                    if want_pop_ticks else None)
+            vtape = (torch.empty((P, D, F, 4), dtype=torch.float32, device=self.device)
+                     if want_value_grad else None)
             opts = _capi.BaForwardOpts(int(noise_is_value), int(want_grad), int(force_exact_lists),
                                        int(no_overflow_rerun), int(replay_waits),
                                        int(force_ring_lists), int(seed) & (2**64 - 1),
                                        None if pop is None else pop.data_ptr(),
                                        None if seed_tensor is None else seed_tensor.data_ptr(),
-                                       int(particle_offset) & 0xFFFFFFFF, int(day_offset) & 0xFFFFFFFF)
+                                       int(particle_offset) & 0xFFFFFFFF, int(day_offset) & 0xFFFFFFFF,
+                                       None if vtape is None else vtape.data_ptr())
             with torch.cuda.nvtx.range("ba.forward"):
                 self._h.forward(P, _ptr(la), _ptr(lr), _ptr(sc), _ptr(nz), opts, _ptr(logp),
                                 _ptr(status), _ptr(ticks), _ptr(tape), self._stream())
         return {"logp": logp, "status": status, "ticks": ticks, "tape": tape, "pop_tick": pop,
-                "_keep": (la, lr, sc, nz, seed_tensor)}
+                "value_tape": vtape, "_keep": (la, lr, sc, nz, seed_tensor)}
 
     def predict(self, lat_airport: torch.Tensor, lat_route: torch.Tensor, scales: torch.Tensor,
                 noise: Optional[torch.Tensor] = None, obs_noise: Optional[torch.Tensor] = None,
@@ -176,6 +182,16 @@ class SimulationPlan:
             with torch.cuda.nvtx.range("ba.backward"):
                 self._h.backward(P, _ptr(dl), _ptr(tape), _ptr(ga), _ptr(gr), _ptr(gs), self._stream())
         return ga, gr, gs
+
+    def backward_values(self, dlogp: torch.Tensor, value_tape: torch.Tensor) -> torch.Tensor:
+        """Cotangent w.r.t. the per-flight site values of a value-mode forward
+        (``ba_backward_values``): ``[P, D, Fmax, 4]``."""
+        P = int(value_tape.shape[0])
+        dl = self._chk(dlogp, (P, self.n_days), "dlogp")
+        with torch.cuda.device(self.device):
+            g = torch.empty_like(value_tape)
+            self._h.backward_values(P, _ptr(dl), _ptr(value_tape), _ptr(g), self._stream())
+        return g
 
     def generate_noise(self, n_particles: int, seed: int) -> torch.Tensor:
         with torch.cuda.device(self.device):

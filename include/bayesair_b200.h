@@ -116,6 +116,12 @@ typedef struct BaForwardOpts {
     uint32_t day_offset;        /* index of the plan's first day in the whole data set: Philox
                                    counters use day_offset + d, so a rank whose plan holds a
                                    subset of the days draws what the full plan would       */
+    float *d_value_tape;        /* nullable, needs noise_is_value: [P, D, Fmax, 4] gradient of
+                                   logp[p, d] w.r.t. the four per-flight site values the noise
+                                   tensor holds (what a guide over those sites needs; SURVEY.md
+                                   App. A.5; wn_network.py:285-302).  Plans without
+                                   cancellations only; particle-days whose lists overflow are
+                                   then NOT re-run (their status keeps the overflow bit)     */
 } BaForwardOpts;
 
 int ba_version(void);
@@ -200,6 +206,12 @@ BaStatus ba_logjoint_host(BaPlan *plan, int32_t n_particles,
                           const BaForwardOpts *opts,
                           float *h_logp, uint32_t *h_status,
                           float *h_g_airport, float *h_g_route, float *h_g_scales);
+
+/* d_g_noise[p, d, f, :] = d_dlogp[p, d] * d_value_tape[p, d, f, :]: the cotangent w.r.t. the
+ * per-flight site values of a value-mode forward (BaForwardOpts.d_value_tape).  The
+ * value-gradient half of the reverse pass; ba_backward gives the latent half. */
+BaStatus ba_backward_values(BaPlan *plan, int32_t n_particles, const float *d_dlogp,
+                            const float *d_value_tape, float *d_g_noise, void *stream);
 
 /* ---- mean-field guide, fused with the simulation's gradient ------------
  * The guide of scripts/wn/train.py's objective when it is a diagonal Normal over the

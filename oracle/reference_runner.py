@@ -76,6 +76,7 @@ def run_reference(
     scales: Sequence[float] = (0.1, 0.1, 0.1),
     want_grad: bool = True,
     strip_observations: bool = False,
+    values: Optional[np.ndarray] = None,
 ) -> Dict[str, object]:
     """One particle through the reference.
 
@@ -88,6 +89,12 @@ def run_reference(
         ``[D, Fmax, 8]``: columns 4-6 drive the three otherwise-observed sites
         (U(0,1) for ``_cancelled``, N(0,1) for ``_simulated_departure_time`` and
         ``_simulated_arrival_time``).
+    values:  ``[D, Fmax, 4]`` -- "value mode": the four latent per-flight sites
+        (departure service time, travel time, arrival service time, turnaround time) are
+        CONDITIONED on these numbers as autograd leaves instead of being drawn, which is what
+        a guide over the per-flight sites does (``wn_network.py:285-302``,
+        AutoMultivariateNormal); the output then also holds ``grad_values [D, Fmax, 4]``, the
+        gradient of the per-flight log-probability w.r.t. them.
     Returns a dict of numpy values (see keys at the bottom).
     """
     pyro, model, _, _ = _import_reference()
@@ -119,6 +126,15 @@ def run_reference(
         for j, c2 in enumerate(codes):
             if i != j:
                 data[f"travel_time_{c}_{c2}"] = lv["travel"][i, j]
+
+    value_leaves = None
+    if values is not None:
+        value_leaves = torch.tensor(np.nan_to_num(np.asarray(values, np.float32), nan=1.0),
+                                    requires_grad=want_grad)
+        for d, ix in enumerate(flight_index):
+            for stem, i in ix.items():
+                for col, suffix in enumerate(SITE_KINDS):
+                    data[f"day{d}_{stem}_{suffix}"] = value_leaves[d, i, col]
 
     pyro.clear_param_store()
     names = ("runway_use_time_std_dev", "travel_time_variation",
@@ -211,7 +227,7 @@ def run_reference(
         t0 = time.perf_counter()
         g_pf = torch.autograd.grad(per_flight, leaves, retain_graph=True, allow_unused=True)
         out["t_backward"] = time.perf_counter() - t0
-        g_tot = torch.autograd.grad(total, leaves, allow_unused=True)
+        g_tot = torch.autograd.grad(total, leaves, allow_unused=True, retain_graph=True)
 
         def npz(g, like):
             return (np.zeros(like.shape, np.float32) if g is None
@@ -225,4 +241,8 @@ def run_reference(
         out["grad_scales_per_flight"] = np.array(
             [0.0 if g is None else float(g) / v for g, v in zip(g_pf[len(keys):], vals)],
             np.float64)
+        if value_leaves is not None:
+            (gv,) = torch.autograd.grad(per_flight, [value_leaves], allow_unused=True)
+            out["grad_values"] = np.zeros(value_leaves.shape, np.float32) if gv is None \
+                else gv.detach().numpy().astype(np.float32)
     return out

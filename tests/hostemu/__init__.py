@@ -95,7 +95,7 @@ class EmuPlan:
 
     def forward(self, latents, scales, noise, *, seed=0, value_mode=False, want_grad=True,
                 exact=False, rerun_overflow=True, shuffle_seed=1, want_pop=False,
-                replay_waits=False, scan2=False):
+                replay_waits=False, scan2=False, want_value_grad=False):
         lib = _load()
         la, lr = self.pack_latents(latents)
         P = la.shape[0]
@@ -108,12 +108,13 @@ class EmuPlan:
         ticks = np.zeros((P, self.D), np.int32)
         tape = np.zeros((P, self.D, self.stride), np.float32) if want_grad else None
         pop = np.zeros((P, self.D, self.Fmax, 2), np.int32) if want_pop else None
+        vtape = np.zeros((P, self.D, self.Fmax, 4), np.float32) if want_value_grad else None
         vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
         if scan2:
             rc = lib.ba_emu_forward2(self.h, P, vp(la), vp(lr), vp(sc), vp(nz), C.c_uint64(seed),
                                      int(value_mode), int(want_grad), int(rerun_overflow),
                                      C.c_uint(shuffle_seed), vp(logp), vp(status), vp(ticks),
-                                     vp(tape), vp(pop))
+                                     vp(tape), vp(pop), vp(vtape))
             if rc != 0:
                 raise RuntimeError("the ring-less scan cannot run this plan")
         else:
@@ -121,7 +122,7 @@ class EmuPlan:
                                int(value_mode), int(want_grad), int(exact), int(rerun_overflow),
                                int(replay_waits), C.c_uint(shuffle_seed), vp(logp), vp(status),
                                vp(ticks), vp(tape), vp(pop))
-        out = dict(logp=logp, status=status, ticks=ticks, pop_tick=pop)
+        out = dict(logp=logp, status=status, ticks=ticks, pop_tick=pop, value_grad=vtape)
         if want_grad:
             dl = np.ones((P, self.D), np.float32)
             ga = np.zeros((P, self.C, self.N), np.float32)

@@ -279,7 +279,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
                       const float *lat_airport, const float *lat_route, const float *scales,
                       const float *noise, uint64_t seed, int value_mode, int want_grad,
                       unsigned shuffle_seed, float *logp, uint32_t *status, int32_t *ticks,
-                      float *tape, int32_t *pop_tick)
+                      float *tape, int32_t *pop_tick, float *vtape = nullptr)
 {
     const int N = plan.N, R = plan.R, D = plan.D;
     const size_t pd = (size_t)p * D + d;
@@ -310,6 +310,8 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     c.particle = p; c.dayidx = d;
     c.grow = c.want_grad ? tape + pd * (size_t)plan.grad_stride : nullptr;
     c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
+    c.vrow = vtape ? vtape + pd * (size_t)plan.Fmax * 4 : nullptr;
+    if (c.vrow) for (int i = 0; i < 4 * plan.Fmax; ++i) c.vrow[i] = 0.0f;
     ba2_carve_scratch(c, (uint32_t *)(((uintptr_t)gs.data() + 15) & ~(uintptr_t)15), day.F, N);
     const uint32_t n_arr = (uint32_t)day.n_arr;
 
@@ -361,6 +363,10 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     c.s_rate = (float *)sh.data(); c.s_mt = c.s_rate + N;
     for (int a = 0; a < N; ++a) ba2_init_airport(c, a, N, true);
     if (!aborted) for (int f = 0; f < day.F; ++f) ba2_epilogue_flight(c, acc[f % 32], f);
+    if (c.vrow && !aborted) {
+        for (int a = 0; a < N; ++a) ba2_value_grad_airport(c, a);
+        for (int f = 0; f < day.F; ++f) ba2_value_grad_finish(c, f);
+    }
     if (c.grow && !aborted) {
         for (int a = 0; a < N; ++a) ba2_epilogue_airport(c, a, N);
         for (int r = 0; r < day.Rd; ++r) ba2_epilogue_route(c, r);
@@ -386,7 +392,7 @@ extern "C" int ba_emu_forward2(const EmuPlan *pl, int P, const float *lat_airpor
                                const float *lat_route, const float *scales, const float *noise,
                                uint64_t seed, int value_mode, int want_grad, int rerun_overflow,
                                unsigned shuffle_seed, float *logp, uint32_t *status,
-                               int32_t *ticks, float *tape, int32_t *pop_tick)
+                               int32_t *ticks, float *tape, int32_t *pop_tick, float *vtape)
 {
     const BaPlanView &plan = pl->host.view;
     if (!plan.scan2_ok) return 1;
@@ -394,8 +400,8 @@ extern "C" int ba_emu_forward2(const EmuPlan *pl, int P, const float *lat_airpor
         for (int p = 0; p < P; ++p) {
             const BaDayView &day = plan.days[d];
             run_item2(plan, day, p, d, lat_airport, lat_route, scales, noise, seed, value_mode,
-                      want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick);
-            if (rerun_overflow && (status[(size_t)p * plan.D + d] & BA_S_OVERFLOW))
+                      want_grad, shuffle_seed, logp, status, ticks, tape, pop_tick, vtape);
+            if (rerun_overflow && !vtape && (status[(size_t)p * plan.D + d] & BA_S_OVERFLOW))
                 run_item<true, false, false>(plan, day, p, d, P, lat_airport, lat_route, scales, noise,
                                              seed, value_mode, want_grad, 0, shuffle_seed, logp, status,
                                              ticks, tape, pop_tick);

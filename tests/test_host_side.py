@@ -478,3 +478,42 @@ def test_plan_cache_fingerprint_sees_edited_observations():
     assert f2 != f0
     st[0].pending_flights[7], st[0].pending_flights[8] = st[0].pending_flights[8], st[0].pending_flights[7]
     assert states_fingerprint(st) != f2
+
+
+# ------------------------------ value mode: gradient w.r.t. the per-flight site values --
+VALUE_GOLDENS = ["tiny4", "twoday5", "congested6", "saturated5", "obscancel4", "top10"]
+
+
+def _value_golden(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + "_valuegrad.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def value_grad_error(got, ref, values):
+    """Per-element relative error of a [D, F, 4] value gradient; flights without values
+    (cancelled, padding) must come out exactly zero."""
+    live = ~np.isnan(values)
+    assert np.all(got[~live] == 0.0)
+    scale = np.maximum(np.abs(ref[live]), 1e-4 * np.abs(ref[live]).max())
+    return float((np.abs(got[live] - ref[live]) / scale).max())
+
+
+@pytest.mark.parametrize("name", VALUE_GOLDENS)
+def test_emulated_value_gradients_vs_reference(name):
+    """d logp / d (per-flight site values) of the ring-less scan (host emulation of the kernel
+    source) against autograd of the UNMODIFIED reference with those sites conditioned on
+    leaf tensors (tests/golden/make_value_golden.py)."""
+    from tests.hostemu import EmuPlan
+    g, v = Golden(name), _value_golden(name)
+    plan = EmuPlan(g.specs, len(g.global_codes), delta_t=g.delta_t)
+    lat = {k: x[None] for k, x in g.latents.items()}
+    vals = np.nan_to_num(v["values"], nan=1.0)[None]
+    for shuffle in (0, 5):
+        o = plan.forward(lat, g.scales, vals, value_mode=True, scan2=True, shuffle_seed=shuffle,
+                         want_value_grad=True)
+        assert (o["status"] == 0).all()
+        assert abs(float(o["logp"].sum()) - float(v["total"])) <= 1e-4 * abs(float(v["total"]))
+        assert value_grad_error(o["value_grad"][0], v["grad_values"], v["values"]) <= 1e-3
+        # the global-latent gradients of the same (value-mode) run are pinned too
+        assert rel_err(o["grads"]["mean_service"][0], v["grad_mean_service"], floor=1e-4) <= 1e-3
+        assert rel_err(o["grads"]["mean_turnaround"][0], v["grad_mean_turnaround"], floor=1e-4) <= 1e-3

@@ -19,7 +19,7 @@ def _all_names():
 
 def golden_names():
     """Fully observed cases (log-prob + gradient fixtures)."""
-    return [n for n in _all_names() if not n.startswith("pred")]
+    return [n for n in _all_names() if not n.startswith("pred") and not n.endswith("_valuegrad")]
 
 
 def predictive_names():
