@@ -1,0 +1,7 @@
+python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_final.log 2>&1; tail -3 gpurun_out/r2_pytest_final.log
+python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; tail -2 gpurun_out/r2_bench_final.err; cat gpurun_out/r2_bench_final.json
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_final_ref.json 2>/dev/null; cat gpurun_out/r2_bench_final_ref.json
+python bench.py --workload cfg5s --steps 5 --no-svi --no-calnf > gpurun_out/r2_bench_cfg5s.json 2>/dev/null; cat gpurun_out/r2_bench_cfg5s.json
+BA_PHASE_PROFILE=1 python tools/profile_forward.py 4096 0.012 10 2 2>&1 | tail -2
+bash tools/make_profiles_r2.sh
+python -c "import __graft_entry__ as g; g.smoke()"
