@@ -6,8 +6,9 @@ import csv
 import sys
 
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 14 and r[0].isdigit()]
-print("# command: python bench.py --steps 2 --warmup 3 --no-svi --no-cpu-baseline  (under ncu "
-      "--metrics gpu__time_duration.sum --clock-control none; per-launch times are serialised)")
+cmd = sys.argv[2] if len(sys.argv) > 2 else "python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+print(f"# command: {cmd}  (under ncu --metrics gpu__time_duration.sum --clock-control none -c 600; "
+      "per-launch times are serialised and cold-cache: the kernels' SHARES are what compares)")
 print("id,kernel,block,grid,gpu__time_duration.sum [ns]")
 tot = collections.Counter()
 for r in rows:

@@ -15,15 +15,16 @@ python tools/launch_list.py gpurun_out/launches_r2.csv > profiles/${TAG}_launch_
   python tools/ncu_ranges.py $REP $LIB $K $(python - <<'PY'
 import re
 src = open("bayesair_b200/csrc/ba_scan2.cuh").read().splitlines()
-marks = [("ba2_flight", "table_loads"), ("ba2_init_airport", "airport_setup"), ("ba2_prologue_flight", "prologue_flight"),
+marks = [("ba2_flight", "table_loads"), ("ba2_init_airport", "airport_setup"), ("ba2_prologue_load", "prologue_flight"),
          ("ba2_bucket_scan", "sort_bucket_scan"), ("ba2_scatter_flight", "sort_scatter"), ("ba2_split_cursor", "sort_split"),
          ("ba2_state_init", "scan_state_init"), ("ba2_insert", "scan_insert"), ("ba2_replay", "scan_replay"),
-         ("ba2_airport_tick", "scan_airport_tick"), ("ba2_epilogue_flight", "epilogue_flight"),
+         ("ba2_airport_tick", "scan_airport_tick"), ("ba2_value_grad_flight", "value_gradients"),
+         ("ba2_epilogue_load", "epilogue_flight"),
          ("ba2_epilogue_airport", "epilogue_sums")]
 pos = []
 for name, label in marks:
     for i, l in enumerate(src):
-        if re.match(r"(BA_DEV|template|void|float|static).*", l) and (name + "(") in l:
+        if re.match(r"(BA_DEV|template|void|float|static|struct Ba2FlightIn|struct Ba2EpiIn).*", l) and (name + "(") in l:
             pos.append((i + 1, label)); break
 pos.sort()
 out = []
