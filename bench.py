@@ -591,8 +591,10 @@ def run_native(args):
                          "algorithmic_bytes_per_particle_day": B,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
                          if peaks else "fallback 6650 GB/s (of fallback)",
-                         "note": "serial tick loop per particle-day: latency/issue bound by "
-                                 "construction (SURVEY.md §8d); see profiles/ for issue-slot use"},
+                         "note": "serial tick loop per particle-day: memory-latency bound by "
+                                 "construction (SURVEY.md §8d; every pipe below 30 %, DRAM at 23 % "
+                                 "of peak, 1.5 MB of DRAM traffic per particle-day against 74 KB "
+                                 "algorithmic); see profiles/ and DESIGN.md §7"},
             "svi_step_ms": svi,
             "calnf_step_ms": calnf,
             "model_call_ms": {"value": model_call_ms,
@@ -602,10 +604,10 @@ def run_native(args):
             "philox_value": philox_value,
             "congested_value": congested_value,
             "regimes": {"value": f"posterior-like latents: mean service {svc} h x LogNormal(0, 0.3); "
-                                 "shared rings spill on demand, no particle-day is re-run",
+                                 "no particle-day is re-run",
                         "congested_value": "prior-like latents: mean service 0.05 h, every hub "
-                                           "queue saturates (long spilled rings); still the "
-                                           "shared-memory variant, no re-runs"},
+                                           "queue saturates (~230 ticks per day instead of ~137, "
+                                           "draw histories replayed); same kernel, no re-runs"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
