@@ -233,7 +233,7 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
                 if ((1 << i) == pl->warps_scan2) pl->grid_scan2 = pl->grids_scan2[i];
             }
             cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device);
-            pl->stride_scan2 = (ba_forward2_scratch_words(pl->host.view.Fmax, N) + 31) & ~31ull;
+            pl->stride_scan2 = (ba_forward2_scratch_words(pl->host.view.Fmax, N, pl->host.view.R) + 31) & ~31ull;
             pl->scan2_ok = ok && pl->grid_scan2 > 0 && pl->sm_count > 0;
             if (pl->scan2_ok) pl->grid_scan2 = gmax;     // sizes the scratch
         }

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         c.grow = c.want_grad ? prm.tape + pd * (size_t)plan.grad_stride : nullptr;
         c.pop_tick = prm.pop_tick ? prm.pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
         c.vrow = prm.vtape ? prm.vtape + pd * (size_t)plan.Fmax * 4 : nullptr;
-        ba2_carve_scratch(c, gscr, day.F, N);
+        ba2_carve_scratch(c, gscr, day.F, N, R);
         const uint32_t n_arr = (uint32_t)day.n_arr;
 
         // ---- setup -----------------------------------------------------------
@@ -518,7 +518,12 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         // ---- epilogue ----------------------------------------------------------
         ba2_sync<NW>();
         c.s_rate = (float *)c.un; c.s_mt = c.s_rate + N;          // the scan state is dead
+        c.accA = (unsigned long long *)(c.un + ((2 * N + 1) & ~1));
         for (int a = tid; a < N; a += NT) ba2_init_airport(c, a, N, true);
+        if (c.grow) {
+            for (int i = tid; i < 3 * N; i += NT) c.accA[i] = 0ull;
+            for (int r = tid; r < day.Rd; r += NT) c.accR[c.rt_gid[r]] = 0ull;
+        }
         ba2_sync<NW>();
         if (!aborted)
             for (int f = tid; f < day.F; f += 2 * NT) {
@@ -590,7 +595,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
 
 size_t ba_forward2_smem_bytes(int n_airports) { return (BA2_RED_WORDS + ba2_smem_words(n_airports)) * 4; }
 
-uint64_t ba_forward2_scratch_words(int Fmax, int n_airports) { return ba2_scratch_words(Fmax, n_airports); }
+uint64_t ba_forward2_scratch_words(int Fmax, int n_airports, int n_routes) { return ba2_scratch_words(Fmax, n_airports, n_routes); }
 
 // warps per particle-day: one up to 128 airports; beyond that the state takes more shared
 // memory per particle-day, and more warps keep the SM's warp count up

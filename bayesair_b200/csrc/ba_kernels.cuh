@@ -54,7 +54,7 @@ cudaError_t ba_launch_forward(const BaFwdParams &p, bool exact, bool tracked, in
                               size_t smem, cudaStream_t s);
 // ring-less scan (ba_scan2.cuh): one-warp CTAs
 size_t ba_forward2_smem_bytes(int n_airports);
-uint64_t ba_forward2_scratch_words(int Fmax, int n_airports);
+uint64_t ba_forward2_scratch_words(int Fmax, int n_airports, int n_routes);
 int ba_forward2_warps(int n_airports);
 int ba_forward2_configure(int nw, size_t smem, int device);
 cudaError_t ba_launch_forward2(const BaFwdParams &p, int nw, int grid, size_t smem, cudaStream_t s);

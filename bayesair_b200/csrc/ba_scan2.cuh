@@ -127,7 +127,10 @@ struct Ba2Ctx {
     uint32_t *glog;                           // [4 F] (tick, assignments before it) of ticks that
                                               //   ended with younger entries still waiting
     float *eps;                               // [F] travel-time draw of every flight, kept for the epilogue
-    float *xdk, *xak, *atk, *ct;              // epilogue contributions (alias S0 / S1)
+    // epilogue: owner sums as 64-bit fixed-point accumulators (integer adds commute: any
+    // order gives the same bits) -- per airport in shared memory, per route in scratch
+    unsigned long long *accA;                 // [3][N]: departures, arrivals, turnaround (value mode)
+    unsigned long long *accR;                 // [R] by global route id
     // outputs
     float *grow;
     int32_t *pop_tick;
@@ -139,19 +142,20 @@ struct Ba2Ctx {
 };
 
 // words of per-warp global scratch
-static inline uint64_t ba2_scratch_words(int F, int N)
+static inline uint64_t ba2_scratch_words(int F, int N, int R)
 {
     const uint64_t f = (uint64_t)F, n = (uint64_t)N;
-    return (f + 4) + 4 * (f + n + 4) + 3 * (f + n + 4) + 4 * f + 2 * f + 4 * f + 2 * (f + n + 4) + 64;
+    return (f + 4) + 4 * (f + n + 4) + 3 * (f + n + 4) + 4 * f + 2 * f + 4 * f + 2 * (f + n + 4) +
+           2 * (uint64_t)R + 64;
 }
 
-BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N)
+BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N, int R)
 {
+    c.accR = (unsigned long long *)g; g += 2 * (((uint32_t)R + 1u) & ~1u);   // 16-byte aligned
     const uint32_t f = (uint32_t)F, fn = ((uint32_t)(F + N) + 3u) & ~3u;
     c.eps = (float *)g; g += (f + 3u) & ~3u;              // 16-byte aligned blocks first
     c.P = (Ba2Pay *)g; g += 4 * fn;
     c.S0 = g; c.S1 = g + 2 * f;
-    c.xdk = (float *)g; c.xak = (float *)g + f; c.atk = (float *)g + 2 * f; c.ct = (float *)g + 3 * f;
     g += 4 * f;
     c.Ak = g; g += fn;
     c.Lb = g; g += 2 * fn; c.lb_stride = fn;
@@ -700,6 +704,11 @@ BA_DEV void ba2_value_grad_finish(Ba2Ctx &c, int f)
     c.vrow[4 * f + 2] += c.rA[lpos];
 }
 
+// fixed point of the owner sums: 2^-28 resolution, +-3.4e10 range
+#define BA2_FX_SCALE 268435456.0f
+BA_DEV long long ba2_fx(float x) { return (long long)llrintf(x * BA2_FX_SCALE); }
+BA_DEV float ba2_unfx(unsigned long long v) { return (float)((double)(long long)v * (1.0 / (double)BA2_FX_SCALE)); }
+
 struct Ba2EpiIn {
     BaFlight fl;
     int lpos, k, j, rt;
@@ -734,7 +743,6 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
     // airport of such a plan (ba_plan.h: BA_SIMPLE_RATIO)
     acc.lp += (double)(cobs == 1u ? c.c1_lp : c.c0_lp);
     if (cobs == 1u) {                 // observed as cancelled: never queued anywhere
-        if (c.want_grad) { c.xdk[k] = 0.0f; c.atk[f] = 0.0f; }
         if (c.pop_tick) { c.pop_tick[2 * f] = -1; c.pop_tick[2 * f + 1] = -1; }
         if (c.vrow) { c.vrow[4 * f] = 0.0f; c.vrow[4 * f + 1] = 0.0f; c.vrow[4 * f + 2] = 0.0f; c.vrow[4 * f + 3] = 0.0f; }
         return;
@@ -769,11 +777,14 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
     if (grad) {
         const float r_d = dy_d * c.inv_sigma2, r_a = dy_a * c.inv_sigma2;
         acc.g_sigma += (dy_d * dy_d + dy_a * dy_a) * c.inv_sigma3 - 2.0f * c.inv_sigma;
+        // owner sums: per origin / destination airport in shared memory, per route in scratch
+        const int N = c.N;
+        float a_dep, a_arr, a_rt;
         if (!c.value_mode) {
-            c.xdk[k] = r_d * wdep;
-            c.xak[j] = r_a * warr;
+            a_dep = r_d * wdep;
+            a_arr = r_a * warr;
             // arrival queue_start = act_dep + tau, tau = T (1 + v_t eps)
-            c.atk[f] = r_a * (1.0f + c.v_t * in.eps) - 1.0f / T;
+            a_rt = r_a * (1.0f + c.v_t * in.eps) - 1.0f / T;
             acc.g_vt += r_a * in.eps * T - c.inv_vt;
             acc.g_vu += -c.inv_vu;
         } else {
@@ -783,14 +794,18 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
             const float mt = c.s_mt[d], tstd = BA_MUL(c.v_u, mt);
             const float dz = (tau - T) / sc;
             const float du = (nz.eps_turn - mt) / tstd;
-            c.xdk[k] = nz.e_dep;
-            c.xak[j] = nz.e_arr;
-            c.atk[f] = dz / sc + (dz * dz - 1.0f) / T;
+            a_dep = nz.e_dep;
+            a_arr = nz.e_arr;
+            a_rt = dz / sc + (dz * dz - 1.0f) / T;
             acc.g_vt += (dz * dz - 1.0f) * c.inv_vt;
-            c.ct[j] = du / tstd + (du * du - 1.0f) / mt;     // arrival order: no other writer
+            BA_ATOMIC_ADD64(c.accA + 2 * N + d, ba2_fx(du / tstd + (du * du - 1.0f) / mt));
             acc.g_vu += (du * du - 1.0f) * c.inv_vu;
         }
+        BA_ATOMIC_ADD64(c.accA + o, ba2_fx(a_dep));
+        BA_ATOMIC_ADD64(c.accA + N + d, ba2_fx(a_arr));
+        BA_ATOMIC_ADD64(c.accR + in.rt, ba2_fx(a_rt));
     }
+    (void)k; (void)j;
 }
 
 // EPILOGUE of one flight (host emulation; the kernel runs the stages itself)
@@ -805,9 +820,7 @@ BA_DEV void ba2_epilogue_airport(Ba2Ctx &c, int a, int Ng)
 {
     const BaAirport A = c.ap[a];
     const float mt = c.s_mt[a], m = c.lat_airport[1 * Ng + A.global];
-    float s_dep = 0.0f, s_arr = 0.0f, s_turn = 0.0f;
-    for (int i = 0; i < A.dep_cnt; ++i) s_dep += c.xdk[A.dep_off + i];
-    for (int i = 0; i < A.arr_cnt; ++i) s_arr += c.xak[A.arr_off + i];
+    const float s_dep = ba2_unfx(c.accA[a]), s_arr = ba2_unfx(c.accA[c.N + a]);
     const float n_ent = (float)(A.dep_live + A.arr_cnt), n_land = (float)A.arr_cnt;
     float g_serv, g_turn;
     if (!c.value_mode) {
@@ -815,10 +828,9 @@ BA_DEV void ba2_epilogue_airport(Ba2Ctx &c, int a, int Ng)
         g_serv = (s_dep + s_arr) / m - n_ent / m;
         g_turn = -n_land / mt;
     } else {
-        for (int i = 0; i < A.arr_cnt; ++i) s_turn += c.ct[A.arr_off + i];
         // log Exponential(x; 1/m) = -log m - x/m
         g_serv = -n_ent / m + (s_dep + s_arr) / (m * m);
-        g_turn = s_turn;
+        g_turn = ba2_unfx(c.accA[2 * c.N + a]);
     }
     const int g = A.global;
     c.grow[0 * Ng + g] = g_turn;
@@ -827,8 +839,6 @@ BA_DEV void ba2_epilogue_airport(Ba2Ctx &c, int a, int Ng)
 
 BA_DEV void ba2_epilogue_route(Ba2Ctx &c, int r)
 {
-    float s = 0.0f;
-    const int b = c.rt_off[r], e = c.rt_off[r + 1];
-    for (int i = b; i < e; ++i) s += c.atk[c.rt_flt[i]];
-    c.grow[c.route_base + c.rt_gid[r]] = s;
+    const int gid = c.rt_gid[r];
+    c.grow[c.route_base + gid] = ba2_unfx(c.accR[gid]);
 }

@@ -69,6 +69,7 @@
 #define BA_ATOMIC_AND(p, v) atomicAnd((p), (v))
 #define BA_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define BA_ATOMIC_DEC(p) atomicSub((p), 1u)
+#define BA_ATOMIC_ADD64(p, v) atomicAdd((p), (unsigned long long)(v))
 #define ba_ctz64(x) (__ffsll((long long)(x)) - 1)
 #define __float_as_uint_portable(x) __float_as_uint(x)
 #define __uint_as_float_portable(x) __uint_as_float(x)
@@ -91,6 +92,7 @@ static inline float __uint_as_float_portable(uint32_t u) { float x; memcpy(&x, &
 static inline uint32_t ba_host_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 #define BA_ATOMIC_ADD(p, v) ba_host_add((p), (v))
 #define BA_ATOMIC_DEC(p) ba_host_dec(p)
+#define BA_ATOMIC_ADD64(p, v) (*(p) += (unsigned long long)(v))
 #define ba_ctz64(x) __builtin_ctzll((unsigned long long)(x))
 #define BA_LOG(x) logf(x)
 #define BA_EXP(x) expf(x)

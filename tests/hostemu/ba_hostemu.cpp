@@ -284,7 +284,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     const int N = plan.N, R = plan.R, D = plan.D;
     const size_t pd = (size_t)p * D + d;
     std::vector<uint32_t> sh(ba2_smem_words(N) + 64, 0);
-    std::vector<uint32_t> gs(ba2_scratch_words(day.F, N) + 16, 0xDEADBEEFu);
+    std::vector<uint32_t> gs(ba2_scratch_words(day.F, N, R) + 16, 0xDEADBEEFu);
     Ba2Ctx c;
     memset(&c, 0, sizeof(c));
     c.nslot = (uint32_t)N;
@@ -312,7 +312,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     c.pop_tick = pop_tick ? pop_tick + pd * (size_t)plan.Fmax * 2 : nullptr;
     c.vrow = vtape ? vtape + pd * (size_t)plan.Fmax * 4 : nullptr;
     if (c.vrow) for (int i = 0; i < 4 * plan.Fmax; ++i) c.vrow[i] = 0.0f;
-    ba2_carve_scratch(c, (uint32_t *)(((uintptr_t)gs.data() + 15) & ~(uintptr_t)15), day.F, N);
+    ba2_carve_scratch(c, (uint32_t *)(((uintptr_t)gs.data() + 15) & ~(uintptr_t)15), day.F, N, R);
     const uint32_t n_arr = (uint32_t)day.n_arr;
 
     for (int a = 0; a < N; ++a) ba2_init_airport(c, a, N, false);
@@ -361,7 +361,10 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     int tick = (int)k;
     if (day.F > 0 && tick < day.last_ready_tick) tick = day.last_ready_tick;
     c.s_rate = (float *)sh.data(); c.s_mt = c.s_rate + N;
+    c.accA = (unsigned long long *)(sh.data() + ((2 * N + 1) & ~1));
     for (int a = 0; a < N; ++a) ba2_init_airport(c, a, N, true);
+    for (int i = 0; i < 3 * N; ++i) c.accA[i] = 0ull;
+    for (int r = 0; r < day.Rd; ++r) c.accR[c.rt_gid[r]] = 0ull;
     if (!aborted) for (int f = 0; f < day.F; ++f) ba2_epilogue_flight(c, acc[f % 32], f);
     if (c.vrow && !aborted) {
         for (int a = 0; a < N; ++a) ba2_value_grad_airport(c, a);
