@@ -451,8 +451,6 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         c.s_rate = (float *)(c.un + BA2_KC + N); c.s_mt = c.s_rate + N;   // behind buckets and cursors
         for (int a = tid; a < N; a += NT) ba2_init_airport(c, a, N, false);
         for (int i = tid; i < BA2_KC; i += NT) c.un[i] = 0;
-        if (c.grow && day.Rd < R)
-            for (int i = tid; i < R; i += NT) c.grow[c.route_base + i] = 0.0f;
         if (c.pop_tick)
             for (int i = 2 * day.F + tid; i < 2 * plan.Fmax; i += NT) c.pop_tick[i] = -1;
         if (c.vrow)
@@ -522,7 +520,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         for (int a = tid; a < N; a += NT) ba2_init_airport(c, a, N, true);
         if (c.grow) {
             for (int i = tid; i < 3 * N; i += NT) c.accA[i] = 0ull;
-            for (int r = tid; r < day.Rd; r += NT) c.accR[c.rt_gid[r]] = 0ull;
+            for (int r = tid; r < R; r += NT) c.accR[r] = 0ull;
         }
         ba2_sync<NW>();
         if (!aborted)
@@ -539,7 +537,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         if (c.grow && !aborted) {
             ba2_sync<NW>();
             for (int s = tid; s < N; s += NT) ba2_epilogue_airport(c, s, N);
-            for (int r = tid; r < day.Rd; r += NT) ba2_epilogue_route(c, r);
+            for (int r = tid; r < R; r += NT) ba2_epilogue_route(c, r);
         }
         if (c.vrow && !aborted) {
             // value mode: wait-mediated part of the gradient w.r.t. the service-time values

@@ -80,6 +80,11 @@ BA_DEV Ba2U2 ba2_ld2(const uint32_t *p) { Ba2U2 v; v.x = p[0]; v.y = p[1]; retur
 BA_DEV void ba2_st2(uint32_t *p, uint32_t a, uint32_t b) { p[0] = a; p[1] = b; }
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define BA2_STREAM_ST(p, v) __stcs((p), (v))      // written once, never re-read by this kernel
+#else
+#define BA2_STREAM_ST(p, v) (*(p) = (v))
+#endif
 #if defined(__CUDA_ARCH__) && !defined(BA2_NO_PREFETCH)
 #define BA2_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
@@ -190,7 +195,8 @@ BA_DEV BaNoise4 ba2_noise(const Ba2Ctx &c, int f)
 {
     if (c.noise) {
 #if defined(__CUDA_ARCH__)
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(c.noise) + f);
+        // read once per phase: streaming (evict-first), the L2 is for the payload records
+        const float4 v = __ldcs(reinterpret_cast<const float4 *>(c.noise) + f);
         BaNoise4 z = {v.x, v.y, v.z, v.w};
 #else
         BaNoise4 z = {c.noise[4 * f], c.noise[4 * f + 1], c.noise[4 * f + 2], c.noise[4 * f + 3]};
@@ -242,7 +248,11 @@ BA_DEV void ba2_prologue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2FlightIn
     const BaNoise4 &nz = in.nz;
     const uint32_t cobs = (fl.od >> 24) & 3u;
     const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
+#if defined(__CUDA_ARCH__)
+    __stcs(c.eps + f, nz.eps_travel);
+#else
     c.eps[f] = nz.eps_travel;
+#endif
     uint32_t key = BA2_NONE;
     if (cobs != 1u) {
         const float rate_o = c.s_rate[o], rate_d = c.s_rate[d], mt = c.s_mt[d];
@@ -711,7 +721,7 @@ BA_DEV float ba2_unfx(unsigned long long v) { return (float)((double)(long long)
 
 struct Ba2EpiIn {
     BaFlight fl;
-    int lpos, k, j, rt;
+    int lpos, rt;
     float eps;
 };
 
@@ -719,8 +729,12 @@ BA_DEV Ba2EpiIn ba2_epilogue_load(const Ba2Ctx &c, int f)
 {
     Ba2EpiIn in;
     in.fl = ba2_flight(c, f);
-    in.lpos = c.pos_live[f]; in.k = c.pos_dep[f]; in.j = c.pos_arr[f]; in.rt = c.route[f];
+    in.lpos = c.pos_live[f]; in.rt = c.route[f];
+#if defined(__CUDA_ARCH__)
+    in.eps = __ldcs(c.eps + f);
+#else
     in.eps = c.eps[f];
+#endif
     return in;
 }
 
@@ -737,7 +751,6 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
 {
     const BaFlight &fl = in.fl;
     const uint32_t cobs = (fl.od >> 24) & 3u;
-    const int k = in.k;
     const int o = (int)(fl.od & 0xFFFu), d = (int)((fl.od >> 12) & 0xFFFu);
     // *_cancelled (network.py:100-109): the cancellation probability is exactly 0 at every
     // airport of such a plan (ba_plan.h: BA_SIMPLE_RATIO)
@@ -747,7 +760,6 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
         if (c.vrow) { c.vrow[4 * f] = 0.0f; c.vrow[4 * f + 1] = 0.0f; c.vrow[4 * f + 2] = 0.0f; c.vrow[4 * f + 3] = 0.0f; }
         return;
     }
-    const int j = in.j;
     if (c.pop_tick) {
         c.pop_tick[2 * f] = pay.q == BA2_NONE ? -1 : (int32_t)pay.q;
         c.pop_tick[2 * f + 1] = (int32_t)__float_as_uint_portable(pay.at);
@@ -805,7 +817,6 @@ BA_DEV void ba2_epilogue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2EpiIn &i
         BA_ATOMIC_ADD64(c.accA + N + d, ba2_fx(a_arr));
         BA_ATOMIC_ADD64(c.accR + in.rt, ba2_fx(a_rt));
     }
-    (void)k; (void)j;
 }
 
 // EPILOGUE of one flight (host emulation; the kernel runs the stages itself)
@@ -833,12 +844,12 @@ BA_DEV void ba2_epilogue_airport(Ba2Ctx &c, int a, int Ng)
         g_turn = ba2_unfx(c.accA[2 * c.N + a]);
     }
     const int g = A.global;
-    c.grow[0 * Ng + g] = g_turn;
-    c.grow[1 * Ng + g] = g_serv;
+    BA2_STREAM_ST(c.grow + 0 * Ng + g, g_turn);
+    BA2_STREAM_ST(c.grow + 1 * Ng + g, g_serv);
 }
 
-BA_DEV void ba2_epilogue_route(Ba2Ctx &c, int r)
+// one GLOBAL route (routes without a flight on this day keep a zero accumulator)
+BA_DEV void ba2_epilogue_route(Ba2Ctx &c, int gid)
 {
-    const int gid = c.rt_gid[r];
-    c.grow[c.route_base + gid] = ba2_unfx(c.accR[gid]);
+    BA2_STREAM_ST(c.grow + c.route_base + gid, ba2_unfx(c.accR[gid]));
 }

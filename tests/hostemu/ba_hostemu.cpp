@@ -364,7 +364,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     c.accA = (unsigned long long *)(sh.data() + ((2 * N + 1) & ~1));
     for (int a = 0; a < N; ++a) ba2_init_airport(c, a, N, true);
     for (int i = 0; i < 3 * N; ++i) c.accA[i] = 0ull;
-    for (int r = 0; r < day.Rd; ++r) c.accR[c.rt_gid[r]] = 0ull;
+    for (int r = 0; r < R; ++r) c.accR[r] = 0ull;
     if (!aborted) for (int f = 0; f < day.F; ++f) ba2_epilogue_flight(c, acc[f % 32], f);
     if (c.vrow && !aborted) {
         for (int a = 0; a < N; ++a) ba2_value_grad_airport(c, a);
@@ -372,7 +372,7 @@ static void run_item2(const BaPlanView &plan, const BaDayView &day, int p, int d
     }
     if (c.grow && !aborted) {
         for (int a = 0; a < N; ++a) ba2_epilogue_airport(c, a, N);
-        for (int r = 0; r < day.Rd; ++r) ba2_epilogue_route(c, r);
+        for (int r = 0; r < R; ++r) ba2_epilogue_route(c, r);
     }
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     for (int i = 0; i < 32; ++i) {
