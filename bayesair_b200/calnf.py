@@ -154,10 +154,9 @@ class CalNFTrainer:
         # ---- mixture label (training.py:180-191) ----
         if self.calibrate and self.label_opt is not None:
             for _ in range(self.substeps):
-                self.label_opt.zero_grad()
-                self.fp.zero_grad()
                 loss = self._elbo(self.mixture_label, self.fplan)
-                loss.backward()
+                # only the label is updated here: no gradient of the flow's parameters is formed
+                (self.mixture_label.grad,) = torch.autograd.grad(loss, [self.mixture_label])
                 if self.world > 1:
                     dist.all_reduce(self.mixture_label.grad, group=self.group)
                 torch.nn.utils.clip_grad_norm_([self.mixture_label], self.grad_clip)

@@ -209,3 +209,35 @@ def test_day_sharded_ranks_sum_to_the_unsharded_gradient():
     a, b = total.cpu().double().numpy(), ref.flat.cpu().double().numpy()
     scale = np.maximum(np.abs(b), 1e-6 * np.abs(b).max())
     assert (np.abs(a - b) / scale).max() < 1e-4, (np.abs(a - b) / scale).max()
+
+
+def test_model_routes_value_gradients_to_a_per_flight_guide():
+    """A guide over the per-flight sites hands their values to the drop-in model through
+    flight_noise(values, noise_is_value=True); the factor's gradient w.r.t. those values
+    equals the reference's autograd (value-mode golden)."""
+    import bayesair_b200 as ba
+    from bayesair_b200.ppl import poutine, pyro
+    from tests.test_host_side import _value_golden, value_grad_error
+    g, v = Golden("twoday5"), _value_golden("twoday5")
+    states = _golden_states(g)
+    dev = torch.device("cuda:0")
+    codes = g.global_codes
+    data = {}
+    for i, c in enumerate(codes):
+        data[f"{c}_mean_turnaround_time"] = torch.tensor(g.latents["mean_turnaround"][i], device=dev)
+        data[f"{c}_mean_service_time"] = torch.tensor(g.latents["mean_service"][i], device=dev)
+        for j, c2 in enumerate(codes):
+            if i != j:
+                data[f"travel_time_{c}_{c2}"] = torch.tensor(g.latents["travel"][i, j], device=dev)
+    pyro.clear_param_store()
+    for nme, s in zip(("runway_use_time_std_dev", "travel_time_variation",
+                       "turnaround_time_variation"), g.scales):
+        pyro.param(nme, torch.tensor(s, device=dev), constraint=torch.distributions.constraints.positive)
+    vals = torch.tensor(np.nan_to_num(v["values"], nan=1.0)[None], device=dev, requires_grad=True)
+    with ba.flight_noise(vals, noise_is_value=True):
+        tr = poutine.trace(poutine.condition(ba.air_traffic_network_model, data=data)).get_trace(
+            states, g.delta_t, device=dev)
+    factor = tr.nodes[ba.FACTOR_NAME]["fn"].log_prob(None).sum()
+    assert abs(float(factor) - float(v["total"])) <= 1e-4 * abs(float(v["total"]))
+    factor.backward()
+    assert value_grad_error(vals.grad[0].cpu().numpy(), v["grad_values"], v["values"]) <= 1e-3
