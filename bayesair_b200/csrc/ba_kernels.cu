@@ -6,8 +6,13 @@
 //                              the runway-queue rings and inbound bags in shared memory
 //                              (plan-time capacities); EXACT=true keeps them in per-CTA
 //                              global scratch with capacities no schedule can overflow.
+//   ba_forward2_kernel<NW>     the ring-less scan of ba_scan2.cuh for plans without aircraft
+//                              bookkeeping and with every flight observed (the training
+//                              configurations): NW warps per (particle, day), one for
+//                              networks up to 128 airports.
 //   ba_backward_kernel         contracts the per-(particle, day) gradient rows written by
-//                              the forward kernel with the cotangent d logp.
+//                              the forward kernels with the cotangent d logp.
+//   ba_backward_values_kernel  the same for the value tape of a value-mode forward.
 //   ba_noise_kernel            materialises the Philox per-flight noise (tests / callers
 //                              that want to keep their draws).
 //   ba_collect_kernel          compacts the particle-days that must be re-run.

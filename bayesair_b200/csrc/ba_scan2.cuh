@@ -628,7 +628,8 @@ BA_DEV bool ba2_airport_tick(const Ba2Ctx &c, uint32_t slot, uint32_t k, float t
 }
 
 // ---------------------------------------------------------------------------
-// EPILOGUE (flight-parallel, then owner sums); SURVEY.md App. A.3 / A.5
+// EPILOGUE (flight-parallel; owner sums through fixed-point accumulators); SURVEY.md
+// App. A.3 / A.5
 // ---------------------------------------------------------------------------
 // ---------------------------------------------------------------------------
 // VALUE MODE: gradient of the log-probability w.r.t. the four per-flight site values (the

@@ -493,6 +493,46 @@ def run_native(args):
         torch.cuda.empty_cache()
         torch.backends.cuda.matmul.allow_tf32 = tf32_prev
 
+    # ---- posterior-predictive forward simulation (BASELINE configs[3]): every observation
+    #      stripped, cancellations on (aircraft bookkeeping at every airport), 10 days ------
+    predictive = None
+    if not args.no_predictive and name == "cfg3":
+        import copy
+        pspecs = []
+        for sp in specs:
+            q = copy.deepcopy(sp)
+            q.act_dep[:] = np.nan; q.act_arr[:] = np.nan; q.cancel_obs[:] = -1
+            pspecs.append(q)
+        Pp = args.predictive_samples
+        pplan = SimulationPlan(pspecs, pspecs[0].codes, delta_t=0.2, include_cancellations=True, device=dev)
+        plat = synth_latents(N, Pp, seed=4 + rank, service_scale=svc, include_cancellations=True,
+                             n_aircraft_mean=8.0)
+        pt = {k: torch.tensor(v, device=dev) for k, v in plat.items()}
+        pla, plr = pplan.pack_latents(pt["mean_turnaround"], pt["mean_service"], pt["travel"],
+                                      pt["log_initial_aircraft"], pt["base_cancel_logprob"])
+        for _ in range(2):
+            po = pplan.predict(pla, plr, scales, None, None, seed=3)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            po = pplan.predict(pla, plr, scales, None, None, seed=3)
+        e1.record()
+        barrier()
+        SimulationPlan.check_status(po["status"])
+        pms = e0.elapsed_time(e1) / 2
+        if world > 1:
+            t = torch.tensor([pms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pms = float(t.item())
+        predictive = {"value": world * Pp * D / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms,
+                      "cancelled_fraction": float((po["sim"][..., 0] == 1).float().mean()),
+                      "config": f"cfg4 at a reduced sample count: the cfg3 network, all 10 days, every "
+                                f"observation stripped, cancellations on, {Pp} samples per GPU (BASELINE "
+                                "configs[3] asks for 65 536: the same kernel, 8x the work), in-kernel Philox"}
+        del pla, plr, po
+        pplan.close()
+
     # ---- the drop-in model() call itself (cfg2 shape): 2N + N(N-1) pyro.sample statements
     #      under trace(condition(...)), scripts/wn/train.py:306-314 -------------------------
     model_call_ms = None
@@ -597,6 +637,7 @@ def run_native(args):
                                  "algorithmic); see profiles/ and DESIGN.md §7"},
             "svi_step_ms": svi,
             "calnf_step_ms": calnf,
+            "predictive": predictive,
             "model_call_ms": {"value": model_call_ms,
                               "config": "drop-in air_traffic_network_model under trace(condition(...)) + "
                                         "log_prob_sum, cfg2 shape (N=100, 1024 particles): 10 100 "
@@ -637,6 +678,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-svi", action="store_true")
     ap.add_argument("--no-calnf", action="store_true")
+    ap.add_argument("--no-predictive", action="store_true")
+    ap.add_argument("--predictive-samples", type=int, default=8192, help="predictive samples per GPU")
     ap.add_argument("--calnf-particles", type=int, default=1024, help="particles per ELBO per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
