@@ -240,6 +240,13 @@ def test_emulated_scan2_vs_golden(name):
         assert rel_err(o["grads"]["scales"][0], g.ref_grad_scales) <= 1e-4
         assert np.array_equal(o["pop_tick"], ex["pop_tick"])
         assert np.array_equal(o["ticks"], ex["ticks"])
+    # without diagnostics (what the benchmark runs): same bars
+    o = plan.forward(lat, g.scales, g.noise[None], scan2=True, want_pop=False)
+    assert (o["status"] == 0).all()
+    assert abs(float(o["logp"].astype(np.float64).sum()) - ref) <= 5e-6 * abs(ref)
+    for k, v in g.ref_grads.items():
+        assert rel_err(o["grads"][k][0], v) <= 1e-4, ("no diagnostics", k)
+    assert rel_err(o["grads"]["scales"][0], g.ref_grad_scales) <= 1e-4
 
 
 SCAN2_CASES = [  # N, [F/day], P, mean service, spread
