@@ -14,6 +14,16 @@ for name in [n for n in golden_names() if n != 'wn100']:
         o = plan.forward(lat, g.scales, g.noise[None], exact=exact, shuffle_seed=5, want_pop=True, replay_waits=exact)
         assert (o['status'] == 0).all(), (name, o['status'])
     o = plan.forward(lat, g.scales, None, seed=7)
+    if plan.scan2_ok:
+        # the ring-less scan: shuffled lanes, with / without diagnostics, Philox, value mode with
+        # value gradients
+        for pop in (True, False):
+            o = plan.forward(lat, g.scales, g.noise[None], scan2=True, shuffle_seed=5, want_pop=pop)
+            assert (o['status'] == 0).all(), (name, 'scan2', o['status'])
+        o = plan.forward(lat, g.scales, None, seed=7, scan2=True)
+        vals = np.nan_to_num(g.ref_values, nan=1.0)[None]
+        o = plan.forward(lat, g.scales, vals, value_mode=True, scan2=True, want_value_grad=True)
+        assert (o['status'] == 0).all(), (name, 'scan2 value mode', o['status'])
 os.environ['BA_Q_MIN'] = '1'; os.environ['BA_Q_DIV'] = '1e9'
 g = Golden('congested6')
 plan = he.EmuPlan(g.specs, len(g.global_codes), g.delta_t, g.max_t, False)

@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer is closed on this GPU pool; instead the kernel's device code
-# (bayesair_b200/csrc/ba_sim.cuh), compiled for the host by tests/hostemu, is run under
+# (bayesair_b200/csrc/ba_sim.cuh, ba_scan2.cuh), compiled for the host by tests/hostemu, is run under
 # AddressSanitizer + UBSan over every golden case, both list variants, spill and overflow.
 set -e
 cd "$(dirname "$0")/.."
