@@ -482,7 +482,18 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         for (int f = tid; f < day.F; f += NT) ba2_scatter_flight(c, f);
         for (int a = tid; a < N; a += NT) ba2_split_cursor(c, a);
         ba2_sync<NW>();
-        if (warp == 0) ba2_split(c, lane, n_arr);              // stable: one warp walks the order
+        // stable split by destination: all warps when their cursor tables fit behind the
+        // prologue's shared tables, else one warp walks the order
+        if (NW > 1 && (size_t)(BA2_KC + 3 * N + NW * N) <= ba2_smem_words(N)) {
+            uint32_t *cnt = c.un + BA2_KC + 3 * N;
+            for (int i = tid; i < NW * N; i += NT) cnt[i] = 0u;
+            __syncthreads();
+            ba2_split_count(c, lane, warp, NW, cnt, n_arr);
+            __syncthreads();
+            for (int a = tid; a < N; a += NT) ba2_split_prefix(c, a, NW, cnt);
+            __syncthreads();
+            ba2_split_walk(c, lane, warp, NW, cnt, n_arr);
+        } else if (warp == 0) ba2_split(c, lane, n_arr);
         const bool aborted = ba2_any<NW>((acc.status & BA_S_OVERFLOW) != 0u);
         BA2_MARK(2);
 

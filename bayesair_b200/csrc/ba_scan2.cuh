@@ -170,6 +170,9 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N, int R)
 }
 
 // shared-memory words per warp
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 static inline size_t ba2_smem_words(int N)
 {
     const size_t nslot = (size_t)N;
@@ -339,15 +342,15 @@ BA_DEV void ba2_split_cursor(Ba2Ctx &c, int a)
     c.Ak[A.as_off + (uint32_t)A.arr_cnt] = BA2_NONE;
 }
 
-// PROLOGUE sweep 3: stable split of the tick-sorted keys by destination.  Device: the warp
-// walks the order 32 keys at a time (match.any ranks equal destinations inside the chunk).
-BA_DEV void ba2_split(Ba2Ctx &c, int lane, uint32_t n_arr)
+// PROLOGUE sweep 3: stable split of the tick-sorted keys by destination.  Device: a warp
+// walks its range of the order 32 keys at a time (match.any ranks equal destinations inside
+// the chunk) with its own cursor per destination.
+BA_DEV void ba2_split_range(Ba2Ctx &c, int lane, uint32_t *cur, uint32_t begin, uint32_t end)
 {
-    uint32_t *cur = c.un + BA2_KC;
 #if defined(__CUDA_ARCH__)
-    for (uint32_t base = 0; base < n_arr; base += 32u) {
+    for (uint32_t base = begin; base < end; base += 32u) {
         const uint32_t i = base + (uint32_t)lane;
-        const bool ok = i < n_arr;
+        const bool ok = i < end;
         const uint32_t act = __ballot_sync(0xffffffffu, ok);
         if (ok) {
             const Ba2U2 kd = ba2_ld2(c.S1 + 2 * i);
@@ -362,9 +365,43 @@ BA_DEV void ba2_split(Ba2Ctx &c, int lane, uint32_t n_arr)
     }
 #else
     (void)lane;
-    for (uint32_t i = 0; i < n_arr; ++i) c.Ak[cur[c.S1[2 * i + 1]]++] = c.S1[2 * i];
+    for (uint32_t i = begin; i < end; ++i) c.Ak[cur[c.S1[2 * i + 1]]++] = c.S1[2 * i];
 #endif
 }
+
+BA_DEV void ba2_split(Ba2Ctx &c, int lane, uint32_t n_arr)
+{
+    ba2_split_range(c, lane, c.un + BA2_KC, 0u, n_arr);
+}
+
+#if defined(__CUDA_ARCH__)
+// With several warps on a particle-day the split runs on all of them: every warp takes a
+// contiguous range of the tick-sorted order, the ranges' per-destination counts are turned
+// into per-warp start cursors (a prefix over the warps, in order: still a stable split).
+// `cnt` = [nw][N] words of shared memory behind the prologue's tables.
+BA_DEV uint32_t ba2_split_chunk(uint32_t n_arr, int nw) { return ((n_arr + (uint32_t)nw - 1u) / (uint32_t)nw + 31u) & ~31u; }
+
+BA_DEV void ba2_split_count(Ba2Ctx &c, int lane, int warp, int nw, uint32_t *cnt, uint32_t n_arr)
+{
+    const uint32_t chunk = ba2_split_chunk(n_arr, nw);
+    const uint32_t begin = min(n_arr, (uint32_t)warp * chunk), end = min(n_arr, begin + chunk);
+    uint32_t *mine = cnt + (size_t)warp * c.N;
+    for (uint32_t i = begin + (uint32_t)lane; i < end; i += 32u) BA_ATOMIC_INC(&mine[c.S1[2 * i + 1]]);
+}
+
+BA_DEV void ba2_split_prefix(Ba2Ctx &c, int a, int nw, uint32_t *cnt)
+{
+    uint32_t run = c.un[BA2_KC + a];
+    for (int w = 0; w < nw; ++w) { const uint32_t t = cnt[(size_t)w * c.N + a]; cnt[(size_t)w * c.N + a] = run; run += t; }
+}
+
+BA_DEV void ba2_split_walk(Ba2Ctx &c, int lane, int warp, int nw, uint32_t *cnt, uint32_t n_arr)
+{
+    const uint32_t chunk = ba2_split_chunk(n_arr, nw);
+    const uint32_t begin = min(n_arr, (uint32_t)warp * chunk), end = min(n_arr, begin + chunk);
+    ba2_split_range(c, lane, cnt + (size_t)warp * c.N, begin, end);
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // SCAN: the warp's lanes walk the airports in rounds, all on one clock

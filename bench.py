@@ -40,8 +40,10 @@ WORKLOADS = {
     "cfg2": (100, [3876], 1024, 0.012),
     # configs[0]: top-10 airports, one day (the reference's own CPU-runnable case)
     "cfg1": (10, [480], 1024, 0.03),
-    # configs[4] scaled to fit a quick run: 500 airports, 20k flights/day, 4 days
-    "cfg5s": (500, [20000] * 4, 512, 0.01),
+    # configs[4] scaled to fit a quick run: 500 airports, 20k flights/day, 4 days; 1332
+    # particles = four full waves of the 1332 particle-days a B200 holds at this size (the full
+    # config is 184 waves: a batch of one and a half waves would measure the idle tail)
+    "cfg5s": (500, [20000] * 4, 1332, 0.01),
 }
 
 
