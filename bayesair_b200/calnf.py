@@ -20,7 +20,7 @@ with a flow guide that buffer is tens of MB, the bandwidth-bound collective of t
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
