@@ -47,6 +47,11 @@ struct BaPlan {
     int sm_count = 0;
     uint64_t stride_scan2 = 0;
     int warps_scan2 = 1;
+    // a batch of one to one and a half waves runs as two concurrent launches: the wave, and its
+    // tail with more warps per particle-day on an auxiliary stream (own scratch)
+    uint32_t *d_scratch_tail = nullptr;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t *d_scratch = nullptr;
     uint64_t stride_fast = 0, stride_exact = 0;
     unsigned int *d_counters = nullptr;  // [0] fast work, [1] exact work, [2] rerun count
@@ -98,6 +103,9 @@ extern "C" void ba_plan_destroy(BaPlan *pl)
     if (pl->d_stage) cudaFree(pl->d_stage);
     if (pl->d_plogp) cudaFree(pl->d_plogp);
     if (pl->host_stream) cudaStreamDestroy(pl->host_stream);
+    if (pl->aux_stream) cudaStreamDestroy(pl->aux_stream);
+    if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+    if (pl->ev_join) cudaEventDestroy(pl->ev_join);
     delete pl;
 }
 
@@ -251,6 +259,15 @@ extern "C" BaStatus ba_plan_create(const BaDayTable *days, int32_t n_days, int32
     pl->allocs.push_back(cnt);
     pl->d_counters = (unsigned int *)cnt;
     BA_PCUDA(cudaStreamCreateWithFlags(&pl->host_stream, cudaStreamNonBlocking));
+    if (pl->scan2_ok && pl->grids_scan2[3] > 0) {
+        void *st = nullptr;
+        BA_PCUDA(cudaMalloc(&st, (size_t)pl->grids_scan2[3] * pl->stride_scan2 * 4));
+        pl->allocs.push_back(st);
+        pl->d_scratch_tail = (uint32_t *)st;
+        BA_PCUDA(cudaStreamCreateWithFlags(&pl->aux_stream, cudaStreamNonBlocking));
+        BA_PCUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+        BA_PCUDA(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+    }
 #undef BA_PCUDA
     *out = pl;
     return BA_OK;
@@ -356,7 +373,31 @@ extern "C" BaStatus ba_forward(BaPlan *pl, int32_t P, const float *d_lat_airport
             //  than letting the persistent CTAs drain the work counter)
             // BA_GRID_CAP: fewer resident particle-days than the SMs hold (occupancy experiments)
             if (const char *e = std::getenv("BA_GRID_CAP")) { int g = std::atoi(e); if (g > 0 && g < grid) grid = g; }
-            BA_CUDA(ba_launch_forward2(prm, nw, grid, pl->smem_scan2, s));
+            // Just over one wave (a strong-scaling shard): the few items beyond the first wave
+            // would run alone on a nearly empty GPU at one warp each.  They run instead as a
+            // second, concurrent launch with eight warps per particle-day, which fills the SMs
+            // as the first launch drains -- as long as they fit ONE wave of such CTAs (measured
+            // on cfg3: 4.97 -> 4.49 ms at 1.08 waves, 4.65 -> 4.17 at 1.01; a tail of a quarter
+            // wave already loses: 5.59 -> 6.66 ms).
+            const long long tail = n_work - grid;
+            if (li == 0 && !pinned_w && tail > 0 && tail <= pl->grids_scan2[3] && pl->d_scratch_tail &&
+                !prm.phase_cycles && !std::getenv("BA_NO_TAIL_LAUNCH")) {
+                BaFwdParams tp = prm;
+                tp.wi_begin = grid; tp.n_work = (int)tail;
+                tp.scratch = pl->d_scratch_tail;
+                tp.work_counter = pl->d_counters + 3;
+                const int tgrid = (int)std::min<long long>(tail, pl->grids_scan2[3]);
+                BA_CUDA(cudaEventRecord(pl->ev_fork, s));
+                BA_CUDA(cudaStreamWaitEvent(pl->aux_stream, pl->ev_fork, 0));
+                prm.n_work = grid;
+                BA_CUDA(ba_launch_forward2(prm, nw, grid, pl->smem_scan2, s));
+                BA_CUDA(ba_launch_forward2(tp, 8, tgrid, pl->smem_scan2, pl->aux_stream));
+                BA_CUDA(cudaEventRecord(pl->ev_join, pl->aux_stream));
+                BA_CUDA(cudaStreamWaitEvent(s, pl->ev_join, 0));
+                prm.n_work = (int)n_work;
+                g_launches++;
+            } else
+                BA_CUDA(ba_launch_forward2(prm, nw, grid, pl->smem_scan2, s));
         } else {
             prm.scratch_stride = pl->stride_fast;
             int grid = (int)std::min<long long>(n_work, pl->grid_fast);

@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(32 * NW, 32 / NW) ba_forward2_kernel(const BaF
         if (wi >= n_work) break;
         int p, d;
         if (prm.work_list) { const int pd = prm.work_list[wi]; p = pd / D; d = pd - p * D; }
-        else { d = wi / prm.P; p = wi - d * prm.P; }     // same-day items adjacent in time
+        else { const int g = wi + prm.wi_begin; d = g / prm.P; p = g - d * prm.P; }   // same-day items adjacent in time
         const size_t pd = (size_t)p * D + d;
         const BaDayView day = plan.days[d];
 

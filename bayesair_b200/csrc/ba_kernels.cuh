@@ -32,6 +32,7 @@ struct BaFwdParams {
     int32_t n_work;
     const unsigned int *n_work_dev; // if set, overrides n_work (device-side count)
     unsigned long long *phase_cycles; // optional [8] per-phase cycle totals (debug, BA_PHASE_PROFILE)
+    int32_t wi_begin;             // first work item of this launch (a batch run as two launches)
 };
 
 struct BaBwdParams {
