@@ -85,3 +85,55 @@ def test_particle_day_grid_is_covered_once():
         assert all(abs(w - 1.0) < 1e-12 for w in weight.values())
     # plenty of particles: the days stay whole
     assert shard_particle_days(4096, 10, 3, 8) == (1536, 512, 0, 10)
+
+
+def _flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bayesair_b200.calnf import FlatParameters
+    from bayesair_b200.flows import ConditionalSplineFlow
+    torch.manual_seed(0)                                  # identical weights on every rank
+    flow = ConditionalSplineFlow(6, 2, hidden_features=(8, 8), transforms=2)
+    for layer in flow.layers:
+        torch.nn.init.normal_(layer.out.weight, std=0.2)
+    fp = FlatParameters(flow)
+    # every rank differentiates its own shard of the same sample set
+    torch.manual_seed(100)
+    z_all = torch.randn(8, 6)
+    start, count = shard_particles(8, rank, world)
+    loss = -flow(torch.tensor([1.0, 0.0])).log_prob(z_all[start:start + count]).sum() / 8.0
+    loss.backward()
+    fp.all_reduce()
+    out.put((rank, fp.grad.clone(), fp.nbytes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_buffer_allreduce_matches_single_process():
+    """The CalNF exchange (calnf.FlatParameters.all_reduce): one collective on the buffer
+    autograd wrote; two ranks over half the samples each equal one process over all."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from bayesair_b200.calnf import FlatParameters
+    from bayesair_b200.flows import ConditionalSplineFlow
+    torch.manual_seed(0)
+    flow = ConditionalSplineFlow(6, 2, hidden_features=(8, 8), transforms=2)
+    for layer in flow.layers:
+        torch.nn.init.normal_(layer.out.weight, std=0.2)
+    fp = FlatParameters(flow)
+    torch.manual_seed(100)
+    z_all = torch.randn(8, 6)
+    (-flow(torch.tensor([1.0, 0.0])).log_prob(z_all).sum() / 8.0).backward()
+    for _, g, nbytes in res:
+        assert nbytes == fp.nbytes
+        assert torch.allclose(g, fp.grad, atol=1e-5, rtol=1e-4)
