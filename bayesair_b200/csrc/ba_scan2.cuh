@@ -126,7 +126,7 @@ struct Ba2Ctx {
                                               //   odd ticks): lpos of the flights served at or
                                               //   after their arrival tick
     uint32_t lb_stride;
-    uint32_t *S0, *S1;                        // [2 F] each, prologue: {key, destination} by flight /
+    uint32_t *S0, *S1;                        // prologue: key by flight [F] / {key, destination} [2 F]
                                               //   sorted by arrival tick
     float *hx;                                // [2 F] history of draws by assignment index
     uint32_t *glog;                           // [4 F] (tick, assignments before it) of ticks that
@@ -160,7 +160,7 @@ BA_DEV void ba2_carve_scratch(Ba2Ctx &c, uint32_t *g, int F, int N, int R)
     const uint32_t f = (uint32_t)F, fn = ((uint32_t)(F + N) + 3u) & ~3u;
     c.eps = (float *)g; g += (f + 3u) & ~3u;              // 16-byte aligned blocks first
     c.P = (Ba2Pay *)g; g += 4 * fn;
-    c.S0 = g; c.S1 = g + 2 * f;
+    c.S0 = g; c.S1 = g + ((f + 1u) & ~1u);
     g += 4 * f;
     c.Ak = g; g += fn;
     c.Lb = g; g += 2 * fn; c.lb_stride = fn;
@@ -291,7 +291,7 @@ BA_DEV void ba2_prologue_compute(Ba2Ctx &c, BaAcc &acc, int f, const Ba2FlightIn
         key = ((uint32_t)kk << 16) | (uint32_t)in.lpos;
         BA_ATOMIC_INC(&c.un[kk]);
     }
-    ba2_st2(c.S0 + 2 * f, key, (uint32_t)d);
+    c.S0[f] = key;
 }
 
 // PROLOGUE sweep 1, one flight (host emulation; the kernel runs the two halves itself)
@@ -328,10 +328,11 @@ BA_DEV void ba2_bucket_scan(Ba2Ctx &c, int lane)
 // PROLOGUE sweep 2: flight -> its place in the tick-sorted order
 BA_DEV void ba2_scatter_flight(Ba2Ctx &c, int f)
 {
-    const Ba2U2 kd = ba2_ld2(c.S0 + 2 * f);
-    if (kd.x == BA2_NONE) return;
-    const uint32_t pos = BA_ATOMIC_INC(&c.un[kd.x >> 16]);
-    ba2_st2(c.S1 + 2 * pos, kd.x, kd.y);
+    const uint32_t key = c.S0[f];
+    if (key == BA2_NONE) return;
+    const uint32_t d = (c.flights[f].od >> 12) & 0xFFFu;   // static table: an L2 hit
+    const uint32_t pos = BA_ATOMIC_INC(&c.un[key >> 16]);
+    ba2_st2(c.S1 + 2 * pos, key, d);
 }
 
 // start cursor of a destination's list (static: the lists have static sizes) + sentinel
