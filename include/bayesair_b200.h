@@ -19,7 +19,9 @@
  *     named h_* are host pointers; the library allocates nothing per call except
  *     inside the opaque plan (static day tables + per-CTA scratch);
  *   - all work is enqueued on the caller's stream (passed as void* = cudaStream_t),
- *     no hidden synchronisation in ba_forward / ba_backward;
+ *     no hidden synchronisation in ba_forward / ba_backward (a batch of just over one
+ *     wave of particle-days forks part of its work to a stream of the plan and joins it
+ *     back with events: still ordered on the caller's stream, and capturable);
  *   - a plan is immutable after creation and bound to one device; calls on one plan
  *     must be stream-ordered (they share the plan's scratch).
  *   - all model arithmetic is fp32, like the reference's.
