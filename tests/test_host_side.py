@@ -524,3 +524,24 @@ def test_emulated_value_gradients_vs_reference(name):
         # the global-latent gradients of the same (value-mode) run are pinned too
         assert rel_err(o["grads"]["mean_service"][0], v["grad_mean_service"], floor=1e-4) <= 1e-3
         assert rel_err(o["grads"]["mean_turnaround"][0], v["grad_mean_turnaround"], floor=1e-4) <= 1e-3
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm): one JSON
+    line, same metric / unit / config dict as the native arm would print, cpu_baseline and e2e
+    blocks describing the run."""
+    import json
+    import subprocess
+    import sys
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--workload", "cfg1", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    assert line["config"] == bench.workload_config("cfg1")
+    assert line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
