@@ -1,3 +1,4 @@
+# Run under `gpurun`: GPU test suite, bench lines (both arms, cfg3 and cfg5s), phase and occupancy tables, ncu captures, smoke.
 python -m pytest tests -m gpu -q > gpurun_out/r2_pytest_final.log 2>&1; tail -3 gpurun_out/r2_pytest_final.log
 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err; tail -2 gpurun_out/r2_bench_final.err; cat gpurun_out/r2_bench_final.json | cut -c1-400
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_final_ref.json 2>/dev/null; cut -c1-200 gpurun_out/r2_bench_final_ref.json
