@@ -65,19 +65,66 @@ def _stack_sites(values: List[torch.Tensor], device):
     return torch.stack(vals, dim=1), P     # [P, n]
 
 
+def _flight_sites(plan, rows, travel, codes, v_t, v_u, P, batched, device):
+    """Declares the four latent per-flight sites of every non-cancelled flight and returns
+    their values as the kernel's ``[P, D, Fmax, 4]`` value tensor plus the sum of their
+    log-probs ``[P]`` (what the kernel's total contains besides the observed sites)."""
+    turnaround, service = rows[0], rows[1]
+    D, F = plan.n_days, plan.max_flights
+    cols = [[None] * F for _ in range(D)]
+    latent_lp = torch.zeros((P,), device=device)
+    one = torch.ones((P,), device=device)
+    for d, spec in enumerate(plan.specs):
+        for f in range(spec.n_flights):
+            if spec.cancel_obs[f] == 1:
+                continue
+            o, dd = int(spec.airport_global[spec.origin[f]]), int(spec.airport_global[spec.dest[f]])
+            stem = f"day{d}_{spec.flight_names[f]}"
+            ms_o, ms_d = _as_batch(service[o], device), _as_batch(service[dd], device)
+            mt_d = _as_batch(turnaround[dd], device)
+            T = _as_batch(travel[(codes[o], codes[dd])], device)
+            sites = (
+                ("_departure_service_time", dist.Exponential(1.0 / ms_o.expand(P))),
+                ("_travel_time", dist.Normal(T.expand(P), T.expand(P) * v_t)),
+                ("_arrival_service_time", dist.Exponential(1.0 / ms_d.expand(P))),
+                ("_turnaround_time", dist.Normal(mt_d.expand(P), v_u * mt_d.expand(P))),
+            )
+            vals = []
+            for suffix, fn in sites:
+                v = _as_batch(pyro.sample(stem + suffix, fn), device).expand(P)
+                latent_lp = latent_lp + fn.log_prob(v)
+                vals.append(v)
+            cols[d][f] = torch.stack(vals, dim=-1)                 # [P, 4]
+    pad = torch.stack([one, one, one, one], dim=-1)
+    values = torch.stack([torch.stack([c if c is not None else pad for c in day], dim=1)
+                          for day in cols], dim=1)                 # [P, D, F, 4]
+    return values.contiguous(), latent_lp
+
+
 def air_traffic_network_model(
     states,
     delta_t: float = 0.1,
     max_t: float = FAR_FUTURE_TIME,
     device=None,
     include_cancellations: bool = False,
+    expose_flight_sites: bool = False,
 ):
     """See the module docstring.  ``device`` must be a CUDA device (``None`` ->
     the current one); the simulation has no CPU path.  Returns ``states``
     unmodified (every caller of the reference ignores the return value); if some
     flight has no observations (``obs=None``) the call is a posterior-predictive
     simulation instead and returns ``[P, D, Fmax, 3]`` (cancelled, departure time,
-    arrival time) -- the reference returns the mutated state objects there."""
+    arrival time) -- the reference returns the mutated state objects there.
+
+    ``expose_flight_sites=True`` (an extension; plans without cancellations, every flight
+    observed) declares the four LATENT per-flight sites of the reference as well --
+    ``day{d}_{flight}_departure_service_time``, ``_travel_time``, ``_arrival_service_time``,
+    ``_turnaround_time`` with the reference's distributions (``types/airport.py:144-147,
+    217-220``, ``network.py:158-163``) -- so that a guide over EVERY latent site
+    (``AutoMultivariateNormal(model)``, ``scripts/wn/wn_network.py:285-302``) proposes them;
+    the kernel then runs in value mode on the proposed values, the factor carries only the
+    observed sites, and gradients reach the values through the kernel's value tape.  This is
+    4F Python statements per day: for the small networks that route is viable for."""
     plan = plan_for_states(states, delta_t, max_t, include_cancellations, device)
     device = plan.device
 
@@ -135,6 +182,15 @@ def air_traffic_network_model(
         sim = out["sim"] if batched else out["sim"][0]
         pyro.deterministic("air_traffic_simulated", sim)
         return sim
+    if expose_flight_sites:
+        if include_cancellations or noise is not None:
+            raise ValueError("expose_flight_sites: plans without cancellations, no flight_noise override")
+        values, latent_lp = _flight_sites(plan, rows, travel, codes, v_t, v_u, P, batched, device)
+        logp = simulate_log_joint(plan, lat_airport, lat_route, scales, values, noise_is_value=True)
+        # the per-flight latent sites are ordinary sites now: the factor keeps the observed ones
+        log_joint = logp.sum(dim=1) - latent_lp
+        pyro.factor(FACTOR_NAME, log_joint if batched else log_joint.reshape(()))
+        return states
     logp = simulate_log_joint(plan, lat_airport, lat_route, scales, noise,
                               seed=seed or 0, noise_is_value=is_value)
     log_joint = logp.sum(dim=1)               # sum over days -> [P]

@@ -241,3 +241,65 @@ def test_model_routes_value_gradients_to_a_per_flight_guide():
     assert abs(float(factor) - float(v["total"])) <= 1e-4 * abs(float(v["total"]))
     factor.backward()
     assert value_grad_error(vals.grad[0].cpu().numpy(), v["grad_values"], v["values"]) <= 1e-3
+
+
+def test_exposed_flight_sites_reproduce_the_reference_trace_and_take_a_guide():
+    """expose_flight_sites=True: the four latent per-flight sites of the reference are real
+    sites again.  Conditioned on the golden's values (globals and per-flight), the trace's
+    log_prob_sum is the reference's total and its gradient w.r.t. the latents the reference's
+    value-mode autograd; an autoguide then covers EVERY latent site, as
+    AutoMultivariateNormal(model) does for the reference (wn_network.py:285-302)."""
+    import bayesair_b200 as ba
+    from bayesair_b200.ppl import USING_REAL_PYRO, poutine, pyro
+    from tests.test_host_side import _value_golden
+    from tests.util import rel_err
+    g, v = Golden("tiny4"), _value_golden("tiny4")
+    states = _golden_states(g)
+    dev = torch.device("cuda:0")
+    codes = g.global_codes
+    ms = torch.tensor(g.latents["mean_service"], device=dev, requires_grad=True)
+    data = {}
+    for i, c in enumerate(codes):
+        data[f"{c}_mean_turnaround_time"] = torch.tensor(g.latents["mean_turnaround"][i], device=dev)
+        data[f"{c}_mean_service_time"] = ms[i]
+        for j, c2 in enumerate(codes):
+            if i != j:
+                data[f"travel_time_{c}_{c2}"] = torch.tensor(g.latents["travel"][i, j], device=dev)
+    kinds = ("departure_service_time", "travel_time", "arrival_service_time", "turnaround_time")
+    n_flight_sites = 0
+    for d, spec in enumerate(g.specs):
+        for f in range(spec.n_flights):
+            if spec.cancel_obs[f] == 1:
+                continue
+            for col, kind in enumerate(kinds):
+                data[f"day{d}_{spec.flight_names[f]}_{kind}"] = torch.tensor(float(v["values"][d, f, col]), device=dev)
+                n_flight_sites += 1
+    pyro.clear_param_store()
+    for nme, s in zip(("runway_use_time_std_dev", "travel_time_variation",
+                       "turnaround_time_variation"), g.scales):
+        pyro.param(nme, torch.tensor(s, device=dev), constraint=torch.distributions.constraints.positive)
+
+    def model(states, dt):
+        return ba.air_traffic_network_model(states, dt, device=dev, expose_flight_sites=True)
+
+    tr = poutine.trace(poutine.condition(model, data=data)).get_trace(states, g.delta_t)
+    total = tr.log_prob_sum()
+    assert abs(float(total) - g.ref_total) <= 1e-4 * abs(g.ref_total)
+    flight_nodes = [n for n in tr.nodes if n.startswith("day")]
+    assert len(flight_nodes) == n_flight_sites
+    per_flight = sum(tr.nodes[n]["fn"].log_prob(tr.nodes[n]["value"]).sum() for n in flight_nodes) \
+        + tr.nodes[ba.FACTOR_NAME]["fn"].log_prob(None).sum()
+    (gm,) = torch.autograd.grad(per_flight, [ms])
+    assert rel_err(gm.cpu().numpy(), v["grad_mean_service"], floor=1e-4) <= 1e-3
+    if USING_REAL_PYRO:
+        return
+    # a guide over every latent site: globals and the 4 per live flight
+    pyro.clear_param_store()
+    torch.manual_seed(0)
+    guide = pyro.infer.autoguide.AutoNormal(model, init_scale=0.02)
+    svi = pyro.infer.SVI(model, guide, pyro.optim.ClippedAdam({"lr": 0.01}),
+                         pyro.infer.Trace_ELBO(num_particles=4, vectorize_particles=True))
+    losses = [svi.step(states, g.delta_t) for _ in range(12)]
+    assert np.isfinite(losses).all()
+    assert guide.latent_dim == n_flight_sites + 2 * len(codes) + len(codes) * (len(codes) - 1)
+    assert np.mean(losses[-4:]) < np.mean(losses[:4])
